@@ -1,0 +1,317 @@
+"""Pin the oracle against the real reference and write ``tests/golden/*.npz``.
+
+Runs ONLY in the build container (needs ``/root/reference``); the fixtures it
+writes are committed and re-checked by ``pytest -m "not gpu"`` and, against the
+CUDA library, by ``pytest -m gpu``.  Usage:  python -m oracle.make_golden
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("DIFFSPLIT_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import samplers_ref as S          # noqa: E402
+from oracle import tiling_ref as TR           # noqa: E402
+from oracle import unet_ref as U              # noqa: E402
+
+UNET_CASES = {
+    # name: (cfg, B, H, W)
+    "sr3_attn": (U.make_cfg("sr3", 3, 2, 16, 8, (1, 2, 2), (8,), 1, 16), 2, 16, 16),
+    "sr3_wide": (U.make_cfg("sr3", 6, 3, 32, 16, (1, 2), (), 2, 16), 1, 16, 24),
+    "ddpm_cifar": (U.make_cfg("ddpm", 9, 6, 16, 16, (1, 2, 4, 8), (), 1, 32), 1, 32, 32),
+    "ddpm_hagen": (U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 2, 64, 64),
+}
+
+
+def _import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference not found at {REF}")
+    sys.path.insert(0, REF)
+    for name in ("albumentations", "skimage", "skimage.io"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["skimage.io"].imread = None
+    sys.modules["albumentations"].Compose = None
+    import model.sr3_modules.unet as sr3_unet
+    import model.sr3_modules.diffusion as sr3_diff
+    import model.ddpm_modules.unet as ddpm_unet
+    import model.ddpm_modules.diffusion as ddpm_diff
+    import model.ddpm_modules.indi as indi
+    import model.ddpm_modules.joint_indi as joint
+    import data.tiling_manager as tm
+    import data.tile_stitcher as ts
+    import data.split_dataset_tiledpred as tp
+    import core.psnr as psnr
+    return types.SimpleNamespace(sr3_unet=sr3_unet, sr3_diff=sr3_diff, ddpm_unet=ddpm_unet,
+                                 ddpm_diff=ddpm_diff, indi=indi, joint=joint, tm=tm, ts=ts, tp=tp, psnr=psnr)
+
+
+def build_ref_unet(R, cfg):
+    mod = R.sr3_unet if cfg["variant"] == "sr3" else R.ddpm_unet
+    return mod.UNet(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"],
+                    inner_channel=cfg["inner_channel"], norm_groups=cfg["norm_groups"],
+                    channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+                    res_blocks=cfg["res_blocks"], dropout=0, image_size=cfg["image_size"]).eval()
+
+
+def time_input(cfg, B, g):
+    if cfg["variant"] == "sr3":
+        return torch.rand((B, 1), generator=g) * 0.98 + 0.01
+    return torch.rand((B,), generator=g)
+
+
+def gen_unet(R):
+    for name, (cfg, B, H, W) in UNET_CASES.items():
+        sd = U.random_state_dict(cfg, seed=11)
+        ref = build_ref_unet(R, cfg)
+        missing = ref.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn((B, cfg["in_channel"], H, W), generator=g)
+        t = time_input(cfg, B, g)
+        with torch.no_grad():
+            y_ref = ref(x, t)
+        y_or = U.unet_forward(sd, cfg, x, t)
+        err = (y_ref - y_or).abs().max().item()
+        print(f"[unet {name}] out {tuple(y_ref.shape)} absmax {y_ref.abs().max():.4f} oracle-vs-reference max err {err:.3e}")
+        assert err <= 2e-6 * max(1.0, y_ref.abs().max().item())
+        wsum = float(sum(v.double().sum() for v in sd.values()))
+        np.savez_compressed(os.path.join(GOLD, f"unet_{name}.npz"), x=x.numpy(), t=t.numpy(),
+                            y=y_ref.numpy(), weight_checksum=np.float64(wsum), seed=np.int64(11))
+        # flop count cross-check with forward hooks on the reference
+    # flops: compare against the published per-sample figures
+    cfgD = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
+    print("[flops] hagen 64^2 per sample GF:", U.count_flops(cfgD, 64, 64) / 1e9, "(BASELINE.md: 0.973)")
+    print("[flops] hagen 512^2 per sample GF:", U.count_flops(cfgD, 512, 512) / 1e9, "(BASELINE.md: 70.72)")
+    cfgB = U.make_cfg("sr3", 6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 128)
+    print("[flops] sr3_16_128 per sample GF:", U.count_flops(cfgB, 128, 128) / 1e9, "(BASELINE.md: 92.35)")
+
+
+class Recorder:
+    """Replaces torch.randn / randn_like inside the reference so that the noise it
+    consumed can be replayed into the oracle (and, on the GPU box, the CUDA path)."""
+
+    _randn = torch.randn
+
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(seed)
+        self.log = []
+
+    def draw(self, shape):
+        z = Recorder._randn(tuple(shape), generator=self.g)
+        self.log.append(z)
+        return z
+
+
+def patched_randn(rec):
+    class Ctx:
+        def __enter__(self_):
+            self_.a, self_.b = torch.randn, torch.randn_like
+            torch.randn = lambda *s, **kw: rec.draw(s[0] if len(s) == 1 and not isinstance(s[0], int) else s)
+            torch.randn_like = lambda x, **kw: rec.draw(x.shape)
+
+        def __exit__(self_, *a):
+            torch.randn, torch.randn_like = self_.a, self_.b
+    return Ctx()
+
+
+class Replay:
+    def __init__(self, log):
+        self.log, self.i = log, 0
+
+    def __call__(self, shape):
+        z = self.log[self.i]
+        self.i += 1
+        assert tuple(z.shape) == tuple(shape), (z.shape, shape)
+        return z
+
+
+def gen_samplers(R):
+    sched = dict(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=0.3)
+    out = {}
+    # ---- schedule tables (T=2000 production schedule + the tiny one) -----------------
+    prod = dict(schedule="linear", n_timestep=2000, linear_start=1e-6, linear_end=1e-2)
+    for nm, so in (("tiny", sched), ("prod", prod)):
+        ref = R.sr3_diff.GaussianDiffusion(None, 8)
+        ref.set_new_noise_schedule(so, "cpu")
+        tab = S.schedule_tables(so)
+        for k in ("betas", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                  "posterior_mean_coef2", "posterior_log_variance_clipped", "alphas_cumprod_prev"):
+            assert np.array_equal(getattr(ref, k).numpy(), tab[k].astype(np.float32)), k
+            out[f"sched_{nm}_{k}"] = getattr(ref, k).numpy()
+        assert np.array_equal(ref.sqrt_alphas_cumprod_prev, tab["sqrt_alphas_cumprod_prev"])
+        out[f"sched_{nm}_sqrt_alphas_cumprod_prev"] = ref.sqrt_alphas_cumprod_prev
+    print("[sched] tables identical (tiny, prod)")
+
+    # ---- SR3 conditional loop with a real (tiny) UNet ---------------------------------
+    cfg = U.make_cfg("sr3", 3, 2, 16, 8, (1, 2), (), 1, 16)
+    sd = U.random_state_dict(cfg, seed=3)
+    net = build_ref_unet(R, cfg)
+    net.load_state_dict(sd)
+    ref = R.sr3_diff.GaussianDiffusion(net, 16, channels=2, conditional=True)
+    ref.set_new_noise_schedule(sched, "cpu")
+    g = torch.Generator().manual_seed(1)
+    cond = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    rec = Recorder(2)
+    import tqdm as _tq
+    R.sr3_diff.tqdm = lambda it, **kw: it
+    with patched_randn(rec):
+        y_ref = ref.p_sample_loop(cond, continous=True)
+    tab = S.schedule_tables(sched)
+    y_or = S.sr3_sample_loop(tab, lambda x, t: U.unet_forward(sd, cfg, x, t), cond, 2, True, Replay(rec.log), continous=True)
+    err = (y_ref - y_or).abs().max().item()
+    print(f"[sr3 loop] {tuple(y_ref.shape)} oracle-vs-reference max err {err:.3e}")
+    assert err < 1e-5
+    out.update(sr3_cond=cond.numpy(), sr3_out=y_ref.numpy(), sr3_noise=np.stack([z.numpy() for z in rec.log]))
+
+    # ---- DDPM conditional loop ---------------------------------------------------------
+    cfgd = U.make_cfg("ddpm", 3, 2, 16, 8, (1, 2), (), 1, 16)
+    sdd = U.random_state_dict(cfgd, seed=4)
+    netd = build_ref_unet(R, cfgd)
+    netd.load_state_dict(sdd)
+    refd = R.ddpm_diff.GaussianDiffusion(netd, 16, channels=2, conditional=True)
+    refd.set_new_noise_schedule(sched, "cpu")
+    R.ddpm_diff.tqdm = lambda it, **kw: it
+    rec = Recorder(6)
+    with patched_randn(rec):
+        y_ref = refd.p_sample_loop(cond, continous=True)
+    y_or = S.ddpm_sample_loop(tab, lambda x, t: U.unet_forward(sdd, cfgd, x, t), cond, 2, True, Replay(rec.log), continous=True)
+    err = (y_ref - y_or).abs().max().item()
+    print(f"[ddpm loop] {tuple(y_ref.shape)} oracle-vs-reference max err {err:.3e}")
+    assert err < 1e-5
+    out.update(ddpm_out=y_ref.numpy(), ddpm_noise=np.stack([z.numpy() for z in rec.log]))
+
+    # ---- InDI / JointIndi ----------------------------------------------------------------
+    cfgi = U.make_cfg("ddpm", 1, 1, 16, 8, (1, 2), (), 1, 16)
+    sd1, sd2 = U.random_state_dict(cfgi, seed=7), U.random_state_dict(cfgi, seed=8)
+    n1, n2 = build_ref_unet(R, cfgi), build_ref_unet(R, cfgi)
+    n1.load_state_dict(sd1)
+    n2.load_state_dict(sd2)
+    R.indi.tqdm = lambda it, **kw: it
+    x_in = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    for T in (1, 4):
+        indi = R.indi.InDI(n1, 16, channels=1, out_channel=1, conditional=False, val_schedule_opt={"n_timestep": T})
+        indi.set_new_noise_schedule({"n_timestep": T}, "cpu")
+        rec = Recorder(20 + T)
+        with patched_randn(rec):
+            y_ref = indi.inference(x_in, continuous=True)
+        y_or = S.indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), x_in, T, Replay(rec.log), continuous=True)
+        err = (y_ref - y_or).abs().max().item()
+        print(f"[indi T={T}] {tuple(y_ref.shape)} oracle-vs-reference max err {err:.3e}")
+        assert err < 1e-5 and y_ref.shape[0] == 2 * (T + 1)
+        out.update({f"indi_T{T}_out": y_ref.numpy(), f"indi_T{T}_noise": np.stack([z.numpy() for z in rec.log])})
+    joint = R.joint.JointIndi(None, 16, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=n1,
+                              denoise_fn_ch2=n2, val_schedule_opt={"n_timestep": 3})
+    joint.set_new_noise_schedule({"n_timestep": 3}, "cpu")
+    rec = Recorder(31)
+    with patched_randn(rec):
+        y_ref = joint.inference(x_in, continuous=True, t_float_start=0.5)
+    y_or = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t),
+                                  lambda x, t: U.unet_forward(sd2, cfgi, x, t), x_in, 3, Replay(rec.log),
+                                  t_float_start=0.5, continuous=True)
+    err = (y_ref - y_or).abs().max().item()
+    print(f"[joint indi] {tuple(y_ref.shape)} oracle-vs-reference max err {err:.3e}")
+    assert err < 1e-5
+    out.update(indi_x=x_in.numpy(), joint_out=y_ref.numpy(), joint_noise=np.stack([z.numpy() for z in rec.log]))
+
+    # ---- PSNR metrics (core/psnr.py) ---------------------------------------------------------
+    gt = torch.rand((3, 32, 32), generator=g) * 900
+    pr = gt + torch.randn((3, 32, 32), generator=g) * 20
+    assert torch.allclose(R.psnr.PSNR(gt, pr), S.psnr(gt, pr), atol=1e-4)
+    assert torch.allclose(R.psnr.RangeInvariantPsnr(gt, pr), S.range_invariant_psnr(gt, pr), atol=1e-4)
+    out.update(psnr_gt=gt.numpy(), psnr_pred=pr.numpy(), psnr=R.psnr.PSNR(gt, pr).numpy(),
+               ripsnr=R.psnr.RangeInvariantPsnr(gt, pr).numpy())
+    np.savez_compressed(os.path.join(GOLD, "samplers.npz"), **out)
+
+
+def gen_tiling(R):
+    shapes = [
+        ((5, 512, 512), (1, 128, 128), (1, 256, 256)),       # the reference unit test
+        ((10, 2048, 2048), (1, 256, 256), (1, 512, 512)),    # split.py:60-61 production
+        ((3, 100, 130), (1, 16, 16), (1, 32, 32)),           # ragged: shifted last row/col
+        ((2, 64, 64), (1, 64, 64), (1, 64, 64)),             # patch == grid, single tile
+        ((1, 33, 47), (1, 8, 4), (1, 16, 12)),
+        ((4, 70, 70), (1, 32, 32), (1, 64, 64)),
+    ]
+    out = {}
+    n = 0
+    for data, grid, patch in shapes:
+        for mode in (TR.TRIM, TR.PAD, TR.SHIFT):
+            ref = R.tm.TileIndexManager(data, grid, patch, mode)
+            tg = TR.TileGrid(data, grid, patch, mode)
+            assert ref.total_grid_count() == tg.total, (data, grid, patch, mode)
+            for d in range(3):
+                assert ref.get_individual_dim_grid_count(d) == tg.counts[d]
+                assert ref.grid_count(d) == tg.strides[d]
+            tab = tg.patch_table()
+            step = max(1, tg.total // 400)
+            for i in list(range(0, tg.total, step)) + [tg.total - 1]:
+                assert tuple(int(v) for v in ref.get_patch_location_from_dataset_idx(i)) == tuple(tab[i])
+                assert tuple(int(v) for v in ref.get_location_from_dataset_idx(i)) == tg.grid_location(i)
+            out[f"tab_{n}_{mode}"] = tab.astype(np.int32)
+            out[f"shape_{n}_{mode}"] = np.array([data, grid, patch], dtype=np.int32)
+        n += 1
+    # stitch: the reference test's construction + a ragged random case
+    import contextlib
+    import io
+    rng = np.random.default_rng(0)
+    for tag, (data, grid, patch) in (("unit", shapes[0]), ("ragged", shapes[2]), ("odd", shapes[4])):
+        tg = TR.TileGrid(data, grid, patch, TR.SHIFT)
+        ref = R.tm.TileIndexManager(data, grid, patch, R.tm.TilingMode.ShiftBoundary)
+        frames = np.arange(2 * np.prod(data)).reshape(data + (2,)).transpose(3, 0, 1, 2).astype(np.float32)   # (C,F,H,W)
+        if patch[1] != patch[2]:
+            continue
+        tiles = TR.crop_tiles(frames, tg)
+        with contextlib.redirect_stdout(io.StringIO()):
+            s_ref = R.ts.stitch_predictions(tiles, ref)
+        s_or = TR.stitch(tiles, tg)
+        assert np.array_equal(s_ref, s_or)
+        assert np.array_equal(s_or, frames.transpose(1, 2, 3, 0)), "stitch(crop(frames)) must be the identity"
+        noise_tiles = rng.standard_normal(tiles.shape).astype(np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            s_ref = R.ts.stitch_predictions(noise_tiles, ref)
+        assert np.array_equal(s_ref, TR.stitch(noise_tiles, tg))
+        if tag == "ragged":
+            out["stitch_ragged_tiles"] = noise_tiles[:, :, ::4, ::4].copy()     # thumbnails only, keep the file small
+            out["stitch_ragged_out_sum"] = np.float64(s_ref.astype(np.float64).sum())
+            out["stitch_ragged_out"] = s_ref
+    # the reference's own dataset-level test (tests/test_tiling_setup.py:35-55) through its dataset class
+    def get_data(*a, **k):
+        d = np.arange(5 * 512 * 512 * 2).reshape(5, 512, 512, 2)
+        return {i: d[..., i] for i in range(2)}
+    import data.split_dataset as sdmod
+    sdmod.load_data = get_data
+    ident = {'mean_input': 0, 'mean_target': np.array([0, 0]), 'std_input': 1, 'std_target': np.array([1, 1]),
+             'target0_max': 1, 'target1_max': 1, 'input_max': 1}
+    with contextlib.redirect_stdout(io.StringIO()):
+        dset = R.tp.SplitDatasetTiledPred('Hagen', None, 256, grid_size=128, upper_clip=False, normalization_dict=ident,
+                                          enable_transforms=False, uncorrelated_channels=False, random_patching=False)
+    tg = TR.TileGrid((5, 512, 512), (1, 128, 128), (1, 256, 256), TR.SHIFT)
+    assert len(dset) == tg.total
+    frames = np.stack([np.stack(get_data()[c]) for c in range(2)])
+    for i in (0, 1, 8, 9, 17, tg.total - 1):
+        item = dset[i]
+        assert tuple(int(v) for v in dset.patch_location(i)) == tg.patch_location(i)
+        assert np.array_equal(item['target'], TR.crop_tiles(frames, tg, [i])[0])
+    print(f"[tiling] {n} shapes x 3 modes identical; stitch identical (unit, ragged); dataset crop identical")
+    np.savez_compressed(os.path.join(GOLD, "tiling.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    R = _import_reference()
+    gen_tiling(R)
+    gen_unet(R)
+    gen_samplers(R)
+    tot = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
+    print(f"golden fixtures written to {GOLD}: {tot / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()
