@@ -1,0 +1,87 @@
+// Miscellaneous C-ABI entry points: error text, device info, and the standalone operator wrappers that the
+// parity tests call one by one.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ds {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" const char* ds_last_error(void) { return g_err; }
+
+extern "C" int ds_version(void) { return 100; }
+
+extern "C" int ds_device_info(int* sm_count, int* max_threads_per_sm, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device: %s", cudaGetErrorString(e));
+        return DS_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp p;
+    DS_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (max_threads_per_sm) *max_threads_per_sm = p.maxThreadsPerMultiProcessor;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return DS_OK;
+}
+
+extern "C" size_t ds_groupnorm_scratch_bytes(int B, int groups) { return gn_scratch_bytes(B, groups); }
+
+extern "C" int ds_groupnorm_swish_f32(const float* d_a, int ca, const float* d_b, int cb, const float* d_gamma,
+                                      const float* d_beta, float* d_out, int B, int H, int W, int groups, int apply_swish,
+                                      void* d_scratch, size_t scratch_bytes, void* stream) {
+    DS_REQUIRE(d_a && d_gamma && d_beta && d_out && d_scratch, "groupnorm: null argument");
+    DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_b), "groupnorm: bad channel split %d+%d", ca, cb);
+    DS_REQUIRE(scratch_bytes >= gn_scratch_bytes(B, groups), "groupnorm: scratch too small");
+    return launch_groupnorm_f32(d_a, ca, d_b, cb, d_gamma, d_beta, d_out, B, H * W, groups, apply_swish, d_scratch,
+                                (cudaStream_t)stream);
+}
+
+static int conv_npad(int cout) {
+    int p = (cout + 15) / 16 * 16;
+    if (p > 32) p = (cout + 63) / 64 * 64;
+    return p;
+}
+
+extern "C" size_t ds_conv2d_scratch_bytes(int cin, int cout, int ksize) {
+    return (size_t)ksize * ksize * cin * conv_npad(cout) * sizeof(float);
+}
+
+extern "C" int ds_conv2d_f32(const float* d_x, const float* d_w_oihw, const float* d_bias, float* d_out, int B, int H, int W,
+                             int cin, int cout, int ksize, int stride, int upsample2x, void* d_scratch, size_t scratch_bytes,
+                             void* stream) {
+    DS_REQUIRE(d_x && d_w_oihw && d_out && d_scratch, "conv2d: null argument");
+    DS_REQUIRE(scratch_bytes >= ds_conv2d_scratch_bytes(cin, cout, ksize), "conv2d: scratch too small");
+    DS_REQUIRE(!(upsample2x && stride != 1), "conv2d: upsample with stride != 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npad = conv_npad(cout);
+    int rc = launch_pack_conv_weight_f32(d_w_oihw, (float*)d_scratch, cout, cin, ksize, npad, st);
+    if (rc != DS_OK) return rc;
+    ConvSrc s;
+    s.a = d_x; s.b = nullptr; s.ca = cin; s.cb = 0; s.nchw = 0; s.Hs = H; s.Ws = W; s.up = upsample2x;
+    const int Hin = upsample2x ? 2 * H : H, Win = upsample2x ? 2 * W : W;
+    const int pad = ksize / 2;
+    const int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
+    ConvEpi e;
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = nullptr; e.out_nchw = 0;
+    return launch_conv_f32(s, (const float*)d_scratch, npad, cout, ksize, stride, B, Ho, Wo, e, d_out, st);
+}
+
+extern "C" int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream) {
+    DS_REQUIRE(d_qkv && d_out, "attention: null argument");
+    return launch_attention_f32(d_qkv, d_out, B, N, C, (cudaStream_t)stream);
+}

@@ -1,0 +1,87 @@
+// Shared helpers for the diffsplit_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+
+#include "../../include/diffsplit_b200.h"
+
+namespace ds {
+
+void set_error(const char* fmt, ...);
+
+#define DS_CHECK_CUDA(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ds::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DS_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define DS_CHECK_LAUNCH(what)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            ds::set_error("launch of %s failed: %s", what, cudaGetErrorString(_e));      \
+            return DS_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define DS_REQUIRE(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            ds::set_error(__VA_ARGS__);                                                  \
+            return DS_ERR_INVALID;                                                       \
+        }                                                                                \
+    } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ----------------------------------------------------------------- fp32 kernels (conv_f32.cu, norm.cu, attention.cu, temb.cu)
+struct ConvSrc {
+    const float* a;     // first source  (ca channels)
+    const float* b;     // second source (cb channels) or nullptr: channel concat [a, b]
+    int ca, cb;
+    int nchw;           // 1: sources are NCHW (external boundary tensors), 0: NHWC
+    int Hs, Ws;         // stored spatial size of the sources
+    int up;             // 1: nearest x2 upsample folded into the gather (logical input = 2Hs x 2Ws)
+};
+
+struct ConvEpi {
+    const float* bias;      // [Npad] or nullptr
+    const float* temb;      // [tlen, temb_stride] conditioning vectors or nullptr
+    int temb_off, temb_stride, temb_bcast;   // value = temb[(temb_bcast ? 0 : b)*temb_stride + temb_off + n]
+    const float* residual;  // NHWC [B,Ho,Wo,Cout] or nullptr
+    int out_nchw;           // 1: write NCHW (external), 0: NHWC
+};
+
+int launch_conv_f32(const ConvSrc& src, const float* w_packed /*[K][Npad]*/, int Npad, int Cout,
+                    int ksize, int stride, int B, int Ho, int Wo, const ConvEpi& epi, float* out,
+                    cudaStream_t st);
+int launch_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int Cout, int Cin, int ks, int Npad,
+                                cudaStream_t st);
+
+int gn_nsplit(int B, int HW, int C);
+size_t gn_scratch_bytes(int B, int G);
+int launch_groupnorm_f32(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta,
+                         float* out, int B, int HW, int G, int swish, void* scratch, cudaStream_t st);
+
+int launch_attention_f32(const float* qkv, float* out, int B, int N, int C, cudaStream_t st);
+
+struct TembParams {
+    int variant;            // DS_UNET_SR3 / DS_UNET_DDPM
+    int dim;                // inner_channel
+    const float* inv_freq;  // ddpm: [dim/2]
+    const float* w1; const float* b1;   // [4dim, dim]
+    const float* w2; const float* b2;   // [dim, 4dim]
+    const float* wf; const float* bf;   // all per-block projections stacked: [total, dim], [total]
+    int total;
+};
+int launch_temb_f32(const TembParams& p, const float* time, int tlen, float* out /*[tlen,total]*/, cudaStream_t st);
+
+}  // namespace ds

@@ -1,0 +1,829 @@
+// UNet handle: architecture walk, weight registry/repacking, workspace planning and the forward launcher.
+//
+// Mirrors the constructor logic of the reference UNets (model/sr3_modules/unet.py:162-233,
+// model/ddpm_modules/unet.py:148-219) to derive (a) the state_dict keys and shapes it must be fed and (b) a
+// flat list of kernel launches ("plan") for a given (B, H, W, precision).  The forward pass
+// (unet.py:235-259) then is a loop over that list on the caller's stream: no allocation, no sync.
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace ds {
+
+// ------------------------------------------------------------------------------------------ weights
+enum WKind { WK_CONV, WK_VEC, WK_LINEAR, WK_BUF };
+
+struct WeightSpec {
+    std::string name;
+    int ndim;
+    int64_t shape[4];
+    WKind kind;
+    size_t off;        // float offset of the packed fp32 copy in the arena
+    size_t elems;      // packed element count
+    size_t off_bf16;   // byte offset of the bf16 pack in the tensor-core arena (convs only)
+    int npad;          // conv: padded Cout ; vec: padded length
+    bool loaded;
+};
+
+struct ConvW {
+    int w = -1, b = -1;
+    int cin = 0, cout = 0, ks = 0, npad = 0;
+};
+struct GNW {
+    int w = -1, b = -1, C = 0;
+};
+struct ResW {
+    GNW gn1, gn2, agn;
+    ConvW conv1, conv2, res, qkv, aout;
+    bool has_res = false, attn = false;
+    int cin = 0, cout = 0;
+    int temb_off = -1;
+    int film_w = -1, film_b = -1;
+};
+enum LKind { L_CONV, L_RES, L_DOWN, L_UP };
+struct Layer {
+    LKind kind;
+    std::string name;
+    ConvW conv;
+    ResW res;
+    int section;   // 0 downs, 1 mid, 2 ups
+};
+
+// ------------------------------------------------------------------------------------------ plan
+enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN };
+constexpr int64_t EXT_XA = -1, EXT_XB = -2, EXT_OUT = -3, NONE = -100;
+
+struct Op {
+    OpKind kind;
+    // conv
+    int64_t src_a = NONE, src_b = NONE;
+    int ca = 0, cb = 0, src_nchw = 0, Hs = 0, Ws = 0, up = 0, stride = 1;
+    int Ho = 0, Wo = 0;
+    const ConvW* cw = nullptr;
+    int temb_off = -1;
+    int64_t residual = NONE, dst = NONE;
+    int out_nchw = 0;
+    // gn
+    const GNW* gw = nullptr;
+    int swish = 0, HW = 0;
+    // attn
+    int N = 0, C = 0;
+};
+
+struct Tap {
+    int64_t off;
+    int C, H, W;
+};
+
+struct Plan {
+    int B, H, W, prec;
+    std::vector<Op> ops;
+    size_t bytes = 0;
+    int64_t temb_buf = NONE, gn_scratch = NONE;
+    std::map<std::string, Tap> taps;
+    int launches = 0;
+};
+
+class Arena {   // first-fit offset allocator used only while planning
+  public:
+    explicit Arena(bool reuse) : reuse_(reuse) {}
+    int64_t alloc(size_t bytes) {
+        bytes = align_up(bytes, 256);
+        if (reuse_) {
+            for (size_t i = 0; i < free_.size(); ++i) {
+                if (free_[i].second >= bytes) {
+                    int64_t off = free_[i].first;
+                    if (free_[i].second == bytes) free_.erase(free_.begin() + i);
+                    else { free_[i].first += bytes; free_[i].second -= bytes; }
+                    size_[off] = bytes;
+                    return off;
+                }
+            }
+        }
+        int64_t off = (int64_t)top_;
+        top_ += bytes;
+        size_[off] = bytes;
+        return off;
+    }
+    void release(int64_t off) {
+        if (off < 0 || !reuse_) return;
+        size_t bytes = size_[off];
+        // insert sorted + coalesce
+        size_t i = 0;
+        while (i < free_.size() && free_[i].first < off) ++i;
+        free_.insert(free_.begin() + i, std::make_pair(off, bytes));
+        if (i + 1 < free_.size() && free_[i].first + (int64_t)free_[i].second == free_[i + 1].first) {
+            free_[i].second += free_[i + 1].second;
+            free_.erase(free_.begin() + i + 1);
+        }
+        if (i > 0 && free_[i - 1].first + (int64_t)free_[i - 1].second == free_[i].first) {
+            free_[i - 1].second += free_[i].second;
+            free_.erase(free_.begin() + i);
+        }
+    }
+    size_t top() const { return top_; }
+
+  private:
+    bool reuse_;
+    size_t top_ = 0;
+    std::vector<std::pair<int64_t, size_t>> free_;
+    std::map<int64_t, size_t> size_;
+};
+
+struct Act {
+    int64_t buf;
+    int C, H, W;
+    int* rc;   // shared refcount
+};
+
+}  // namespace ds
+
+using namespace ds;
+
+struct ds_unet {
+    ds_unet_desc d;
+    std::vector<WeightSpec> specs;
+    std::map<std::string, int> by_name;
+    std::vector<Layer> layers;
+    GNW final_gn;
+    ConvW final_conv;
+    int temb_total = 0;
+    int w_inv_freq = -1, w_l1 = -1, b_l1 = -1, w_l2 = -1, b_l2 = -1;
+    size_t film_off = 0, film_bias_off = 0;     // stacked per-block projection [total, dim] / [total]
+    size_t arena_floats = 0;
+    size_t arena_bf16_bytes = 0;
+    float* d_arena = nullptr;
+    uint8_t* d_arena_bf16 = nullptr;
+    bool weights_ready = false;
+    std::vector<Plan*> plans;
+    bool keep_taps = false;
+
+    const float* wp(int i) const { return d_arena + specs[i].off; }
+};
+
+namespace ds {
+
+static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initializer_list<int64_t> shape, int npad = 0) {
+    WeightSpec s;
+    s.name = name;
+    s.kind = kind;
+    s.ndim = (int)shape.size();
+    int i = 0;
+    for (int d = 0; d < 4; ++d) s.shape[d] = 1;
+    for (auto v : shape) s.shape[i++] = v;
+    s.npad = npad;
+    s.loaded = false;
+    s.off_bf16 = 0;
+    size_t elems = 1;
+    if (kind == WK_CONV) elems = (size_t)s.shape[1] * s.shape[2] * s.shape[3] * npad;
+    else if (kind == WK_VEC) elems = (size_t)(npad ? npad : s.shape[0]);
+    else for (int d = 0; d < s.ndim; ++d) elems *= (size_t)s.shape[d];
+    s.elems = elems;
+    s.off = n->arena_floats;
+    n->arena_floats += align_up(elems, 64);
+    if (kind == WK_CONV) {
+        s.off_bf16 = n->arena_bf16_bytes;
+        n->arena_bf16_bytes += align_up(tc_packed_weight_bytes((int)s.shape[0], (int)s.shape[1], (int)s.shape[2]), 1024);
+    }
+    n->by_name[name] = (int)n->specs.size();
+    n->specs.push_back(s);
+    return (int)n->specs.size() - 1;
+}
+
+static int npad_of(int cout) {
+    int p = (cout + 15) / 16 * 16;
+    if (p > 32) p = (cout + 63) / 64 * 64;
+    return p;
+}
+
+static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int ks, bool bias = true) {
+    ConvW c;
+    c.cin = cin; c.cout = cout; c.ks = ks; c.npad = npad_of(cout);
+    c.w = add_spec(n, p + ".weight", WK_CONV, {cout, cin, ks, ks}, c.npad);
+    if (bias) c.b = add_spec(n, p + ".bias", WK_VEC, {cout}, c.npad);
+    return c;
+}
+
+static GNW add_gn(ds_unet* n, const std::string& p, int C) {
+    GNW g;
+    g.C = C;
+    g.w = add_spec(n, p + ".weight", WK_VEC, {C});
+    g.b = add_spec(n, p + ".bias", WK_VEC, {C});
+    return g;
+}
+
+static bool in_attn_res(const ds_unet_desc& d, int res) {
+    for (int i = 0; i < d.n_attn_res; ++i) if (d.attn_res[i] == res) return true;
+    return false;
+}
+
+static ResW add_res(ds_unet* n, const std::string& p, int cin, int cout, bool attn) {
+    const ds_unet_desc& d = n->d;
+    ResW r;
+    r.cin = cin; r.cout = cout; r.attn = attn; r.has_res = cin != cout;
+    const std::string rb = p + ".res_block";
+    // registration order follows the reference module's state_dict order
+    if (d.with_time_emb) {
+        // sr3: FeatureWiseAffine.noise_func[0]; ddpm: mlp = [Swish, Linear] -> index 1
+        const std::string f = d.variant == DS_UNET_SR3 ? rb + ".noise_func.noise_func.0" : rb + ".mlp.1";
+        r.film_w = add_spec(n, f + ".weight", WK_LINEAR, {cout, d.inner_channel});
+        r.film_b = add_spec(n, f + ".bias", WK_VEC, {cout});
+        r.temb_off = n->temb_total;
+        n->temb_total += cout;
+    }
+    r.gn1 = add_gn(n, rb + ".block1.block.0", cin);
+    r.conv1 = add_conv(n, rb + ".block1.block.3", cin, cout, 3);
+    r.gn2 = add_gn(n, rb + ".block2.block.0", cout);
+    r.conv2 = add_conv(n, rb + ".block2.block.3", cout, cout, 3);
+    if (r.has_res) r.res = add_conv(n, rb + ".res_conv", cin, cout, 1);
+    if (attn) {
+        r.agn = add_gn(n, p + ".attn.norm", cout);
+        r.qkv = add_conv(n, p + ".attn.qkv", cout, 3 * cout, 1, false);
+        r.aout = add_conv(n, p + ".attn.out", cout, cout, 1);
+    }
+    return r;
+}
+
+static int build_arch(ds_unet* n) {
+    const ds_unet_desc& d = n->d;
+    DS_REQUIRE(d.variant == DS_UNET_SR3 || d.variant == DS_UNET_DDPM, "unet: unknown variant %d", d.variant);
+    DS_REQUIRE(d.n_mults >= 1 && d.n_mults <= DS_MAX_LEVELS, "unet: n_mults %d outside [1,%d]", d.n_mults, DS_MAX_LEVELS);
+    DS_REQUIRE(d.n_attn_res >= 0 && d.n_attn_res <= DS_MAX_LEVELS, "unet: n_attn_res %d", d.n_attn_res);
+    DS_REQUIRE(d.in_channel > 0 && d.out_channel > 0 && d.inner_channel > 0 && d.res_blocks >= 0, "unet: bad channel counts");
+    DS_REQUIRE(d.norm_groups > 0 && d.norm_groups <= 64, "unet: norm_groups %d outside [1,64]", d.norm_groups);
+    DS_REQUIRE(d.inner_channel % 2 == 0 && d.inner_channel <= 256, "unet: inner_channel %d must be even and <= 256", d.inner_channel);
+    const int inner = d.inner_channel;
+    if (d.with_time_emb) {
+        const std::string key = d.variant == DS_UNET_SR3 ? "noise_level_mlp" : "time_mlp";
+        if (d.variant == DS_UNET_DDPM) n->w_inv_freq = add_spec(n, key + ".0.inv_freq", WK_BUF, {inner / 2});
+        n->w_l1 = add_spec(n, key + ".1.weight", WK_LINEAR, {4 * inner, inner});
+        n->b_l1 = add_spec(n, key + ".1.bias", WK_VEC, {4 * inner});
+        n->w_l2 = add_spec(n, key + ".3.weight", WK_LINEAR, {inner, 4 * inner});
+        n->b_l2 = add_spec(n, key + ".3.bias", WK_VEC, {inner});
+    }
+    std::vector<int> skip_ch;
+    int ch = inner, res = d.image_size, idx = 0;
+    {
+        Layer L; L.kind = L_CONV; L.name = "downs.0"; L.section = 0;
+        L.conv = add_conv(n, "downs.0", d.in_channel, inner, 3);
+        n->layers.push_back(L);
+        skip_ch.push_back(inner);
+        idx = 1;
+    }
+    for (int lvl = 0; lvl < d.n_mults; ++lvl) {
+        const int cout = inner * d.channel_mults[lvl];
+        DS_REQUIRE(d.channel_mults[lvl] > 0, "unet: channel multiplier %d", d.channel_mults[lvl]);
+        for (int r = 0; r < d.res_blocks; ++r) {
+            Layer L; L.kind = L_RES; L.name = "downs." + std::to_string(idx++); L.section = 0;
+            L.res = add_res(n, L.name, ch, cout, in_attn_res(d, res));
+            n->layers.push_back(L);
+            ch = cout;
+            skip_ch.push_back(ch);
+        }
+        if (lvl != d.n_mults - 1) {
+            Layer L; L.kind = L_DOWN; L.name = "downs." + std::to_string(idx++); L.section = 0;
+            L.conv = add_conv(n, L.name + ".conv", ch, ch, 3);
+            n->layers.push_back(L);
+            skip_ch.push_back(ch);
+            res /= 2;
+        }
+    }
+    for (int m = 0; m < 2; ++m) {
+        Layer L; L.kind = L_RES; L.name = "mid." + std::to_string(m); L.section = 1;
+        L.res = add_res(n, L.name, ch, ch, m == 0);
+        n->layers.push_back(L);
+    }
+    idx = 0;
+    for (int lvl = d.n_mults - 1; lvl >= 0; --lvl) {
+        const int cout = inner * d.channel_mults[lvl];
+        for (int r = 0; r < d.res_blocks + 1; ++r) {
+            DS_REQUIRE(!skip_ch.empty(), "unet: skip stack underflow");
+            Layer L; L.kind = L_RES; L.name = "ups." + std::to_string(idx++); L.section = 2;
+            L.res = add_res(n, L.name, ch + skip_ch.back(), cout, in_attn_res(d, res));
+            skip_ch.pop_back();
+            n->layers.push_back(L);
+            ch = cout;
+        }
+        if (lvl >= 1) {
+            Layer L; L.kind = L_UP; L.name = "ups." + std::to_string(idx++); L.section = 2;
+            L.conv = add_conv(n, L.name + ".conv", ch, ch, 3);
+            n->layers.push_back(L);
+            res *= 2;
+        }
+    }
+    n->final_gn = add_gn(n, "final_conv.block.0", ch);
+    n->final_conv = add_conv(n, "final_conv.block.3", ch, d.out_channel, 3);
+    // every GroupNorm must divide evenly
+    for (auto& s : n->specs)
+        if (s.kind == WK_VEC && s.name.find(".block.0.weight") != std::string::npos)
+            DS_REQUIRE(s.shape[0] % d.norm_groups == 0, "unet: %s has %lld channels, not divisible by %d groups", s.name.c_str(),
+                       (long long)s.shape[0], d.norm_groups);
+    // stacked conditioning projection
+    n->film_off = n->arena_floats;
+    n->arena_floats += align_up((size_t)n->temb_total * inner, 64);
+    n->film_bias_off = n->arena_floats;
+    n->arena_floats += align_up((size_t)n->temb_total, 64);
+    return DS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ planning
+struct Planner {
+    ds_unet* n;
+    Plan* p;
+    Arena arena;
+    int B;
+    size_t esz;   // activation element size
+    Planner(ds_unet* n_, Plan* p_, bool reuse) : n(n_), p(p_), arena(reuse) {}
+
+    Act make(int C, int H, int W) {
+        Act a;
+        a.C = C; a.H = H; a.W = W;
+        a.buf = arena.alloc((size_t)B * H * W * C * esz);
+        a.rc = new int(1);
+        return a;
+    }
+    void retain(Act& a) { if (a.rc) ++*a.rc; }
+    void release(Act& a) {
+        if (!a.rc) return;
+        if (--*a.rc == 0) { arena.release(a.buf); delete a.rc; }
+        a.rc = nullptr;
+    }
+    void tap(const std::string& name, const Act& a) { p->taps[name] = Tap{a.buf, a.C, a.H, a.W}; }
+
+    void gn(const Act& a, const Act* b, const GNW& g, int swish, const Act& out) {
+        Op o; o.kind = OP_GN;
+        o.src_a = a.buf; o.ca = a.C;
+        if (b) { o.src_b = b->buf; o.cb = b->C; }
+        o.gw = &g; o.swish = swish; o.HW = a.H * a.W; o.dst = out.buf;
+        p->ops.push_back(o);
+    }
+    void conv(const Act& a, const Act* b, const ConvW& w, int stride, int up, int temb_off, const Act* residual, const Act& out) {
+        Op o; o.kind = OP_CONV;
+        o.src_a = a.buf; o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
+        if (b) { o.src_b = b->buf; o.cb = b->C; }
+        o.cw = &w; o.stride = stride; o.up = up; o.temb_off = temb_off;
+        o.Ho = out.H; o.Wo = out.W;
+        if (residual) o.residual = residual->buf;
+        o.dst = out.buf;
+        p->ops.push_back(o);
+    }
+
+    Act resblock(const Layer& L, Act x, const Act* skip) {
+        const ResW& r = L.res;
+        const int H = x.H, W = x.W;
+        Act a1 = make(r.cin, H, W);
+        gn(x, skip, r.gn1, 1, a1);
+        Act h = make(r.cout, H, W);
+        conv(a1, nullptr, r.conv1, 1, 0, r.temb_off, nullptr, h);
+        release(a1);
+        Act a2 = make(r.cout, H, W);
+        gn(h, nullptr, r.gn2, 1, a2);
+        release(h);
+        Act resid = x;
+        Act rbuf; rbuf.rc = nullptr;
+        if (r.has_res) {
+            rbuf = make(r.cout, H, W);
+            conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
+            resid = rbuf;
+        }
+        Act out = make(r.cout, H, W);
+        conv(a2, nullptr, r.conv2, 1, 0, -1, &resid, out);
+        release(a2);
+        if (r.has_res) release(rbuf);
+        if (r.attn) {
+            Act nrm = make(r.cout, H, W);
+            gn(out, nullptr, r.agn, 0, nrm);
+            Act qkv = make(3 * r.cout, H, W);
+            conv(nrm, nullptr, r.qkv, 1, 0, -1, nullptr, qkv);
+            release(nrm);
+            Act att = make(r.cout, H, W);
+            Op o; o.kind = OP_ATTN; o.src_a = qkv.buf; o.dst = att.buf; o.N = H * W; o.C = r.cout;
+            p->ops.push_back(o);
+            release(qkv);
+            Act out2 = make(r.cout, H, W);
+            conv(att, nullptr, r.aout, 1, 0, -1, &out, out2);
+            release(att);
+            release(out);
+            out = out2;
+        }
+        return out;
+    }
+};
+
+static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
+    const ds_unet_desc& d = n->d;
+    const int down = 1 << (d.n_mults - 1);
+    DS_REQUIRE(B > 0 && H > 0 && W > 0, "unet: bad shape B=%d H=%d W=%d", B, H, W);
+    DS_REQUIRE(H % down == 0 && W % down == 0, "unet: H=%d W=%d must be divisible by %d", H, W, down);
+    DS_REQUIRE(prec == DS_PREC_FP32 || prec == DS_PREC_BF16, "unet: unknown precision %d", prec);
+    Plan* p = new Plan();
+    p->B = B; p->H = H; p->W = W; p->prec = prec;
+    Planner P(n, p, !n->keep_taps);
+    P.B = B;
+    P.esz = 4;   // fp32 activations in both modes for now; the bf16 path converts inside its kernels
+    if (d.with_time_emb) p->temb_buf = P.arena.alloc((size_t)B * n->temb_total * sizeof(float));
+    p->gn_scratch = P.arena.alloc(gn_scratch_bytes(B, d.norm_groups));
+
+    std::vector<Act> skips;
+    Act x; x.rc = nullptr;
+    int h = H, w = W;
+    for (const Layer& L : n->layers) {
+        if (L.section == 0) {
+            if (L.kind == L_CONV) {
+                Act o = P.make(L.conv.cout, h, w);
+                Op op; op.kind = OP_CONV;
+                op.src_a = EXT_XA; op.src_b = EXT_XB; op.src_nchw = 1; op.Hs = h; op.Ws = w;
+                op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.buf;
+                p->ops.push_back(op);
+                x = o;
+            } else if (L.kind == L_RES) {
+                Act o = P.resblock(L, x, nullptr);
+                P.release(x);
+                x = o;
+            } else {
+                h /= 2; w /= 2;
+                Act o = P.make(L.conv.cout, h, w);
+                P.conv(x, nullptr, L.conv, 2, 0, -1, nullptr, o);
+                P.release(x);
+                x = o;
+            }
+            P.retain(x);
+            Act s = x;
+            skips.push_back(s);
+        } else if (L.section == 1) {
+            Act o = P.resblock(L, x, nullptr);
+            P.release(x);
+            x = o;
+        } else {
+            if (L.kind == L_RES) {
+                Act s = skips.back();
+                skips.pop_back();
+                DS_REQUIRE(s.H == x.H && s.W == x.W, "unet: skip shape mismatch at %s", L.name.c_str());
+                Act o = P.resblock(L, x, &s);
+                P.release(x);
+                P.release(s);
+                x = o;
+            } else {
+                Act o = P.make(L.conv.cout, 2 * x.H, 2 * x.W);
+                P.conv(x, nullptr, L.conv, 1, 1, -1, nullptr, o);
+                P.release(x);
+                x = o;
+            }
+        }
+        P.tap(L.name, x);
+    }
+    Act fa = P.make(x.C, x.H, x.W);
+    P.gn(x, nullptr, n->final_gn, 1, fa);
+    P.release(x);
+    {
+        Op op; op.kind = OP_CONV;
+        op.src_a = fa.buf; op.ca = fa.C; op.Hs = fa.H; op.Ws = fa.W;
+        op.cw = &n->final_conv; op.Ho = fa.H; op.Wo = fa.W; op.dst = EXT_OUT; op.out_nchw = 1;
+        p->ops.push_back(op);
+    }
+    P.release(fa);
+    p->bytes = P.arena.top();
+    int launches = d.with_time_emb ? 1 : 0;
+    for (auto& o : p->ops) launches += (o.kind == OP_GN) ? 2 : 1;
+    p->launches = launches;
+    *out = p;
+    return DS_OK;
+}
+
+static int get_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
+    for (Plan* p : n->plans)
+        if (p->B == B && p->H == H && p->W == W && p->prec == prec) { *out = p; return DS_OK; }
+    Plan* p = nullptr;
+    int rc = build_plan(n, B, H, W, prec, &p);
+    if (rc != DS_OK) return rc;
+    if (n->plans.size() >= 16) { delete n->plans.front(); n->plans.erase(n->plans.begin()); }
+    n->plans.push_back(p);
+    *out = p;
+    return DS_OK;
+}
+
+}  // namespace ds
+
+// ============================================================================================ C ABI
+extern "C" int ds_unet_create(const ds_unet_desc* desc, ds_unet** out) {
+    DS_REQUIRE(desc && out, "unet_create: null argument");
+    ds_unet* n = new ds_unet();
+    n->d = *desc;
+    const char* e = getenv("DIFFSPLIT_B200_TAPS");
+    n->keep_taps = e && e[0] == '1';
+    int rc = build_arch(n);
+    if (rc != DS_OK) { delete n; return rc; }
+    *out = n;
+    return DS_OK;
+}
+
+extern "C" void ds_unet_destroy(ds_unet* n) {
+    if (!n) return;
+    if (n->d_arena) cudaFree(n->d_arena);
+    if (n->d_arena_bf16) cudaFree(n->d_arena_bf16);
+    for (Plan* p : n->plans) delete p;
+    delete n;
+}
+
+extern "C" int ds_unet_num_weights(const ds_unet* n) { return n ? (int)n->specs.size() : 0; }
+
+extern "C" const char* ds_unet_weight_name(const ds_unet* n, int i) {
+    if (!n || i < 0 || i >= (int)n->specs.size()) return nullptr;
+    return n->specs[i].name.c_str();
+}
+
+extern "C" int ds_unet_weight_shape(const ds_unet* n, int i, int32_t* ndim, int64_t shape[4]) {
+    DS_REQUIRE(n && i >= 0 && i < (int)n->specs.size() && ndim && shape, "unet_weight_shape: bad index %d", i);
+    *ndim = n->specs[i].ndim;
+    for (int d = 0; d < 4; ++d) shape[d] = n->specs[i].shape[d];
+    return DS_OK;
+}
+
+extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cnt, void* stream) {
+    DS_REQUIRE(n && ws && cnt > 0, "unet_load_weights: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!n->d_arena) {
+        DS_CHECK_CUDA(cudaMalloc(&n->d_arena, n->arena_floats * sizeof(float)));
+        DS_CHECK_CUDA(cudaMemsetAsync(n->d_arena, 0, n->arena_floats * sizeof(float), st));
+        DS_CHECK_CUDA(cudaMalloc(&n->d_arena_bf16, n->arena_bf16_bytes ? n->arena_bf16_bytes : 256));
+        DS_CHECK_CUDA(cudaMemsetAsync(n->d_arena_bf16, 0, n->arena_bf16_bytes ? n->arena_bf16_bytes : 256, st));
+    }
+    for (int i = 0; i < cnt; ++i) {
+        const ds_tensor_view& v = ws[i];
+        DS_REQUIRE(v.name && v.d_data, "unet_load_weights: entry %d has a null name/pointer", i);
+        auto it = n->by_name.find(v.name);
+        if (it == n->by_name.end()) continue;      // foreign keys (e.g. sampler buffers) are ignored
+        WeightSpec& s = n->specs[it->second];
+        bool ok = v.ndim == s.ndim;
+        for (int d = 0; ok && d < s.ndim; ++d) ok = v.shape[d] == s.shape[d];
+        if (!ok) {
+            set_error("unet_load_weights: %s has shape [%lld,%lld,%lld,%lld] (ndim %d), expected [%lld,%lld,%lld,%lld] (ndim %d)",
+                      v.name, (long long)v.shape[0], (long long)v.shape[1], (long long)v.shape[2], (long long)v.shape[3], v.ndim,
+                      (long long)s.shape[0], (long long)s.shape[1], (long long)s.shape[2], (long long)s.shape[3], s.ndim);
+            return DS_ERR_WEIGHT;
+        }
+        float* dst = n->d_arena + s.off;
+        const float* src = (const float*)v.d_data;
+        if (s.kind == WK_CONV) {
+            int rc = launch_pack_conv_weight_f32(src, dst, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.npad, st);
+            if (rc != DS_OK) return rc;
+            rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_bf16, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
+            if (rc != DS_OK) return rc;
+        } else {
+            size_t cnt_el = 1;
+            for (int d = 0; d < s.ndim; ++d) cnt_el *= (size_t)s.shape[d];
+            DS_CHECK_CUDA(cudaMemcpyAsync(dst, src, cnt_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        s.loaded = true;
+    }
+    for (auto& s : n->specs) {
+        if (!s.loaded) {
+            if (s.kind == WK_BUF) continue;       // inv_freq is recomputed below if it was not supplied
+            set_error("unet_load_weights: missing weight %s", s.name.c_str());
+            return DS_ERR_WEIGHT;
+        }
+    }
+    if (n->w_inv_freq >= 0 && !n->specs[n->w_inv_freq].loaded) {
+        const int half = n->d.inner_channel / 2;
+        std::vector<float> f(half);
+        for (int j = 0; j < half; ++j) f[j] = expf((float)(2 * j) * (float)(-log(10000.0) / (double)n->d.inner_channel));
+        DS_CHECK_CUDA(cudaMemcpyAsync(n->d_arena + n->specs[n->w_inv_freq].off, f.data(), half * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+        DS_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+    // stack the per-block conditioning projections
+    if (n->d.with_time_emb) {
+        const int dim = n->d.inner_channel;
+        for (const Layer& L : n->layers) {
+            if (L.kind != L_RES) continue;
+            const ResW& r = L.res;
+            DS_CHECK_CUDA(cudaMemcpyAsync(n->d_arena + n->film_off + (size_t)r.temb_off * dim, n->wp(r.film_w),
+                                          (size_t)r.cout * dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            DS_CHECK_CUDA(cudaMemcpyAsync(n->d_arena + n->film_bias_off + r.temb_off, n->wp(r.film_b),
+                                          (size_t)r.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    n->weights_ready = true;
+    return DS_OK;
+}
+
+extern "C" size_t ds_unet_workspace_bytes(ds_unet* n, int B, int H, int W, int precision) {
+    if (!n) return 0;
+    Plan* p = nullptr;
+    if (get_plan(n, B, H, W, precision, &p) != DS_OK) return 0;
+    return p->bytes;
+}
+
+extern "C" int ds_unet_launches(ds_unet* n, int B, int H, int W, int precision) {
+    if (!n) return 0;
+    Plan* p = nullptr;
+    if (get_plan(n, B, H, W, precision, &p) != DS_OK) return 0;
+    return p->launches;
+}
+
+extern "C" double ds_unet_flops(const ds_unet* n, int H, int W) {
+    if (!n) return 0.0;
+    double fl = 0.0;
+    int h = H, w = W;
+    auto res = [&](const ResW& r) {
+        double f = 2.0 * h * w * 9.0 * ((double)r.cin * r.cout + (double)r.cout * r.cout);
+        if (r.has_res) f += 2.0 * h * w * (double)r.cin * r.cout;
+        if (r.attn) {
+            const double N = (double)h * w, C = r.cout;
+            f += 2.0 * N * C * 3.0 * C + 2.0 * N * C * C + 4.0 * N * N * C;
+        }
+        return f;
+    };
+    for (const Layer& L : n->layers) {
+        if (L.kind == L_RES) fl += res(L.res);
+        else {
+            if (L.kind == L_DOWN) { h /= 2; w /= 2; }
+            if (L.kind == L_UP) { h *= 2; w *= 2; }
+            fl += 2.0 * h * w * 9.0 * (double)L.conv.cin * L.conv.cout;
+        }
+    }
+    fl += 2.0 * h * w * 9.0 * (double)n->final_conv.cin * n->final_conv.cout;
+    return fl;
+}
+
+namespace ds {
+struct Prof {
+    ds_op_profile* out;
+    int max_ops, n;
+    cudaEvent_t e0, e1;
+};
+}  // namespace ds
+
+static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb, int cb, const float* d_time,
+                       int time_len, float* d_out, int B, int H, int W, int precision, void* d_ws, size_t ws_bytes,
+                       void* stream, Prof* prof) {
+    DS_REQUIRE(n && d_xa && d_out && d_ws, "unet_forward: null argument");
+    DS_REQUIRE(n->weights_ready, "unet_forward: weights not loaded");
+    DS_REQUIRE(ca + cb == n->d.in_channel && ca > 0 && cb >= 0 && (cb == 0 || d_xb),
+               "unet_forward: input channels %d+%d != in_channel %d", ca, cb, n->d.in_channel);
+    DS_REQUIRE(!n->d.with_time_emb || (d_time && (time_len == 1 || time_len == B)),
+               "unet_forward: time must have 1 or B=%d entries (got %d)", B, time_len);
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan* p = nullptr;
+    int rc = get_plan(n, B, H, W, precision, &p);
+    if (rc != DS_OK) return rc;
+    if (ws_bytes < p->bytes) {
+        set_error("unet_forward: workspace %zu < required %zu bytes", ws_bytes, p->bytes);
+        return DS_ERR_WORKSPACE;
+    }
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "unet_forward: workspace must be 256-byte aligned");
+    uint8_t* base = (uint8_t*)d_ws;
+    auto ptr = [&](int64_t off) -> float* {
+        if (off == EXT_XA) return const_cast<float*>(d_xa);
+        if (off == EXT_XB) return const_cast<float*>(d_xb);
+        if (off == EXT_OUT) return d_out;
+        if (off == NONE) return nullptr;
+        return reinterpret_cast<float*>(base + off);
+    };
+    float* temb = nullptr;
+    if (n->d.with_time_emb) {
+        TembParams tp;
+        tp.variant = n->d.variant;
+        tp.dim = n->d.inner_channel;
+        tp.inv_freq = n->w_inv_freq >= 0 ? n->wp(n->w_inv_freq) : nullptr;
+        tp.w1 = n->wp(n->w_l1); tp.b1 = n->wp(n->b_l1);
+        tp.w2 = n->wp(n->w_l2); tp.b2 = n->wp(n->b_l2);
+        tp.wf = n->d_arena + n->film_off; tp.bf = n->d_arena + n->film_bias_off;
+        tp.total = n->temb_total;
+        temb = ptr(p->temb_buf);
+        if (prof) cudaEventRecord(prof->e0, st);
+        rc = launch_temb_f32(tp, d_time, time_len, temb, st);
+        if (rc != DS_OK) return rc;
+        if (prof && prof->n < prof->max_ops) {
+            cudaEventRecord(prof->e1, st);
+            cudaEventSynchronize(prof->e1);
+            ds_op_profile& r = prof->out[prof->n++];
+            memset(&r, 0, sizeof(r));
+            r.kind = 0;
+            cudaEventElapsedTime(&r.ms, prof->e0, prof->e1);
+            r.launches = 1;
+        }
+    }
+    void* gn_scratch = ptr(p->gn_scratch);
+    const bool tc = precision == DS_PREC_BF16;
+    for (const Op& o : p->ops) {
+        bool used_tc = false;
+        if (prof) cudaEventRecord(prof->e0, st);
+        switch (o.kind) {
+            case OP_GN:
+                rc = launch_groupnorm_f32(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B,
+                                          o.HW, n->d.norm_groups, o.swish, gn_scratch, st);
+                break;
+            case OP_CONV: {
+                ConvSrc s;
+                s.a = ptr(o.src_a); s.b = ptr(o.src_b);
+                s.ca = o.src_nchw ? ca : o.ca; s.cb = o.src_nchw ? cb : o.cb;
+                s.nchw = o.src_nchw; s.Hs = o.Hs; s.Ws = o.Ws; s.up = o.up;
+                ConvEpi e;
+                e.bias = o.cw->b >= 0 ? n->wp(o.cw->b) : nullptr;
+                e.temb = o.temb_off >= 0 ? temb : nullptr;
+                e.temb_off = o.temb_off >= 0 ? o.temb_off : 0;
+                e.temb_stride = n->temb_total;
+                e.temb_bcast = (time_len == 1);
+                e.residual = ptr(o.residual);
+                e.out_nchw = o.out_nchw;
+                if (tc && tc_conv_supported(s, o.cw->cout, o.cw->ks, o.stride, e)) {
+                    used_tc = true;
+                    rc = tc_launch_conv(s, n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, o.cw->cout, o.cw->ks, o.stride, B, o.Ho,
+                                        o.Wo, e, ptr(o.dst), st);
+                } else {
+                    rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
+                                         ptr(o.dst), st);
+                }
+                break;
+            }
+            case OP_ATTN:
+                rc = launch_attention_f32(ptr(o.src_a), ptr(o.dst), B, o.N, o.C, st);
+                break;
+            default:
+                rc = DS_OK;
+        }
+        if (rc != DS_OK) return rc;
+        if (prof && prof->n < prof->max_ops) {
+            cudaEventRecord(prof->e1, st);
+            cudaEventSynchronize(prof->e1);
+            ds_op_profile& r = prof->out[prof->n++];
+            memset(&r, 0, sizeof(r));
+            cudaEventElapsedTime(&r.ms, prof->e0, prof->e1);
+            r.launches = 1;
+            if (o.kind == OP_CONV) {
+                const int cin = o.src_nchw ? ca + cb : o.ca + o.cb;
+                r.kind = used_tc ? 4 : 1;
+                r.cin = cin; r.cout = o.cw->cout; r.ksize = o.cw->ks; r.h = o.Ho; r.w = o.Wo;
+                r.flops = 2.0 * B * o.Ho * o.Wo * (double)o.cw->ks * o.cw->ks * cin * o.cw->cout;
+                r.bytes = 4.0 * B * ((double)o.Hs * o.Ws * cin + (double)o.Ho * o.Wo * o.cw->cout *
+                                     (o.residual != NONE ? 2.0 : 1.0)) + 4.0 * o.cw->ks * o.cw->ks * cin * o.cw->cout;
+            } else if (o.kind == OP_GN) {
+                r.kind = 2;
+                r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;
+                r.launches = 2;
+                r.bytes = 4.0 * B * (double)o.HW * (o.ca + o.cb) * 3.0;   // standalone two-pass: 2 reads + 1 write
+            } else if (o.kind == OP_ATTN) {
+                r.kind = 3;
+                r.cin = r.cout = o.C; r.h = o.N; r.w = 1;
+                r.flops = 4.0 * B * (double)o.N * o.N * o.C;
+                r.bytes = 4.0 * B * (double)o.N * o.C * 4.0;
+            }
+        }
+    }
+    return DS_OK;
+}
+
+extern "C" int ds_unet_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb, int cb, const float* d_time,
+                               int time_len, float* d_out, int B, int H, int W, int precision, void* d_ws, size_t ws_bytes,
+                               void* stream) {
+    return run_forward(n, d_xa, ca, d_xb, cb, d_time, time_len, d_out, B, H, W, precision, d_ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int ds_unet_forward_profiled(ds_unet* n, const float* d_xa, int ca, const float* d_xb, int cb,
+                                        const float* d_time, int time_len, float* d_out, int B, int H, int W, int precision,
+                                        void* d_ws, size_t ws_bytes, void* stream, ds_op_profile* ops, int max_ops,
+                                        int* n_ops) {
+    DS_REQUIRE(ops && n_ops && max_ops > 0, "unet_forward_profiled: null argument");
+    Prof pr;
+    pr.out = ops; pr.max_ops = max_ops; pr.n = 0;
+    DS_CHECK_CUDA(cudaEventCreate(&pr.e0));
+    DS_CHECK_CUDA(cudaEventCreate(&pr.e1));
+    int rc = run_forward(n, d_xa, ca, d_xb, cb, d_time, time_len, d_out, B, H, W, precision, d_ws, ws_bytes, stream, &pr);
+    cudaEventDestroy(pr.e0);
+    cudaEventDestroy(pr.e1);
+    *n_ops = pr.n;
+    return rc;
+}
+
+namespace ds {
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int64_t total) {
+    for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t b = i / ((int64_t)C * HW);
+        const int64_t r = i - b * C * HW;
+        const int c = (int)(r / HW), p = (int)(r - (int64_t)c * HW);
+        dst[i] = src[(b * HW + p) * C + c];
+    }
+}
+}  // namespace ds
+
+extern "C" int ds_unet_read_tap(ds_unet* n, const char* name, float* d_out, size_t out_elems, void* d_ws, void* stream) {
+    DS_REQUIRE(n && name && d_out && d_ws, "unet_read_tap: null argument");
+    DS_REQUIRE(n->keep_taps, "unet_read_tap: create the net with DIFFSPLIT_B200_TAPS=1 (buffers are recycled otherwise)");
+    DS_REQUIRE(!n->plans.empty(), "unet_read_tap: no forward has been planned");
+    Plan* p = n->plans.back();
+    auto it = p->taps.find(name);
+    DS_REQUIRE(it != p->taps.end(), "unet_read_tap: unknown tap %s", name);
+    const Tap& t = it->second;
+    const int64_t total = (int64_t)p->B * t.C * t.H * t.W;
+    DS_REQUIRE((size_t)total <= out_elems, "unet_read_tap: output too small (%zu < %lld)", out_elems, (long long)total);
+    const float* src = reinterpret_cast<const float*>((uint8_t*)d_ws + t.off);
+    int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d_out, t.C, t.H * t.W, total);
+    DS_CHECK_LAUNCH("nhwc_to_nchw");
+    return DS_OK;
+}

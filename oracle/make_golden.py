@@ -66,6 +66,26 @@ def time_input(cfg, B, g):
     return torch.rand((B,), generator=g)
 
 
+def gen_keys(R):
+    """state_dict key lists (name -> shape) of the reference modules: the checkpoint side of the boundary."""
+    import json
+    cases = dict(UNET_CASES)
+    cases["sr3_16_128"] = (U.make_cfg("sr3", 6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 128), 1, 128, 128)
+    cases["sr3_64_512"] = (U.make_cfg("sr3", 6, 3, 64, 16, (1, 2, 4, 8, 16), (), 1, 512), 1, 512, 512)
+    out = {}
+    for name, (cfg, _, _, _) in cases.items():
+        ref = build_ref_unet(R, cfg)
+        out[name] = dict(cfg={k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()},
+                         keys={k: list(v.shape) for k, v in ref.state_dict().items()})
+        assert set(out[name]["keys"]) == set(U.random_state_dict(cfg).keys()), name
+    g = R.sr3_diff.GaussianDiffusion(build_ref_unet(R, UNET_CASES["sr3_attn"][0]), 16, channels=2)
+    g.set_new_noise_schedule(dict(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=0.3), "cpu")
+    out["sr3_sampler_keys"] = [k for k in g.state_dict().keys() if not k.startswith("denoise_fn.")]
+    with open(os.path.join(GOLD, "state_dict_keys.json"), "w") as fh:
+        json.dump(out, fh, indent=0, sort_keys=True)
+    print(f"[keys] recorded state_dict keys for {len(cases)} architectures")
+
+
 def gen_unet(R):
     for name, (cfg, B, H, W) in UNET_CASES.items():
         sd = U.random_state_dict(cfg, seed=11)
@@ -307,6 +327,7 @@ def main():
     torch.set_num_threads(8)
     R = _import_reference()
     gen_tiling(R)
+    gen_keys(R)
     gen_unet(R)
     gen_samplers(R)
     tot = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
