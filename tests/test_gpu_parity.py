@@ -1,0 +1,382 @@
+"""GPU suite: the CUDA path (through the C ABI / the reference-shaped Python boundary) against the oracle, the
+golden vectors recorded from the real reference, and size-independent properties at BASELINE sizes.
+
+Tolerances (north_star): per-step UNet output max-rel-err <= 1e-5 in fp32 mode, <= 1e-2 in bf16 mode, where
+rel-err = max|y - ref| / max|ref|; sampler updates with injected noise: <= 1e-5 abs on O(1) images; tile
+indexing / stitching: bit-exact; Philox replay vs torch.randn on the same device: bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from diffsplitting_b200 import _lib
+from diffsplitting_b200.data import TiledFrames, TileIndexManager, TilingMode, stitch_predictions
+from diffsplitting_b200.model import create_model
+from diffsplitting_b200.model.samplers import GaussianDiffusionDdpm, GaussianDiffusionSr3, InDI, JointIndi
+from diffsplitting_b200.model.unet import UNet
+from oracle import philox_ref as PH
+from oracle import samplers_ref as S
+from oracle import tiling_ref as TR
+from oracle import unet_ref as U
+from oracle.make_golden import UNET_CASES, Replay
+from tests.configs import make_opt
+
+DEV = "cuda"
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+
+
+def relerr(y, ref):
+    return float((y.double().cpu() - ref.double().cpu()).abs().max() / ref.double().abs().max().clamp_min(1e-12))
+
+
+def build(cfg, sd=None, precision="fp32"):
+    net = UNet(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], inner_channel=cfg["inner_channel"],
+               norm_groups=cfg["norm_groups"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+               res_blocks=cfg["res_blocks"], image_size=cfg["image_size"], variant=cfg["variant"], precision=precision)
+    if sd is not None:
+        net.load_state_dict(sd, strict=True)
+    return net.to(DEV).eval()
+
+
+def sptr():
+    return _lib.stream_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ RNG
+@pytest.mark.parametrize("numel", [100, 12345, 16 * 64 * 64, 8 * 3 * 512 * 512 + 7])
+def test_philox_replays_torch_randn_bit_exact(numel):
+    sms, mt, major, _ = _lib.device_info(0)
+    assert major == 10, "sm_100 device expected"
+    gen = torch.cuda.default_generators[0]
+    torch.manual_seed(1234)
+    gen.set_offset(40)
+    grid = min(sms * (mt // 256), (numel + 255) // 256)
+    threads, inc = 256 * grid, ((numel - 1) // (256 * grid * 4) + 1) * 4
+    mine = torch.empty(numel, device=DEV)
+    _lib.check(_lib.lib().ds_randn_axpy(None, 1.0, mine.data_ptr(), numel, gen.initial_seed(), gen.get_offset(), None,
+                                        inc, threads, sptr()))
+    ref = torch.randn(numel, device=DEV)
+    assert gen.get_offset() == 40 + inc, "offset bookkeeping differs from torch"
+    assert torch.equal(mine, ref)
+    if numel <= 1 << 16:
+        cpu = PH.randn_like_cuda(numel, 1234, 40, sms, mt)
+        assert np.abs(cpu - ref.cpu().numpy()).max() < 1e-5
+        assert PH.offset_increment(numel, sms, mt) == inc
+
+
+# ------------------------------------------------------------------------------------------------ operators
+@pytest.mark.parametrize("cin,cout,ks,stride,up,B,H,W", [
+    (16, 16, 3, 1, 0, 2, 16, 16), (48, 16, 3, 1, 0, 1, 24, 20), (32, 32, 3, 2, 0, 2, 16, 16), (64, 64, 3, 1, 1, 1, 8, 12),
+    (128, 384, 1, 1, 0, 2, 8, 8), (3, 16, 3, 1, 0, 1, 9, 11), (16, 2, 3, 1, 0, 2, 16, 16), (192, 64, 1, 1, 0, 1, 16, 16),
+    (256, 128, 3, 1, 0, 1, 8, 8)])
+def test_conv_operator(cin, cout, ks, stride, up, B, H, W):
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn((B, cin, H, W), generator=g)
+    w = torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5
+    b = torch.randn((cout,), generator=g)
+    xr = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    ref = F.conv2d(xr.double(), w.double(), b.double(), stride=stride, padding=ks // 2).float()
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty((B, ref.shape[2], ref.shape[3], cout), device=DEV)
+    nb = _lib.lib().ds_conv2d_scratch_bytes(cin, cout, ks)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    wd, bd = w.to(DEV), b.to(DEV)
+    _lib.check(_lib.lib().ds_conv2d_f32(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), B, H, W, cin, cout, ks,
+                                        stride, up, scratch.data_ptr(), nb, sptr()))
+    assert relerr(out.permute(0, 3, 1, 2), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("ca,cb,G,B,HW,swish", [(16, 0, 16, 2, (16, 16), 1), (16, 32, 16, 1, (12, 20), 1), (128, 0, 16, 3, (8, 8), 0),
+                                                 (512, 256, 32, 1, (4, 4), 1), (32, 0, 8, 16, (64, 64), 1), (2048, 0, 16, 1, (8, 8), 1)])
+def test_groupnorm_swish_operator(ca, cb, G, B, HW, swish):
+    H, W = HW
+    g = torch.Generator().manual_seed(ca + cb)
+    x = torch.randn((B, ca + cb, H, W), generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(ca + cb, generator=g), torch.randn(ca + cb, generator=g)
+    ref = F.group_norm(x.double(), G, gamma.double(), beta.double(), eps=1e-5)
+    if swish:
+        ref = ref * torch.sigmoid(ref)
+    xa = x[:, :ca].permute(0, 2, 3, 1).contiguous().to(DEV)
+    xb = x[:, ca:].permute(0, 2, 3, 1).contiguous().to(DEV) if cb else None
+    out = torch.empty((B, H, W, ca + cb), device=DEV)
+    nb = _lib.lib().ds_groupnorm_scratch_bytes(B, G)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    gd, bd = gamma.to(DEV), beta.to(DEV)
+    _lib.check(_lib.lib().ds_groupnorm_swish_f32(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, gd.data_ptr(),
+                                                 bd.data_ptr(), out.data_ptr(), B, H, W, G, swish, scratch.data_ptr(), nb, sptr()))
+    assert relerr(out.permute(0, 3, 1, 2), ref.float()) <= 1e-5
+
+
+@pytest.mark.parametrize("B,N,Cc", [(2, 16, 128), (1, 64, 32), (2, 100, 64), (1, 256, 512), (1, 1024, 128), (1, 40, 1024)])
+def test_attention_operator(B, N, Cc):
+    g = torch.Generator().manual_seed(N + Cc)
+    qkv = torch.randn((B, N, 3 * Cc), generator=g)
+    q, k, v = qkv.double().split(Cc, dim=2)
+    a = torch.softmax(q @ k.transpose(1, 2) / Cc ** 0.5, dim=-1)
+    ref = (a @ v).float()
+    qd = qkv.to(DEV)
+    out = torch.empty((B, N, Cc), device=DEV)
+    _lib.check(_lib.lib().ds_attention_f32(qd.data_ptr(), out.data_ptr(), B, N, Cc, sptr()))
+    assert relerr(out, ref) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ UNet
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", list(UNET_CASES))
+def test_unet_matches_reference_golden(gold_dir, case, precision):
+    cfg, B, H, W = UNET_CASES[case]
+    gd = np.load(os.path.join(gold_dir, f"unet_{case}.npz"))
+    sd = U.random_state_dict(cfg, seed=int(gd["seed"]))
+    net = build(cfg, sd, precision)
+    y = net(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]).to(DEV))
+    e = relerr(y, torch.from_numpy(gd["y"]))
+    print(f"[unet {case} {precision}] rel err vs reference golden {e:.3e}")
+    assert e <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,cfg,B,H,W,cond", [
+    ("hagen64_b16", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 16, 64, 64, 0),
+    ("cifar_sr3_cond", U.make_cfg("sr3", 9, 6, 16, 16, (1, 2, 4, 8), (), 1, 32), 1, 32, 32, 3),
+    ("sr3_attn_all_levels", U.make_cfg("sr3", 6, 3, 32, 8, (1, 2, 2), (32, 16, 8), 2, 32), 2, 32, 32, 3),
+    ("splitting_128", U.make_cfg("sr3", 3, 2, 16, 16, (1, 2, 4, 8), (), 1, 512), 1, 128, 96, 1),
+    ("bcast_time", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4), (), 1, 32), 3, 16, 16, 0)])
+def test_unet_matches_oracle(name, cfg, B, H, W, cond, precision):
+    sd = U.random_state_dict(cfg, seed=21)
+    net = build(cfg, sd, precision)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((B, cfg["in_channel"], H, W), generator=g)
+    if cfg["variant"] == "sr3":
+        t = torch.rand((B, 1), generator=g) * 0.9 + 0.05
+    else:
+        t = torch.rand((1,) if name == "bcast_time" else (B,), generator=g)
+    ref = U.unet_forward(sd, cfg, x, t)
+    if cond:      # split input: the condition / state concat is never materialised
+        y = net(x[:, cond:].to(DEV), t.to(DEV), cond=x[:, :cond].to(DEV))
+    else:
+        y = net(x.to(DEV), t.to(DEV))
+    e = relerr(y, ref)
+    print(f"[unet {name} {precision}] rel err vs oracle {e:.3e}")
+    assert e <= TOL[precision]
+
+
+# ------------------------------------------------------------------------------------------------ samplers
+SCHED = dict(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=0.3)
+
+
+def _nets():
+    cfg = U.make_cfg("sr3", 3, 2, 16, 8, (1, 2), (), 1, 16)
+    cfgd = U.make_cfg("ddpm", 3, 2, 16, 8, (1, 2), (), 1, 16)
+    cfgi = U.make_cfg("ddpm", 1, 1, 16, 8, (1, 2), (), 1, 16)
+    return (cfg, U.random_state_dict(cfg, seed=3)), (cfgd, U.random_state_dict(cfgd, seed=4)), \
+        (cfgi, U.random_state_dict(cfgi, seed=7), U.random_state_dict(cfgi, seed=8))
+
+
+def test_sr3_and_ddpm_steps_match_reference_golden_with_injected_noise(gold_dir):
+    gd = np.load(os.path.join(gold_dir, "samplers.npz"))
+    (cfg, sd), (cfgd, sdd), _ = _nets()
+    cond = torch.from_numpy(gd["sr3_cond"]).to(DEV)
+    for cls, c, s, key, always in ((GaussianDiffusionSr3, cfg, sd, "sr3", False), (GaussianDiffusionDdpm, cfgd, sdd, "ddpm", True)):
+        netG = cls(build(c, s), 16, channels=2, conditional=True).to(DEV)
+        netG.set_new_noise_schedule(SCHED, DEV)
+        noise = torch.from_numpy(gd[f"{key}_noise"]).to(DEV)
+        out = torch.from_numpy(gd[f"{key}_out"])        # [cond.repeat, x_5, ..., x_0], B = 2
+        img = noise[0]
+        ni = 1
+        for step, t in enumerate(reversed(range(6))):
+            z = None
+            if always or t > 0:
+                z = noise[ni]
+                ni += 1
+            tt = torch.full((2,), t, device=DEV, dtype=torch.long) if always else t
+            img = netG.p_sample(img, tt, condition_x=cond, noise=z if z is not None else torch.zeros_like(img))
+            e = float((img.cpu() - out[2 * (step + 1):2 * (step + 2)]).abs().max())
+            assert e < 2e-5, (key, t, e)
+
+
+def test_indi_steps_match_reference_golden_with_injected_noise(gold_dir):
+    gd = np.load(os.path.join(gold_dir, "samplers.npz"))
+    _, _, (cfgi, sd1, sd2) = _nets()
+    x_in = torch.from_numpy(gd["indi_x"]).to(DEV)
+    for T in (1, 4):
+        indi = InDI(build(cfgi, sd1), 16, channels=1, out_channel=1, conditional=False, val_schedule_opt={"n_timestep": T})
+        noise = torch.from_numpy(gd[f"indi_T{T}_noise"]).to(DEV)
+        out = torch.from_numpy(gd[f"indi_T{T}_out"])
+        x_t = x_in + noise[0] * (0.01 * torch.Tensor([1.0])).to(DEV)
+        delta, cur = 1.0 / T, 1.0
+        for i in range(T):
+            x_t = indi.inference_one_step(x_t, delta, cur, noise=noise[i + 1])
+            cur -= delta
+            assert float((x_t.cpu() - out[2 * (i + 1):2 * (i + 2)]).abs().max()) < 2e-5
+
+
+def _cuda_draws(seed, shapes):
+    torch.manual_seed(seed)
+    return [torch.randn(s, device=DEV).cpu() for s in shapes]
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_seeded_loops_replay_the_reference_rng_stream(graph, monkeypatch):
+    """Seeded run through the public API (CUDA-graph loop, in-kernel Philox) == oracle fed with the draws
+    torch.randn would have produced on this device, and the torch generator ends where the reference leaves it."""
+    monkeypatch.setenv("DIFFSPLIT_B200_GRAPH", graph)
+    (cfg, sd), (cfgd, sdd), (cfgi, sd1, sd2) = _nets()
+    g = torch.Generator().manual_seed(1)
+    cond = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    gen = torch.cuda.default_generators[0]
+    tab = S.schedule_tables(SCHED)
+    # SR3: initial draw + one per step with t > 0
+    netG = GaussianDiffusionSr3(build(cfg, sd), 16, channels=2, conditional=True).to(DEV)
+    netG.set_new_noise_schedule(SCHED, DEV)
+    draws = _cuda_draws(77, [(2, 2, 16, 16)] * 6)
+    end_offset = gen.get_offset()
+    torch.manual_seed(77)
+    y = netG.super_resolution(cond.to(DEV), continous=True)
+    assert gen.get_offset() == end_offset
+    ref = S.sr3_sample_loop(tab, lambda x, t: U.unet_forward(sd, cfg, x, t), cond, 2, True, Replay(draws), continous=True)
+    assert y.shape == ref.shape and float((y.cpu() - ref).abs().max()) < 5e-5
+    last = netG.super_resolution(cond.to(DEV), continous=False)
+    assert last.shape == (2, 16, 16)                       # ret_img[-1]: last batch element only (reference quirk)
+    # DDPM: draws on every step
+    netD = GaussianDiffusionDdpm(build(cfgd, sdd), 16, channels=2, conditional=True).to(DEV)
+    netD.set_new_noise_schedule(SCHED, DEV)
+    draws = _cuda_draws(78, [(2, 2, 16, 16)] * 7)
+    end_offset = gen.get_offset()
+    torch.manual_seed(78)
+    y = netD.p_sample_loop(cond.to(DEV), continous=True)
+    assert gen.get_offset() == end_offset
+    ref = S.ddpm_sample_loop(tab, lambda x, t: U.unet_forward(sdd, cfgd, x, t), cond, 2, True, Replay(draws), continous=True)
+    assert float((y.cpu() - ref).abs().max()) < 5e-5
+    # JointIndi: channel 1 fully, then channel 2
+    joint = JointIndi(None, 16, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=build(cfgi, sd1),
+                      denoise_fn_ch2=build(cfgi, sd2), val_schedule_opt={"n_timestep": 3}).to(DEV)
+    joint.set_new_noise_schedule({"n_timestep": 3}, DEV)
+    x_in = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    draws = _cuda_draws(79, [(2, 1, 16, 16)] * 8)
+    end_offset = gen.get_offset()
+    torch.manual_seed(79)
+    y = joint.inference(x_in.to(DEV), continuous=True, t_float_start=0.5)
+    assert gen.get_offset() == end_offset
+    ref = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), lambda x, t: U.unet_forward(sd2, cfgi, x, t),
+                                 x_in, 3, Replay(draws), t_float_start=0.5, continuous=True)
+    assert y.shape == ref.shape == (8, 2, 16, 16) and float((y.cpu() - ref).abs().max()) < 5e-5
+    for T in (1, 2, 10):                                   # tests/test_joint_indi.py of the reference: T+1 snapshots
+        assert joint.inference(x_in[:1].to(DEV), continuous=True, num_timesteps=T).shape[0] == T + 1
+    assert joint.inference(x_in.to(DEV)).shape == (1, 2, 16, 16)          # ret_img[-1:]
+    # repeated call with the same seed through the cached graph gives the same bits
+    torch.manual_seed(79)
+    y2 = joint.inference(x_in.to(DEV), continuous=True, t_float_start=0.5)
+    assert torch.equal(y, y2)
+
+
+def test_final_psnr_within_point1_db_of_oracle():
+    """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 20 InDI chain)."""
+    cfgi = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
+    sd1, sd2 = U.random_state_dict(cfgi, seed=7), U.random_state_dict(cfgi, seed=8)
+    g = torch.Generator().manual_seed(4)
+    x_in = torch.rand((2, 1, 64, 64), generator=g) * 2 - 1
+    target = torch.rand((2, 2, 64, 64), generator=g) * 2 - 1
+    for precision in ("fp32", "bf16"):
+        joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=build(cfgi, sd1, precision),
+                          denoise_fn_ch2=build(cfgi, sd2, precision), val_schedule_opt={"n_timestep": 20}).to(DEV)
+        joint.set_new_noise_schedule({"n_timestep": 20}, DEV)
+        draws = _cuda_draws(5, [(2, 1, 64, 64)] * 42)
+        torch.manual_seed(5)
+        y = joint.inference(x_in.to(DEV), continuous=True)[-2:].cpu()
+        ref = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), lambda x, t: U.unet_forward(sd2, cfgi, x, t),
+                                     x_in, 20, Replay(draws), continuous=True)[-2:]
+        for c in range(2):
+            d = (S.psnr(target[:, c], y[:, c]) - S.psnr(target[:, c], ref[:, c])).abs().max()
+            print(f"[psnr {precision}] ch{c} delta {float(d):.4f} dB")
+            assert float(d) < 0.1
+
+
+# ------------------------------------------------------------------------------------------------ tiling
+@pytest.mark.parametrize("data,grid,patch", [((5, 512, 512), (1, 128, 128), (1, 256, 256)), ((3, 100, 130), (1, 16, 16), (1, 32, 32)),
+                                             ((2, 64, 64), (1, 64, 64), (1, 64, 64)), ((4, 70, 70), (1, 32, 32), (1, 64, 64)),
+                                             ((1, 8, 8), (1, 2, 2), (1, 8, 8))])
+def test_crop_and_stitch_bit_exact_vs_oracle(data, grid, patch):
+    tg = TR.TileGrid(data, grid, patch, TR.SHIFT)
+    mgr = TileIndexManager(data, grid, patch, TilingMode.ShiftBoundary)
+    rng = np.random.default_rng(3)
+    frames = rng.standard_normal((2,) + data).astype(np.float32)
+    tf = TiledFrames(frames, patch[1], grid[1])
+    assert len(tf) == tg.total
+    tiles = tf.raw_tiles(0, tg.total)
+    assert np.array_equal(tiles.cpu().numpy(), TR.crop_tiles(frames, tg))
+    assert np.array_equal(tf.raw_tiles(1, 1).cpu().numpy(), TR.crop_tiles(frames, tg, [1])) if tg.total > 1 else True
+    noise_tiles = rng.standard_normal(tiles.shape).astype(np.float32)
+    out = stitch_predictions(noise_tiles, mgr)             # numpy in -> numpy out, like the reference
+    assert isinstance(out, np.ndarray) and np.array_equal(out, TR.stitch(noise_tiles, tg))
+    out_t = stitch_predictions(tiles, mgr)                 # device in -> device out
+    assert torch.equal(out_t.cpu(), torch.from_numpy(frames.transpose(1, 2, 3, 0)))
+
+
+def test_stitch_golden_and_trim_mode(gold_dir):
+    gd = np.load(os.path.join(gold_dir, "tiling.npz"))
+    tg = TR.TileGrid((3, 100, 130), (1, 16, 16), (1, 32, 32), TR.SHIFT)
+    rng = np.random.default_rng(0)
+    rng.standard_normal((45, 2, 256, 256)).astype(np.float32)
+    tiles = rng.standard_normal((tg.total, 2, 32, 32)).astype(np.float32)
+    mgr = TileIndexManager((3, 100, 130), (1, 16, 16), (1, 32, 32), TilingMode.ShiftBoundary)
+    assert np.array_equal(stitch_predictions(tiles, mgr), gd["stitch_ragged_out"])      # reference's own output
+    tgt = TR.TileGrid((2, 80, 80), (1, 16, 16), (1, 32, 32), TR.TRIM)
+    mt = TileIndexManager((2, 80, 80), (1, 16, 16), (1, 32, 32), TilingMode.TrimBoundary)
+    tl = rng.standard_normal((tgt.total, 1, 32, 32)).astype(np.float32)
+    assert np.array_equal(stitch_predictions(tl, mt), TR.stitch(tl, tgt))               # uncovered border stays 0
+    with pytest.raises(ValueError):
+        stitch_predictions(tl[:-1], mt)
+
+
+def test_full_size_tiling_identity_uint16():
+    """BASELINE size: 10 x 2048^2 x 2 channels, 490 tiles of 512^2: stitch(crop(frames)) == frames, bit-exact, and
+    normalise+mix equals the numpy expression of SplitDataset (float64 constants, one rounding)."""
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, 1994, size=(2, 10, 2048, 2048), dtype=np.uint16)
+    nd = {"mean_input": 1210.5, "std_input": 1210.5, "mean_target": np.array([600.25, 610.25]), "std_target": np.array([600.25, 610.25])}
+    tf = TiledFrames(frames, 512, 256, normalization_dict=nd)
+    assert len(tf) == 490
+    tiles = tf.raw_tiles(0, 490)
+    out = stitch_predictions(tiles, tf.tile_manager)
+    assert out.shape == (10, 2048, 2048, 2)
+    assert torch.equal(out.cpu(), torch.from_numpy(frames.astype(np.float32)).permute(1, 2, 3, 0))
+    tg = TR.TileGrid((10, 2048, 2048), (1, 256, 256), (1, 512, 512), TR.SHIFT)
+    idx = [0, 6, 48, 489]
+    raw = TR.crop_tiles(frames, tg, idx)
+    inp_ref, tar_ref = TR.normalise_and_mix(raw, nd["mean_target"], nd["std_target"], nd["mean_input"], nd["std_input"])
+    for j, i in enumerate(idx):
+        inp, tar = tf.batch(i, 1)
+        assert np.array_equal(inp.cpu().numpy()[0], inp_ref[j]) and np.array_equal(tar.cpu().numpy()[0], tar_ref[j])
+        item = tf[i]
+        assert np.array_equal(item["input"], inp_ref[j])
+
+
+# ------------------------------------------------------------------------------------------------ wrapper
+def test_create_model_test_and_checkpoint_round_trip(tmp_path):
+    opt = make_opt("splitting_hagen_indi_joint")
+    opt["path"]["checkpoint"] = str(tmp_path)
+    m = create_model(opt)
+    m.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], schedule_phase="val")
+    g = torch.Generator().manual_seed(0)
+    data = {"input": torch.rand((1, 1, 64, 64), generator=g), "target": torch.rand((1, 2, 64, 64), generator=g)}
+    m.feed_data(data)
+    torch.manual_seed(3)
+    m.test(continuous=True)
+    vis = m.get_current_visuals()
+    assert vis["prediction"].shape == (4, 2, 64, 64) and vis["prediction"].device.type == "cpu"
+    assert vis["input"].shape == (1, 1, 64, 64) and torch.isfinite(vis["prediction"]).all()
+    m.save_network(1, 10)
+    opt2 = make_opt("splitting_hagen_indi_joint")
+    opt2["path"]["resume_state"] = os.path.join(str(tmp_path), "I10_E1")
+    m2 = create_model(opt2)
+    m2.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], schedule_phase="val")
+    m2.feed_data(data)
+    torch.manual_seed(3)
+    m2.test(continuous=True)
+    assert torch.equal(m2.get_current_visuals()["prediction"], vis["prediction"])
