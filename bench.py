@@ -83,9 +83,9 @@ def oracle_step_fn(w, Bs):
         state = dict(x=x, t=1.0)
 
         def step():
-            if state["t"] - delta < 0:
+            if state["t"] < delta * 0.5:
                 state["t"] = 1.0
-            state["x"] = S.indi_one_step(den, state["x"], delta, state["t"], 0.01, torch.randn(x.shape, generator=g))
+            state["x"] = S.indi_one_step(den, state["x"], delta, state["t"], 0.01, torch.randn(x.shape, generator=g), strict=False)
             state["t"] -= delta
     else:
         tab = S.schedule_tables(dict(schedule="linear", n_timestep=T, linear_start=1e-6, linear_end=1e-2))

@@ -369,6 +369,14 @@ class GaussianDiffusionDdpm(_GaussianDiffusion):
 
 
 # --------------------------------------------------------------------------------------------- InDI
+def _delta_ok(delta_t, t_cur):
+    """indi.py:64 asserts ``delta_t <= t_cur`` on a python float that the loop decrements T times (indi.py:88); the
+    rounding of that accumulation makes the reference raise on its LAST step for many (T, t_start), e.g. T=1000 or
+    T=20 with t_start=1.0 (cur = 0.00099999999999912 < delta = 0.001).  Conscious fix: the check tolerates the
+    accumulated rounding (1e-9 relative); every case the reference completes is unchanged."""
+    return delta_t <= t_cur * (1 + 1e-9) + 1e-300
+
+
 class InDI(_SamplerBase):
     def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", out_channel=2, lr_reduction=None,
                  conditional=True, schedule_opt=None, val_schedule_opt=None, e=0.01, **ignored):
@@ -396,7 +404,7 @@ class InDI(_SamplerBase):
         cur = t_start
         rows, times = [], []
         for _ in range(T):
-            assert delta <= cur, "delta_t should be less than or equal to t_cur."
+            assert _delta_ok(delta, cur), "delta_t should be less than or equal to t_cur."
             t32 = torch.Tensor([cur])
             w = delta / t32
             rows.append(torch.stack([torch.zeros(1), torch.zeros(1), w, 1 - w, self.e * (t32 - delta)], dim=1))
@@ -408,7 +416,7 @@ class InDI(_SamplerBase):
 
     @torch.no_grad()
     def inference_one_step(self, x_t, delta_t, t_cur, noise=None):
-        assert delta_t <= t_cur, "delta_t should be less than or equal to t_cur."
+        assert _delta_ok(delta_t, t_cur), "delta_t should be less than or equal to t_cur."
         _lib.require_cuda(x_t, "inference_one_step input")
         net = self.denoise_fn
         net.commit()

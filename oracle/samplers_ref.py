@@ -160,9 +160,11 @@ def ddpm_sample_loop(tab, denoise, x_in, channels: int, conditional: bool, draw:
 
 # ----------------------------------------------------------------------------- InDI
 @torch.no_grad()
-def indi_one_step(denoise, x_t: Tensor, delta_t: float, t_cur: float, e: float, noise: Tensor):
-    """indi.py:62-69: x <- (d/t) x0 + (1-d/t) x + z * e*(t-d); python-float t cast to fp32."""
-    assert delta_t <= t_cur
+def indi_one_step(denoise, x_t: Tensor, delta_t: float, t_cur: float, e: float, noise: Tensor, strict: bool = True):
+    """indi.py:62-69: x <- (d/t) x0 + (1-d/t) x + z * e*(t-d); python-float t cast to fp32.
+    ``strict`` keeps the reference's assertion, which fires on the last step for many (T, t_start) because of the
+    accumulated rounding of ``cur_t -= delta`` (e.g. T=1000, t_start=1.0); strict=False tolerates that rounding."""
+    assert delta_t <= t_cur * ((1 + 1e-9) if not strict else 1.0)
     t32 = torch.Tensor([t_cur])
     x0 = denoise(x_t, t32)
     z = noise * (e * (t32 - delta_t))
@@ -171,7 +173,7 @@ def indi_one_step(denoise, x_t: Tensor, delta_t: float, t_cur: float, e: float, 
 
 @torch.no_grad()
 def indi_inference(denoise, x_in: Tensor, num_timesteps: int, draw: Callable, e: float = 0.01,
-                   out_channel: int = 1, t_float_start: float = 1.0, continuous=False):
+                   out_channel: int = 1, t_float_start: float = 1.0, continuous=False, strict: bool = True):
     """indi.py:71-95.  RNG is consumed once before the loop and once per step (also the last)."""
     inter = 1 | (num_timesteps // 20)
     x_in = torch.cat([x_in] * out_channel, dim=1)
@@ -180,7 +182,7 @@ def indi_inference(denoise, x_in: Tensor, num_timesteps: int, draw: Callable, e:
     cur_t = t_float_start
     ret = x_t
     for idx in range(num_timesteps):
-        x_t = indi_one_step(denoise, x_t, delta, cur_t, e, draw(x_t.shape))
+        x_t = indi_one_step(denoise, x_t, delta, cur_t, e, draw(x_t.shape), strict)
         cur_t -= delta
         if idx % inter == 0 or idx == num_timesteps - 1:
             ret = torch.cat([ret, x_t], dim=0)
@@ -189,10 +191,10 @@ def indi_inference(denoise, x_in: Tensor, num_timesteps: int, draw: Callable, e:
 
 @torch.no_grad()
 def joint_indi_inference(denoise1, denoise2, x_in, num_timesteps, draw, e=0.01, out_channel=1,
-                         t_float_start=0.5, continuous=False):
+                         t_float_start=0.5, continuous=False, strict: bool = True):
     """joint_indi.py:131-135: channel 1 fully sampled first, then channel 2 with 1-t_start."""
-    c1 = indi_inference(denoise1, x_in, num_timesteps, draw, e, out_channel, t_float_start, continuous)
-    c2 = indi_inference(denoise2, x_in, num_timesteps, draw, e, out_channel, 1 - t_float_start, continuous)
+    c1 = indi_inference(denoise1, x_in, num_timesteps, draw, e, out_channel, t_float_start, continuous, strict)
+    c2 = indi_inference(denoise2, x_in, num_timesteps, draw, e, out_channel, 1 - t_float_start, continuous, strict)
     return torch.cat([c1, c2], dim=1)
 
 

@@ -242,3 +242,21 @@ def test_install_aliases():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_indi_last_step_rounding_is_tolerated():
+    """The reference's `assert delta_t <= t_cur` (indi.py:64) fires on the last step for T=1000, t_start=1.0 because
+    cur_t is a python float decremented T times; the port tolerates exactly that rounding and nothing more."""
+    indi = InDI(None, 8, channels=1, out_channel=1, conditional=False, val_schedule_opt={"n_timestep": 4})
+    for T, ts in ((1000, 1.0), (20, 0.5), (50, 1.0), (3, 0.5), (16, 0.5)):
+        coef, ttab = indi._tables(T, ts)
+        assert coef.shape == (T, 5) and torch.isfinite(coef).all()
+    d, cur = 1.0 / 1000, 1.0
+    for _ in range(999):
+        cur -= d
+    assert not d <= cur                      # the reference raises here
+    with pytest.raises(AssertionError):
+        S.indi_one_step(lambda x, t: x, torch.zeros(1, 1, 2, 2), d, cur, 0.01, torch.zeros(1, 1, 2, 2))
+    S.indi_one_step(lambda x, t: x, torch.zeros(1, 1, 2, 2), d, cur, 0.01, torch.zeros(1, 1, 2, 2), strict=False)
+    with pytest.raises(AssertionError):
+        indi.inference_one_step(torch.zeros(1, 1, 2, 2), 0.2, 0.1)       # a genuinely too large delta still asserts

@@ -276,7 +276,8 @@ def test_seeded_loops_replay_the_reference_rng_stream(graph, monkeypatch):
 
 
 def test_final_psnr_within_point1_db_of_oracle():
-    """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 20 InDI chain)."""
+    """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 16 InDI chain;
+    T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation)."""
     cfgi = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
     sd1, sd2 = U.random_state_dict(cfgi, seed=7), U.random_state_dict(cfgi, seed=8)
     g = torch.Generator().manual_seed(4)
@@ -284,13 +285,13 @@ def test_final_psnr_within_point1_db_of_oracle():
     target = torch.rand((2, 2, 64, 64), generator=g) * 2 - 1
     for precision in ("fp32", "bf16"):
         joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=build(cfgi, sd1, precision),
-                          denoise_fn_ch2=build(cfgi, sd2, precision), val_schedule_opt={"n_timestep": 20}).to(DEV)
-        joint.set_new_noise_schedule({"n_timestep": 20}, DEV)
-        draws = _cuda_draws(5, [(2, 1, 64, 64)] * 42)
+                          denoise_fn_ch2=build(cfgi, sd2, precision), val_schedule_opt={"n_timestep": 16}).to(DEV)
+        joint.set_new_noise_schedule({"n_timestep": 16}, DEV)
+        draws = _cuda_draws(5, [(2, 1, 64, 64)] * 34)
         torch.manual_seed(5)
         y = joint.inference(x_in.to(DEV), continuous=True)[-2:].cpu()
         ref = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), lambda x, t: U.unet_forward(sd2, cfgi, x, t),
-                                     x_in, 20, Replay(draws), continuous=True)[-2:]
+                                     x_in, 16, Replay(draws), continuous=True)[-2:]
         for c in range(2):
             d = (S.psnr(target[:, c], y[:, c]) - S.psnr(target[:, c], ref[:, c])).abs().max()
             print(f"[psnr {precision}] ch{c} delta {float(d):.4f} dB")
