@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace ds {
 
@@ -47,8 +48,8 @@ extern "C" int ds_groupnorm_swish_f32(const float* d_a, int ca, const float* d_b
     DS_REQUIRE(d_a && d_gamma && d_beta && d_out && d_scratch, "groupnorm: null argument");
     DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_b), "groupnorm: bad channel split %d+%d", ca, cb);
     DS_REQUIRE(scratch_bytes >= gn_scratch_bytes(B, groups), "groupnorm: scratch too small");
-    return launch_groupnorm_f32(d_a, ca, d_b, cb, d_gamma, d_beta, d_out, B, H * W, groups, apply_swish, d_scratch,
-                                (cudaStream_t)stream);
+    return launch_groupnorm(d_a, ca, d_b, cb, d_gamma, d_beta, d_out, B, H * W, groups, apply_swish, d_scratch, 0,
+                            (cudaStream_t)stream);
 }
 
 static int conv_npad(int cout) {
@@ -78,10 +79,36 @@ extern "C" int ds_conv2d_f32(const float* d_x, const float* d_w_oihw, const floa
     const int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
     ConvEpi e;
     e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = nullptr; e.out_nchw = 0;
+    e.out_bf16 = 0;
     return launch_conv_f32(s, (const float*)d_scratch, npad, cout, ksize, stride, B, Ho, Wo, e, d_out, st);
 }
 
 extern "C" int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream) {
     DS_REQUIRE(d_qkv && d_out, "attention: null argument");
-    return launch_attention_f32(d_qkv, d_out, B, N, C, (cudaStream_t)stream);
+    return launch_attention(d_qkv, d_out, B, N, C, 0, (cudaStream_t)stream);
+}
+
+extern "C" size_t ds_conv2d_bf16_scratch_bytes(int cin, int cout, int ksize) {
+    return align_up(tc_packed_weight_bytes(cout, cin, ksize), 1024);
+}
+
+extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb, const float* d_w_oihw, const float* d_bias,
+                              const void* d_residual, void* d_out, int out_f32_nchw, int B, int H, int W, int cout, int ksize,
+                              int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream) {
+    DS_REQUIRE(d_xa && d_w_oihw && d_out && d_scratch, "conv2d_bf16: null argument");
+    DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_xb), "conv2d_bf16: bad channel split %d+%d", ca, cb);
+    DS_REQUIRE(scratch_bytes >= ds_conv2d_bf16_scratch_bytes(ca + cb, cout, ksize), "conv2d_bf16: scratch too small");
+    DS_REQUIRE(tc_conv_shape_supported(ca, cb, ksize, stride, upsample2x, H, W),
+               "conv2d_bf16: unsupported shape (channels must be multiples of 16; stride 2 needs even H, W)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kc = tc_pick_kc(ca, cb);
+    int rc = tc_pack_conv_weight(d_w_oihw, (uint8_t*)d_scratch, cout, ca + cb, ksize, upsample2x, kc, st);
+    if (rc != DS_OK) return rc;
+    TcConvPlan plan;
+    rc = tc_build_conv(&plan, d_xa, ca, d_xb, cb, H, W, B, cout, ksize, stride, upsample2x);
+    if (rc != DS_OK) return rc;
+    ConvEpi e;
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = nullptr;
+    e.out_nchw = out_f32_nchw; e.out_bf16 = 0;
+    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, 0, d_residual, d_out, st);
 }

@@ -16,9 +16,13 @@ constexpr int AQ = 32;     // queries per CTA
 constexpr int AK = 32;     // keys per inner block
 constexpr int AC = 32;     // channel chunk of the score dot product
 
-template <int CV>
-__global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                            int N, int C) {
+__device__ __forceinline__ float ld_f32(const float* p) { return *p; }
+__device__ __forceinline__ float ld_f32(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_f32(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int CV, typename T>
+__global__ void __launch_bounds__(256) attention_f32_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int C) {
     constexpr int CPT = CV / 32;                 // output channels per thread
     __shared__ float Qs[AQ][AC + 1];
     __shared__ float Ks[AK][AC + 1];
@@ -31,7 +35,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
     const int cs = blockIdx.y * CV;
     const int b = blockIdx.z;
     const size_t row3 = (size_t)3 * C;
-    const float* base = qkv + (size_t)b * N * row3;
+    const T* base = qkv + (size_t)b * N * row3;
     const float scale_div = sqrtf((float)C);
 
     // score role: 2x2 micro-tile
@@ -57,8 +61,8 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
                 const int idx = t + 256 * i;
                 const int r = idx >> 5, c = idx & 31;
                 const bool cin = (c0 + c) < C;
-                Qs[r][c] = (q0 + r < N && cin) ? base[(size_t)(q0 + r) * row3 + c0 + c] : 0.f;
-                Ks[r][c] = (k0 + r < N && cin) ? base[(size_t)(k0 + r) * row3 + C + c0 + c] : 0.f;
+                Qs[r][c] = (q0 + r < N && cin) ? ld_f32(base + (size_t)(q0 + r) * row3 + c0 + c) : 0.f;
+                Ks[r][c] = (k0 + r < N && cin) ? ld_f32(base + (size_t)(k0 + r) * row3 + C + c0 + c) : 0.f;
             }
             __syncthreads();
 #pragma unroll
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
         // V tile for this key block
         for (int idx = t; idx < AK * CV; idx += 256) {
             const int r = idx / CV, c = idx - r * CV;
-            Vs[r][c] = (k0 + r < N) ? base[(size_t)(k0 + r) * row3 + 2 * C + cs + c] : 0.f;
+            Vs[r][c] = (k0 + r < N) ? ld_f32(base + (size_t)(k0 + r) * row3 + 2 * C + cs + c) : 0.f;
         }
         const bool ka_ok = (k0 + 2 * sx) < N, kb_ok = (k0 + 2 * sx + 1) < N;
         Ss[2 * sy][2 * sx] = ka_ok ? s00 / scale_div : -INFINITY;
@@ -135,19 +139,25 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
         if (q >= N) continue;
         const float inv = s_l[4 * og + i];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) out[((size_t)b * N + q) * C + cs + oc + j] = acc[i][j] / inv;
+        for (int j = 0; j < CPT; ++j) st_f32(out + ((size_t)b * N + q) * C + cs + oc + j, acc[i][j] / inv);
     }
 }
 
-int launch_attention_f32(const float* qkv, float* out, int B, int N, int C, cudaStream_t st) {
-    DS_REQUIRE(B > 0 && N > 0 && C > 0 && C % 32 == 0, "attention: unsupported shape B=%d N=%d C=%d (C %% 32)", B, N, C);
+template <typename T>
+static void launch_attn_t(const T* qkv, T* out, int B, int N, int C, cudaStream_t st) {
     if (C % 128 == 0) {
-        attention_f32_kernel<128><<<dim3(cdiv(N, AQ), C / 128, B), 256, 0, st>>>(qkv, out, N, C);
+        attention_f32_kernel<128, T><<<dim3(cdiv(N, AQ), C / 128, B), 256, 0, st>>>(qkv, out, N, C);
     } else if (C % 64 == 0) {
-        attention_f32_kernel<64><<<dim3(cdiv(N, AQ), C / 64, B), 256, 0, st>>>(qkv, out, N, C);
+        attention_f32_kernel<64, T><<<dim3(cdiv(N, AQ), C / 64, B), 256, 0, st>>>(qkv, out, N, C);
     } else {
-        attention_f32_kernel<32><<<dim3(cdiv(N, AQ), C / 32, B), 256, 0, st>>>(qkv, out, N, C);
+        attention_f32_kernel<32, T><<<dim3(cdiv(N, AQ), C / 32, B), 256, 0, st>>>(qkv, out, N, C);
     }
+}
+
+int launch_attention(const void* qkv, void* out, int B, int N, int C, int bf16, cudaStream_t st) {
+    DS_REQUIRE(B > 0 && N > 0 && C > 0 && C % 32 == 0, "attention: unsupported shape B=%d N=%d C=%d (C %% 32)", B, N, C);
+    if (bf16) launch_attn_t((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, B, N, C, st);
+    else launch_attn_t((const float*)qkv, (float*)out, B, N, C, st);
     DS_CHECK_LAUNCH("attention_f32");
     return DS_OK;
 }

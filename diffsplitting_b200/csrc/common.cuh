@@ -58,6 +58,7 @@ struct ConvEpi {
     int temb_off, temb_stride, temb_bcast;   // value = temb[(temb_bcast ? 0 : b)*temb_stride + temb_off + n]
     const float* residual;  // NHWC [B,Ho,Wo,Cout] or nullptr
     int out_nchw;           // 1: write NCHW (external), 0: NHWC
+    int out_bf16;           // fp32 kernel only: write bf16 NHWC (entry conv of the bf16 path)
 };
 
 int launch_conv_f32(const ConvSrc& src, const float* w_packed /*[K][Npad]*/, int Npad, int Cout,
@@ -68,10 +69,11 @@ int launch_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int Cout, 
 
 int gn_nsplit(int B, int HW, int C);
 size_t gn_scratch_bytes(int B, int G);
-int launch_groupnorm_f32(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta,
-                         float* out, int B, int HW, int G, int swish, void* scratch, cudaStream_t st);
+// bf16 != 0: a, b and out are __nv_bfloat16 (statistics and normalisation still in fp32 / fp64)
+int launch_groupnorm(const void* a, int ca, const void* b, int cb, const float* gamma, const float* beta,
+                     void* out, int B, int HW, int G, int swish, void* scratch, int bf16, cudaStream_t st);
 
-int launch_attention_f32(const float* qkv, float* out, int B, int N, int C, cudaStream_t st);
+int launch_attention(const void* qkv, void* out, int B, int N, int C, int bf16, cudaStream_t st);
 
 struct TembParams {
     int variant;            // DS_UNET_SR3 / DS_UNET_DDPM

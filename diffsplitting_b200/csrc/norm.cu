@@ -29,14 +29,19 @@ int gn_nsplit(int B, int HW, int C) {
 
 size_t gn_scratch_bytes(int B, int G) { return (size_t)B * GN_MAX_SPLIT * G * 2 * sizeof(double); }
 
-__device__ __forceinline__ float load_cat(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
-                                          size_t pix, int c) {
-    return (c < ca) ? a[pix * ca + c] : b[pix * cb + (c - ca)];
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f32(float* p, float v) { *p = v; }
+__device__ __forceinline__ void from_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T>
+__device__ __forceinline__ float load_cat(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb, size_t pix, int c) {
+    return to_f32((c < ca) ? a[pix * ca + c] : b[pix * cb + (c - ca)]);
 }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ a, int ca,
-                                                               const float* __restrict__ b, int cb, int HW, int G,
-                                                               int nsplit, double* __restrict__ partial) {
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb,
+                                                               int HW, int G, int nsplit, double* __restrict__ partial) {
     const int C = ca + cb;
     const int cpg = C / G;
     const int bi = blockIdx.y, sp = blockIdx.x;
@@ -89,10 +94,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     }
 }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ a, int ca,
-                                                               const float* __restrict__ b, int cb,
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb,
                                                                const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float* __restrict__ out,
+                                                               const float* __restrict__ beta, T* __restrict__ out,
                                                                int HW, int G, int nsplit, int nchunk, int swish,
                                                                const double* __restrict__ partial) {
     const int C = ca + cb;
@@ -126,25 +131,31 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
         float y = (x - s_mean[g]) * s_rstd[g];
         y = fmaf(y, gamma[c], beta[c]);
         if (swish) y = y / (1.0f + expf(-y));
-        out[(base + p) * C + c] = y;
+        from_f32(out + (base + p) * C + c, y);
     }
 }
 
-int launch_groupnorm_f32(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta,
-                         float* out, int B, int HW, int G, int swish, void* scratch, cudaStream_t st) {
+int launch_groupnorm(const void* a, int ca, const void* b, int cb, const float* gamma, const float* beta, void* out, int B,
+                     int HW, int G, int swish, void* scratch, int bf16, cudaStream_t st) {
     const int C = ca + cb;
     DS_REQUIRE(G >= 1 && G <= GN_MAX_GROUPS && C % G == 0, "groupnorm: %d channels not divisible into %d groups (max %d)",
                C, G, GN_MAX_GROUPS);
     const int nsplit = gn_nsplit(B, HW, C);
     double* partial = reinterpret_cast<double*>(scratch);
-    gn_stats_kernel<<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial);
+    typedef __nv_bfloat16 bf;
+    if (bf16) gn_stats_kernel<bf><<<dim3(nsplit, B), GN_THREADS, 0, st>>>((const bf*)a, ca, (const bf*)b, cb, HW, G, nsplit, partial);
+    else gn_stats_kernel<float><<<dim3(nsplit, B), GN_THREADS, 0, st>>>((const float*)a, ca, (const float*)b, cb, HW, G, nsplit, partial);
     DS_CHECK_LAUNCH("gn_stats");
     int64_t total = (int64_t)HW * C;
     int nchunk = (int)((total + 16383) / 16384);
     if (nchunk > 65535) nchunk = 65535;
     if (nchunk < 1) nchunk = 1;
-    gn_apply_kernel<<<dim3(nchunk, B), GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, out, HW, G, nsplit, nchunk,
-                                                           swish, partial);
+    if (bf16)
+        gn_apply_kernel<bf><<<dim3(nchunk, B), GN_THREADS, 0, st>>>((const bf*)a, ca, (const bf*)b, cb, gamma, beta, (bf*)out, HW, G,
+                                                                   nsplit, nchunk, swish, partial);
+    else
+        gn_apply_kernel<float><<<dim3(nchunk, B), GN_THREADS, 0, st>>>((const float*)a, ca, (const float*)b, cb, gamma, beta,
+                                                                      (float*)out, HW, G, nsplit, nchunk, swish, partial);
     DS_CHECK_LAUNCH("gn_apply");
     return DS_OK;
 }

@@ -1,12 +1,534 @@
-// placeholder until the tcgen05 kernel lands: reports "unsupported" so every conv takes the fp32 path
+// bf16 implicit-GEMM convolution on the 5th-generation tensor cores (precision mode DS_PREC_BF16).
+//
+//   out[m, n] = sum_{tap, c} A_tap[m, c] * W[n, tap, c]      m = output pixel, n = output channel
+//
+//  * A operand: bf16 NHWC activations, one TMA 4-D tile load per (filter tap, channel chunk): box
+//    {KC channels, tw, th, tb} at coordinates {c0, x0+dx, y0+dy, b0}; out-of-bounds coordinates are zero-filled
+//    by the TMA unit, which IS the conv's zero padding.  tw*th*tb = 128 output pixels = the UMMA M.
+//  * B operand: weights pre-packed (once, at load time) into the exact swizzled shared-memory image of every
+//    (tap, chunk) unit, fetched with a 1-D bulk copy (cp.async.bulk) - no descriptor needed.
+//  * tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (16..128), K=16 per instruction, fp32 accumulators in TMEM,
+//    issued by one thread; smem slots are released by tcgen05.commit -> mbarrier.
+//  * Epilogue: 4 warps, tcgen05.ld (32 lanes x 32 bit x 16 columns), + bias + conditioning vector + residual,
+//    bf16 NHWC (or fp32 NCHW for the network output) stores.
+//
+// Folded into the load path (reference model/sr3_modules/unet.py):
+//   - skip / condition concat (:255): two source tensors = two tensor maps, consecutive K ranges
+//   - Downsample 3x3 stride 2 (:68-74): four parity views of the input (base pointer offset, doubled strides)
+//   - Upsample nearest x2 + 3x3 (:58-65): four output-parity classes, each a 2x2 conv on the LOW-resolution
+//     input with pre-summed weights (2.25x fewer MACs, no 4x intermediate)
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "tc.cuh"
 
 namespace ds {
-size_t tc_packed_weight_bytes(int, int, int) { return 0; }
-int tc_pack_conv_weight(const float*, uint8_t*, int, int, int, cudaStream_t) { return DS_OK; }
-bool tc_conv_supported(const ConvSrc&, int, int, int, const ConvEpi&) { return false; }
-int tc_launch_conv(const ConvSrc&, const uint8_t*, int, int, int, int, int, int, const ConvEpi&, float*, cudaStream_t) {
-    set_error("tensor-core conv not built");
-    return DS_ERR_INVALID;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost TMA / MMA completion traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout (2=SW128, 4=SW64, 6=SW32)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (8u * row_bytes) >> 4;          // 8-row group stride
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int TC_THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_MAX_TAPS = 9;
+
+struct TcParams {
+    CUtensorMap maps[8];              // [source (a=0, b=1) * 4 + view]; view = stride-2 parity plane or 0
+    const uint8_t* w;                 // packed weights: [class][n_tile][unit][BN x KC swizzled image]
+    const float* bias;                // [Cout] or null
+    const float* temb;                // conditioning vectors or null
+    int temb_off, temb_stride, temb_bcast;
+    const __nv_bfloat16* residual;    // bf16 NHWC [B,Ho,Wo,Cout] or null
+    void* out;                        // bf16 NHWC, or fp32 NCHW when out_f32_nchw
+    int out_f32_nchw;
+    int B, H, W;                      // tile space (= output size; for upsample: the LOW-res size)
+    int Ho, Wo;                       // output tensor size (2H x 2W for upsample)
+    int Cout, BN, n_tiles;
+    int KC, chunks_a, chunks_b;       // channel chunking of the two sources
+    int ntaps, nclasses;              // taps per class, output parity classes (4 for upsample, else 1)
+    int tw, th, tb, tiles_x, tiles_y; // 128-pixel tile = tw x th x tb
+    int stages;
+    int8_t tap_dx[4][TC_MAX_TAPS], tap_dy[4][TC_MAX_TAPS], tap_view[4][TC_MAX_TAPS];   // per class
+    int up;                           // output pixel = (2y + class/2, 2x + class%2)
+};
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_bytes = 128u * p.KC * 2u, b_bytes = (uint32_t)p.BN * p.KC * 2u;
+    const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
+    const uint32_t bar_base = base + p.stages * stage_bytes;           // full[stages], empty[stages], tmem_full, tmem slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+    const uint32_t tfull_bar = bar_base + 16u * p.stages;
+    const uint32_t tmem_slot = tfull_bar + 8u;
+
+    // tile coordinates
+    int bid = blockIdx.x;
+    const int tx_i = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty_i = bid % p.tiles_y; bid /= p.tiles_y;
+    const int tb_i = bid;
+    const int x0 = tx_i * p.tw, y0 = ty_i * p.th, b0 = tb_i * p.tb;
+    const int nt = blockIdx.y, cls = blockIdx.z;
+    const int units_per_tap = p.chunks_a + p.chunks_b;
+    const int U = p.ntaps * units_per_tap;
+    const uint32_t tmem_cols = p.BN <= 32 ? 32u : (p.BN <= 64 ? 64u : 128u);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t* wsrc = p.w + ((size_t)(cls * p.n_tiles + nt) * U) * b_bytes;
+            for (int u = 0; u < U; ++u) {
+                const int s = u % p.stages;
+                const uint32_t ph = (u / p.stages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int tap = u / units_per_tap, cc = u - tap * units_per_tap;
+                const int src = cc < p.chunks_a ? 0 : 1;
+                const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
+                const CUtensorMap* map = &p.maps[src * 4 + p.tap_view[cls][tap]];
+                const uint32_t dstA = base + s * stage_bytes;
+                mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+                tma_load_4d(dstA, map, full_bar(s), c0, x0 + p.tap_dx[cls][tap], y0 + p.tap_dy[cls][tap], b0);
+                bulk_load(dstA + a_bytes, wsrc + (size_t)u * b_bytes, b_bytes, full_bar(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t row_bytes = p.KC * 2u;
+            for (int u = 0; u < U; ++u) {
+                const int s = u % p.stages;
+                const uint32_t ph = (u / p.stages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * stage_bytes;
+                const uint64_t adesc = make_smem_desc(sa, row_bytes), bdesc = make_smem_desc(sa + a_bytes, row_bytes);
+                for (int k = 0; k < p.KC / 16; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
+                umma_commit(empty_bar(s));        // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tfull_bar);               // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) == output rows
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int xl = m % p.tw, yl = (m / p.tw) % p.th, bl = m / (p.tw * p.th);
+        const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
+        const bool valid = x < p.W && y < p.H && b < p.B;
+        int oy = y, ox = x;
+        if (p.up) { oy = 2 * y + (cls >> 1); ox = 2 * x + (cls & 1); }
+        const size_t pix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+        const int n_base = nt * p.BN;
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!valid) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            const int n0 = n_base + c0;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += p.bias[n0 + j];
+            }
+            if (p.temb) {
+                const float* te = p.temb + (size_t)(p.temb_bcast ? 0 : b) * p.temb_stride + p.temb_off + n0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += te[j];
+            }
+            if (p.out_f32_nchw) {
+                float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < p.Cout) o[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
+            } else if (n0 + 16 <= p.Cout) {
+                if (p.residual) {
+                    const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0);
+                    const uint4 r0 = r[0], r1 = r[1];
+                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                        f[2 * j] += __low2float(h);
+                        f[2 * j + 1] += __high2float(h);
+                    }
+                }
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0);
+                o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (n0 + j < p.Cout) {
+                        float val = f[j];
+                        if (p.residual) val += __bfloat162float(p.residual[pix * p.Cout + n0 + j]);
+                        o[n0 + j] = __float2bfloat16_rn(val);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+// Swizzle<B,4,3> on byte offsets inside a tile whose rows are `row_bytes` wide (B = log2(row_bytes/16)).
+__host__ __device__ inline uint32_t swizzle_offset(uint32_t row, uint32_t byte_in_row, uint32_t row_bytes) {
+    const uint32_t off = row * row_bytes + byte_in_row;
+    const uint32_t bits = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+    return off ^ (((off >> 7) & bits) << 4);
+}
+
+struct PackGeom {
+    int cout, cin, ks, up, BN, n_tiles, KC, chunks, ntaps, nclasses;
+};
+
+static int tc_bn(int cout) {
+    const int npad = (cout + 15) / 16 * 16;
+    if (npad <= 128) return npad <= 16 ? 16 : (npad <= 32 ? 32 : (npad <= 64 ? 64 : 128));
+    return 128;
+}
+
+static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc) {
+    PackGeom g;
+    g.cout = cout; g.cin = cin; g.ks = ks; g.up = up;
+    g.BN = tc_bn(cout);
+    g.n_tiles = (cout + g.BN - 1) / g.BN;
+    g.KC = kc;
+    g.chunks = cin / kc;
+    g.ntaps = up ? 4 : ks * ks;
+    g.nclasses = up ? 4 : 1;
+    return g;
+}
+
+int tc_pick_kc(int ca, int cb) {
+    for (int kc = 64; kc >= 16; kc >>= 1)
+        if (ca % kc == 0 && cb % kc == 0) return kc;
+    return 0;
+}
+
+size_t tc_packed_weight_bytes(int cout, int cin, int ks) {
+    // worst case over the variants a layer can be packed for (KC = 16, upsample classes)
+    const int bn = tc_bn(cout);
+    const int nt = (cout + bn - 1) / bn;
+    const size_t plain = (size_t)nt * bn * ks * ks * cin * 2;
+    const size_t upv = ks == 3 ? (size_t)4 * nt * bn * 4 * cin * 2 : 0;
+    return plain > upv ? plain : upv;
+}
+
+__global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, PackGeom g) {
+    const int U = g.ntaps * g.chunks;
+    const size_t total = (size_t)g.nclasses * g.n_tiles * U * g.BN * g.KC;
+    const uint32_t row_bytes = g.KC * 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int k = (int)(r % g.KC); r /= g.KC;
+        const int row = (int)(r % g.BN); r /= g.BN;
+        const int u = (int)(r % U); r /= U;
+        const int nt = (int)(r % g.n_tiles); r /= g.n_tiles;
+        const int cls = (int)r;
+        const int tap = u / g.chunks, c = (u - tap * g.chunks) * g.KC + k;
+        const int n = nt * g.BN + row;
+        float v = 0.f;
+        if (n < g.cout) {
+            const float* wn = w + ((size_t)n * g.cin + c) * g.ks * g.ks;
+            if (!g.up) {
+                v = wn[tap];
+            } else {
+                // class (a, b) = output parity; tap (ty, tx) of the 2x2 conv on the low-res input.
+                // rows: a=0: ty0 <- r{0}, ty1 <- r{1,2};  a=1: ty0 <- r{0,1}, ty1 <- r{2}   (same for columns)
+                const int a = cls >> 1, b = cls & 1, ty = tap >> 1, tx = tap & 1;
+                const int r_lo = a == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2);
+                const int r_hi = a == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+                const int s_lo = b == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2);
+                const int s_hi = b == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+                for (int rr = r_lo; rr <= r_hi; ++rr)
+                    for (int ss = s_lo; ss <= s_hi; ++ss) v += wn[rr * 3 + ss];
+            }
+        }
+        const size_t tile = ((size_t)(cls * g.n_tiles + nt) * U + u) * ((size_t)g.BN * row_bytes);
+        *reinterpret_cast<__nv_bfloat16*>(out + tile + swizzle_offset(row, k * 2, row_bytes)) = __float2bfloat16_rn(v);
+    }
+}
+
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, cudaStream_t st) {
+    DS_REQUIRE(kc == 16 || kc == 32 || kc == 64, "tc_pack: KC %d", kc);
+    DS_REQUIRE(cin % kc == 0, "tc_pack: cin %d not a multiple of KC %d", cin, kc);
+    PackGeom g = pack_geom(cout, cin, ks, up, kc);
+    const size_t total = (size_t)g.nclasses * g.n_tiles * g.ntaps * g.chunks * g.BN * g.KC;
+    int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    pack_tc_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, packed, g);
+    DS_CHECK_LAUNCH("pack_tc_weight");
+    return DS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host launch
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encoder() {
+    if (g_encode) return DS_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DS_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return DS_OK;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, size_t sx, size_t sy, size_t sb, int kc,
+                      int tw, int th, int tb) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sb};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for C=%d W=%d H=%d B=%d box=(%d,%d,%d,%d)", (int)r, C, W, H, B, kc, tw, th, tb);
+        return DS_ERR_CUDA;
+    }
+    return DS_OK;
+}
+
+bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws) {
+    if (tc_pick_kc(ca, cb) == 0 || ca <= 0) return false;
+    if (!(ks == 1 || ks == 3)) return false;
+    if (stride == 2 && (ks != 3 || up || (Hs & 1) || (Ws & 1))) return false;
+    if (up && (ks != 3 || stride != 1)) return false;
+    return true;
+}
+
+static int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
+                  int stride, int up) {
+    int rc = get_encoder();
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws), "tc conv: unsupported shape");
+    TcParams& p = *reinterpret_cast<TcParams*>(plan->params);
+    static_assert(sizeof(TcParams) <= sizeof(plan->params), "TcConvPlan::params too small");
+    memset(&p, 0, sizeof(p));
+    const int kc = tc_pick_kc(ca, cb);
+    // tile space
+    const int H = stride == 2 ? Hs / 2 : Hs, W = stride == 2 ? Ws / 2 : Ws;
+    p.B = B; p.H = H; p.W = W;
+    p.Ho = up ? 2 * H : H; p.Wo = up ? 2 * W : W;
+    p.up = up;
+    // 128-pixel tile: pick the power-of-two width with the least padded columns, prefer wide
+    int best_tw = 1, best_waste = 1 << 30;
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+        if (tw > 2 * pow2_floor(W) && tw > 1) continue;
+        const int waste = ((W + tw - 1) / tw) * tw - W;
+        if (waste < best_waste) { best_waste = waste; best_tw = tw; }
+    }
+    p.tw = best_tw;
+    int th = 128 / p.tw;
+    const int hp = pow2_floor(H) < H ? 2 * pow2_floor(H) : H;       // smallest power of two >= H
+    if (th > hp) th = hp;
+    p.th = th;
+    p.tb = 128 / (p.tw * p.th);
+    p.tiles_x = (W + p.tw - 1) / p.tw;
+    p.tiles_y = (H + p.th - 1) / p.th;
+    const int tiles_b = (B + p.tb - 1) / p.tb;
+    p.Cout = cout;
+    p.BN = tc_bn(cout);
+    p.n_tiles = (cout + p.BN - 1) / p.BN;
+    p.KC = kc;
+    p.chunks_a = ca / kc;
+    p.chunks_b = cb / kc;
+    p.ntaps = up ? 4 : ks * ks;
+    p.nclasses = up ? 4 : 1;
+    for (int cls = 0; cls < p.nclasses; ++cls) {
+        for (int t = 0; t < p.ntaps; ++t) {
+            int dy, dx, view = 0;
+            if (up) {
+                const int a = cls >> 1, b = cls & 1, ty = t >> 1, tx = t & 1;
+                dy = a == 0 ? ty - 1 : ty;
+                dx = b == 0 ? tx - 1 : tx;
+            } else if (stride == 2) {
+                const int r = t / 3, s = t % 3;
+                // input row 2*oy + r - 1:  r=0 -> parity 1 of row oy-1;  r=1 -> parity 0 of oy;  r=2 -> parity 1 of oy
+                const int py = r == 1 ? 0 : 1, px = s == 1 ? 0 : 1;
+                dy = r == 0 ? -1 : 0;
+                dx = s == 0 ? -1 : 0;
+                view = py * 2 + px;
+            } else {
+                dy = ks == 3 ? t / 3 - 1 : 0;
+                dx = ks == 3 ? t % 3 - 1 : 0;
+            }
+            p.tap_dy[cls][t] = (int8_t)dy; p.tap_dx[cls][t] = (int8_t)dx; p.tap_view[cls][t] = (int8_t)view;
+        }
+    }
+    // tensor maps
+    for (int s = 0; s < 2; ++s) {
+        const void* ptr = s == 0 ? src_a : src_b;
+        const int C = s == 0 ? ca : cb;
+        if (!ptr || C == 0) continue;
+        const size_t e = 2;
+        if (stride == 2) {
+            for (int v = 0; v < 4; ++v) {
+                const int py = v >> 1, px = v & 1;
+                const uint8_t* bp = (const uint8_t*)ptr + ((size_t)py * Ws + px) * C * e;
+                rc = encode_map(&p.maps[s * 4 + v], bp, C, Ws / 2, Hs / 2, B, 2 * (size_t)C * e, 2 * (size_t)Ws * C * e,
+                                (size_t)Hs * Ws * C * e, kc, p.tw, p.th, p.tb);
+                if (rc != DS_OK) return rc;
+            }
+        } else {
+            rc = encode_map(&p.maps[s * 4], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, p.tw,
+                            p.th, p.tb);
+            if (rc != DS_OK) return rc;
+        }
+    }
+    // pipeline depth: up to 6 stages within ~96 KB
+    const uint32_t stage_bytes = (uint32_t)align_up(128u * kc * 2u + (uint32_t)p.BN * kc * 2u, 1024);
+    const int U = p.ntaps * (p.chunks_a + p.chunks_b);
+    int stages = (int)(98304 / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > U) stages = U;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    plan->smem_bytes = stages * stage_bytes + 16 * stages + 32 + 1024;
+    plan->grid_x = p.tiles_x * p.tiles_y * tiles_b;
+    plan->grid_y = p.n_tiles;
+    plan->grid_z = p.nclasses;
+    plan->kc = kc;
+    return DS_OK;
+}
+
+int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, int temb_bcast, const void* residual_bf16,
+                   void* out, cudaStream_t st) {
+    TcParams p = *reinterpret_cast<const TcParams*>(plan->params);
+    p.w = w_packed;
+    p.bias = epi.bias;
+    p.temb = epi.temb;
+    p.temb_off = epi.temb_off;
+    p.temb_stride = epi.temb_stride;
+    p.temb_bcast = temb_bcast;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16);
+    p.out = out;
+    p.out_f32_nchw = epi.out_nchw;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    conv_tc_kernel<<<dim3(plan->grid_x, plan->grid_y, plan->grid_z), TC_THREADS, plan->smem_bytes, st>>>(p);
+    DS_CHECK_LAUNCH("conv_tc");
+    return DS_OK;
+}
+
 }  // namespace ds

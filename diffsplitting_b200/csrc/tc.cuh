@@ -1,14 +1,22 @@
-// bf16 tensor-core (tcgen05 / TMEM) convolution path, precision mode DS_PREC_BF16.
+// bf16 tensor-core (tcgen05 / TMEM / TMA) convolution path, precision mode DS_PREC_BF16.  See tc.cu.
 #pragma once
 #include "common.cuh"
 
 namespace ds {
 
-// bytes of the UMMA-ready bf16 pack of one OIHW conv weight
-size_t tc_packed_weight_bytes(int cout, int cin, int ks);
-int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);
-bool tc_conv_supported(const ConvSrc& src, int cout, int ks, int stride, const ConvEpi& epi);
-int tc_launch_conv(const ConvSrc& src, const uint8_t* w_packed, int cout, int ks, int stride, int B, int Ho, int Wo,
-                   const ConvEpi& epi, float* out, cudaStream_t st);
+struct TcConvPlan {
+    alignas(64) uint8_t params[2048];     // a TcParams (tensor maps + geometry), filled by tc_build_conv
+    int smem_bytes, grid_x, grid_y, grid_z, kc;
+};
+
+int tc_pick_kc(int ca, int cb);                                    // 64 / 32 / 16, or 0 if unsupported
+bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws);
+size_t tc_packed_weight_bytes(int cout, int cin, int ks);          // upper bound over packing variants
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, cudaStream_t st);
+// geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 NHWC [B,Hs,Ws,c]
+int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
+                  int stride, int up);
+int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, int temb_bcast, const void* residual_bf16,
+                   void* out, cudaStream_t st);
 
 }  // namespace ds

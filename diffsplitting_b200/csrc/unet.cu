@@ -26,6 +26,7 @@ struct WeightSpec {
     size_t elems;      // packed element count
     size_t off_bf16;   // byte offset of the bf16 pack in the tensor-core arena (convs only)
     int npad;          // conv: padded Cout ; vec: padded length
+    int tc_kc, tc_up;  // tensor-core pack variant (tc_kc == 0: layer has no bf16 pack)
     bool loaded;
 };
 
@@ -82,6 +83,8 @@ struct Tap {
 struct Plan {
     int B, H, W, prec;
     std::vector<Op> ops;
+    std::vector<TcConvPlan> tc;          // per op (bf16 mode): TMA descriptors + launch geometry
+    const void* tc_ws = nullptr;         // workspace base the descriptors were encoded for
     size_t bytes = 0;
     int64_t temb_buf = NONE, gn_scratch = NONE;
     std::map<std::string, Tap> taps;
@@ -178,6 +181,8 @@ static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initia
     s.npad = npad;
     s.loaded = false;
     s.off_bf16 = 0;
+    s.tc_kc = 0;
+    s.tc_up = 0;
     size_t elems = 1;
     if (kind == WK_CONV) elems = (size_t)s.shape[1] * s.shape[2] * s.shape[3] * npad;
     else if (kind == WK_VEC) elems = (size_t)(npad ? npad : s.shape[0]);
@@ -200,10 +205,18 @@ static int npad_of(int cout) {
     return p;
 }
 
-static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int ks, bool bias = true) {
+// ca/cb: channel split of the input as the kernels will see it (two-source concat), up: nearest-x2 folded in,
+// tc = false: the layer never runs on the tensor-core path (entry conv reads fp32 NCHW)
+static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int ks, bool bias = true, int ca = -1, int cb = 0,
+                      int up = 0, bool tc = true) {
     ConvW c;
     c.cin = cin; c.cout = cout; c.ks = ks; c.npad = npad_of(cout);
     c.w = add_spec(n, p + ".weight", WK_CONV, {cout, cin, ks, ks}, c.npad);
+    if (ca < 0) ca = cin;
+    if (tc) {
+        n->specs[c.w].tc_kc = tc_pick_kc(ca, cb);
+        n->specs[c.w].tc_up = up;
+    }
     if (bias) c.b = add_spec(n, p + ".bias", WK_VEC, {cout}, c.npad);
     return c;
 }
@@ -221,7 +234,7 @@ static bool in_attn_res(const ds_unet_desc& d, int res) {
     return false;
 }
 
-static ResW add_res(ds_unet* n, const std::string& p, int cin, int cout, bool attn) {
+static ResW add_res(ds_unet* n, const std::string& p, int cin, int cout, bool attn, int skip = 0) {
     const ds_unet_desc& d = n->d;
     ResW r;
     r.cin = cin; r.cout = cout; r.attn = attn; r.has_res = cin != cout;
@@ -239,7 +252,7 @@ static ResW add_res(ds_unet* n, const std::string& p, int cin, int cout, bool at
     r.conv1 = add_conv(n, rb + ".block1.block.3", cin, cout, 3);
     r.gn2 = add_gn(n, rb + ".block2.block.0", cout);
     r.conv2 = add_conv(n, rb + ".block2.block.3", cout, cout, 3);
-    if (r.has_res) r.res = add_conv(n, rb + ".res_conv", cin, cout, 1);
+    if (r.has_res) r.res = add_conv(n, rb + ".res_conv", cin, cout, 1, true, cin - skip, skip);
     if (attn) {
         r.agn = add_gn(n, p + ".attn.norm", cout);
         r.qkv = add_conv(n, p + ".attn.qkv", cout, 3 * cout, 1, false);
@@ -269,7 +282,7 @@ static int build_arch(ds_unet* n) {
     int ch = inner, res = d.image_size, idx = 0;
     {
         Layer L; L.kind = L_CONV; L.name = "downs.0"; L.section = 0;
-        L.conv = add_conv(n, "downs.0", d.in_channel, inner, 3);
+        L.conv = add_conv(n, "downs.0", d.in_channel, inner, 3, true, -1, 0, 0, false);
         n->layers.push_back(L);
         skip_ch.push_back(inner);
         idx = 1;
@@ -303,14 +316,14 @@ static int build_arch(ds_unet* n) {
         for (int r = 0; r < d.res_blocks + 1; ++r) {
             DS_REQUIRE(!skip_ch.empty(), "unet: skip stack underflow");
             Layer L; L.kind = L_RES; L.name = "ups." + std::to_string(idx++); L.section = 2;
-            L.res = add_res(n, L.name, ch + skip_ch.back(), cout, in_attn_res(d, res));
+            L.res = add_res(n, L.name, ch + skip_ch.back(), cout, in_attn_res(d, res), skip_ch.back());
             skip_ch.pop_back();
             n->layers.push_back(L);
             ch = cout;
         }
         if (lvl >= 1) {
             Layer L; L.kind = L_UP; L.name = "ups." + std::to_string(idx++); L.section = 2;
-            L.conv = add_conv(n, L.name + ".conv", ch, ch, 3);
+            L.conv = add_conv(n, L.name + ".conv", ch, ch, 3, true, -1, 0, 1);
             n->layers.push_back(L);
             res *= 2;
         }
@@ -424,7 +437,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     p->B = B; p->H = H; p->W = W; p->prec = prec;
     Planner P(n, p, !n->keep_taps);
     P.B = B;
-    P.esz = 4;   // fp32 activations in both modes for now; the bf16 path converts inside its kernels
+    P.esz = prec == DS_PREC_BF16 ? 2 : 4;
     if (d.with_time_emb) p->temb_buf = P.arena.alloc((size_t)B * n->temb_total * sizeof(float));
     p->gn_scratch = P.arena.alloc(gn_scratch_bytes(B, d.norm_groups));
 
@@ -571,8 +584,11 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
         if (s.kind == WK_CONV) {
             int rc = launch_pack_conv_weight_f32(src, dst, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.npad, st);
             if (rc != DS_OK) return rc;
-            rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_bf16, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
-            if (rc != DS_OK) return rc;
+            if (s.tc_kc) {
+                rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_bf16, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
+                                         s.tc_up, s.tc_kc, st);
+                if (rc != DS_OK) return rc;
+            }
         } else {
             size_t cnt_el = 1;
             for (int d = 0; d < s.ndim; ++d) cnt_el *= (size_t)s.shape[d];
@@ -710,13 +726,35 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
     }
     void* gn_scratch = ptr(p->gn_scratch);
     const bool tc = precision == DS_PREC_BF16;
+    if (tc && p->tc_ws != d_ws) {
+        // (re)encode the TMA descriptors for this workspace address
+        p->tc.assign(p->ops.size(), TcConvPlan());
+        for (size_t i = 0; i < p->ops.size(); ++i) {
+            const Op& o = p->ops[i];
+            if (o.kind != OP_CONV || o.src_nchw) continue;
+            if (!n->specs[o.cw->w].tc_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws)) {
+                set_error("unet_forward: bf16 mode needs channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
+                          n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
+                return DS_ERR_INVALID;
+            }
+            rc = tc_build_conv(&p->tc[i], ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, o.Hs, o.Ws, B, o.cw->cout, o.cw->ks, o.stride, o.up);
+            if (rc != DS_OK) return rc;
+            if (p->tc[i].kc != n->specs[o.cw->w].tc_kc) {
+                set_error("unet_forward: internal error, K-chunk mismatch for %s", n->specs[o.cw->w].name.c_str());
+                return DS_ERR_INVALID;
+            }
+        }
+        p->tc_ws = d_ws;
+    }
+    size_t op_index = 0;
     for (const Op& o : p->ops) {
         bool used_tc = false;
+        const size_t oi = op_index++;
         if (prof) cudaEventRecord(prof->e0, st);
         switch (o.kind) {
             case OP_GN:
-                rc = launch_groupnorm_f32(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B,
-                                          o.HW, n->d.norm_groups, o.swish, gn_scratch, st);
+                rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
+                                      n->d.norm_groups, o.swish, gn_scratch, tc ? 1 : 0, st);
                 break;
             case OP_CONV: {
                 ConvSrc s;
@@ -731,10 +769,11 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.temb_bcast = (time_len == 1);
                 e.residual = ptr(o.residual);
                 e.out_nchw = o.out_nchw;
-                if (tc && tc_conv_supported(s, o.cw->cout, o.cw->ks, o.stride, e)) {
+                e.out_bf16 = (tc && !o.out_nchw) ? 1 : 0;
+                if (tc && !o.src_nchw) {
                     used_tc = true;
-                    rc = tc_launch_conv(s, n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, o.cw->cout, o.cw->ks, o.stride, B, o.Ho,
-                                        o.Wo, e, ptr(o.dst), st);
+                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, e.temb_bcast, ptr(o.residual),
+                                        ptr(o.dst), st);
                 } else {
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
                                          ptr(o.dst), st);
@@ -742,7 +781,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 break;
             }
             case OP_ATTN:
-                rc = launch_attention_f32(ptr(o.src_a), ptr(o.dst), B, o.N, o.C, st);
+                rc = launch_attention(ptr(o.src_a), ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
                 break;
             default:
                 rc = DS_OK;
@@ -801,12 +840,13 @@ extern "C" int ds_unet_forward_profiled(ds_unet* n, const float* d_xa, int ca, c
 }
 
 namespace ds {
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int64_t total) {
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int C, int HW, int64_t total, int bf16) {
     for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int64_t b = i / ((int64_t)C * HW);
         const int64_t r = i - b * C * HW;
         const int c = (int)(r / HW), p = (int)(r - (int64_t)c * HW);
-        dst[i] = src[(b * HW + p) * C + c];
+        const int64_t j = (b * HW + p) * C + c;
+        dst[i] = bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[j]) : reinterpret_cast<const float*>(src)[j];
     }
 }
 }  // namespace ds
@@ -821,9 +861,9 @@ extern "C" int ds_unet_read_tap(ds_unet* n, const char* name, float* d_out, size
     const Tap& t = it->second;
     const int64_t total = (int64_t)p->B * t.C * t.H * t.W;
     DS_REQUIRE((size_t)total <= out_elems, "unet_read_tap: output too small (%zu < %lld)", out_elems, (long long)total);
-    const float* src = reinterpret_cast<const float*>((uint8_t*)d_ws + t.off);
+    const void* src = (uint8_t*)d_ws + t.off;
     int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d_out, t.C, t.H * t.W, total);
+    nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d_out, t.C, t.H * t.W, total, p->prec == DS_PREC_BF16);
     DS_CHECK_LAUNCH("nhwc_to_nchw");
     return DS_OK;
 }

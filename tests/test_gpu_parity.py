@@ -92,6 +92,50 @@ def test_conv_operator(cin, cout, ks, stride, up, B, H, W):
     assert relerr(out.permute(0, 3, 1, 2), ref) <= 1e-5
 
 
+TC_CASES = [
+    # ca, cb, cout, ks, stride, up, B, H, W, residual, out_nchw
+    (16, 0, 16, 3, 1, 0, 2, 16, 16, 0, 0), (32, 0, 32, 3, 1, 0, 1, 32, 32, 0, 0), (64, 0, 64, 3, 1, 0, 2, 8, 8, 1, 0),
+    (128, 0, 128, 3, 1, 0, 16, 8, 8, 1, 0), (32, 16, 16, 3, 1, 0, 2, 16, 16, 0, 0), (128, 64, 128, 1, 1, 0, 1, 16, 16, 0, 0),
+    (16, 0, 16, 3, 2, 0, 2, 16, 16, 0, 0), (64, 0, 64, 3, 2, 0, 1, 32, 32, 0, 0), (32, 0, 32, 3, 1, 1, 2, 8, 8, 0, 0),
+    (128, 0, 128, 3, 1, 1, 1, 16, 16, 0, 0), (16, 0, 1, 3, 1, 0, 2, 16, 16, 0, 1), (16, 0, 6, 3, 1, 0, 1, 32, 32, 0, 1),
+    (128, 0, 384, 1, 1, 0, 2, 8, 8, 0, 0), (16, 0, 16, 3, 1, 0, 1, 24, 20, 1, 0), (256, 0, 256, 3, 1, 0, 1, 4, 4, 0, 0),
+    (16, 0, 16, 3, 1, 0, 16, 64, 64, 1, 0), (48, 0, 16, 3, 1, 0, 1, 128, 128, 0, 0), (192, 0, 64, 3, 1, 0, 2, 16, 16, 0, 0),
+    (512, 0, 512, 3, 1, 0, 1, 16, 16, 1, 0)]
+
+
+@pytest.mark.parametrize("ca,cb,cout,ks,stride,up,B,H,W,residual,out_nchw", TC_CASES)
+def test_conv_tc_operator(ca, cb, cout, ks, stride, up, B, H, W, residual, out_nchw):
+    """tcgen05 implicit-GEMM conv vs an fp64 conv of the same bf16-rounded operands (tolerance: bf16 output rounding)."""
+    g = torch.Generator().manual_seed(ca * 3 + cout + ks + H)
+    cin = ca + cb
+    x = torch.randn((B, cin, H, W), generator=g).bfloat16()
+    w = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5)
+    b = torch.randn((cout,), generator=g)
+    xr = F.interpolate(x.float(), scale_factor=2, mode="nearest") if up else x.float()
+    ref = F.conv2d(xr.double(), w.bfloat16().double(), b.double(), stride=stride, padding=ks // 2)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    res = None
+    if residual:
+        res = torch.randn((B, cout, Ho, Wo), generator=g).bfloat16()
+        ref = ref + res.double()
+    xa = x[:, :ca].permute(0, 2, 3, 1).contiguous().to(DEV)
+    xb = x[:, ca:].permute(0, 2, 3, 1).contiguous().to(DEV) if cb else None
+    rd = res.permute(0, 2, 3, 1).contiguous().to(DEV) if residual else None
+    out = torch.full((B, cout, Ho, Wo), float("nan"), device=DEV) if out_nchw else \
+        torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    nb = _lib.lib().ds_conv2d_bf16_scratch_bytes(cin, cout, ks)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+    wd, bd = w.to(DEV), b.to(DEV)
+    _lib.check(_lib.lib().ds_conv2d_bf16(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, wd.data_ptr(), bd.data_ptr(),
+                                         None if rd is None else rd.data_ptr(), out.data_ptr(), out_nchw, B, H, W, cout, ks, stride,
+                                         up, scratch.data_ptr(), nb, sptr()))
+    torch.cuda.synchronize()
+    y = out if out_nchw else out.float().permute(0, 3, 1, 2)
+    e = relerr(y, ref.float())
+    print(f"[conv_tc {ca}+{cb}->{cout} k{ks} s{stride} up{up} {B}x{H}x{W}] rel err {e:.3e}")
+    assert e <= (1e-2 if up else 5e-3)
+
+
 @pytest.mark.parametrize("ca,cb,G,B,HW,swish", [(16, 0, 16, 2, (16, 16), 1), (16, 32, 16, 1, (12, 20), 1), (128, 0, 16, 3, (8, 8), 0),
                                                  (512, 256, 32, 1, (4, 4), 1), (32, 0, 8, 16, (64, 64), 1), (2048, 0, 16, 1, (8, 8), 1)])
 def test_groupnorm_swish_operator(ca, cb, G, B, HW, swish):
