@@ -254,8 +254,11 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DIFFSPLIT_B200_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-calls", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if args.no_graph:
+        os.environ["DIFFSPLIT_B200_GRAPH"] = "0"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

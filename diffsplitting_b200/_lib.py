@@ -73,8 +73,8 @@ _SIGS = {
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ds_conv2d_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ds_conv2d_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                 C.c_size_t, C.c_void_p]),
+                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "ds_conv2d_bf16_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ds_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ds_sampler_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),

@@ -40,6 +40,21 @@ extern "C" int ds_device_info(int* sm_count, int* max_threads_per_sm, int* cc_ma
     return DS_OK;
 }
 
+namespace ds {
+int gn_counters(unsigned** out) {
+    static unsigned* bufs[64] = {nullptr};
+    int dev = 0;
+    DS_CHECK_CUDA(cudaGetDevice(&dev));
+    DS_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (!bufs[dev]) {
+        DS_CHECK_CUDA(cudaMalloc(&bufs[dev], GN_MAX_BATCH * sizeof(unsigned)));
+        DS_CHECK_CUDA(cudaMemset(bufs[dev], 0, GN_MAX_BATCH * sizeof(unsigned)));
+    }
+    *out = bufs[dev];
+    return DS_OK;
+}
+}  // namespace ds
+
 extern "C" size_t ds_groupnorm_scratch_bytes(int B, int groups) { return gn_scratch_bytes(B, groups); }
 
 extern "C" int ds_groupnorm_swish_f32(const float* d_a, int ca, const float* d_b, int cb, const float* d_gamma,
@@ -48,7 +63,10 @@ extern "C" int ds_groupnorm_swish_f32(const float* d_a, int ca, const float* d_b
     DS_REQUIRE(d_a && d_gamma && d_beta && d_out && d_scratch, "groupnorm: null argument");
     DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_b), "groupnorm: bad channel split %d+%d", ca, cb);
     DS_REQUIRE(scratch_bytes >= gn_scratch_bytes(B, groups), "groupnorm: scratch too small");
-    return launch_groupnorm(d_a, ca, d_b, cb, d_gamma, d_beta, d_out, B, H * W, groups, apply_swish, d_scratch, 0,
+    unsigned* counters = nullptr;
+    int rc = gn_counters(&counters);
+    if (rc != DS_OK) return rc;
+    return launch_groupnorm(d_a, ca, d_b, cb, d_gamma, d_beta, d_out, B, H * W, groups, apply_swish, d_scratch, counters, 0,
                             (cudaStream_t)stream);
 }
 
@@ -79,7 +97,7 @@ extern "C" int ds_conv2d_f32(const float* d_x, const float* d_w_oihw, const floa
     const int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
     ConvEpi e;
     e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = nullptr; e.out_nchw = 0;
-    e.out_bf16 = 0;
+    e.out2_bf16 = nullptr;
     return launch_conv_f32(s, (const float*)d_scratch, npad, cout, ksize, stride, B, Ho, Wo, e, d_out, st);
 }
 
@@ -93,8 +111,9 @@ extern "C" size_t ds_conv2d_bf16_scratch_bytes(int cin, int cout, int ksize) {
 }
 
 extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb, const float* d_w_oihw, const float* d_bias,
-                              const void* d_residual, void* d_out, int out_f32_nchw, int B, int H, int W, int cout, int ksize,
-                              int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream) {
+                              const float* d_residual, void* d_out, float* d_out_f32, int out_f32_nchw, int B, int H, int W,
+                              int cout, int ksize, int stride, int upsample2x, void* d_scratch, size_t scratch_bytes,
+                              void* stream) {
     DS_REQUIRE(d_xa && d_w_oihw && d_out && d_scratch, "conv2d_bf16: null argument");
     DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_xb), "conv2d_bf16: bad channel split %d+%d", ca, cb);
     DS_REQUIRE(scratch_bytes >= ds_conv2d_bf16_scratch_bytes(ca + cb, cout, ksize), "conv2d_bf16: scratch too small");
@@ -108,7 +127,8 @@ extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb
     rc = tc_build_conv(&plan, d_xa, ca, d_xb, cb, H, W, B, cout, ksize, stride, upsample2x);
     if (rc != DS_OK) return rc;
     ConvEpi e;
-    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = nullptr;
-    e.out_nchw = out_f32_nchw; e.out_bf16 = 0;
-    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, 0, d_residual, d_out, st);
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0;
+    e.residual = (const float*)d_residual;
+    e.out_nchw = out_f32_nchw; e.out2_bf16 = nullptr;
+    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, d_out_f32, out_f32_nchw ? nullptr : d_out, out_f32_nchw ? (float*)d_out : nullptr, st);
 }

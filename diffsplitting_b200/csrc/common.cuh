@@ -58,7 +58,7 @@ struct ConvEpi {
     int temb_off, temb_stride, temb_bcast;   // value = temb[(temb_bcast ? 0 : b)*temb_stride + temb_off + n]
     const float* residual;  // NHWC [B,Ho,Wo,Cout] or nullptr
     int out_nchw;           // 1: write NCHW (external), 0: NHWC
-    int out_bf16;           // fp32 kernel only: write bf16 NHWC (entry conv of the bf16 path)
+    void* out2_bf16;        // fp32 kernel only: additionally write a bf16 NHWC copy (entry conv of the bf16 path)
 };
 
 int launch_conv_f32(const ConvSrc& src, const float* w_packed /*[K][Npad]*/, int Npad, int Cout,
@@ -69,9 +69,13 @@ int launch_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int Cout, 
 
 int gn_nsplit(int B, int HW, int C);
 size_t gn_scratch_bytes(int B, int G);
-// bf16 != 0: a, b and out are __nv_bfloat16 (statistics and normalisation still in fp32 / fp64)
-int launch_groupnorm(const void* a, int ca, const void* b, int cb, const float* gamma, const float* beta,
-                     void* out, int B, int HW, int G, int swish, void* scratch, int bf16, cudaStream_t st);
+constexpr int GN_MAX_BATCH = 4096;
+// fp32 in (the residual stream is fp32 in both precision modes); out fp32, or bf16 = tensor-core operand format.
+// counters: GN_MAX_BATCH zero-initialised, self-resetting uint32 (library-owned, see gn_counters()).
+int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta,
+                     void* out, int B, int HW, int G, int swish, void* scratch, unsigned* counters, int out_bf16,
+                     cudaStream_t st);
+int gn_counters(unsigned** out);     // per-device buffer, allocated on first use (never inside graph capture)
 
 int launch_attention(const void* qkv, void* out, int B, int N, int C, int bf16, cudaStream_t st);
 

@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvArgs p) {
             if (p.epi.bias) v += p.epi.bias[n];
             if (p.epi.temb) v += p.epi.temb[(size_t)(p.epi.temb_bcast ? 0 : b) * p.epi.temb_stride + p.epi.temb_off + n];
             if (p.epi.residual) v += p.epi.residual[(size_t)m * p.Cout + n];
-            if (p.epi.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)m * p.Cout + n] = __float2bfloat16_rn(v);
-            else if (p.epi.out_nchw) p.out[((size_t)b * p.Cout + n) * HWo + pix] = v;
+            if (p.epi.out_nchw) p.out[((size_t)b * p.Cout + n) * HWo + pix] = v;
             else p.out[(size_t)m * p.Cout + n] = v;
+            if (p.epi.out2_bf16) reinterpret_cast<__nv_bfloat16*>(p.epi.out2_bf16)[(size_t)m * p.Cout + n] = __float2bfloat16_rn(v);
         }
     }
 }

@@ -1,12 +1,15 @@
-// fp32 GroupNorm(+Swish) over NHWC activations, optionally over the channel concat of two sources.
+// GroupNorm(+Swish) over NHWC activations, optionally over the channel concat of two sources.
 //
 // Reference: Block = nn.GroupNorm(groups, dim) -> Swish (model/sr3_modules/unet.py:53-55, 80-91) and
 // SelfAttention.norm (:119); eps = 1e-5, biased variance, affine.
 //
-// Two launches: (1) partial (sum, sum-of-squares) per (b, pixel slab, group), per-thread fp32 partials over
-// short runs combined in fp64 in a fixed order (deterministic, no atomics); (2) every CTA of the apply
-// kernel re-reduces the <=64 slab partials of its sample in fp64, then normalises its own pixel slab:
-// y = (x - mean) * rstd * gamma + beta ; y * sigmoid(y).  Algorithmic traffic: 2 reads + 1 write.
+// Two launches, both HBM/L2-bandwidth kernels (2 reads + 1 write algorithmic):
+//  (1) gn_stats: per (sample, pixel slab) partial (sum, sum of squares) per group - 16-byte vector loads, per-thread
+//      fp32 runs of <= 32 values flushed into fp64, combined in a FIXED order (no atomics on data => deterministic).
+//      The last CTA of every sample (detected with one self-resetting counter) folds the <= 64 slab partials in
+//      fp64 and publishes (mean, rstd) per group.
+//  (2) gn_apply: y = (x - mean) * rstd * gamma + beta ; y * sigmoid(y); fp32 in, fp32 or bf16 out (bf16 = the
+//      operand format of the tensor-core convolutions), 16-byte loads, 8/16-byte stores.
 #include "common.cuh"
 
 namespace ds {
@@ -16,10 +19,9 @@ constexpr int GN_MAX_SPLIT = 64;
 constexpr int GN_MAX_GROUPS = 64;
 
 int gn_nsplit(int B, int HW, int C) {
-    // enough CTAs to cover the machine, but at least ~2048 elements per CTA
     int64_t per = (int64_t)HW * C;
     int want = (int)((592 + B - 1) / B);
-    int cap = (int)((per + 2047) / 2048);
+    int cap = (int)((per + 4095) / 4096);
     int n = want < cap ? want : cap;
     if (n > GN_MAX_SPLIT) n = GN_MAX_SPLIT;
     if (n > HW) n = HW;
@@ -27,135 +29,227 @@ int gn_nsplit(int B, int HW, int C) {
     return n;
 }
 
-size_t gn_scratch_bytes(int B, int G) { return (size_t)B * GN_MAX_SPLIT * G * 2 * sizeof(double); }
+// scratch layout: [B][GN_MAX_SPLIT][G] double2 partials | [B][G] float2 (mean, rstd)
+static size_t gn_partial_bytes(int B, int G) { return (size_t)B * GN_MAX_SPLIT * G * 2 * sizeof(double); }
+size_t gn_scratch_bytes(int B, int G) { return gn_partial_bytes(B, G) + align_up((size_t)B * G * 2 * sizeof(float), 256); }
 
-__device__ __forceinline__ float to_f32(float v) { return v; }
-__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
-__device__ __forceinline__ void from_f32(float* p, float v) { *p = v; }
-__device__ __forceinline__ void from_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
-template <typename T>
-__device__ __forceinline__ float load_cat(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb, size_t pix, int c) {
-    return to_f32((c < ca) ? a[pix * ca + c] : b[pix * cb + (c - ca)]);
+__device__ __forceinline__ float4 load4(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, size_t pix, int c) {
+    const float* p = (c < ca) ? a + pix * ca + c : b + pix * cb + (c - ca);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float load1(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, size_t pix, int c) {
+    return (c < ca) ? a[pix * ca + c] : b[pix * cb + (c - ca)];
 }
 
-template <typename T>
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb,
-                                                               int HW, int G, int nsplit, double* __restrict__ partial) {
+// VEC: C % 4 == 0, C/4 <= 256, both sources 16-byte aligned with channel counts % 4 == 0
+template <bool VEC>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
+                                                               int cb, int HW, int G, int nsplit, double* __restrict__ partial,
+                                                               float2* __restrict__ stats, unsigned* __restrict__ counters) {
     const int C = ca + cb;
     const int cpg = C / G;
     const int bi = blockIdx.y, sp = blockIdx.x;
     const int p0 = (int)((int64_t)HW * sp / nsplit), p1 = (int)((int64_t)HW * (sp + 1) / nsplit);
     const int t = threadIdx.x;
-    __shared__ double s_sum[GN_THREADS], s_sq[GN_THREADS];
+    __shared__ double s_sum[GN_THREADS * 4], s_sq[GN_THREADS * 4];
     __shared__ double g_sum[GN_MAX_GROUPS], g_sq[GN_MAX_GROUPS];
+    __shared__ bool s_last;
     if (t < G) { g_sum[t] = 0.0; g_sq[t] = 0.0; }
     __syncthreads();
     const size_t base = (size_t)bi * HW;
-    for (int c0 = 0; c0 < C; c0 += GN_THREADS) {
-        const int cw = min(GN_THREADS, C - c0);          // channels handled in this sweep
-        const int rows = GN_THREADS / cw;                 // pixels processed in parallel
-        const int r = t / cw, c = c0 + (t - r * cw);
-        double ds_ = 0.0, dq = 0.0;
+    if (VEC) {
+        const int q = C >> 2;                     // channel quads
+        const int rows = GN_THREADS / q;
+        const int r = t / q, cq = t - r * q;
+        double ds_[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
         if (r < rows) {
-            float s = 0.f, q = 0.f;
+            float s[4] = {0, 0, 0, 0}, qq[4] = {0, 0, 0, 0};
             int run = 0;
             for (int p = p0 + r; p < p1; p += rows) {
-                const float v = load_cat(a, ca, b, cb, base + p, c);
-                s += v;
-                q = fmaf(v, v, q);
-                if (++run == 32) { ds_ += (double)s; dq += (double)q; s = 0.f; q = 0.f; run = 0; }
-            }
-            ds_ += (double)s;
-            dq += (double)q;
-        }
-        s_sum[t] = ds_;
-        s_sq[t] = dq;
-        __syncthreads();
-        // thread g (< G) gathers the entries of its group inside this sweep, fixed order
-        if (t < G) {
-            const int glo = t * cpg, ghi = glo + cpg;      // channel range of group t
-            const int lo = max(glo, c0), hi = min(ghi, c0 + cw);
-            double s = 0.0, q = 0.0;
-            for (int rr = 0; rr < rows; ++rr)
-                for (int cc = lo; cc < hi; ++cc) {
-                    s += s_sum[rr * cw + (cc - c0)];
-                    q += s_sq[rr * cw + (cc - c0)];
+                const float4 v = load4(a, ca, b, cb, base + p, cq * 4);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                qq[0] = fmaf(v.x, v.x, qq[0]); qq[1] = fmaf(v.y, v.y, qq[1]);
+                qq[2] = fmaf(v.z, v.z, qq[2]); qq[3] = fmaf(v.w, v.w, qq[3]);
+                if (++run == 32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { ds_[j] += (double)s[j]; dq[j] += (double)qq[j]; s[j] = 0.f; qq[j] = 0.f; }
+                    run = 0;
                 }
-            g_sum[t] += s;
-            g_sq[t] += q;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ds_[j] += (double)s[j]; dq[j] += (double)qq[j]; }
+        }
+        // entry index = r * C + channel
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (r < rows) { s_sum[r * C + cq * 4 + j] = ds_[j]; s_sq[r * C + cq * 4 + j] = dq[j]; }
         }
         __syncthreads();
+        if (t < G) {
+            double s = 0.0, qv = 0.0;
+            for (int rr = 0; rr < rows; ++rr)
+                for (int cc = t * cpg; cc < (t + 1) * cpg; ++cc) { s += s_sum[rr * C + cc]; qv += s_sq[rr * C + cc]; }
+            g_sum[t] = s;
+            g_sq[t] = qv;
+        }
+    } else {
+        for (int c0 = 0; c0 < C; c0 += GN_THREADS) {
+            const int cw = min(GN_THREADS, C - c0);
+            const int rows = GN_THREADS / cw;
+            const int r = t / cw, c = c0 + (t - r * cw);
+            double ds_ = 0.0, dq = 0.0;
+            if (r < rows) {
+                float s = 0.f, q = 0.f;
+                int run = 0;
+                for (int p = p0 + r; p < p1; p += rows) {
+                    const float v = load1(a, ca, b, cb, base + p, c);
+                    s += v;
+                    q = fmaf(v, v, q);
+                    if (++run == 32) { ds_ += (double)s; dq += (double)q; s = 0.f; q = 0.f; run = 0; }
+                }
+                ds_ += (double)s;
+                dq += (double)q;
+            }
+            s_sum[t] = ds_;
+            s_sq[t] = dq;
+            __syncthreads();
+            if (t < G) {
+                const int glo = t * cpg, ghi = glo + cpg;
+                const int lo = max(glo, c0), hi = min(ghi, c0 + cw);
+                double s = 0.0, q = 0.0;
+                for (int rr = 0; rr < rows; ++rr)
+                    for (int cc = lo; cc < hi; ++cc) { s += s_sum[rr * cw + (cc - c0)]; q += s_sq[rr * cw + (cc - c0)]; }
+                g_sum[t] += s;
+                g_sq[t] += q;
+            }
+            __syncthreads();
+        }
     }
     if (t < G) {
         double* dst = partial + (((size_t)bi * GN_MAX_SPLIT + sp) * G + t) * 2;
         dst[0] = g_sum[t];
         dst[1] = g_sq[t];
     }
+    // ---- last CTA of this sample publishes (mean, rstd)
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(&counters[bi], 1u) == (unsigned)nsplit - 1u);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (t < G) {
+            double s = 0.0, q = 0.0;
+            const double* src = partial + ((size_t)bi * GN_MAX_SPLIT * G + t) * 2;
+            for (int k = 0; k < nsplit; ++k) {
+                s += __ldcg(src + (size_t)k * G * 2);
+                q += __ldcg(src + (size_t)k * G * 2 + 1);
+            }
+            const double n = (double)HW * cpg;
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            stats[(size_t)bi * G + t] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+        }
+        if (t == 0) counters[bi] = 0u;
+    }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restrict__ a, int ca, const T* __restrict__ b, int cb,
-                                                               const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, T* __restrict__ out,
-                                                               int HW, int G, int nsplit, int nchunk, int swish,
-                                                               const double* __restrict__ partial) {
+__device__ __forceinline__ float swish_f(float y, bool fast) {
+    return fast ? __fdividef(y, 1.0f + __expf(-y)) : y / (1.0f + expf(-y));
+}
+
+template <typename Tout, bool VEC>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
+                                                               int cb, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, Tout* __restrict__ out, int HW,
+                                                               int G, int nchunk, int swish, const float2* __restrict__ stats) {
     const int C = ca + cb;
     const int cpg = C / G;
     const int bi = blockIdx.y;
     const int t = threadIdx.x;
+    constexpr bool kFast = sizeof(Tout) == 2;          // bf16 output: fast exp is below the output rounding
     __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
     if (t < G) {
-        double s = 0.0, q = 0.0;
-        for (int sp = 0; sp < nsplit; ++sp) {
-            const double* src = partial + (((size_t)bi * GN_MAX_SPLIT + sp) * G + t) * 2;
-            s += src[0];
-            q += src[1];
-        }
-        const double n = (double)HW * cpg;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[t] = (float)mean;
-        s_rstd[t] = (float)(1.0 / sqrt(var + 1e-5));
+        const float2 st = stats[(size_t)bi * G + t];
+        s_mean[t] = st.x;
+        s_rstd[t] = st.y;
     }
     __syncthreads();
-    const int64_t total = (int64_t)HW * C;
-    const int64_t e0 = total * blockIdx.x / nchunk, e1 = total * (blockIdx.x + 1) / nchunk;
     const size_t base = (size_t)bi * HW;
-    for (int64_t e = e0 + t; e < e1; e += GN_THREADS) {
-        const int p = (int)(e / C);
-        const int c = (int)(e - (int64_t)p * C);
-        const int g = c / cpg;
-        const float x = load_cat(a, ca, b, cb, base + p, c);
-        float y = (x - s_mean[g]) * s_rstd[g];
-        y = fmaf(y, gamma[c], beta[c]);
-        if (swish) y = y / (1.0f + expf(-y));
-        from_f32(out + (base + p) * C + c, y);
+    if (VEC) {
+        const int q = C >> 2;
+        const int total = HW * q;                        // vectors in this sample (< 2^31 by construction)
+        const int v0 = (int)((int64_t)total * blockIdx.x / nchunk), v1 = (int)((int64_t)total * (blockIdx.x + 1) / nchunk);
+        for (int v = v0 + t; v < v1; v += GN_THREADS) {
+            const int p = v / q, c = (v - p * q) * 4;
+            const float4 x = load4(a, ca, b, cb, base + p, c);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w}, bs[4] = {be.x, be.y, be.z, be.w};
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = (c + j) / cpg;
+                float yy = (xs[j] - s_mean[g]) * s_rstd[g];
+                yy = fmaf(yy, gs[j], bs[j]);
+                y[j] = swish ? swish_f(yy, kFast) : yy;
+            }
+            Tout* o = out + (base + p) * C + c;
+            if constexpr (sizeof(Tout) == 2) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]), hi = __floats2bfloat162_rn(y[2], y[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(o) = pk;
+            } else {
+                *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+    } else {
+        const int64_t total = (int64_t)HW * C;
+        const int64_t e0 = total * blockIdx.x / nchunk, e1 = total * (blockIdx.x + 1) / nchunk;
+        for (int64_t e = e0 + t; e < e1; e += GN_THREADS) {
+            const int p = (int)(e / C);
+            const int c = (int)(e - (int64_t)p * C);
+            const int g = c / cpg;
+            float y = (load1(a, ca, b, cb, base + p, c) - s_mean[g]) * s_rstd[g];
+            y = fmaf(y, gamma[c], beta[c]);
+            if (swish) y = swish_f(y, kFast);
+            if constexpr (sizeof(Tout) == 2) out[(base + p) * C + c] = __float2bfloat16_rn(y);
+            else out[(base + p) * C + c] = y;
+        }
     }
 }
 
-int launch_groupnorm(const void* a, int ca, const void* b, int cb, const float* gamma, const float* beta, void* out, int B,
-                     int HW, int G, int swish, void* scratch, int bf16, cudaStream_t st) {
+int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta, void* out, int B,
+                     int HW, int G, int swish, void* scratch, unsigned* counters, int out_bf16, cudaStream_t st) {
     const int C = ca + cb;
     DS_REQUIRE(G >= 1 && G <= GN_MAX_GROUPS && C % G == 0, "groupnorm: %d channels not divisible into %d groups (max %d)",
                C, G, GN_MAX_GROUPS);
+    DS_REQUIRE((int64_t)HW * C < (1ll << 31), "groupnorm: sample too large");
+    DS_REQUIRE(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
     const int nsplit = gn_nsplit(B, HW, C);
     double* partial = reinterpret_cast<double*>(scratch);
-    typedef __nv_bfloat16 bf;
-    if (bf16) gn_stats_kernel<bf><<<dim3(nsplit, B), GN_THREADS, 0, st>>>((const bf*)a, ca, (const bf*)b, cb, HW, G, nsplit, partial);
-    else gn_stats_kernel<float><<<dim3(nsplit, B), GN_THREADS, 0, st>>>((const float*)a, ca, (const float*)b, cb, HW, G, nsplit, partial);
+    float2* stats = reinterpret_cast<float2*>((uint8_t*)scratch + gn_partial_bytes(B, G));
+    const bool vec = (ca % 4 == 0) && (cb % 4 == 0) && (C / 4 <= GN_THREADS) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                     (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+    if (vec) gn_stats_kernel<true><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+    else gn_stats_kernel<false><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
     DS_CHECK_LAUNCH("gn_stats");
-    int64_t total = (int64_t)HW * C;
-    int nchunk = (int)((total + 16383) / 16384);
+    const int64_t total = (int64_t)HW * C;
+    int nchunk = (int)((total + 4095) / 4096);
     if (nchunk > 65535) nchunk = 65535;
     if (nchunk < 1) nchunk = 1;
-    if (bf16)
-        gn_apply_kernel<bf><<<dim3(nchunk, B), GN_THREADS, 0, st>>>((const bf*)a, ca, (const bf*)b, cb, gamma, beta, (bf*)out, HW, G,
-                                                                   nsplit, nchunk, swish, partial);
-    else
-        gn_apply_kernel<float><<<dim3(nchunk, B), GN_THREADS, 0, st>>>((const float*)a, ca, (const float*)b, cb, gamma, beta,
-                                                                      (float*)out, HW, G, nsplit, nchunk, swish, partial);
+    const dim3 grid(nchunk, B);
+    typedef __nv_bfloat16 bf;
+    if (out_bf16) {
+        if (vec) gn_apply_kernel<bf, true><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats);
+        else gn_apply_kernel<bf, false><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats);
+    } else {
+        if (vec) gn_apply_kernel<float, true><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats);
+        else gn_apply_kernel<float, false><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats);
+    }
     DS_CHECK_LAUNCH("gn_apply");
     return DS_OK;
 }

@@ -112,13 +112,15 @@ constexpr int TC_MAX_TAPS = 9;
 
 struct TcParams {
     CUtensorMap maps[8];              // [source (a=0, b=1) * 4 + view]; view = stride-2 parity plane or 0
-    const uint8_t* w;                 // packed weights: [class][n_tile][unit][BN x KC swizzled image]
+    const uint8_t* w;                 // packed weights: [class][unit][16-row block][16 x KC swizzled image]
     const float* bias;                // [Cout] or null
     const float* temb;                // conditioning vectors or null
     int temb_off, temb_stride, temb_bcast;
-    const __nv_bfloat16* residual;    // bf16 NHWC [B,Ho,Wo,Cout] or null
-    void* out;                        // bf16 NHWC, or fp32 NCHW when out_f32_nchw
-    int out_f32_nchw;
+    const float* residual;            // fp32 NHWC [B,Ho,Wo,Cout] or null (the residual stream stays fp32)
+    float* out_f32;                   // fp32 NHWC or null   (consumers: GroupNorm statistics, residual adds)
+    __nv_bfloat16* out_b16;           // bf16 NHWC or null   (consumers: TMA-fed convolutions, attention)
+    float* out_nchw;                  // fp32 NCHW or null   (the network output)
+    int nb16;                         // 16-row weight blocks per (class, unit) = ceil(Cout / 16)
     int B, H, W;                      // tile space (= output size; for upsample: the LOW-res size)
     int Ho, Wo;                       // output tensor size (2H x 2W for upsample)
     int Cout, BN, n_tiles;
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint8_t* wsrc = p.w + ((size_t)(cls * p.n_tiles + nt) * U) * b_bytes;
+            const size_t blk16 = (size_t)16 * p.KC * 2;
+            const uint8_t* wsrc = p.w + ((size_t)cls * U * p.nb16 + (size_t)nt * (p.BN / 16)) * blk16;
             for (int u = 0; u < U; ++u) {
                 const int s = u % p.stages;
                 const uint32_t ph = (u / p.stages) & 1;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const uint32_t dstA = base + s * stage_bytes;
                 mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
                 tma_load_4d(dstA, map, full_bar(s), c0, x0 + p.tap_dx[cls][tap], y0 + p.tap_dy[cls][tap], b0);
-                bulk_load(dstA + a_bytes, wsrc + (size_t)u * b_bytes, b_bytes, full_bar(s));
+                bulk_load(dstA + a_bytes, wsrc + (size_t)u * p.nb16 * blk16, b_bytes, full_bar(s));
             }
         }
         __syncwarp();
@@ -232,40 +235,45 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += te[j];
             }
-            if (p.out_f32_nchw) {
-                float* o = reinterpret_cast<float*>(p.out);
+            if (p.out_nchw) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (n0 + j < p.Cout) o[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
+                    if (n0 + j < p.Cout) p.out_nchw[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
             } else if (n0 + 16 <= p.Cout) {
+                const size_t off = pix * p.Cout + n0;
                 if (p.residual) {
-                    const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + n0);
-                    const uint4 r0 = r[0], r1 = r[1];
-                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    const float4* r = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                        f[2 * j] += __low2float(h);
-                        f[2 * j + 1] += __high2float(h);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 rv = __ldg(r + j);
+                        f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
                     }
                 }
-                uint32_t w[8];
+                if (p.out_f32) {
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
-                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0);
-                o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                if (p.out_b16) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(p.out_b16 + off);
+                    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
             } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (n0 + j < p.Cout) {
+                        const size_t off = pix * p.Cout + n0 + j;
                         float val = f[j];
-                        if (p.residual) val += __bfloat162float(p.residual[pix * p.Cout + n0 + j]);
-                        o[n0 + j] = __float2bfloat16_rn(val);
+                        if (p.residual) val += p.residual[off];
+                        if (p.out_f32) p.out_f32[off] = val;
+                        if (p.out_b16) p.out_b16[off] = __float2bfloat16_rn(val);
                     }
                 }
             }
@@ -288,20 +296,21 @@ __host__ __device__ inline uint32_t swizzle_offset(uint32_t row, uint32_t byte_i
 }
 
 struct PackGeom {
-    int cout, cin, ks, up, BN, n_tiles, KC, chunks, ntaps, nclasses;
+    int cout, cin, ks, up, nb16, KC, chunks, ntaps, nclasses;
 };
 
+// largest N tile (16..128) that divides the 16-padded channel count
 static int tc_bn(int cout) {
     const int npad = (cout + 15) / 16 * 16;
-    if (npad <= 128) return npad <= 16 ? 16 : (npad <= 32 ? 32 : (npad <= 64 ? 64 : 128));
-    return 128;
+    for (int bn = 128; bn > 16; bn >>= 1)
+        if (npad % bn == 0) return bn;
+    return 16;
 }
 
 static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc) {
     PackGeom g;
     g.cout = cout; g.cin = cin; g.ks = ks; g.up = up;
-    g.BN = tc_bn(cout);
-    g.n_tiles = (cout + g.BN - 1) / g.BN;
+    g.nb16 = (cout + 15) / 16;
     g.KC = kc;
     g.chunks = cin / kc;
     g.ntaps = up ? 4 : ks * ks;
@@ -316,27 +325,26 @@ int tc_pick_kc(int ca, int cb) {
 }
 
 size_t tc_packed_weight_bytes(int cout, int cin, int ks) {
-    // worst case over the variants a layer can be packed for (KC = 16, upsample classes)
-    const int bn = tc_bn(cout);
-    const int nt = (cout + bn - 1) / bn;
-    const size_t plain = (size_t)nt * bn * ks * ks * cin * 2;
-    const size_t upv = ks == 3 ? (size_t)4 * nt * bn * 4 * cin * 2 : 0;
+    // worst case over the variants a layer can be packed for (plain taps vs. 4 upsample classes x 4 taps)
+    const size_t npad = (size_t)(cout + 15) / 16 * 16;
+    const size_t plain = npad * ks * ks * cin * 2;
+    const size_t upv = ks == 3 ? (size_t)4 * npad * 4 * cin * 2 : 0;
     return plain > upv ? plain : upv;
 }
 
 __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, PackGeom g) {
     const int U = g.ntaps * g.chunks;
-    const size_t total = (size_t)g.nclasses * g.n_tiles * U * g.BN * g.KC;
+    const size_t total = (size_t)g.nclasses * U * g.nb16 * 16 * g.KC;
     const uint32_t row_bytes = g.KC * 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int k = (int)(r % g.KC); r /= g.KC;
-        const int row = (int)(r % g.BN); r /= g.BN;
+        const int row = (int)(r % 16); r /= 16;
+        const int nb = (int)(r % g.nb16); r /= g.nb16;
         const int u = (int)(r % U); r /= U;
-        const int nt = (int)(r % g.n_tiles); r /= g.n_tiles;
         const int cls = (int)r;
         const int tap = u / g.chunks, c = (u - tap * g.chunks) * g.KC + k;
-        const int n = nt * g.BN + row;
+        const int n = nb * 16 + row;
         float v = 0.f;
         if (n < g.cout) {
             const float* wn = w + ((size_t)n * g.cin + c) * g.ks * g.ks;
@@ -354,8 +362,9 @@ __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __re
                     for (int ss = s_lo; ss <= s_hi; ++ss) v += wn[rr * 3 + ss];
             }
         }
-        const size_t tile = ((size_t)(cls * g.n_tiles + nt) * U + u) * ((size_t)g.BN * row_bytes);
-        *reinterpret_cast<__nv_bfloat16*>(out + tile + swizzle_offset(row, k * 2, row_bytes)) = __float2bfloat16_rn(v);
+        // a BN-row operand tile is BN/16 consecutive blocks: the swizzle has an 8-row period, so blocks are independent
+        const size_t blk = (((size_t)cls * U + u) * g.nb16 + nb) * ((size_t)16 * row_bytes);
+        *reinterpret_cast<__nv_bfloat16*>(out + blk + swizzle_offset(row, k * 2, row_bytes)) = __float2bfloat16_rn(v);
     }
 }
 
@@ -363,7 +372,7 @@ int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin,
     DS_REQUIRE(kc == 16 || kc == 32 || kc == 64, "tc_pack: KC %d", kc);
     DS_REQUIRE(cin % kc == 0, "tc_pack: cin %d not a multiple of KC %d", cin, kc);
     PackGeom g = pack_geom(cout, cin, ks, up, kc);
-    const size_t total = (size_t)g.nclasses * g.n_tiles * g.ntaps * g.chunks * g.BN * g.KC;
+    const size_t total = (size_t)g.nclasses * g.ntaps * g.chunks * g.nb16 * 16 * g.KC;
     int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
     pack_tc_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, packed, g);
     DS_CHECK_LAUNCH("pack_tc_weight");
@@ -445,8 +454,13 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     p.tiles_y = (H + p.th - 1) / p.th;
     const int tiles_b = (B + p.tb - 1) / p.tb;
     p.Cout = cout;
-    p.BN = tc_bn(cout);
-    p.n_tiles = (cout + p.BN - 1) / p.BN;
+    p.nb16 = (cout + 15) / 16;
+    // N tile: as wide as divides the padded channel count, narrowed until the grid covers the machine
+    int bn = tc_bn(cout);
+    const int m_tiles = p.tiles_x * p.tiles_y * tiles_b * (up ? 4 : 1);
+    while (bn > 16 && m_tiles * ((p.nb16 * 16) / bn) < 120) bn >>= 1;
+    p.BN = bn;
+    p.n_tiles = (p.nb16 * 16) / bn;
     p.KC = kc;
     p.chunks_a = ca / kc;
     p.chunks_b = cb / kc;
@@ -509,18 +523,19 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     return DS_OK;
 }
 
-int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, int temb_bcast, const void* residual_bf16,
-                   void* out, cudaStream_t st) {
+int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
+                   float* out_nchw, cudaStream_t st) {
     TcParams p = *reinterpret_cast<const TcParams*>(plan->params);
     p.w = w_packed;
     p.bias = epi.bias;
     p.temb = epi.temb;
     p.temb_off = epi.temb_off;
     p.temb_stride = epi.temb_stride;
-    p.temb_bcast = temb_bcast;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16);
-    p.out = out;
-    p.out_f32_nchw = epi.out_nchw;
+    p.temb_bcast = epi.temb_bcast;
+    p.residual = epi.residual;
+    p.out_f32 = out_f32;
+    p.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16);
+    p.out_nchw = out_nchw;
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

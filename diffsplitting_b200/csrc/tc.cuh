@@ -16,7 +16,8 @@ int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin,
 // geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 NHWC [B,Hs,Ws,c]
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
                   int stride, int up);
-int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, int temb_bcast, const void* residual_bf16,
-                   void* out, cudaStream_t st);
+// epi.bias / temb / residual (fp32 NHWC) as in the fp32 kernel; any subset of the three outputs may be given
+int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
+                   float* out_nchw, cudaStream_t st);
 
 }  // namespace ds

@@ -60,13 +60,15 @@ constexpr int64_t EXT_XA = -1, EXT_XB = -2, EXT_OUT = -3, NONE = -100;
 
 struct Op {
     OpKind kind;
-    // conv
+    // sources: GroupNorm reads the fp32 copies, tensor-core convs the bf16 copies, fp32 convs fp32
     int64_t src_a = NONE, src_b = NONE;
     int ca = 0, cb = 0, src_nchw = 0, Hs = 0, Ws = 0, up = 0, stride = 1;
     int Ho = 0, Wo = 0;
     const ConvW* cw = nullptr;
     int temb_off = -1;
-    int64_t residual = NONE, dst = NONE;
+    int64_t residual = NONE;             // fp32 NHWC
+    int64_t dst = NONE;                  // fp32 NHWC (or EXT_OUT), may be NONE in bf16 mode
+    int64_t dst_b16 = NONE;              // bf16 NHWC copy (bf16 mode only)
     int out_nchw = 0;
     // gn
     const GNW* gw = nullptr;
@@ -77,7 +79,7 @@ struct Op {
 
 struct Tap {
     int64_t off;
-    int C, H, W;
+    int C, H, W, bf16;
 };
 
 struct Plan {
@@ -138,9 +140,9 @@ class Arena {   // first-fit offset allocator used only while planning
 };
 
 struct Act {
-    int64_t buf;
-    int C, H, W;
-    int* rc;   // shared refcount
+    int64_t f32 = NONE, b16 = NONE;      // workspace offsets of the fp32 / bf16 copies
+    int C = 0, H = 0, W = 0;
+    int* rc = nullptr;                   // shared refcount
 };
 
 }  // namespace ds
@@ -344,80 +346,91 @@ static int build_arch(ds_unet* n) {
 }
 
 // ------------------------------------------------------------------------------------------ planning
+enum Fmt { F32 = 1, B16 = 2 };
+
 struct Planner {
     ds_unet* n;
     Plan* p;
     Arena arena;
     int B;
-    size_t esz;   // activation element size
+    bool tc;          // bf16 mode: tensor-core convs (bf16 operands), fp32 residual stream
     Planner(ds_unet* n_, Plan* p_, bool reuse) : n(n_), p(p_), arena(reuse) {}
 
-    Act make(int C, int H, int W) {
+    // what a tensor is stored as.  fp32 mode: always fp32.  bf16 mode: block-level tensors keep both copies (GroupNorm
+    // statistics / residual adds read fp32, TMA-fed convs read bf16), conv operands are bf16 only, hidden = fp32 only.
+    Act make(int C, int H, int W, int fmt) {
         Act a;
         a.C = C; a.H = H; a.W = W;
-        a.buf = arena.alloc((size_t)B * H * W * C * esz);
+        if (!tc) fmt = F32;
+        if (fmt & F32) a.f32 = arena.alloc((size_t)B * H * W * C * 4);
+        if (fmt & B16) a.b16 = arena.alloc((size_t)B * H * W * C * 2);
         a.rc = new int(1);
         return a;
     }
     void retain(Act& a) { if (a.rc) ++*a.rc; }
     void release(Act& a) {
         if (!a.rc) return;
-        if (--*a.rc == 0) { arena.release(a.buf); delete a.rc; }
+        if (--*a.rc == 0) { arena.release(a.f32); arena.release(a.b16); delete a.rc; }
         a.rc = nullptr;
     }
-    void tap(const std::string& name, const Act& a) { p->taps[name] = Tap{a.buf, a.C, a.H, a.W}; }
+    void tap(const std::string& name, const Act& a) {
+        p->taps[name] = a.f32 != NONE ? Tap{a.f32, a.C, a.H, a.W, 0} : Tap{a.b16, a.C, a.H, a.W, 1};
+    }
+    int64_t conv_src(const Act& a) const { return tc ? a.b16 : a.f32; }
 
     void gn(const Act& a, const Act* b, const GNW& g, int swish, const Act& out) {
         Op o; o.kind = OP_GN;
-        o.src_a = a.buf; o.ca = a.C;
-        if (b) { o.src_b = b->buf; o.cb = b->C; }
-        o.gw = &g; o.swish = swish; o.HW = a.H * a.W; o.dst = out.buf;
+        o.src_a = a.f32; o.ca = a.C;
+        if (b) { o.src_b = b->f32; o.cb = b->C; }
+        o.gw = &g; o.swish = swish; o.HW = a.H * a.W;
+        o.dst = out.f32; o.dst_b16 = out.b16;
         p->ops.push_back(o);
     }
     void conv(const Act& a, const Act* b, const ConvW& w, int stride, int up, int temb_off, const Act* residual, const Act& out) {
         Op o; o.kind = OP_CONV;
-        o.src_a = a.buf; o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
-        if (b) { o.src_b = b->buf; o.cb = b->C; }
+        o.src_a = conv_src(a); o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
+        if (b) { o.src_b = conv_src(*b); o.cb = b->C; }
         o.cw = &w; o.stride = stride; o.up = up; o.temb_off = temb_off;
         o.Ho = out.H; o.Wo = out.W;
-        if (residual) o.residual = residual->buf;
-        o.dst = out.buf;
+        if (residual) o.residual = residual->f32;
+        o.dst = out.f32; o.dst_b16 = out.b16;
         p->ops.push_back(o);
     }
 
     Act resblock(const Layer& L, Act x, const Act* skip) {
         const ResW& r = L.res;
         const int H = x.H, W = x.W;
-        Act a1 = make(r.cin, H, W);
+        Act a1 = make(r.cin, H, W, B16);
         gn(x, skip, r.gn1, 1, a1);
-        Act h = make(r.cout, H, W);
+        Act h = make(r.cout, H, W, F32);
         conv(a1, nullptr, r.conv1, 1, 0, r.temb_off, nullptr, h);
         release(a1);
-        Act a2 = make(r.cout, H, W);
+        Act a2 = make(r.cout, H, W, B16);
         gn(h, nullptr, r.gn2, 1, a2);
         release(h);
         Act resid = x;
-        Act rbuf; rbuf.rc = nullptr;
+        Act rbuf;
         if (r.has_res) {
-            rbuf = make(r.cout, H, W);
+            rbuf = make(r.cout, H, W, F32);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
             resid = rbuf;
         }
-        Act out = make(r.cout, H, W);
+        Act out = make(r.cout, H, W, F32 | B16);
         conv(a2, nullptr, r.conv2, 1, 0, -1, &resid, out);
         release(a2);
         if (r.has_res) release(rbuf);
         if (r.attn) {
-            Act nrm = make(r.cout, H, W);
+            Act nrm = make(r.cout, H, W, B16);
             gn(out, nullptr, r.agn, 0, nrm);
-            Act qkv = make(3 * r.cout, H, W);
+            Act qkv = make(3 * r.cout, H, W, B16);
             conv(nrm, nullptr, r.qkv, 1, 0, -1, nullptr, qkv);
             release(nrm);
-            Act att = make(r.cout, H, W);
-            Op o; o.kind = OP_ATTN; o.src_a = qkv.buf; o.dst = att.buf; o.N = H * W; o.C = r.cout;
+            Act att = make(r.cout, H, W, B16);
+            Op o; o.kind = OP_ATTN;
+            o.src_a = conv_src(qkv); o.dst = att.f32; o.dst_b16 = att.b16; o.N = H * W; o.C = r.cout;
             p->ops.push_back(o);
             release(qkv);
-            Act out2 = make(r.cout, H, W);
+            Act out2 = make(r.cout, H, W, F32 | B16);
             conv(att, nullptr, r.aout, 1, 0, -1, &out, out2);
             release(att);
             release(out);
@@ -431,26 +444,27 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     const ds_unet_desc& d = n->d;
     const int down = 1 << (d.n_mults - 1);
     DS_REQUIRE(B > 0 && H > 0 && W > 0, "unet: bad shape B=%d H=%d W=%d", B, H, W);
+    DS_REQUIRE(B <= GN_MAX_BATCH, "unet: batch %d > %d", B, GN_MAX_BATCH);
     DS_REQUIRE(H % down == 0 && W % down == 0, "unet: H=%d W=%d must be divisible by %d", H, W, down);
     DS_REQUIRE(prec == DS_PREC_FP32 || prec == DS_PREC_BF16, "unet: unknown precision %d", prec);
     Plan* p = new Plan();
     p->B = B; p->H = H; p->W = W; p->prec = prec;
     Planner P(n, p, !n->keep_taps);
     P.B = B;
-    P.esz = prec == DS_PREC_BF16 ? 2 : 4;
+    P.tc = prec == DS_PREC_BF16;
     if (d.with_time_emb) p->temb_buf = P.arena.alloc((size_t)B * n->temb_total * sizeof(float));
     p->gn_scratch = P.arena.alloc(gn_scratch_bytes(B, d.norm_groups));
 
     std::vector<Act> skips;
-    Act x; x.rc = nullptr;
+    Act x;
     int h = H, w = W;
     for (const Layer& L : n->layers) {
         if (L.section == 0) {
             if (L.kind == L_CONV) {
-                Act o = P.make(L.conv.cout, h, w);
+                Act o = P.make(L.conv.cout, h, w, F32 | B16);
                 Op op; op.kind = OP_CONV;
                 op.src_a = EXT_XA; op.src_b = EXT_XB; op.src_nchw = 1; op.Hs = h; op.Ws = w;
-                op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.buf;
+                op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.f32; op.dst_b16 = o.b16;
                 p->ops.push_back(op);
                 x = o;
             } else if (L.kind == L_RES) {
@@ -459,7 +473,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
                 x = o;
             } else {
                 h /= 2; w /= 2;
-                Act o = P.make(L.conv.cout, h, w);
+                Act o = P.make(L.conv.cout, h, w, F32 | B16);
                 P.conv(x, nullptr, L.conv, 2, 0, -1, nullptr, o);
                 P.release(x);
                 x = o;
@@ -481,7 +495,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
                 P.release(s);
                 x = o;
             } else {
-                Act o = P.make(L.conv.cout, 2 * x.H, 2 * x.W);
+                Act o = P.make(L.conv.cout, 2 * x.H, 2 * x.W, F32 | B16);
                 P.conv(x, nullptr, L.conv, 1, 1, -1, nullptr, o);
                 P.release(x);
                 x = o;
@@ -489,12 +503,12 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
         }
         P.tap(L.name, x);
     }
-    Act fa = P.make(x.C, x.H, x.W);
+    Act fa = P.make(x.C, x.H, x.W, B16);
     P.gn(x, nullptr, n->final_gn, 1, fa);
     P.release(x);
     {
         Op op; op.kind = OP_CONV;
-        op.src_a = fa.buf; op.ca = fa.C; op.Hs = fa.H; op.Ws = fa.W;
+        op.src_a = P.conv_src(fa); op.ca = fa.C; op.Hs = fa.H; op.Ws = fa.W;
         op.cw = &n->final_conv; op.Ho = fa.H; op.Wo = fa.W; op.dst = EXT_OUT; op.out_nchw = 1;
         p->ops.push_back(op);
     }
@@ -506,6 +520,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     *out = p;
     return DS_OK;
 }
+
 
 static int get_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     for (Plan* p : n->plans)
@@ -623,6 +638,11 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
                                           (size_t)r.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
     }
+    {
+        unsigned* counters = nullptr;
+        int rc2 = gn_counters(&counters);     // first use allocates: must not happen inside a graph capture
+        if (rc2 != DS_OK) return rc2;
+    }
     n->weights_ready = true;
     return DS_OK;
 }
@@ -725,6 +745,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         }
     }
     void* gn_scratch = ptr(p->gn_scratch);
+    unsigned* counters = nullptr;
+    rc = gn_counters(&counters);
+    if (rc != DS_OK) return rc;
     const bool tc = precision == DS_PREC_BF16;
     if (tc && p->tc_ws != d_ws) {
         // (re)encode the TMA descriptors for this workspace address
@@ -753,8 +776,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         if (prof) cudaEventRecord(prof->e0, st);
         switch (o.kind) {
             case OP_GN:
-                rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
-                                      n->d.norm_groups, o.swish, gn_scratch, tc ? 1 : 0, st);
+                rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b),
+                                      tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.HW, n->d.norm_groups, o.swish, gn_scratch,
+                                      counters, tc ? 1 : 0, st);
                 break;
             case OP_CONV: {
                 ConvSrc s;
@@ -769,11 +793,11 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.temb_bcast = (time_len == 1);
                 e.residual = ptr(o.residual);
                 e.out_nchw = o.out_nchw;
-                e.out_bf16 = (tc && !o.out_nchw) ? 1 : 0;
+                e.out2_bf16 = ptr(o.dst_b16);
                 if (tc && !o.src_nchw) {
                     used_tc = true;
-                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, e.temb_bcast, ptr(o.residual),
-                                        ptr(o.dst), st);
+                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, o.out_nchw ? nullptr : ptr(o.dst),
+                                        ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, st);
                 } else {
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
                                          ptr(o.dst), st);
@@ -781,7 +805,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 break;
             }
             case OP_ATTN:
-                rc = launch_attention(ptr(o.src_a), ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
+                rc = launch_attention(ptr(o.src_a), tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
                 break;
             default:
                 rc = DS_OK;
@@ -863,7 +887,7 @@ extern "C" int ds_unet_read_tap(ds_unet* n, const char* name, float* d_out, size
     DS_REQUIRE((size_t)total <= out_elems, "unet_read_tap: output too small (%zu < %lld)", out_elems, (long long)total);
     const void* src = (uint8_t*)d_ws + t.off;
     int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d_out, t.C, t.H * t.W, total, p->prec == DS_PREC_BF16);
+    nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, d_out, t.C, t.H * t.W, total, t.bf16);
     DS_CHECK_LAUNCH("nhwc_to_nchw");
     return DS_OK;
 }

@@ -121,12 +121,13 @@ int ds_conv2d_f32(const float* d_x, const float* d_w_oihw, const float* d_bias, 
 size_t ds_conv2d_scratch_bytes(int cin, int cout, int ksize);
 /* bf16 tensor-core convolution (tcgen05 + TMEM + TMA), the operator DS_PREC_BF16 forwards are built from.
  * d_xa / d_xb: bf16 NHWC sources (channel concat; d_xb may be NULL), channel counts multiples of 16;
- * d_residual: bf16 NHWC [B,Ho,Wo,cout] or NULL; output bf16 NHWC, or fp32 NCHW if out_f32_nchw.
+ * d_residual: fp32 NHWC [B,Ho,Wo,cout] or NULL (the residual stream stays fp32); d_out: bf16 NHWC, or fp32 NCHW if
+ * out_f32_nchw; d_out_f32 (optional): an additional fp32 NHWC copy of the result.
  * stride 2 = Downsample (unet.py:68-74); upsample2x = nearest x2 + 3x3 (unet.py:58-65) computed as four 2x2
  * convolutions on the low-resolution input with pre-summed weights. */
 int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb, const float* d_w_oihw, const float* d_bias,
-                   const void* d_residual, void* d_out, int out_f32_nchw, int B, int H, int W, int cout, int ksize,
-                   int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream);
+                   const float* d_residual, void* d_out, float* d_out_f32, int out_f32_nchw, int B, int H, int W, int cout,
+                   int ksize, int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream);
 size_t ds_conv2d_bf16_scratch_bytes(int cin, int cout, int ksize);
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]
  * (softmax(q k^T / sqrt(C)) v, unet.py:132-139) */

@@ -116,24 +116,28 @@ def test_conv_tc_operator(ca, cb, cout, ks, stride, up, B, H, W, residual, out_n
     Ho, Wo = ref.shape[2], ref.shape[3]
     res = None
     if residual:
-        res = torch.randn((B, cout, Ho, Wo), generator=g).bfloat16()
+        res = torch.randn((B, cout, Ho, Wo), generator=g)
         ref = ref + res.double()
     xa = x[:, :ca].permute(0, 2, 3, 1).contiguous().to(DEV)
     xb = x[:, ca:].permute(0, 2, 3, 1).contiguous().to(DEV) if cb else None
     rd = res.permute(0, 2, 3, 1).contiguous().to(DEV) if residual else None
     out = torch.full((B, cout, Ho, Wo), float("nan"), device=DEV) if out_nchw else \
         torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out32 = None if out_nchw else torch.full((B, Ho, Wo, cout), float("nan"), device=DEV)
     nb = _lib.lib().ds_conv2d_bf16_scratch_bytes(cin, cout, ks)
     scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
     wd, bd = w.to(DEV), b.to(DEV)
     _lib.check(_lib.lib().ds_conv2d_bf16(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, wd.data_ptr(), bd.data_ptr(),
-                                         None if rd is None else rd.data_ptr(), out.data_ptr(), out_nchw, B, H, W, cout, ks, stride,
+                                         None if rd is None else rd.data_ptr(), out.data_ptr(),
+                                         None if out32 is None else out32.data_ptr(), out_nchw, B, H, W, cout, ks, stride,
                                          up, scratch.data_ptr(), nb, sptr()))
     torch.cuda.synchronize()
     y = out if out_nchw else out.float().permute(0, 3, 1, 2)
     e = relerr(y, ref.float())
-    print(f"[conv_tc {ca}+{cb}->{cout} k{ks} s{stride} up{up} {B}x{H}x{W}] rel err {e:.3e}")
+    e32 = relerr(out32.permute(0, 3, 1, 2), ref.float()) if out32 is not None else 0.0
+    print(f"[conv_tc {ca}+{cb}->{cout} k{ks} s{stride} up{up} {B}x{H}x{W}] rel err bf16 out {e:.3e}, fp32 out {e32:.3e}")
     assert e <= (1e-2 if up else 5e-3)
+    assert e32 <= (1e-2 if up else 1e-5)       # fp32 accumulation of exact bf16 products: only summation order differs
 
 
 @pytest.mark.parametrize("ca,cb,G,B,HW,swish", [(16, 0, 16, 2, (16, 16), 1), (16, 32, 16, 1, (12, 20), 1), (128, 0, 16, 3, (8, 8), 0),
