@@ -65,17 +65,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
         if (r < rows) {
             float s[4] = {0, 0, 0, 0}, qq[4] = {0, 0, 0, 0};
             int run = 0;
-            for (int p = p0 + r; p < p1; p += rows) {
-                const float4 v = load4(a, ca, b, cb, base + p, cq * 4);
+            auto acc = [&](const float4& v) {
                 s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
                 qq[0] = fmaf(v.x, v.x, qq[0]); qq[1] = fmaf(v.y, v.y, qq[1]);
                 qq[2] = fmaf(v.z, v.z, qq[2]); qq[3] = fmaf(v.w, v.w, qq[3]);
-                if (++run == 32) {
+            };
+            int p = p0 + r;
+            for (; p + 3 * rows < p1; p += 4 * rows) {      // 4 independent 16-byte loads in flight
+                const float4 v0 = load4(a, ca, b, cb, base + p, cq * 4);
+                const float4 v1 = load4(a, ca, b, cb, base + p + rows, cq * 4);
+                const float4 v2 = load4(a, ca, b, cb, base + p + 2 * rows, cq * 4);
+                const float4 v3 = load4(a, ca, b, cb, base + p + 3 * rows, cq * 4);
+                acc(v0); acc(v1); acc(v2); acc(v3);
+                run += 4;
+                if (run >= 32) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { ds_[j] += (double)s[j]; dq[j] += (double)qq[j]; s[j] = 0.f; qq[j] = 0.f; }
                     run = 0;
                 }
             }
+            for (; p < p1; p += rows) acc(load4(a, ca, b, cb, base + p, cq * 4));
 #pragma unroll
             for (int j = 0; j < 4; ++j) { ds_[j] += (double)s[j]; dq[j] += (double)qq[j]; }
         }
@@ -137,13 +146,24 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     __syncthreads();
     if (s_last) {
         __threadfence();
+        // all threads fetch: thread (slice, g) sums every `slices`-th slab partial, then a fixed-order fold
+        const int slices = GN_THREADS / G;
+        const int g = t % G, sl = t / G;
+        double ps = 0.0, pq = 0.0;
+        if (sl < slices) {
+            const double* src = partial + ((size_t)bi * GN_MAX_SPLIT * G + g) * 2;
+            for (int k = sl; k < nsplit; k += slices) {
+                ps += __ldcg(src + (size_t)k * G * 2);
+                pq += __ldcg(src + (size_t)k * G * 2 + 1);
+            }
+        }
+        __syncthreads();
+        s_sum[t] = ps;
+        s_sq[t] = pq;
+        __syncthreads();
         if (t < G) {
             double s = 0.0, q = 0.0;
-            const double* src = partial + ((size_t)bi * GN_MAX_SPLIT * G + t) * 2;
-            for (int k = 0; k < nsplit; ++k) {
-                s += __ldcg(src + (size_t)k * G * 2);
-                q += __ldcg(src + (size_t)k * G * 2 + 1);
-            }
+            for (int k = 0; k < slices; ++k) { s += s_sum[k * G + t]; q += s_sq[k * G + t]; }
             const double n = (double)HW * cpg;
             const double mean = s / n;
             double var = q / n - mean * mean;
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
         const int q = C >> 2;
         const int total = HW * q;                        // vectors in this sample (< 2^31 by construction)
         const int v0 = (int)((int64_t)total * blockIdx.x / nchunk), v1 = (int)((int64_t)total * (blockIdx.x + 1) / nchunk);
+#pragma unroll 4
         for (int v = v0 + t; v < v1; v += GN_THREADS) {
             const int p = v / q, c = (v - p * q) * 4;
             const float4 x = load4(a, ca, b, cb, base + p, c);

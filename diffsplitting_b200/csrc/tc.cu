@@ -507,11 +507,13 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             if (rc != DS_OK) return rc;
         }
     }
-    // pipeline depth: up to 6 stages within ~96 KB
+    // pipeline depth: every (tap, chunk) unit is one TMA round trip (~1 us), so small units need many slots in flight:
+    // up to 16 stages within 72 KB (3 CTAs / SM) for small tiles, up to 160 KB (1 CTA / SM) for the large ones
     const uint32_t stage_bytes = (uint32_t)align_up(128u * kc * 2u + (uint32_t)p.BN * kc * 2u, 1024);
     const int U = p.ntaps * (p.chunks_a + p.chunks_b);
-    int stages = (int)(98304 / stage_bytes);
-    if (stages > 6) stages = 6;
+    const uint32_t budget = stage_bytes <= 8192 ? 73728u : 163840u;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 16) stages = 16;
     if (stages > U) stages = U;
     if (stages < 1) stages = 1;
     p.stages = stages;

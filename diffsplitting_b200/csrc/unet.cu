@@ -166,6 +166,7 @@ struct ds_unet {
     bool weights_ready = false;
     std::vector<Plan*> plans;
     bool keep_taps = false;
+    int skip_mask = 0;                   // timing experiments only (DIFFSPLIT_B200_SKIP): bit OpKind = do not launch
 
     const float* wp(int i) const { return d_arena + specs[i].off; }
 };
@@ -543,6 +544,8 @@ extern "C" int ds_unet_create(const ds_unet_desc* desc, ds_unet** out) {
     n->d = *desc;
     const char* e = getenv("DIFFSPLIT_B200_TAPS");
     n->keep_taps = e && e[0] == '1';
+    const char* sk = getenv("DIFFSPLIT_B200_SKIP");
+    if (sk) n->skip_mask = atoi(sk);
     int rc = build_arch(n);
     if (rc != DS_OK) { delete n; return rc; }
     *out = n;
@@ -773,6 +776,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
     for (const Op& o : p->ops) {
         bool used_tc = false;
         const size_t oi = op_index++;
+        if (n->skip_mask & (1 << (int)o.kind)) continue;
         if (prof) cudaEventRecord(prof->e0, st);
         switch (o.kind) {
             case OP_GN:
