@@ -268,6 +268,11 @@ def main():
         return
 
     import torch.distributed as dist
+    # stdout carries exactly ONE JSON line: everything else written to fd 1 while running (e.g. NCCL's version banner)
+    # is redirected to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     args.warmup = max(3, args.warmup)
@@ -353,13 +358,14 @@ def main():
     if rank == 0:
         pk = peaks()
         agg = {}
-        reps = 5
+        reps = 3
         xin = eng.x if eng.cond is None else eng.cond
         xb = None if eng.cond is None else eng.x
         net.profile(xin, xb, eng.time)
+        per_op = None
         for _ in range(reps):
-            flush.fill_(1)
-            for o in net.profile(xin, xb, eng.time):
+            per_op = net.profile(xin, xb, eng.time)      # every operator: 1 warm-up + 20 back-to-back launches per event pair
+            for o in per_op:
                 a = agg.setdefault(o["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
                 a["ms"] += o["ms"]; a["flops"] += o["flops"]; a["bytes"] += o["bytes"]; a["launches"] += o["launches"]
         tot = sum(a["ms"] for a in agg.values())
@@ -378,7 +384,11 @@ def main():
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
         roof.update({"traffic": None, "kernel": top, "share_of_step": a["ms"] / tot, "peak_source": pk["src"],
                      "per_launch_us": a["ms"] / a["launches"] * 1e3,
-                     "note": "algorithmic bytes|flops of all launches of this kernel in one step / their summed CUDA-event time"})
+                     "note": "algorithmic bytes|flops of all launches of this kernel in one step / their summed CUDA-event time "
+                             "(each operator timed as 20 back-to-back launches after 1 warm-up, L2 warm as in the real chain)"})
+        if os.environ.get("DIFFSPLIT_B200_DUMP_OPS"):
+            with open(os.environ["DIFFSPLIT_B200_DUMP_OPS"], "w") as fh:
+                json.dump(per_op, fh, indent=0)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -401,6 +411,8 @@ def main():
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "clocks": clk, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
                 "wall_s_timed_region": t_wall}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
