@@ -132,3 +132,37 @@ extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb
     e.out_nchw = out_f32_nchw; e.out2_bf16 = nullptr;
     return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, d_out_f32, out_f32_nchw ? nullptr : d_out, out_f32_nchw ? (float*)d_out : nullptr, st);
 }
+
+extern "C" size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ksize) {
+    return align_up(halo_packed_weight_bytes(cout, cin, ksize), 1024) + align_up(gn_scratch_bytes(B, groups), 256);
+}
+
+extern "C" int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma, const float* d_beta,
+                              int groups, int apply_swish, const float* d_w_oihw, const float* d_bias, const float* d_residual,
+                              void* d_out_b16, float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch,
+                              size_t scratch_bytes, void* stream) {
+    DS_REQUIRE(d_xa && d_w_oihw && d_scratch && (d_out_b16 || d_out_f32), "gnconv_bf16: null argument");
+    DS_REQUIRE(scratch_bytes >= ds_gnconv_bf16_scratch_bytes(B, groups > 0 ? groups : 1, ca + cb, cout, ksize),
+               "gnconv_bf16: scratch too small");
+    DS_REQUIRE(halo_conv_supported(ca, cb, cout, ksize, B, H, W),
+               "gnconv_bf16: unsupported shape (channel counts multiples of 8, total a multiple of 16 and <= 128)");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* wp = (uint8_t*)d_scratch;
+    void* gscratch = wp + align_up(halo_packed_weight_bytes(cout, ca + cb, ksize), 1024);
+    int rc = halo_pack_conv_weight(d_w_oihw, wp, cout, ca + cb, ksize, st);
+    if (rc != DS_OK) return rc;
+    const float2* stats = nullptr;
+    if (groups > 0) {
+        unsigned* counters = nullptr;
+        rc = gn_counters(&counters);
+        if (rc != DS_OK) return rc;
+        rc = launch_gn_stats(d_xa, ca, d_xb, cb, B, H * W, groups, gscratch, counters, st);
+        if (rc != DS_OK) return rc;
+        stats = gn_stats_ptr(gscratch, B, groups);
+    }
+    ConvEpi e;
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = d_residual;
+    e.out_nchw = 0; e.out2_bf16 = nullptr;
+    return halo_launch_conv(d_xa, ca, d_xb, cb, stats, d_gamma, d_beta, groups, apply_swish, wp, cout, ksize, B, H, W, e, d_out_f32,
+                            d_out_b16, nullptr, st);
+}

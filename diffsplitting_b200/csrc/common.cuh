@@ -75,6 +75,9 @@ constexpr int GN_MAX_BATCH = 4096;
 int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta,
                      void* out, int B, int HW, int G, int swish, void* scratch, unsigned* counters, int out_bf16,
                      cudaStream_t st);
+int launch_gn_stats(const float* a, int ca, const float* b, int cb, int B, int HW, int G, void* scratch, unsigned* counters,
+                    cudaStream_t st);
+float2* gn_stats_ptr(void* scratch, int B, int G);
 int gn_counters(unsigned** out);     // per-device buffer, allocated on first use (never inside graph capture)
 
 int launch_attention(const void* qkv, void* out, int B, int N, int C, int bf16, cudaStream_t st);

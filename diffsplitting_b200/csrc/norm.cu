@@ -242,6 +242,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
     }
 }
 
+float2* gn_stats_ptr(void* scratch, int B, int G) {
+    return reinterpret_cast<float2*>((uint8_t*)scratch + gn_partial_bytes(B, G));
+}
+
+static bool gn_vec_ok(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta) {
+    const int C = ca + cb;
+    return (ca % 4 == 0) && (cb % 4 == 0) && (C / 4 <= GN_THREADS) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+           (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
+           (gamma == nullptr || (reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
+           (beta == nullptr || (reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+}
+
+// statistics only: (mean, rstd) per (sample, group) -> gn_stats_ptr(scratch); the normalisation itself is then fused
+// into the consumer convolution's operand staging (tc_halo.cu)
+int launch_gn_stats(const float* a, int ca, const float* b, int cb, int B, int HW, int G, void* scratch, unsigned* counters,
+                    cudaStream_t st) {
+    const int C = ca + cb;
+    DS_REQUIRE(G >= 1 && G <= GN_MAX_GROUPS && C % G == 0, "groupnorm: %d channels not divisible into %d groups (max %d)",
+               C, G, GN_MAX_GROUPS);
+    DS_REQUIRE((int64_t)HW * C < (1ll << 31), "groupnorm: sample too large");
+    DS_REQUIRE(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
+    const int nsplit = gn_nsplit(B, HW, C);
+    double* partial = reinterpret_cast<double*>(scratch);
+    float2* stats = gn_stats_ptr(scratch, B, G);
+    if (gn_vec_ok(a, ca, b, cb, nullptr, nullptr))
+        gn_stats_kernel<true><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+    else
+        gn_stats_kernel<false><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+    DS_CHECK_LAUNCH("gn_stats");
+    return DS_OK;
+}
+
 int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float* gamma, const float* beta, void* out, int B,
                      int HW, int G, int swish, void* scratch, unsigned* counters, int out_bf16, cudaStream_t st) {
     const int C = ca + cb;

@@ -1,0 +1,293 @@
+// Fused  GroupNorm-apply + Swish -> 3x3 / 1x1 convolution  on the tensor cores, operands staged through registers.
+//
+// Why a second tensor-core conv kernel: for the 16..128-channel layers of the splitting UNets the TMA im2col path
+// (tc.cu) fetches every input pixel 9 times in 32..128-byte rows and needs a separate normalisation pass before it.
+// Here each CTA
+//   1. loads the raw fp32 input pixels it needs ONCE per filter row (3 row segments of 130 pixels, 16-byte loads),
+//      applies the per-(sample, channel) GroupNorm scale/shift + Swish of the reference Block
+//      (model/sr3_modules/unet.py:80-91) in registers, converts to bf16 and writes the UMMA no-swizzle K-major layout
+//      [8-channel plane][pixel][16 B];
+//   2. issues all 9 taps x C/16 tcgen05.mma from that one copy: in the ZERO-PADDED, row-major flattened image
+//      (pitch W+2) a filter tap is a constant shift of the flat index, i.e. just a different descriptor start address;
+//   3. runs the common epilogue (bias, conditioning vector, fp32 residual, fp32 / bf16 stores).
+// One tile = 128 consecutive flat padded positions (border positions are computed and discarded: 6 % waste at 64^2).
+// The channel concat of the up path (unet.py:255) is two source pointers; weights arrive with cp.async.bulk.
+#include "tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace ds {
+
+constexpr int HALO_THREADS = 192;
+constexpr int HALO_SEG_PX = 136;           // 128 outputs + 2 halo pixels, padded to a multiple of 8
+constexpr int HALO_MAX_SAMPLES = 12;
+constexpr uint32_t HALO_PLANE_BYTES = HALO_SEG_PX * 16;
+constexpr size_t HALO_SMEM_LIMIT = 200 * 1024;
+
+struct HaloParams {
+    const float* src_a; const float* src_b;     // fp32 NHWC [B,H,W,ca|cb]
+    int ca, cb;
+    const float2* stats;                        // (mean, rstd) [B][G] of the concat input, or null = identity
+    const float* gamma; const float* beta;
+    int G, swish;
+    const uint8_t* w;                           // bf16 [tap][kstep][plane(2)][Npad][8]
+    TcEpi epi;
+    int B, H, W, Wp, HpWp, total_q;
+    int C, ksteps, ntaps, BN, n_tiles, Npad;
+};
+
+// no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
+// LBO between the two 8-element K halves of one K=16 step
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = p.C >> 3;
+    const int nseg = p.ntaps == 9 ? 3 : 1;
+    const uint32_t seg_bytes = P * HALO_PLANE_BYTES;
+    const uint32_t a_off = 0, b_off = nseg * seg_bytes;
+    const uint32_t b_tile = (uint32_t)p.BN * 16u;                       // one (tap, kstep, plane) block
+    const uint32_t b_bytes = (uint32_t)p.ntaps * p.ksteps * 2u * b_tile;
+    const uint32_t tab_off = b_off + b_bytes;
+    const int q0 = blockIdx.x * 128;
+    const int nt = blockIdx.y;
+    // samples touched by the loaded span [q0 - Wp - 1, q0 + 128 + Wp]
+    int b_first = (q0 - p.Wp - 1) / p.HpWp;
+    if (q0 - p.Wp - 1 < 0) b_first = 0;
+    int b_last = (q0 + 128 + p.Wp) / p.HpWp;
+    if (b_last > p.B - 1) b_last = p.B - 1;
+    const int nsamp = b_last - b_first + 1;
+    const uint32_t bar_off = (tab_off + (uint32_t)nsamp * p.C * 8u + 15u) & ~15u;
+    const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
+    const uint32_t tmem_cols = p.BN <= 32 ? 32u : (p.BN <= 64 ? 64u : 128u);
+
+    if (tid == 0) {
+        mbar_init(bfull, 1);
+        mbar_init(mma_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // ---- weights: ntaps * ksteps * 2 blocks of BN x 16 B, fetched asynchronously while the operands are staged
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bfull, b_bytes);
+        __syncwarp();
+        const int ncopy = p.ntaps * p.ksteps * 2;
+        for (int i = lane; i < ncopy; i += 32)
+            bulk_load(base + b_off + i * b_tile, p.w + ((size_t)i * p.Npad + (size_t)nt * p.BN) * 16, b_tile, bfull);
+    }
+
+    // ---- per (sample in tile, channel) scale / shift of the fused GroupNorm
+    float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
+    {
+        const int cpg = p.stats ? p.C / p.G : 1;
+        for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
+            const int s = i / p.C, c = i - s * p.C;
+            float a = 1.f, sh = 0.f;
+            if (p.stats) {
+                const float2 st = p.stats[(size_t)(b_first + s) * p.G + c / cpg];
+                a = st.y * p.gamma[c];
+                sh = p.beta[c] - st.x * a;
+            }
+            tab[i] = make_float2(a, sh);
+        }
+    }
+    __syncthreads();
+
+    // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [plane][pixel][16 B]
+    {
+        const int total = nseg * P * HALO_SEG_PX;
+        for (int idx = tid; idx < total; idx += HALO_THREADS) {
+            const int px = idx % HALO_SEG_PX;
+            const int t2 = idx / HALO_SEG_PX;
+            const int kp = t2 % P, seg = t2 / P;
+            const int segr = nseg == 3 ? seg : 1;
+            const int q = q0 + (segr - 1) * p.Wp - 1 + px;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (q >= 0 && q < p.total_q) {
+                const int b = q / p.HpWp;
+                const int rq = q - b * p.HpWp;
+                const int yy = rq / p.Wp, xx = rq - yy * p.Wp;
+                if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
+                    const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
+                    const int c0 = kp * 8;
+                    const float* src = c0 < p.ca ? p.src_a + pix * p.ca + c0 : p.src_b + pix * p.cb + (c0 - p.ca);
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    const float2* tb = tab + (b - b_first) * p.C + c0;
+                    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 sc = tb[j];
+                        float y = fmaf(x[j], sc.x, sc.y);
+                        if (p.swish) y = __fdividef(y, 1.0f + __expf(-y));
+                        x[j] = y;
+                    }
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    val = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            const uint32_t dst = base + a_off + seg * seg_bytes + kp * HALO_PLANE_BYTES + px * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+        }
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(bfull, 0);
+            tc_fence_after();
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int r = nseg == 3 ? tap / 3 : 0;
+                const int s = nseg == 3 ? tap % 3 : 1;
+                for (int kk = 0; kk < p.ksteps; ++kk) {
+                    const uint32_t a_addr = base + a_off + r * seg_bytes + (2 * kk) * HALO_PLANE_BYTES + s * 16;
+                    const uint32_t b_addr = base + b_off + (uint32_t)((tap * p.ksteps + kk) * 2) * b_tile;
+                    umma_bf16(tmem_base, make_desc_nosw(a_addr, HALO_PLANE_BYTES, 128u), make_desc_nosw(b_addr, b_tile, 128u),
+                              idesc, (tap | kk) ? 1u : 0u);
+                }
+            }
+            umma_commit(mma_done);
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        const int qd = warp & 3;
+        const int m = qd * 32 + lane;
+        const int q = q0 + m;
+        bool valid = q < p.total_q;
+        int b = 0, oy = 0, ox = 0;
+        if (valid) {
+            b = q / p.HpWp;
+            const int rq = q - b * p.HpWp;
+            const int yy = rq / p.Wp, xx = rq - yy * p.Wp;
+            valid = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
+            oy = yy - 1;
+            ox = xx - 1;
+        }
+        mbar_wait(mma_done, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+            if (valid) tc_epilogue_store(p.epi, v, b, oy, ox, nt * p.BN + c0);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static size_t halo_smem_bytes(int C, int ntaps, int BN, int nsamp) {
+    const int nseg = ntaps == 9 ? 3 : 1;
+    return (size_t)nseg * (C / 8) * HALO_PLANE_BYTES + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 + 64 + 128;
+}
+
+static int halo_samples_per_tile(int H, int W) {
+    const int Wp = W + 2, HpWp = (H + 2) * Wp;
+    return (128 + 2 * Wp + 2) / HpWp + 2;
+}
+
+static int halo_pick_bn(int cout, int C, int ntaps, int nsamp, int64_t m_tiles) {
+    const int npad = (cout + 15) / 16 * 16;
+    int bn = 16;
+    for (int c = 128; c >= 16; c >>= 1)
+        if (npad % c == 0) { bn = c; break; }
+    while (bn > 16 && (halo_smem_bytes(C, ntaps, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < 120)) bn >>= 1;
+    return bn;
+}
+
+bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) {
+    const int C = ca + cb;
+    if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 128) return false;
+    if (!(ks == 1 || ks == 3)) return false;
+    if ((int64_t)B * (H + 2) * (W + 2) >= (1ll << 31) - 4096) return false;
+    const int nsamp = halo_samples_per_tile(H, W);
+    if (nsamp > HALO_MAX_SAMPLES) return false;
+    return halo_smem_bytes(C, ks * ks, 16, nsamp) <= HALO_SMEM_LIMIT;
+}
+
+size_t halo_packed_weight_bytes(int cout, int cin, int ks) {
+    return (size_t)ks * ks * cin * ((cout + 15) / 16 * 16) * 2;
+}
+
+__global__ void pack_halo_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int ks,
+                                        int npad) {
+    const int ntaps = ks * ks;
+    const size_t total = (size_t)ntaps * cin * npad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int j = (int)(r % 8); r /= 8;
+        const int n = (int)(r % npad); r /= npad;
+        const int plane = (int)(r % 2); r /= 2;
+        const int kk = (int)(r % (cin / 16)); r /= (cin / 16);
+        const int tap = (int)r;
+        const int c = kk * 16 + plane * 8 + j;
+        const float v = n < cout ? w[((size_t)n * cin + c) * ntaps + tap] : 0.f;
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st) {
+    DS_REQUIRE(cin % 16 == 0, "halo_pack: cin %d not a multiple of 16", cin);
+    const int npad = (cout + 15) / 16 * 16;
+    const size_t total = (size_t)ks * ks * cin * npad;
+    int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+    pack_halo_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, ks, npad);
+    DS_CHECK_LAUNCH("pack_halo_weight");
+    return DS_OK;
+}
+
+int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const float2* stats, const float* gamma,
+                     const float* beta, int G, int swish, const uint8_t* w_packed, int cout, int ks, int B, int H, int W,
+                     const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw, cudaStream_t st) {
+    DS_REQUIRE(halo_conv_supported(ca, cb, cout, ks, B, H, W), "halo conv: unsupported shape");
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.src_a = src_a; p.src_b = src_b; p.ca = ca; p.cb = cb;
+    p.stats = stats; p.gamma = gamma; p.beta = beta; p.G = G; p.swish = swish;
+    p.w = w_packed;
+    p.epi.bias = epi.bias; p.epi.temb = epi.temb; p.epi.temb_off = epi.temb_off; p.epi.temb_stride = epi.temb_stride;
+    p.epi.temb_bcast = epi.temb_bcast; p.epi.residual = epi.residual;
+    p.epi.out_f32 = out_f32; p.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); p.epi.out_nchw = out_nchw;
+    p.epi.Cout = cout; p.epi.Ho = H; p.epi.Wo = W;
+    p.B = B; p.H = H; p.W = W; p.Wp = W + 2; p.HpWp = (H + 2) * (W + 2);
+    p.total_q = B * p.HpWp;
+    p.C = ca + cb; p.ksteps = p.C / 16; p.ntaps = ks * ks;
+    p.Npad = (cout + 15) / 16 * 16;
+    const int nsamp = halo_samples_per_tile(H, W);
+    const int64_t m_tiles = ((int64_t)p.total_q + 127) / 128;
+    p.BN = halo_pick_bn(cout, p.C, p.ntaps, nsamp, m_tiles);
+    p.n_tiles = p.Npad / p.BN;
+    const size_t smem = halo_smem_bytes(p.C, p.ntaps, p.BN, nsamp);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        attr_set = true;
+    }
+    conv_halo_kernel<<<dim3((unsigned)m_tiles, p.n_tiles, 1), HALO_THREADS, smem, st>>>(p);
+    DS_CHECK_LAUNCH("conv_halo");
+    return DS_OK;
+}
+
+}  // namespace ds

@@ -1,0 +1,164 @@
+// PTX wrappers shared by the tensor-core kernels (mbarrier, TMA / bulk copies, TMEM, tcgen05.mma / ld / commit) and the
+// common epilogue (bias + conditioning vector + fp32 residual -> fp32 NHWC / bf16 NHWC / fp32 NCHW stores).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ds {
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost TMA / MMA completion traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout (2=SW128, 4=SW64, 6=SW32)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (8u * row_bytes) >> 4;          // 8-row group stride
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+
+// ------------------------------------------------------------------------------------------ shared epilogue
+struct TcEpi {
+    const float* bias;                // [Cout] or null
+    const float* temb;                // conditioning vectors or null
+    int temb_off, temb_stride, temb_bcast;
+    const float* residual;            // fp32 NHWC [B,Ho,Wo,Cout] or null (the residual stream stays fp32)
+    float* out_f32;                   // fp32 NHWC or null   (consumers: GroupNorm statistics, residual adds)
+    __nv_bfloat16* out_b16;           // bf16 NHWC or null   (consumers: TMA-fed convolutions, attention)
+    float* out_nchw;                  // fp32 NCHW or null   (the network output)
+    int Cout, Ho, Wo;
+};
+
+// one thread = one output pixel (b, oy, ox), 16 consecutive output channels starting at n0, accumulators in v[16]
+__device__ __forceinline__ void tc_epilogue_store(const TcEpi& p, const uint32_t (&v)[16], int b, int oy, int ox, int n0) {
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    const size_t pix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += p.bias[n0 + j];
+    }
+    if (p.temb) {
+        const float* te = p.temb + (size_t)(p.temb_bcast ? 0 : b) * p.temb_stride + p.temb_off + n0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += te[j];
+    }
+    if (p.out_nchw) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.Cout) p.out_nchw[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
+    } else if (n0 + 16 <= p.Cout) {
+        const size_t off = pix * p.Cout + n0;
+        if (p.residual) {
+            const float4* r = reinterpret_cast<const float4*>(p.residual + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 rv = __ldg(r + j);
+                f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
+            }
+        }
+        if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (p.out_b16) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            uint4* o = reinterpret_cast<uint4*>(p.out_b16 + off);
+            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (n0 + j < p.Cout) {
+                const size_t off = pix * p.Cout + n0 + j;
+                float val = f[j];
+                if (p.residual) val += p.residual[off];
+                if (p.out_f32) p.out_f32[off] = val;
+                if (p.out_b16) p.out_b16[off] = __float2bfloat16_rn(val);
+            }
+        }
+    }
+}
+
+}  // namespace ds

@@ -27,6 +27,8 @@ struct WeightSpec {
     size_t off_bf16;   // byte offset of the bf16 pack in the tensor-core arena (convs only)
     int npad;          // conv: padded Cout ; vec: padded length
     int tc_kc, tc_up;  // tensor-core pack variant (tc_kc == 0: layer has no bf16 pack)
+    bool halo;         // additionally packed for the fused GroupNorm+Swish->conv kernel (tc_halo.cu)
+    size_t off_halo;   // byte offset of that pack in the bf16 arena
     bool loaded;
 };
 
@@ -55,7 +57,7 @@ struct Layer {
 };
 
 // ------------------------------------------------------------------------------------------ plan
-enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN };
+enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN, OP_GN_STATS };
 constexpr int64_t EXT_XA = -1, EXT_XB = -2, EXT_OUT = -3, NONE = -100;
 
 struct Op {
@@ -73,6 +75,10 @@ struct Op {
     // gn
     const GNW* gw = nullptr;
     int swish = 0, HW = 0;
+    // conv with the GroupNorm(+Swish) of its input fused into the operand staging (sources are the fp32 copies)
+    int halo = 0;
+    const GNW* fgn = nullptr;
+    int fswish = 0;
     // attn
     int N = 0, C = 0;
 };
@@ -186,6 +192,8 @@ static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initia
     s.off_bf16 = 0;
     s.tc_kc = 0;
     s.tc_up = 0;
+    s.halo = false;
+    s.off_halo = 0;
     size_t elems = 1;
     if (kind == WK_CONV) elems = (size_t)s.shape[1] * s.shape[2] * s.shape[3] * npad;
     else if (kind == WK_VEC) elems = (size_t)(npad ? npad : s.shape[0]);
@@ -211,7 +219,7 @@ static int npad_of(int cout) {
 // ca/cb: channel split of the input as the kernels will see it (two-source concat), up: nearest-x2 folded in,
 // tc = false: the layer never runs on the tensor-core path (entry conv reads fp32 NCHW)
 static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int ks, bool bias = true, int ca = -1, int cb = 0,
-                      int up = 0, bool tc = true) {
+                      int up = 0, bool tc = true, bool halo = false) {
     ConvW c;
     c.cin = cin; c.cout = cout; c.ks = ks; c.npad = npad_of(cout);
     c.w = add_spec(n, p + ".weight", WK_CONV, {cout, cin, ks, ks}, c.npad);
@@ -219,6 +227,11 @@ static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int k
     if (tc) {
         n->specs[c.w].tc_kc = tc_pick_kc(ca, cb);
         n->specs[c.w].tc_up = up;
+    }
+    if (halo && cin % 16 == 0 && cin <= 128) {
+        n->specs[c.w].halo = true;
+        n->specs[c.w].off_halo = n->arena_bf16_bytes;
+        n->arena_bf16_bytes += align_up(halo_packed_weight_bytes(cout, cin, ks), 1024);
     }
     if (bias) c.b = add_spec(n, p + ".bias", WK_VEC, {cout}, c.npad);
     return c;
@@ -252,13 +265,13 @@ static ResW add_res(ds_unet* n, const std::string& p, int cin, int cout, bool at
         n->temb_total += cout;
     }
     r.gn1 = add_gn(n, rb + ".block1.block.0", cin);
-    r.conv1 = add_conv(n, rb + ".block1.block.3", cin, cout, 3);
+    r.conv1 = add_conv(n, rb + ".block1.block.3", cin, cout, 3, true, -1, 0, 0, true, true);
     r.gn2 = add_gn(n, rb + ".block2.block.0", cout);
-    r.conv2 = add_conv(n, rb + ".block2.block.3", cout, cout, 3);
+    r.conv2 = add_conv(n, rb + ".block2.block.3", cout, cout, 3, true, -1, 0, 0, true, true);
     if (r.has_res) r.res = add_conv(n, rb + ".res_conv", cin, cout, 1, true, cin - skip, skip);
     if (attn) {
         r.agn = add_gn(n, p + ".attn.norm", cout);
-        r.qkv = add_conv(n, p + ".attn.qkv", cout, 3 * cout, 1, false);
+        r.qkv = add_conv(n, p + ".attn.qkv", cout, 3 * cout, 1, false, -1, 0, 0, true, true);
         r.aout = add_conv(n, p + ".attn.out", cout, cout, 1);
     }
     return r;
@@ -332,7 +345,7 @@ static int build_arch(ds_unet* n) {
         }
     }
     n->final_gn = add_gn(n, "final_conv.block.0", ch);
-    n->final_conv = add_conv(n, "final_conv.block.3", ch, d.out_channel, 3);
+    n->final_conv = add_conv(n, "final_conv.block.3", ch, d.out_channel, 3, true, -1, 0, 0, true, true);
     // every GroupNorm must divide evenly
     for (auto& s : n->specs)
         if (s.kind == WK_VEC && s.name.find(".block.0.weight") != std::string::npos)
@@ -398,17 +411,38 @@ struct Planner {
         p->ops.push_back(o);
     }
 
+    // out = conv(swish?(GroupNorm(cat[a, b])))  -  one statistics pass + one fused tensor-core kernel when the shape
+    // allows it, else GroupNorm-apply into a bf16 operand tensor followed by the TMA-fed conv
+    void gn_conv(const Act& a, const Act* b, const GNW& g, int swish, const ConvW& w, int temb_off, const Act* residual,
+                 const Act& out) {
+        const int cb = b ? b->C : 0;
+        if (tc && n->specs[w.w].halo && halo_conv_supported(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
+            Op s; s.kind = OP_GN_STATS;
+            s.src_a = a.f32; s.ca = a.C;
+            if (b) { s.src_b = b->f32; s.cb = cb; }
+            s.gw = &g; s.HW = a.H * a.W;
+            p->ops.push_back(s);
+            Op o; o.kind = OP_CONV;
+            o.halo = 1; o.fgn = &g; o.fswish = swish;
+            o.src_a = a.f32; o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
+            if (b) { o.src_b = b->f32; o.cb = cb; }
+            o.cw = &w; o.temb_off = temb_off; o.Ho = out.H; o.Wo = out.W;
+            if (residual) o.residual = residual->f32;
+            o.dst = out.f32; o.dst_b16 = out.b16;
+            p->ops.push_back(o);
+            return;
+        }
+        Act act = make(a.C + cb, a.H, a.W, B16);
+        gn(a, b, g, swish, act);
+        conv(act, nullptr, w, 1, 0, temb_off, residual, out);
+        release(act);
+    }
+
     Act resblock(const Layer& L, Act x, const Act* skip) {
         const ResW& r = L.res;
         const int H = x.H, W = x.W;
-        Act a1 = make(r.cin, H, W, B16);
-        gn(x, skip, r.gn1, 1, a1);
         Act h = make(r.cout, H, W, F32);
-        conv(a1, nullptr, r.conv1, 1, 0, r.temb_off, nullptr, h);
-        release(a1);
-        Act a2 = make(r.cout, H, W, B16);
-        gn(h, nullptr, r.gn2, 1, a2);
-        release(h);
+        gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act resid = x;
         Act rbuf;
         if (r.has_res) {
@@ -417,15 +451,12 @@ struct Planner {
             resid = rbuf;
         }
         Act out = make(r.cout, H, W, F32 | B16);
-        conv(a2, nullptr, r.conv2, 1, 0, -1, &resid, out);
-        release(a2);
+        gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, &resid, out);
+        release(h);
         if (r.has_res) release(rbuf);
         if (r.attn) {
-            Act nrm = make(r.cout, H, W, B16);
-            gn(out, nullptr, r.agn, 0, nrm);
             Act qkv = make(3 * r.cout, H, W, B16);
-            conv(nrm, nullptr, r.qkv, 1, 0, -1, nullptr, qkv);
-            release(nrm);
+            gn_conv(out, nullptr, r.agn, 0, r.qkv, -1, nullptr, qkv);
             Act att = make(r.cout, H, W, B16);
             Op o; o.kind = OP_ATTN;
             o.src_a = conv_src(qkv); o.dst = att.f32; o.dst_b16 = att.b16; o.N = H * W; o.C = r.cout;
@@ -504,19 +535,18 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
         }
         P.tap(L.name, x);
     }
-    Act fa = P.make(x.C, x.H, x.W, B16);
-    P.gn(x, nullptr, n->final_gn, 1, fa);
-    P.release(x);
     {
-        Op op; op.kind = OP_CONV;
-        op.src_a = P.conv_src(fa); op.ca = fa.C; op.Hs = fa.H; op.Ws = fa.W;
-        op.cw = &n->final_conv; op.Ho = fa.H; op.Wo = fa.W; op.dst = EXT_OUT; op.out_nchw = 1;
-        p->ops.push_back(op);
+        Act ext;                       // the network output: external fp32 NCHW
+        ext.f32 = EXT_OUT; ext.C = n->final_conv.cout; ext.H = x.H; ext.W = x.W;
+        const size_t first_new = p->ops.size();
+        P.gn_conv(x, nullptr, n->final_gn, 1, n->final_conv, -1, nullptr, ext);
+        for (size_t i = first_new; i < p->ops.size(); ++i)
+            if (p->ops[i].kind == OP_CONV) p->ops[i].out_nchw = 1;
     }
-    P.release(fa);
+    P.release(x);
     p->bytes = P.arena.top();
     int launches = d.with_time_emb ? 1 : 0;
-    for (auto& o : p->ops) launches += (o.kind == OP_GN) ? 2 : 1;
+    for (auto& o : p->ops) launches += (o.kind == OP_GN) ? 2 : 1;      // GroupNorm = statistics + apply
     p->launches = launches;
     *out = p;
     return DS_OK;
@@ -605,6 +635,10 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
             if (s.tc_kc) {
                 rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_bf16, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
                                          s.tc_up, s.tc_kc, st);
+                if (rc != DS_OK) return rc;
+            }
+            if (s.halo) {
+                rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
                 if (rc != DS_OK) return rc;
             }
         } else {
@@ -765,7 +799,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         p->tc.assign(p->ops.size(), TcConvPlan());
         for (size_t i = 0; i < p->ops.size(); ++i) {
             const Op& o = p->ops[i];
-            if (o.kind != OP_CONV || o.src_nchw) continue;
+            if (o.kind != OP_CONV || o.src_nchw || o.halo) continue;
             if (!n->specs[o.cw->w].tc_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws)) {
                 set_error("unet_forward: bf16 mode needs channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
                           n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
@@ -794,6 +828,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                                       tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.HW, n->d.norm_groups, o.swish, gn_scratch,
                                       counters, tc ? 1 : 0, st);
                 break;
+            case OP_GN_STATS:
+                rc = launch_gn_stats(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, B, o.HW, n->d.norm_groups, gn_scratch, counters, st);
+                break;
             case OP_CONV: {
                 ConvSrc s;
                 s.a = ptr(o.src_a); s.b = ptr(o.src_b);
@@ -808,7 +845,13 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.residual = ptr(o.residual);
                 e.out_nchw = o.out_nchw;
                 e.out2_bf16 = ptr(o.dst_b16);
-                if (tc && !o.src_nchw) {
+                if (o.halo) {
+                    used_tc = true;
+                    rc = halo_launch_conv(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, gn_stats_ptr(gn_scratch, B, n->d.norm_groups),
+                                          n->wp(o.fgn->w), n->wp(o.fgn->b), n->d.norm_groups, o.fswish,
+                                          n->d_arena_bf16 + n->specs[o.cw->w].off_halo, o.cw->cout, o.cw->ks, B, o.Hs, o.Ws, e,
+                                          o.out_nchw ? nullptr : ptr(o.dst), ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, st);
+                } else if (tc && !o.src_nchw) {
                     used_tc = true;
                     rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, o.out_nchw ? nullptr : ptr(o.dst),
                                         ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, st);
@@ -836,11 +879,15 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
             r.launches = 1;
             if (o.kind == OP_CONV) {
                 const int cin = o.src_nchw ? ca + cb : o.ca + o.cb;
-                r.kind = used_tc ? 4 : 1;
+                r.kind = o.halo ? 6 : (used_tc ? 4 : 1);
                 r.cin = cin; r.cout = o.cw->cout; r.ksize = o.cw->ks; r.h = o.Ho; r.w = o.Wo;
                 r.flops = 2.0 * B * o.Ho * o.Wo * (double)o.cw->ks * o.cw->ks * cin * o.cw->cout;
                 r.bytes = 4.0 * B * ((double)o.Hs * o.Ws * cin + (double)o.Ho * o.Wo * o.cw->cout *
                                      (o.residual != NONE ? 2.0 : 1.0)) + 4.0 * o.cw->ks * o.cw->ks * cin * o.cw->cout;
+            } else if (o.kind == OP_GN_STATS) {
+                r.kind = 5;
+                r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;
+                r.bytes = 4.0 * B * (double)o.HW * (o.ca + o.cb);        // one read
             } else if (o.kind == OP_GN) {
                 r.kind = 2;
                 r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;

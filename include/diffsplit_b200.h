@@ -88,7 +88,8 @@ double ds_unet_flops(const ds_unet* net, int H, int W);
 /* number of kernels one forward enqueues (for bench.py's gpu_launches) */
 int  ds_unet_launches(ds_unet* net, int B, int H, int W, int precision);
 /* measurement: the same forward with a CUDA-event pair around every operator (synchronises; not capturable).
- * kind: 0 conditioning MLP, 1 conv fp32 (CUDA cores), 2 group-norm(+swish) (2 launches), 3 attention, 4 conv bf16 (tcgen05).
+ * kind: 0 conditioning MLP, 1 conv fp32 (CUDA cores), 2 group-norm(+swish) (2 launches), 3 attention, 4 conv bf16
+ * (tcgen05, TMA-fed), 5 group-norm statistics only, 6 fused group-norm-apply + swish + conv bf16 (tcgen05, staged).
  * flops / bytes are the ALGORITHMIC figures of that operator for the whole batch. */
 typedef struct ds_op_profile {
     int32_t kind, cin, cout, ksize, h, w, launches;
@@ -129,6 +130,14 @@ int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb, const flo
                    const float* d_residual, void* d_out, float* d_out_f32, int out_f32_nchw, int B, int H, int W, int cout,
                    int ksize, int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream);
 size_t ds_conv2d_bf16_scratch_bytes(int cin, int cout, int ksize);
+/* fused Block (unet.py:80-91): GroupNorm(groups) -> Swish -> Conv(ksize 3 or 1, stride 1) over the channel concat of two
+ * fp32 NHWC sources, as ONE tensor-core kernel after a statistics pass (groups == 0: plain conv of the raw input).
+ * Total input channels: multiple of 16, <= 128.  Outputs: bf16 NHWC and / or fp32 NHWC. */
+int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma, const float* d_beta,
+                   int groups, int apply_swish, const float* d_w_oihw, const float* d_bias, const float* d_residual,
+                   void* d_out_b16, float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch,
+                   size_t scratch_bytes, void* stream);
+size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ksize);
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]
  * (softmax(q k^T / sqrt(C)) v, unet.py:132-139) */
 int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream);
