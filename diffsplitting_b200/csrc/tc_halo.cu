@@ -20,8 +20,24 @@ namespace ds {
 constexpr int HALO_THREADS = 192;
 constexpr int HALO_SEG_PX = 136;           // 128 outputs + 2 halo pixels, padded to a multiple of 8
 constexpr int HALO_MAX_SAMPLES = 12;
-constexpr uint32_t HALO_PLANE_BYTES = HALO_SEG_PX * 16;
 constexpr size_t HALO_SMEM_LIMIT = 200 * 1024;
+
+// n / d for 0 <= n < 2^31 with a precomputed multiplier (CUTLASS FastDivmod scheme): no integer division on device
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t lg = 0;
+    while ((1u << lg) < d) ++lg;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
 
 struct HaloParams {
     const float* src_a; const float* src_b;     // fp32 NHWC [B,H,W,ca|cb]
@@ -33,6 +49,10 @@ struct HaloParams {
     TcEpi epi;
     int B, H, W, Wp, HpWp, total_q;
     int C, ksteps, ntaps, BN, n_tiles, Npad;
+    // operand buffer geometry: `contig` = the three filter-row segments overlap inside ONE contiguous run of the flat
+    // padded index space (W + 2 <= 139): every pixel is staged exactly once; else three separate 136-pixel segments
+    int contig, plane_px, seg_stride_px;
+    FastDiv div_hpwp, div_wp, div_planepx;
 };
 
 // no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
@@ -48,9 +68,8 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     uint8_t* gbase = smem_raw + (base - raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = p.C >> 3;
-    const int nseg = p.ntaps == 9 ? 3 : 1;
-    const uint32_t seg_bytes = P * HALO_PLANE_BYTES;
-    const uint32_t a_off = 0, b_off = nseg * seg_bytes;
+    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
+    const uint32_t a_off = 0, b_off = P * plane_bytes;
     const uint32_t b_tile = (uint32_t)p.BN * 16u;                       // one (tap, kstep, plane) block
     const uint32_t b_bytes = (uint32_t)p.ntaps * p.ksteps * 2u * b_tile;
     const uint32_t tab_off = b_off + b_bytes;
@@ -106,18 +125,24 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
 
     // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [plane][pixel][16 B]
     {
-        const int total = nseg * P * HALO_SEG_PX;
+        const int total = P * p.plane_px;
+        const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
+#pragma unroll 2
         for (int idx = tid; idx < total; idx += HALO_THREADS) {
-            const int px = idx % HALO_SEG_PX;
-            const int t2 = idx / HALO_SEG_PX;
-            const int kp = t2 % P, seg = t2 / P;
-            const int segr = nseg == 3 ? seg : 1;
-            const int q = q0 + (segr - 1) * p.Wp - 1 + px;
+            const int kp = fdiv(idx, p.div_planepx);
+            const int px = idx - kp * p.plane_px;
+            int q;
+            if (p.contig) {
+                q = q_first + px;
+            } else {
+                const int seg = px / HALO_SEG_PX;
+                q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
+            }
             uint4 val = make_uint4(0u, 0u, 0u, 0u);
             if (q >= 0 && q < p.total_q) {
-                const int b = q / p.HpWp;
+                const int b = fdiv(q, p.div_hpwp);
                 const int rq = q - b * p.HpWp;
-                const int yy = rq / p.Wp, xx = rq - yy * p.Wp;
+                const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
                 if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
                     const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
                     const int c0 = kp * 8;
@@ -130,7 +155,12 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
                     for (int j = 0; j < 8; ++j) {
                         const float2 sc = tb[j];
                         float y = fmaf(x[j], sc.x, sc.y);
-                        if (p.swish) y = __fdividef(y, 1.0f + __expf(-y));
+                        if (p.swish) {                      // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                            const float h = 0.5f * y;
+                            float th;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                            y = fmaf(h, th, h);
+                        }
                         x[j] = y;
                     }
                     uint32_t w[4];
@@ -142,7 +172,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
                     val = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            const uint32_t dst = base + a_off + seg * seg_bytes + kp * HALO_PLANE_BYTES + px * 16;
+            const uint32_t dst = base + a_off + kp * plane_bytes + px * 16;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
         }
     }
@@ -155,12 +185,12 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             tc_fence_after();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int r = nseg == 3 ? tap / 3 : 0;
-                const int s = nseg == 3 ? tap % 3 : 1;
+                const int r = p.ntaps == 9 ? tap / 3 : 0;
+                const int s = p.ntaps == 9 ? tap % 3 : 1;
                 for (int kk = 0; kk < p.ksteps; ++kk) {
-                    const uint32_t a_addr = base + a_off + r * seg_bytes + (2 * kk) * HALO_PLANE_BYTES + s * 16;
+                    const uint32_t a_addr = base + a_off + (2 * kk) * plane_bytes + (uint32_t)(r * p.seg_stride_px + s) * 16u;
                     const uint32_t b_addr = base + b_off + (uint32_t)((tap * p.ksteps + kk) * 2) * b_tile;
-                    umma_bf16(tmem_base, make_desc_nosw(a_addr, HALO_PLANE_BYTES, 128u), make_desc_nosw(b_addr, b_tile, 128u),
+                    umma_bf16(tmem_base, make_desc_nosw(a_addr, plane_bytes, 128u), make_desc_nosw(b_addr, b_tile, 128u),
                               idesc, (tap | kk) ? 1u : 0u);
                 }
             }
@@ -174,9 +204,9 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         bool valid = q < p.total_q;
         int b = 0, oy = 0, ox = 0;
         if (valid) {
-            b = q / p.HpWp;
+            b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
-            const int yy = rq / p.Wp, xx = rq - yy * p.Wp;
+            const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
             valid = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
             oy = yy - 1;
             ox = xx - 1;
@@ -198,9 +228,14 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static size_t halo_smem_bytes(int C, int ntaps, int BN, int nsamp) {
-    const int nseg = ntaps == 9 ? 3 : 1;
-    return (size_t)nseg * (C / 8) * HALO_PLANE_BYTES + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 + 64 + 128;
+static int halo_plane_px(int ntaps, int W) {
+    if (ntaps == 1) return HALO_SEG_PX;
+    const int contig = 130 + 2 * (W + 2);
+    return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
+}
+
+static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp) {
+    return (size_t)(C / 8) * halo_plane_px(ntaps, W) * 16 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 + 64 + 128;
 }
 
 static int halo_samples_per_tile(int H, int W) {
@@ -208,12 +243,14 @@ static int halo_samples_per_tile(int H, int W) {
     return (128 + 2 * Wp + 2) / HpWp + 2;
 }
 
-static int halo_pick_bn(int cout, int C, int ntaps, int nsamp, int64_t m_tiles) {
+static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_tiles) {
     const int npad = (cout + 15) / 16 * 16;
     int bn = 16;
     for (int c = 128; c >= 16; c >>= 1)
         if (npad % c == 0) { bn = c; break; }
-    while (bn > 16 && (halo_smem_bytes(C, ntaps, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < 120)) bn >>= 1;
+    // every N tile re-stages (and re-normalises) the same operand pixels: only split N for shared memory or when the
+    // grid would leave most SMs idle
+    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < 48)) bn >>= 1;
     return bn;
 }
 
@@ -224,7 +261,7 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) 
     if ((int64_t)B * (H + 2) * (W + 2) >= (1ll << 31) - 4096) return false;
     const int nsamp = halo_samples_per_tile(H, W);
     if (nsamp > HALO_MAX_SAMPLES) return false;
-    return halo_smem_bytes(C, ks * ks, 16, nsamp) <= HALO_SMEM_LIMIT;
+    return halo_smem_bytes(C, ks * ks, W, 16, nsamp) <= HALO_SMEM_LIMIT;
 }
 
 size_t halo_packed_weight_bytes(int cout, int cin, int ks) {
@@ -277,9 +314,15 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.Npad = (cout + 15) / 16 * 16;
     const int nsamp = halo_samples_per_tile(H, W);
     const int64_t m_tiles = ((int64_t)p.total_q + 127) / 128;
-    p.BN = halo_pick_bn(cout, p.C, p.ntaps, nsamp, m_tiles);
+    p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles);
     p.n_tiles = p.Npad / p.BN;
-    const size_t smem = halo_smem_bytes(p.C, p.ntaps, p.BN, nsamp);
+    p.plane_px = halo_plane_px(p.ntaps, W);
+    p.contig = (p.ntaps == 1 || p.plane_px != 3 * HALO_SEG_PX) ? 1 : 0;
+    p.seg_stride_px = p.ntaps == 1 ? 0 : (p.contig ? p.Wp : HALO_SEG_PX);
+    p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
+    p.div_wp = make_fastdiv((uint32_t)p.Wp);
+    p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
+    const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp);
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));

@@ -1,0 +1,83 @@
+"""Warm micro-benchmark of single operators through the C ABI (CUDA-graph of 50 launches, replayed): real per-launch
+GPU time without host launch overhead.  Usage: python tools/op_microbench.py [gnconv|conv_tc|gn] ca cb cout ks B H W"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diffsplitting_b200 import _lib  # noqa: E402
+
+DEV = "cuda"
+
+
+def timed_graph(fn, n=50, reps=20):
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1000 / (n * reps)
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "gnconv"
+    ca, cb, cout, ks, B, H, W = [int(v) for v in (sys.argv[2:9] if len(sys.argv) >= 9 else "16 0 16 3 16 64 64".split())]
+    cin = ca + cb
+    L = _lib.lib()
+    sp = lambda: _lib.stream_ptr()
+    g = torch.Generator().manual_seed(0)
+    w = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5).to(DEV)
+    bias = torch.randn((cout,), generator=g).to(DEV)
+    gamma, beta = torch.ones(cin, device=DEV), torch.zeros(cin, device=DEV)
+    xa32 = torch.randn((B, H, W, ca), generator=g).to(DEV)
+    xb32 = torch.randn((B, H, W, cb), generator=g).to(DEV) if cb else None
+    out16 = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=DEV)
+    out32 = torch.empty((B, H, W, cout), device=DEV)
+    res = torch.randn((B, H, W, cout), generator=g).to(DEV)
+    if kind == "gnconv":
+        nb = L.ds_gnconv_bf16_scratch_bytes(B, 16, cin, cout, ks)
+        scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+
+        def fn():
+            _lib.check(L.ds_gnconv_bf16(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
+                                        beta.data_ptr(), 16, 1, w.data_ptr(), bias.data_ptr(), res.data_ptr(), out16.data_ptr(),
+                                        out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sp()))
+        us = timed_graph(fn)
+        print(f"gnconv (pack + gn_stats + conv_halo) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (3 kernels)")
+    elif kind == "conv_tc":
+        xa = xa32.bfloat16()
+        xb = xb32.bfloat16() if cb else None
+        nb = L.ds_conv2d_bf16_scratch_bytes(cin, cout, ks)
+        scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+
+        def fn():
+            _lib.check(L.ds_conv2d_bf16(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, w.data_ptr(), bias.data_ptr(),
+                                        res.data_ptr(), out16.data_ptr(), out32.data_ptr(), 0, B, H, W, cout, ks, 1, 0,
+                                        scratch.data_ptr(), nb, sp()))
+        us = timed_graph(fn)
+        print(f"conv_tc (pack + conv_tc) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (2 kernels)")
+    else:
+        nb = L.ds_groupnorm_scratch_bytes(B, 16)
+        scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+        out = torch.empty((B, H, W, cin), device=DEV)
+
+        def fn():
+            _lib.check(L.ds_groupnorm_swish_f32(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
+                                                beta.data_ptr(), out.data_ptr(), B, H, W, 16, 1, scratch.data_ptr(), nb, sp()))
+        us = timed_graph(fn)
+        print(f"groupnorm (stats + apply, fp32 out) C={cin} {B}x{H}x{W}: {us:.2f} us per call (2 kernels)")
+
+
+if __name__ == "__main__":
+    main()
