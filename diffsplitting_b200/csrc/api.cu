@@ -18,6 +18,17 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace ds
 
+namespace ds {
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DIFFSPLIT_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+}  // namespace ds
+
 using namespace ds;
 
 extern "C" const char* ds_last_error(void) { return g_err; }
@@ -130,7 +141,8 @@ extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb
     e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0;
     e.residual = (const float*)d_residual;
     e.out_nchw = out_f32_nchw; e.out2_bf16 = nullptr;
-    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, d_out_f32, out_f32_nchw ? nullptr : d_out, out_f32_nchw ? (float*)d_out : nullptr, st);
+    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, d_out_f32, out_f32_nchw ? nullptr : d_out,
+                          out_f32_nchw ? (float*)d_out : nullptr, nullptr, st);
 }
 
 extern "C" size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ksize) {
@@ -163,6 +175,8 @@ extern "C" int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int 
     ConvEpi e;
     e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = d_residual;
     e.out_nchw = 0; e.out2_bf16 = nullptr;
-    return halo_launch_conv(d_xa, ca, d_xb, cb, stats, d_gamma, d_beta, groups, apply_swish, wp, cout, ksize, B, H, W, e, d_out_f32,
-                            d_out_b16, nullptr, st);
+    HaloNorm nm;
+    nm.stats = stats; nm.sums_a = nullptr; nm.sums_b = nullptr; nm.gamma = d_gamma; nm.beta = d_beta; nm.G = groups;
+    nm.swish = apply_swish;
+    return halo_launch_conv(d_xa, ca, d_xb, cb, nm, wp, cout, ksize, B, H, W, e, d_out_f32, d_out_b16, nullptr, nullptr, st);
 }

@@ -39,6 +39,29 @@ void set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining; everything it does before pdl_wait() (barrier / TMEM setup, constant weight fetches) overlaps
+// the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -78,6 +101,10 @@ int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float
 int launch_gn_stats(const float* a, int ca, const float* b, int cb, int B, int HW, int G, void* scratch, unsigned* counters,
                     cudaStream_t st);
 float2* gn_stats_ptr(void* scratch, int B, int G);
+int launch_gn_apply_sums(const float* a, int ca, const float* b, int cb, const double* sums_a, const double* sums_b,
+                         const float* gamma, const float* beta, void* out, int B, int HW, int G, int swish, int out_bf16,
+                         cudaStream_t st);
+int launch_ch_sums(const float* x, int C, int B, int HW, double* out /*[B][C][2], pre-zeroed*/, cudaStream_t st);
 int gn_counters(unsigned** out);     // per-device buffer, allocated on first use (never inside graph capture)
 
 int launch_attention(const void* qkv, void* out, int B, int N, int C, int bf16, cudaStream_t st);

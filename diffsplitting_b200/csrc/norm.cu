@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     __shared__ double s_sum[GN_THREADS * 4], s_sq[GN_THREADS * 4];
     __shared__ double g_sum[GN_MAX_GROUPS], g_sq[GN_MAX_GROUPS];
     __shared__ bool s_last;
+    pdl_wait();
+    pdl_trigger();
     if (t < G) { g_sum[t] = 0.0; g_sq[t] = 0.0; }
     __syncthreads();
     const size_t base = (size_t)bi * HW;
@@ -182,17 +184,36 @@ template <typename Tout, bool VEC>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
                                                                int cb, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, Tout* __restrict__ out, int HW,
-                                                               int G, int nchunk, int swish, const float2* __restrict__ stats) {
+                                                               int G, int nchunk, int swish, const float2* __restrict__ stats,
+                                                               const double* __restrict__ sums_a,
+                                                               const double* __restrict__ sums_b) {
     const int C = ca + cb;
     const int cpg = C / G;
     const int bi = blockIdx.y;
     const int t = threadIdx.x;
     constexpr bool kFast = sizeof(Tout) == 2;          // bf16 output: fast exp is below the output rounding
     __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+    pdl_wait();
+    pdl_trigger();
     if (t < G) {
-        const float2 st = stats[(size_t)bi * G + t];
-        s_mean[t] = st.x;
-        s_rstd[t] = st.y;
+        if (sums_a) {        // per-channel fp64 (sum, sumsq) emitted by the producers' epilogues
+            double sm = 0.0, sq = 0.0;
+            for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
+                const double* src = c < ca ? sums_a + ((size_t)bi * ca + c) * 2 : sums_b + ((size_t)bi * cb + (c - ca)) * 2;
+                sm += src[0];
+                sq += src[1];
+            }
+            const double n = (double)HW * cpg;
+            const double mean = sm / n;
+            double var = sq / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[t] = (float)mean;
+            s_rstd[t] = (float)(1.0 / sqrt(var + 1e-5));
+        } else {
+            const float2 st = stats[(size_t)bi * G + t];
+            s_mean[t] = st.x;
+            s_rstd[t] = st.y;
+        }
     }
     __syncthreads();
     const size_t base = (size_t)bi * HW;
@@ -267,9 +288,9 @@ int launch_gn_stats(const float* a, int ca, const float* b, int cb, int B, int H
     double* partial = reinterpret_cast<double*>(scratch);
     float2* stats = gn_stats_ptr(scratch, B, G);
     if (gn_vec_ok(a, ca, b, cb, nullptr, nullptr))
-        gn_stats_kernel<true><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+        launch_pdl(gn_stats_kernel<true>, dim3(nsplit, B), dim3(GN_THREADS), 0, st, a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
     else
-        gn_stats_kernel<false><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+        launch_pdl(gn_stats_kernel<false>, dim3(nsplit, B), dim3(GN_THREADS), 0, st, a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
     DS_CHECK_LAUNCH("gn_stats");
     return DS_OK;
 }
@@ -287,8 +308,8 @@ int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float
     const bool vec = (ca % 4 == 0) && (cb % 4 == 0) && (C / 4 <= GN_THREADS) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                      (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
-    if (vec) gn_stats_kernel<true><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
-    else gn_stats_kernel<false><<<dim3(nsplit, B), GN_THREADS, 0, st>>>(a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+    if (vec) launch_pdl(gn_stats_kernel<true>, dim3(nsplit, B), dim3(GN_THREADS), 0, st, a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
+    else launch_pdl(gn_stats_kernel<false>, dim3(nsplit, B), dim3(GN_THREADS), 0, st, a, ca, b, cb, HW, G, nsplit, partial, stats, counters);
     DS_CHECK_LAUNCH("gn_stats");
     const int64_t total = (int64_t)HW * C;
     int nchunk = (int)((total + 4095) / 4096);
@@ -297,13 +318,85 @@ int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float
     const dim3 grid(nchunk, B);
     typedef __nv_bfloat16 bf;
     if (out_bf16) {
-        if (vec) gn_apply_kernel<bf, true><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats);
-        else gn_apply_kernel<bf, false><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats);
+        if (vec) launch_pdl(gn_apply_kernel<bf, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats, nullptr, nullptr);
+        else launch_pdl(gn_apply_kernel<bf, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, stats, nullptr, nullptr);
     } else {
-        if (vec) gn_apply_kernel<float, true><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats);
-        else gn_apply_kernel<float, false><<<grid, GN_THREADS, 0, st>>>(a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats);
+        if (vec) launch_pdl(gn_apply_kernel<float, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats, nullptr, nullptr);
+        else launch_pdl(gn_apply_kernel<float, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, stats, nullptr, nullptr);
     }
     DS_CHECK_LAUNCH("gn_apply");
+    return DS_OK;
+}
+
+// ---- bf16 mode: statistics arrive as per-channel fp64 sums from the producers' epilogues; only the apply pass runs
+int launch_gn_apply_sums(const float* a, int ca, const float* b, int cb, const double* sums_a, const double* sums_b,
+                         const float* gamma, const float* beta, void* out, int B, int HW, int G, int swish, int out_bf16,
+                         cudaStream_t st) {
+    const int C = ca + cb;
+    DS_REQUIRE(G >= 1 && G <= GN_MAX_GROUPS && C % G == 0, "groupnorm: %d channels not divisible into %d groups", C, G);
+    DS_REQUIRE((int64_t)HW * C < (1ll << 31), "groupnorm: sample too large");
+    const bool vec = gn_vec_ok(a, ca, b, cb, gamma, beta);
+    const int64_t total = (int64_t)HW * C;
+    int nchunk = (int)((total + 4095) / 4096);
+    if (nchunk > 65535) nchunk = 65535;
+    if (nchunk < 1) nchunk = 1;
+    const dim3 grid(nchunk, B);
+    typedef __nv_bfloat16 bf;
+    if (out_bf16) {
+        if (vec) launch_pdl(gn_apply_kernel<bf, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
+        else launch_pdl(gn_apply_kernel<bf, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
+    } else {
+        if (vec) launch_pdl(gn_apply_kernel<float, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
+        else launch_pdl(gn_apply_kernel<float, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
+    }
+    DS_CHECK_LAUNCH("gn_apply");
+    return DS_OK;
+}
+
+// per-channel (sum, sumsq) of a tensor whose producer cannot emit them (the fp32 entry conv): out[b][c][2] += ...
+__global__ void __launch_bounds__(GN_THREADS) ch_sums_kernel(const float* __restrict__ x, int C, int HW, int nsplit,
+                                                              double* __restrict__ out) {
+    const int bi = blockIdx.y, sp = blockIdx.x, t = threadIdx.x;
+    const int p0 = (int)((int64_t)HW * sp / nsplit), p1 = (int)((int64_t)HW * (sp + 1) / nsplit);
+    __shared__ double s_sum[GN_THREADS], s_sq[GN_THREADS];
+    pdl_wait();
+    pdl_trigger();
+    const size_t base = (size_t)bi * HW;
+    for (int c0 = 0; c0 < C; c0 += GN_THREADS) {
+        const int cw = min(GN_THREADS, C - c0);
+        const int rows = GN_THREADS / cw;
+        const int r = t / cw, c = c0 + (t - r * cw);
+        double ds_ = 0.0, dq = 0.0;
+        if (r < rows) {
+            float s = 0.f, q = 0.f;
+            int run = 0;
+            for (int p = p0 + r; p < p1; p += rows) {
+                const float v = x[(base + p) * C + c];
+                s += v;
+                q = fmaf(v, v, q);
+                if (++run == 32) { ds_ += (double)s; dq += (double)q; s = 0.f; q = 0.f; run = 0; }
+            }
+            ds_ += (double)s;
+            dq += (double)q;
+        }
+        s_sum[t] = ds_;
+        s_sq[t] = dq;
+        __syncthreads();
+        if (t < cw) {
+            double s = 0.0, q = 0.0;
+            for (int rr = 0; rr < rows; ++rr) { s += s_sum[rr * cw + t]; q += s_sq[rr * cw + t]; }
+            double* dst = out + ((size_t)bi * C + c0 + t) * 2;
+            atomicAdd(dst, s);
+            atomicAdd(dst + 1, q);
+        }
+        __syncthreads();
+    }
+}
+
+int launch_ch_sums(const float* x, int C, int B, int HW, double* out, cudaStream_t st) {
+    const int nsplit = gn_nsplit(B, HW, C);
+    launch_pdl(ch_sums_kernel, dim3(nsplit, B), dim3(GN_THREADS), 0, st, x, C, HW, nsplit, out);
+    DS_CHECK_LAUNCH("ch_sums");
     return DS_OK;
 }
 

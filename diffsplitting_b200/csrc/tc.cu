@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t tfull_bar = bar_base + 16u * p.stages;
     const uint32_t tmem_slot = tfull_bar + 8u;
+    uint8_t* red = smem_raw + (tmem_slot + 16u - smem_u32(smem_raw));      // epilogue reduction buffer (TC_RED_BYTES)
 
     // tile coordinates
     int bid = blockIdx.x;
@@ -78,6 +79,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -127,12 +130,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         int oy = y, ox = x;
         if (p.up) { oy = 2 * y + (cls >> 1); ox = 2 * x + (cls & 1); }
         const int n_base = nt * p.BN;
+        float add[16];
+        if (valid) tc_epilogue_addend(p.epi, b, oy, ox, n_base, add);       // in flight while the MMAs run
         mbar_wait(tfull_bar, 0);
         tc_fence_after();
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) tc_epilogue_store(p.epi, v, b, oy, ox, n_base + c0);
+            float f[16];
+            if (valid) {
+                if (c0) tc_epilogue_addend(p.epi, b, oy, ox, n_base + c0, add);
+                tc_epilogue_write(p.epi, v, add, b, oy, ox, n_base + c0, f);
+            }
+            if (p.epi.sums_out) tc_epilogue_stats(p.epi, f, valid, b, n_base + c0, m, (int)threadIdx.x - 64, red);
         }
         tc_fence_before();
     }
@@ -373,7 +383,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     if (stages > U) stages = U;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + 16 * stages + 32 + 1024;
+    plan->smem_bytes = stages * stage_bytes + 16 * stages + 32 + 1024 + TC_RED_BYTES;
     plan->grid_x = p.tiles_x * p.tiles_y * tiles_b;
     plan->grid_y = p.n_tiles;
     plan->grid_z = p.nclasses;
@@ -382,7 +392,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
 }
 
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
-                   float* out_nchw, cudaStream_t st) {
+                   float* out_nchw, double* sums_out, cudaStream_t st) {
     TcParams p = *reinterpret_cast<const TcParams*>(plan->params);
     p.w = w_packed;
     p.epi.bias = epi.bias;
@@ -394,13 +404,14 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
     p.epi.out_f32 = out_f32;
     p.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16);
     p.epi.out_nchw = out_nchw;
+    p.epi.sums_out = sums_out;
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    conv_tc_kernel<<<dim3(plan->grid_x, plan->grid_y, plan->grid_z), TC_THREADS, plan->smem_bytes, st>>>(p);
-    DS_CHECK_LAUNCH("conv_tc");
+    DS_CHECK_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid_x, plan->grid_y, plan->grid_z), dim3(TC_THREADS),
+                             (size_t)plan->smem_bytes, st, p));
     return DS_OK;
 }
 

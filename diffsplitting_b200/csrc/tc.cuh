@@ -17,16 +17,25 @@ int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin,
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
                   int stride, int up);
 // epi.bias / temb / residual (fp32 NHWC) as in the fp32 kernel; any subset of the three outputs may be given
+// sums_out (optional): [B][cout][2] fp64 accumulators (zeroed by the caller) receiving per-channel sum / sum of squares
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
-                   float* out_nchw, cudaStream_t st);
+                   float* out_nchw, double* sums_out, cudaStream_t st);
 
 // ---- fused GroupNorm-apply + Swish -> conv, operands staged through registers (tc_halo.cu); sources fp32 NHWC
 bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W);
 size_t halo_packed_weight_bytes(int cout, int cin, int ks);
 int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);
-// stats: (mean, rstd) [B][G] over the concat input (null: no normalisation, swish ignored unless set)
-int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const float2* stats, const float* gamma,
-                     const float* beta, int G, int swish, const uint8_t* w_packed, int cout, int ks, int B, int H, int W,
-                     const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw, cudaStream_t st);
+// GroupNorm statistics of the concat input: either `stats` = (mean, rstd) [B][G], or per-channel fp64 (sum, sumsq)
+// accumulators of the two sources `sums_a` [B][ca][2] / `sums_b` [B][cb][2] (as emitted by the producers' epilogues);
+// all null: no normalisation.
+struct HaloNorm {
+    const float2* stats;
+    const double* sums_a; const double* sums_b;
+    const float* gamma; const float* beta;
+    int G, swish;
+};
+int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
+                     int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
+                     double* sums_out, cudaStream_t st);
 
 }  // namespace ds

@@ -20,6 +20,7 @@ namespace ds {
 constexpr int HALO_THREADS = 192;
 constexpr int HALO_SEG_PX = 136;           // 128 outputs + 2 halo pixels, padded to a multiple of 8
 constexpr int HALO_MAX_SAMPLES = 12;
+constexpr int HALO_MAX_GROUPS = 64;
 constexpr size_t HALO_SMEM_LIMIT = 200 * 1024;
 
 // n / d for 0 <= n < 2^31 with a precomputed multiplier (CUTLASS FastDivmod scheme): no integer division on device
@@ -42,7 +43,8 @@ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ?
 struct HaloParams {
     const float* src_a; const float* src_b;     // fp32 NHWC [B,H,W,ca|cb]
     int ca, cb;
-    const float2* stats;                        // (mean, rstd) [B][G] of the concat input, or null = identity
+    const float2* stats;                        // (mean, rstd) [B][G] of the concat input, or
+    const double* sums_a; const double* sums_b; // per-channel fp64 (sum, sumsq) [B][ca|cb][2]; all null = identity
     const float* gamma; const float* beta;
     int G, swish;
     const uint8_t* w;                           // bf16 [tap][kstep][plane(2)][Npad][8]
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     const int nsamp = b_last - b_first + 1;
     const uint32_t bar_off = (tab_off + (uint32_t)nsamp * p.C * 8u + 15u) & ~15u;
     const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
+    uint8_t* red = gbase + bar_off + 32u;                                          // epilogue reduction buffer
     const uint32_t tmem_cols = p.BN <= 32 ? 32u : (p.BN <= 64 ? 64u : 128u);
 
     if (tid == 0) {
@@ -106,75 +109,123 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             bulk_load(base + b_off + i * b_tile, p.w + ((size_t)i * p.Npad + (size_t)nt * p.BN) * 16, b_tile, bfull);
     }
 
-    // ---- per (sample in tile, channel) scale / shift of the fused GroupNorm
+    pdl_wait();          // everything above (barriers, TMEM, weight fetch) overlapped the previous kernel's tail
+    pdl_trigger();
+
+    // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [plane][pixel][16 B].
+    // The raw pixel loads of the first batch are issued BEFORE the scale/shift table is built, so the two global-memory
+    // round trips (statistics / affine parameters and pixels) overlap.
     float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
+    const int total = P * p.plane_px;
+    const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
+    constexpr int NB = 4;                                  // chunks in flight per thread
+    struct Chunk { float4 v0, v1; uint32_t dst; int tabi; };
+    auto issue = [&](int idx, Chunk& ch) {
+        ch.tabi = -1;
+        ch.dst = 0xFFFFFFFFu;
+        if (idx >= total) return;
+        const int kp = fdiv(idx, p.div_planepx);
+        const int px = idx - kp * p.plane_px;
+        int q;
+        if (p.contig) {
+            q = q_first + px;
+        } else {
+            const int seg = px / HALO_SEG_PX;
+            q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
+        }
+        ch.dst = base + a_off + kp * plane_bytes + px * 16;
+        if (q >= 0 && q < p.total_q) {
+            const int b = fdiv(q, p.div_hpwp);
+            const int rq = q - b * p.HpWp;
+            const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
+            if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
+                const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
+                const int c0 = kp * 8;
+                const float* src = c0 < p.ca ? p.src_a + pix * p.ca + c0 : p.src_b + pix * p.cb + (c0 - p.ca);
+                ch.v0 = __ldg(reinterpret_cast<const float4*>(src));
+                ch.v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                ch.tabi = (b - b_first) * p.C + c0;
+            }
+        }
+    };
+    auto finish = [&](const Chunk& ch) {
+        if (ch.dst == 0xFFFFFFFFu) return;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (ch.tabi >= 0) {
+            const float2* tb = tab + ch.tabi;
+            float x[8] = {ch.v0.x, ch.v0.y, ch.v0.z, ch.v0.w, ch.v1.x, ch.v1.y, ch.v1.z, ch.v1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 sc = tb[j];
+                float y = fmaf(x[j], sc.x, sc.y);
+                if (p.swish) {                      // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                    const float h = 0.5f * y;
+                    float th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                    y = fmaf(h, th, h);
+                }
+                x[j] = y;
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            val = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ch.dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+    };
+
+    Chunk cur[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) issue(tid + u * HALO_THREADS, cur[u]);
+
+    // ---- per (sample in tile, channel) scale / shift of the fused GroupNorm: a = rstd * gamma, sh = beta - mean * a
     {
-        const int cpg = p.stats ? p.C / p.G : 1;
+        const bool norm = p.stats || p.sums_a;
+        const int cpg = norm ? p.C / p.G : 1;
+        const double cnt = (double)p.H * p.W * cpg;
         for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
-            const int s = i / p.C, c = i - s * p.C;
+            const int s = i / p.C, c = i - s * p.C, b = b_first + s;
             float a = 1.f, sh = 0.f;
-            if (p.stats) {
-                const float2 st = p.stats[(size_t)(b_first + s) * p.G + c / cpg];
-                a = st.y * p.gamma[c];
-                sh = p.beta[c] - st.x * a;
+            if (norm) {
+                float mean, rstd;
+                if (p.sums_a) {
+                    // fold the producers' per-channel fp64 sums of this channel's group (it may straddle the two sources)
+                    const int g = c / cpg;
+                    double sm = 0.0, sq = 0.0;
+                    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+                        const double* src = cc < p.ca ? p.sums_a + ((size_t)b * p.ca + cc) * 2
+                                                      : p.sums_b + ((size_t)b * p.cb + (cc - p.ca)) * 2;
+                        sm += src[0];
+                        sq += src[1];
+                    }
+                    const double mu = sm / cnt;
+                    double var = sq / cnt - mu * mu;
+                    if (var < 0.0) var = 0.0;
+                    mean = (float)mu;
+                    rstd = (float)(1.0 / sqrt(var + 1e-5));
+                } else {
+                    const float2 st = p.stats[(size_t)b * p.G + c / cpg];
+                    mean = st.x;
+                    rstd = st.y;
+                }
+                a = rstd * p.gamma[c];
+                sh = p.beta[c] - mean * a;
             }
             tab[i] = make_float2(a, sh);
         }
     }
     __syncthreads();
 
-    // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [plane][pixel][16 B]
-    {
-        const int total = P * p.plane_px;
-        const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
-#pragma unroll 2
-        for (int idx = tid; idx < total; idx += HALO_THREADS) {
-            const int kp = fdiv(idx, p.div_planepx);
-            const int px = idx - kp * p.plane_px;
-            int q;
-            if (p.contig) {
-                q = q_first + px;
-            } else {
-                const int seg = px / HALO_SEG_PX;
-                q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
-            }
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (q >= 0 && q < p.total_q) {
-                const int b = fdiv(q, p.div_hpwp);
-                const int rq = q - b * p.HpWp;
-                const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
-                if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
-                    const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
-                    const int c0 = kp * 8;
-                    const float* src = c0 < p.ca ? p.src_a + pix * p.ca + c0 : p.src_b + pix * p.cb + (c0 - p.ca);
-                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                    const float2* tb = tab + (b - b_first) * p.C + c0;
-                    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 sc = tb[j];
-                        float y = fmaf(x[j], sc.x, sc.y);
-                        if (p.swish) {                      // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
-                            const float h = 0.5f * y;
-                            float th;
-                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                            y = fmaf(h, th, h);
-                        }
-                        x[j] = y;
-                    }
-                    uint32_t w[4];
+    for (int u = 0; u < NB; ++u) finish(cur[u]);
+    for (int i0 = tid + NB * HALO_THREADS; i0 < total; i0 += NB * HALO_THREADS) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    val = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-            const uint32_t dst = base + a_off + kp * plane_bytes + px * 16;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-        }
+        for (int u = 0; u < NB; ++u) issue(i0 + u * HALO_THREADS, cur[u]);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) finish(cur[u]);
     }
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -211,12 +262,19 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             oy = yy - 1;
             ox = xx - 1;
         }
+        float add[16];
+        if (valid) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN, add);      // in flight while the MMAs run
         mbar_wait(mma_done, 0);
         tc_fence_after();
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
-            if (valid) tc_epilogue_store(p.epi, v, b, oy, ox, nt * p.BN + c0);
+            float f[16];
+            if (valid) {
+                if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
+                tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
+            }
+            if (p.epi.sums_out) tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, red);
         }
         tc_fence_before();
     }
@@ -235,7 +293,8 @@ static int halo_plane_px(int ntaps, int W) {
 }
 
 static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp) {
-    return (size_t)(C / 8) * halo_plane_px(ntaps, W) * 16 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 + 64 + 128;
+    return (size_t)(C / 8) * halo_plane_px(ntaps, W) * 16 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
+           64 + TC_RED_BYTES + 128;
 }
 
 static int halo_samples_per_tile(int H, int W) {
@@ -295,14 +354,17 @@ int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int ci
     return DS_OK;
 }
 
-int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const float2* stats, const float* gamma,
-                     const float* beta, int G, int swish, const uint8_t* w_packed, int cout, int ks, int B, int H, int W,
-                     const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw, cudaStream_t st) {
+int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
+                     int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
+                     double* sums_out, cudaStream_t st) {
     DS_REQUIRE(halo_conv_supported(ca, cb, cout, ks, B, H, W), "halo conv: unsupported shape");
     HaloParams p;
     memset(&p, 0, sizeof(p));
     p.src_a = src_a; p.src_b = src_b; p.ca = ca; p.cb = cb;
-    p.stats = stats; p.gamma = gamma; p.beta = beta; p.G = G; p.swish = swish;
+    p.stats = norm.stats; p.sums_a = norm.sums_a; p.sums_b = norm.sums_b;
+    p.gamma = norm.gamma; p.beta = norm.beta; p.G = norm.G > 0 ? norm.G : 1; p.swish = norm.swish;
+    DS_REQUIRE(p.G <= HALO_MAX_GROUPS, "halo conv: %d groups > %d", p.G, HALO_MAX_GROUPS);
+    p.epi.sums_out = sums_out;
     p.w = w_packed;
     p.epi.bias = epi.bias; p.epi.temb = epi.temb; p.epi.temb_off = epi.temb_off; p.epi.temb_stride = epi.temb_stride;
     p.epi.temb_bcast = epi.temb_bcast; p.epi.residual = epi.residual;
@@ -328,8 +390,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
-    conv_halo_kernel<<<dim3((unsigned)m_tiles, p.n_tiles, 1), HALO_THREADS, smem, st>>>(p);
-    DS_CHECK_LAUNCH("conv_halo");
+    DS_CHECK_CUDA(launch_pdl(conv_halo_kernel, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(HALO_THREADS), smem, st, p));
     return DS_OK;
 }
 

@@ -99,38 +99,58 @@ struct TcEpi {
     float* out_f32;                   // fp32 NHWC or null   (consumers: GroupNorm statistics, residual adds)
     __nv_bfloat16* out_b16;           // bf16 NHWC or null   (consumers: TMA-fed convolutions, attention)
     float* out_nchw;                  // fp32 NCHW or null   (the network output)
+    double* sums_out;                 // [B][Cout][2] (sum, sum of squares) accumulators of the OUTPUT tensor or null:
+                                      // the GroupNorm statistics of the consumer, produced here instead of by a pass over HBM
     int Cout, Ho, Wo;
 };
 
+constexpr int TC_RED_LD = 17;                                   // padded row of the epilogue reduction buffer
+constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD * 4 + 128 * 4;   // [128 rows][17] fp32 + [128] sample ids
+
 // one thread = one output pixel (b, oy, ox), 16 consecutive output channels starting at n0, accumulators in v[16]
-__device__ __forceinline__ void tc_epilogue_store(const TcEpi& p, const uint32_t (&v)[16], int b, int oy, int ox, int n0) {
-    float f[16];
+// Everything the epilogue ADDS to the accumulators of one (pixel, 16-channel chunk): bias + conditioning vector + fp32
+// residual.  Split from the store so that these global loads are issued BEFORE the thread waits for the MMAs.
+__device__ __forceinline__ void tc_epilogue_addend(const TcEpi& p, int b, int oy, int ox, int n0, float (&add)[16]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-    const size_t pix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+    for (int j = 0; j < 16; ++j) add[j] = 0.f;
     if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += p.bias[n0 + j];
+        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] = __ldg(p.bias + n0 + j);
     }
     if (p.temb) {
         const float* te = p.temb + (size_t)(p.temb_bcast ? 0 : b) * p.temb_stride + p.temb_off + n0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) f[j] += te[j];
+        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += __ldg(te + j);
     }
-    if (p.out_nchw) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (n0 + j < p.Cout) p.out_nchw[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
-    } else if (n0 + 16 <= p.Cout) {
-        const size_t off = pix * p.Cout + n0;
-        if (p.residual) {
+    if (p.residual) {
+        const size_t off = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + n0;
+        if (n0 + 16 <= p.Cout) {
             const float4* r = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 rv = __ldg(r + j);
-                f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
+                add[4 * j] += rv.x; add[4 * j + 1] += rv.y; add[4 * j + 2] += rv.z; add[4 * j + 3] += rv.w;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += __ldg(p.residual + off + j);
         }
+    }
+}
+
+// f[] = accumulators + addend, stored as fp32 NHWC / bf16 NHWC / fp32 NCHW
+__device__ __forceinline__ void tc_epilogue_write(const TcEpi& p, const uint32_t (&v)[16], const float (&add)[16], int b, int oy,
+                                                  int ox, int n0, float (&f)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + add[j];
+    if (p.out_nchw) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.Cout) p.out_nchw[(((size_t)b * p.Cout + n0 + j) * p.Ho + oy) * p.Wo + ox] = f[j];
+        return;
+    }
+    const size_t off = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + n0;
+    if (n0 + 16 <= p.Cout) {
         if (p.out_f32) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
@@ -151,14 +171,53 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& p, const uint32_t
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             if (n0 + j < p.Cout) {
-                const size_t off = pix * p.Cout + n0 + j;
-                float val = f[j];
-                if (p.residual) val += p.residual[off];
-                if (p.out_f32) p.out_f32[off] = val;
-                if (p.out_b16) p.out_b16[off] = __float2bfloat16_rn(val);
+                if (p.out_f32) p.out_f32[off + j] = f[j];
+                if (p.out_b16) p.out_b16[off + j] = __float2bfloat16_rn(f[j]);
             }
         }
     }
+}
+
+// Per-channel (sum, sum of squares) of one 128-row x 16-channel epilogue chunk, per sample, accumulated into sums_out.
+// Called by the 128 epilogue threads (te = 0..127, row m of the tile); `red` = TC_RED_BYTES of shared memory.
+// Transposed pass: thread (channel c = te & 15, row group te >> 4) walks 16 consecutive rows in fp32 and flushes one
+// fp64 atomic pair per sample it meets (rows are ordered by sample), so the summation tree is fixed up to the order of
+// the fp64 atomics.
+__device__ __forceinline__ void tc_epilogue_stats(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int m, int te,
+                                                  uint8_t* red_raw) {
+    float* red = reinterpret_cast<float*>(red_raw);
+    int* sb = reinterpret_cast<int*>(red_raw + 128 * TC_RED_LD * 4);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) red[m * TC_RED_LD + j] = valid ? f[j] : 0.f;
+    sb[m] = valid ? b : -1;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    {
+        const int c = te & 15, r0 = (te >> 4) * 16;
+        const bool cok = n0 + c < p.Cout;
+        int cur = -1;
+        float s = 0.f, q = 0.f;
+        for (int r = r0; r < r0 + 16; ++r) {
+            const int bb = sb[r];
+            if (bb < 0) continue;
+            if (bb != cur) {
+                if (cur >= 0 && cok) {
+                    double* dst = p.sums_out + ((size_t)cur * p.Cout + n0 + c) * 2;
+                    atomicAdd(dst, (double)s);
+                    atomicAdd(dst + 1, (double)q);
+                }
+                cur = bb; s = 0.f; q = 0.f;
+            }
+            const float v = red[r * TC_RED_LD + c];
+            s += v;
+            q = fmaf(v, v, q);
+        }
+        if (cur >= 0 && cok) {
+            double* dst = p.sums_out + ((size_t)cur * p.Cout + n0 + c) * 2;
+            atomicAdd(dst, (double)s);
+            atomicAdd(dst + 1, (double)q);
+        }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 }  // namespace ds

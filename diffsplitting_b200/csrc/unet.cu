@@ -57,7 +57,7 @@ struct Layer {
 };
 
 // ------------------------------------------------------------------------------------------ plan
-enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN, OP_GN_STATS };
+enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN, OP_GN_STATS, OP_CH_SUMS };
 constexpr int64_t EXT_XA = -1, EXT_XB = -2, EXT_OUT = -3, NONE = -100;
 
 struct Op {
@@ -79,6 +79,9 @@ struct Op {
     int halo = 0;
     const GNW* fgn = nullptr;
     int fswish = 0;
+    // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
+    int64_t sums_out = NONE;             // slot the producer's epilogue accumulates into
+    int64_t sums_a = NONE, sums_b = NONE;   // slots of the (two) sources a fused / apply-only GroupNorm reads
     // attn
     int N = 0, C = 0;
 };
@@ -95,6 +98,7 @@ struct Plan {
     const void* tc_ws = nullptr;         // workspace base the descriptors were encoded for
     size_t bytes = 0;
     int64_t temb_buf = NONE, gn_scratch = NONE;
+    size_t stats_base = 0, stats_bytes = 0;   // per-channel fp64 statistics slots, zeroed at the start of every forward
     std::map<std::string, Tap> taps;
     int launches = 0;
 };
@@ -147,6 +151,7 @@ class Arena {   // first-fit offset allocator used only while planning
 
 struct Act {
     int64_t f32 = NONE, b16 = NONE;      // workspace offsets of the fp32 / bf16 copies
+    int64_t sums = NONE;                 // offset of the tensor's per-channel statistics slot (bf16 mode)
     int C = 0, H = 0, W = 0;
     int* rc = nullptr;                   // shared refcount
 };
@@ -368,14 +373,19 @@ struct Planner {
     Arena arena;
     int B;
     bool tc;          // bf16 mode: tensor-core convs (bf16 operands), fp32 residual stream
+    size_t stats_top = 0;
     Planner(ds_unet* n_, Plan* p_, bool reuse) : n(n_), p(p_), arena(reuse) {}
 
     // what a tensor is stored as.  fp32 mode: always fp32.  bf16 mode: block-level tensors keep both copies (GroupNorm
     // statistics / residual adds read fp32, TMA-fed convs read bf16), conv operands are bf16 only, hidden = fp32 only.
-    Act make(int C, int H, int W, int fmt) {
+    Act make(int C, int H, int W, int fmt, bool want_sums = true) {
         Act a;
         a.C = C; a.H = H; a.W = W;
         if (!tc) fmt = F32;
+        if (tc && (fmt & F32) && want_sums) {       // a GroupNorm will read this tensor: its producer emits the statistics
+            a.sums = (int64_t)stats_top;
+            stats_top += align_up((size_t)B * C * 2 * sizeof(double), 256);
+        }
         if (fmt & F32) a.f32 = arena.alloc((size_t)B * H * W * C * 4);
         if (fmt & B16) a.b16 = arena.alloc((size_t)B * H * W * C * 2);
         a.rc = new int(1);
@@ -398,6 +408,8 @@ struct Planner {
         if (b) { o.src_b = b->f32; o.cb = b->C; }
         o.gw = &g; o.swish = swish; o.HW = a.H * a.W;
         o.dst = out.f32; o.dst_b16 = out.b16;
+        o.sums_a = a.sums;
+        if (b) o.sums_b = b->sums;
         p->ops.push_back(o);
     }
     void conv(const Act& a, const Act* b, const ConvW& w, int stride, int up, int temb_off, const Act* residual, const Act& out) {
@@ -408,6 +420,7 @@ struct Planner {
         o.Ho = out.H; o.Wo = out.W;
         if (residual) o.residual = residual->f32;
         o.dst = out.f32; o.dst_b16 = out.b16;
+        o.sums_out = out.sums;
         p->ops.push_back(o);
     }
 
@@ -417,12 +430,10 @@ struct Planner {
                  const Act& out) {
         const int cb = b ? b->C : 0;
         if (tc && n->specs[w.w].halo && halo_conv_supported(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
-            Op s; s.kind = OP_GN_STATS;
-            s.src_a = a.f32; s.ca = a.C;
-            if (b) { s.src_b = b->f32; s.cb = cb; }
-            s.gw = &g; s.HW = a.H * a.W;
-            p->ops.push_back(s);
             Op o; o.kind = OP_CONV;
+            o.sums_a = a.sums;
+            if (b) o.sums_b = b->sums;
+            o.sums_out = out.sums;
             o.halo = 1; o.fgn = &g; o.fswish = swish;
             o.src_a = a.f32; o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
             if (b) { o.src_b = b->f32; o.cb = cb; }
@@ -446,7 +457,7 @@ struct Planner {
         Act resid = x;
         Act rbuf;
         if (r.has_res) {
-            rbuf = make(r.cout, H, W, F32);
+            rbuf = make(r.cout, H, W, F32, false);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
             resid = rbuf;
         }
@@ -498,6 +509,11 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
                 op.src_a = EXT_XA; op.src_b = EXT_XB; op.src_nchw = 1; op.Hs = h; op.Ws = w;
                 op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.f32; op.dst_b16 = o.b16;
                 p->ops.push_back(op);
+                if (P.tc) {       // the CUDA-core entry conv does not emit statistics: one small pass over its output
+                    Op cs; cs.kind = OP_CH_SUMS;
+                    cs.src_a = o.f32; cs.ca = o.C; cs.HW = h * w; cs.sums_out = o.sums;
+                    p->ops.push_back(cs);
+                }
                 x = o;
             } else if (L.kind == L_RES) {
                 Act o = P.resblock(L, x, nullptr);
@@ -544,9 +560,12 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
             if (p->ops[i].kind == OP_CONV) p->ops[i].out_nchw = 1;
     }
     P.release(x);
-    p->bytes = P.arena.top();
+    p->stats_base = align_up(P.arena.top(), 256);
+    p->stats_bytes = P.stats_top;
+    p->bytes = p->stats_base + p->stats_bytes;
     int launches = d.with_time_emb ? 1 : 0;
-    for (auto& o : p->ops) launches += (o.kind == OP_GN) ? 2 : 1;      // GroupNorm = statistics + apply
+    for (auto& o : p->ops) launches += (o.kind == OP_GN && !P.tc) ? 2 : 1;      // fp32 GroupNorm = statistics + apply
+    if (P.tc && p->stats_bytes) ++launches;                                      // the statistics-arena memset
     p->launches = launches;
     *out = p;
     return DS_OK;
@@ -814,6 +833,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         }
         p->tc_ws = d_ws;
     }
+    auto sums = [&](int64_t off) -> double* {
+        return off == NONE ? nullptr : reinterpret_cast<double*>(base + p->stats_base + off);
+    };
+    if (tc && p->stats_bytes) DS_CHECK_CUDA(cudaMemsetAsync(base + p->stats_base, 0, p->stats_bytes, st));
     size_t op_index = 0;
     for (const Op& o : p->ops) {
         bool used_tc = false;
@@ -824,9 +847,15 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         if (prof && rep_i == 1) cudaEventRecord(prof->e0, st);
         switch (o.kind) {
             case OP_GN:
-                rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b),
-                                      tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.HW, n->d.norm_groups, o.swish, gn_scratch,
-                                      counters, tc ? 1 : 0, st);
+                if (tc)
+                    rc = launch_gn_apply_sums(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, sums(o.sums_a), sums(o.sums_b), n->wp(o.gw->w),
+                                              n->wp(o.gw->b), ptr(o.dst_b16), B, o.HW, n->d.norm_groups, o.swish, 1, st);
+                else
+                    rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
+                                          n->d.norm_groups, o.swish, gn_scratch, counters, 0, st);
+                break;
+            case OP_CH_SUMS:
+                rc = launch_ch_sums(ptr(o.src_a), o.ca, B, o.HW, sums(o.sums_out), st);
                 break;
             case OP_GN_STATS:
                 rc = launch_gn_stats(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, B, o.HW, n->d.norm_groups, gn_scratch, counters, st);
@@ -847,14 +876,16 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.out2_bf16 = ptr(o.dst_b16);
                 if (o.halo) {
                     used_tc = true;
-                    rc = halo_launch_conv(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, gn_stats_ptr(gn_scratch, B, n->d.norm_groups),
-                                          n->wp(o.fgn->w), n->wp(o.fgn->b), n->d.norm_groups, o.fswish,
-                                          n->d_arena_bf16 + n->specs[o.cw->w].off_halo, o.cw->cout, o.cw->ks, B, o.Hs, o.Ws, e,
-                                          o.out_nchw ? nullptr : ptr(o.dst), ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, st);
+                    HaloNorm nm;
+                    nm.stats = nullptr; nm.sums_a = sums(o.sums_a); nm.sums_b = sums(o.sums_b);
+                    nm.gamma = n->wp(o.fgn->w); nm.beta = n->wp(o.fgn->b); nm.G = n->d.norm_groups; nm.swish = o.fswish;
+                    rc = halo_launch_conv(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, nm, n->d_arena_bf16 + n->specs[o.cw->w].off_halo,
+                                          o.cw->cout, o.cw->ks, B, o.Hs, o.Ws, e, o.out_nchw ? nullptr : ptr(o.dst), ptr(o.dst_b16),
+                                          o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st);
                 } else if (tc && !o.src_nchw) {
                     used_tc = true;
                     rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, o.out_nchw ? nullptr : ptr(o.dst),
-                                        ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, st);
+                                        ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st);
                 } else {
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
                                          ptr(o.dst), st);
@@ -884,7 +915,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 r.flops = 2.0 * B * o.Ho * o.Wo * (double)o.cw->ks * o.cw->ks * cin * o.cw->cout;
                 r.bytes = 4.0 * B * ((double)o.Hs * o.Ws * cin + (double)o.Ho * o.Wo * o.cw->cout *
                                      (o.residual != NONE ? 2.0 : 1.0)) + 4.0 * o.cw->ks * o.cw->ks * cin * o.cw->cout;
-            } else if (o.kind == OP_GN_STATS) {
+            } else if (o.kind == OP_GN_STATS || o.kind == OP_CH_SUMS) {
                 r.kind = 5;
                 r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;
                 r.bytes = 4.0 * B * (double)o.HW * (o.ca + o.cb);        // one read
