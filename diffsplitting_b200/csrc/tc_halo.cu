@@ -12,6 +12,11 @@
 //   3. runs the common epilogue (bias, conditioning vector, fp32 residual, fp32 / bf16 stores).
 // One tile = 128 consecutive flat padded positions (border positions are computed and discarded: 6 % waste at 64^2).
 // The channel concat of the up path (unet.py:255) is two source pointers; weights arrive with cp.async.bulk.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <vector>
+
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -41,13 +46,16 @@ static FastDiv make_fastdiv(uint32_t d) {
 __device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
 
 struct HaloParams {
+    CUtensorMap wmap;                           // packed weights as a 3-D tensor (128 bf16 = one 16-row x 8-channel plane
+                                                // of a block, 16-channel block, (tap, kstep, plane)): one TMA load lands the
+                                                // CTA's BN output channels as [tap][kstep][plane][BN rows][16 B]
     const float* src_a; const float* src_b;     // fp32 NHWC [B,H,W,ca|cb]
     int ca, cb;
     const float2* stats;                        // (mean, rstd) [B][G] of the concat input, or
     const double* sums_a; const double* sums_b; // per-channel fp64 (sum, sumsq) [B][ca|cb][2]; all null = identity
     const float* gamma; const float* beta;
     int G, swish;
-    const uint8_t* w;                           // bf16 [tap][kstep][plane(2)][Npad][8]
+    const uint8_t* w;                           // bf16 [16-channel block][tap][kstep][plane(2)][16 rows][8]
     TcEpi epi;
     int B, H, W, Wp, HpWp, total_q;
     int C, ksteps, ntaps, BN, n_tiles, Npad;
@@ -55,7 +63,9 @@ struct HaloParams {
     // padded index space (W + 2 <= 139): every pixel is staged exactly once; else three separate 136-pixel segments
     int contig, plane_px, seg_stride_px;
     FastDiv div_hpwp, div_wp, div_planepx;
+    long long* dbg;                             // optional per-CTA phase timestamps (clock64), 8 per CTA
 };
+#define HALO_STAMP(i) do { if (p.dbg && tid == (i >= 5 ? 64 : 0)) p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
 // no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
 // LBO between the two 8-element K halves of one K=16 step
@@ -72,8 +82,9 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     const int P = p.C >> 3;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const uint32_t a_off = 0, b_off = P * plane_bytes;
-    const uint32_t b_tile = (uint32_t)p.BN * 16u;                       // one (tap, kstep, plane) block
-    const uint32_t b_bytes = (uint32_t)p.ntaps * p.ksteps * 2u * b_tile;
+    // weights of one 16-output-channel block: [tap][kstep][plane(2)][16 rows][16 B]; a CTA owns BN/16 consecutive blocks
+    const uint32_t blk_bytes = (uint32_t)p.ntaps * p.ksteps * 512u;
+    const uint32_t b_bytes = (uint32_t)(p.BN >> 4) * blk_bytes;
     const uint32_t tab_off = b_off + b_bytes;
     const int q0 = blockIdx.x * 128;
     const int nt = blockIdx.y;
@@ -86,12 +97,23 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     const uint32_t bar_off = (tab_off + (uint32_t)nsamp * p.C * 8u + 15u) & ~15u;
     const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
     uint8_t* red = gbase + bar_off + 32u;                                          // epilogue reduction buffer
-    const uint32_t tmem_cols = p.BN <= 32 ? 32u : (p.BN <= 64 ? 64u : 128u);
+    // NA independent accumulators: back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency
+    // (~150 cycles each, measured); rotating over NA column ranges lets them pipeline, the epilogue adds them up
+    const int NA = 1;       // (rotating over several accumulators was measured slower: the MMAs are operand-fetch bound)
+    const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
 
+    HALO_STAMP(0);
     if (tid == 0) {
         mbar_init(bfull, 1);
         mbar_init(mma_done, 1);
         fence_barrier_init();
+        // ---- weights: ONE bulk copy (constant data: may run before the predecessor kernel has finished)
+        mbar_expect_tx(bfull, b_bytes);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                base + b_off),
+            "l"(reinterpret_cast<uint64_t>(&p.wmap)), "r"(bfull), "r"(0), "r"(nt * (p.BN >> 4)), "r"(0)
+            : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
@@ -100,32 +122,19 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    // ---- weights: ntaps * ksteps * 2 blocks of BN x 16 B, fetched asynchronously while the operands are staged
-    if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(bfull, b_bytes);
-        __syncwarp();
-        const int ncopy = p.ntaps * p.ksteps * 2;
-        for (int i = lane; i < ncopy; i += 32)
-            bulk_load(base + b_off + i * b_tile, p.w + ((size_t)i * p.Npad + (size_t)nt * p.BN) * 16, b_tile, bfull);
-    }
-
+    HALO_STAMP(1);
     pdl_wait();          // everything above (barriers, TMEM, weight fetch) overlapped the previous kernel's tail
     pdl_trigger();
+    HALO_STAMP(2);
 
-    // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [plane][pixel][16 B].
-    // The raw pixel loads of the first batch are issued BEFORE the scale/shift table is built, so the two global-memory
-    // round trips (statistics / affine parameters and pixels) overlap.
+    // ---- operand staging: raw fp32 -> normalise -> Swish -> bf16 -> [8-channel plane][pixel][16 B].
+    // One thread = one pixel of the staged run (index decode once per pixel), looping over the channel planes with two
+    // planes (4 x 16-byte loads) in flight.  The first loads are issued BEFORE the scale/shift table is built, so the two
+    // global-memory round trips (statistics / affine parameters and pixels) overlap.
     float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
-    const int total = P * p.plane_px;
     const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
-    constexpr int NB = 4;                                  // chunks in flight per thread
-    struct Chunk { float4 v0, v1; uint32_t dst; int tabi; };
-    auto issue = [&](int idx, Chunk& ch) {
-        ch.tabi = -1;
-        ch.dst = 0xFFFFFFFFu;
-        if (idx >= total) return;
-        const int kp = fdiv(idx, p.div_planepx);
-        const int px = idx - kp * p.plane_px;
+    struct Pix { const float* a; const float* b; int tabi; uint32_t dst; };   // a == nullptr: zero padding
+    auto decode = [&](int px, Pix& px_) {
         int q;
         if (p.contig) {
             q = q_first + px;
@@ -133,38 +142,48 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             const int seg = px / HALO_SEG_PX;
             q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
         }
-        ch.dst = base + a_off + kp * plane_bytes + px * 16;
+        px_.a = nullptr;
+        px_.b = nullptr;
+        px_.tabi = 0;
+        px_.dst = base + a_off + px * 16;
         if (q >= 0 && q < p.total_q) {
             const int b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
             const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
             if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
                 const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
-                const int c0 = kp * 8;
-                const float* src = c0 < p.ca ? p.src_a + pix * p.ca + c0 : p.src_b + pix * p.cb + (c0 - p.ca);
-                ch.v0 = __ldg(reinterpret_cast<const float4*>(src));
-                ch.v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                ch.tabi = (b - b_first) * p.C + c0;
+                px_.a = p.src_a + pix * p.ca;
+                px_.b = p.src_b ? p.src_b + pix * p.cb : nullptr;
+                px_.tabi = (b - b_first) * p.C;
             }
         }
     };
-    auto finish = [&](const Chunk& ch) {
-        if (ch.dst == 0xFFFFFFFFu) return;
+    auto load_plane = [&](const Pix& px_, int kp, float4& v0, float4& v1) {
+        if (!px_.a) return;
+        const int c0 = kp * 8;
+        const float* src = c0 < p.ca ? px_.a + c0 : px_.b + (c0 - p.ca);
+        v0 = __ldg(reinterpret_cast<const float4*>(src));
+        v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    };
+    auto store_plane = [&](const Pix& px_, int kp, const float4& v0, const float4& v1) {
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (ch.tabi >= 0) {
-            const float2* tb = tab + ch.tabi;
-            float x[8] = {ch.v0.x, ch.v0.y, ch.v0.z, ch.v0.w, ch.v1.x, ch.v1.y, ch.v1.z, ch.v1.w};
+        if (px_.a) {
+            const float4* tb = reinterpret_cast<const float4*>(tab + px_.tabi + kp * 8);     // (a, sh) pairs of 2 channels
+            float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float2 sc = tb[j];
-                float y = fmaf(x[j], sc.x, sc.y);
-                if (p.swish) {                      // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
-                    const float h = 0.5f * y;
+            for (int j = 0; j < 4; ++j) {
+                const float4 sc = tb[j];
+                x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
+                x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
+            }
+            if (p.swish) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {           // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                    const float h = 0.5f * x[j];
                     float th;
                     asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                    y = fmaf(h, th, h);
+                    x[j] = fmaf(h, th, h);
                 }
-                x[j] = y;
             }
             uint32_t w[4];
 #pragma unroll
@@ -174,18 +193,37 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             }
             val = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ch.dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+        const uint32_t dst = px_.dst + kp * plane_bytes;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
     };
 
-    Chunk cur[NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u) issue(tid + u * HALO_THREADS, cur[u]);
+    // work item = (pixel, pair of channel planes): decode once, four 16-byte loads; two items in flight per thread
+    const int npairs = P >> 1;
+    const int items = npairs * p.plane_px;
+    struct Item { Pix px; int kp; float4 v[4]; bool on; };
+    auto issue = [&](int idx, Item& it) {
+        it.on = idx < items;
+        if (!it.on) return;
+        const int pp = fdiv(idx, p.div_planepx);
+        decode(idx - pp * p.plane_px, it.px);
+        it.kp = 2 * pp;
+        load_plane(it.px, it.kp, it.v[0], it.v[1]);
+        load_plane(it.px, it.kp + 1, it.v[2], it.v[3]);
+    };
+    auto finish = [&](const Item& it) {
+        if (!it.on) return;
+        store_plane(it.px, it.kp, it.v[0], it.v[1]);
+        store_plane(it.px, it.kp + 1, it.v[2], it.v[3]);
+    };
+    Item it0, it1;
+    issue(tid, it0);
+    issue(tid + HALO_THREADS, it1);
 
     // ---- per (sample in tile, channel) scale / shift of the fused GroupNorm: a = rstd * gamma, sh = beta - mean * a
     {
         const bool norm = p.stats || p.sums_a;
         const int cpg = norm ? p.C / p.G : 1;
-        const double cnt = (double)p.H * p.W * cpg;
+        const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
         for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
             const int s = i / p.C, c = i - s * p.C, b = b_first + s;
             float a = 1.f, sh = 0.f;
@@ -201,11 +239,11 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
                         sm += src[0];
                         sq += src[1];
                     }
-                    const double mu = sm / cnt;
-                    double var = sq / cnt - mu * mu;
+                    const double mu = sm * inv_cnt;
+                    double var = sq * inv_cnt - mu * mu;
                     if (var < 0.0) var = 0.0;
                     mean = (float)mu;
-                    rstd = (float)(1.0 / sqrt(var + 1e-5));
+                    rstd = rsqrtf((float)var + 1e-5f);
                 } else {
                     const float2 st = p.stats[(size_t)b * p.G + c / cpg];
                     mean = st.x;
@@ -218,31 +256,42 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         }
     }
     __syncthreads();
+    HALO_STAMP(3);
 
-#pragma unroll
-    for (int u = 0; u < NB; ++u) finish(cur[u]);
-    for (int i0 = tid + NB * HALO_THREADS; i0 < total; i0 += NB * HALO_THREADS) {
-#pragma unroll
-        for (int u = 0; u < NB; ++u) issue(i0 + u * HALO_THREADS, cur[u]);
-#pragma unroll
-        for (int u = 0; u < NB; ++u) finish(cur[u]);
+    finish(it0);
+    finish(it1);
+    for (int i0 = tid + 2 * HALO_THREADS; i0 < items; i0 += 2 * HALO_THREADS) {
+        issue(i0, it0);
+        issue(i0 + HALO_THREADS, it1);
+        finish(it0);
+        finish(it1);
     }
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
+    HALO_STAMP(4);
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_wait(bfull, 0);
             tc_fence_after();
+            // Descriptors differ only in the 14-bit start-address field: 32-bit adds.  B image of (tap, kstep): two planes of
+            // BN rows x 16 B (LBO = BN * 16), 8-row groups 128 B apart.
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+            const uint32_t a_lo0 = (((base + a_off) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
+            const uint32_t b_lo0 = (((base + b_off) & 0x3FFFFu) >> 4) | ((uint32_t)p.BN << 16);      // LBO = BN * 16 B
+            const uint32_t a_kstep = (2u * plane_bytes) >> 4;
+            const uint32_t b_kstep = (uint32_t)p.BN * 2u;                                              // 2 planes of BN * 16 B
+            uint32_t b_lo = b_lo0;
             for (int tap = 0; tap < p.ntaps; ++tap) {
                 const int r = p.ntaps == 9 ? tap / 3 : 0;
-                const int s = p.ntaps == 9 ? tap % 3 : 1;
+                const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
+                uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
                 for (int kk = 0; kk < p.ksteps; ++kk) {
-                    const uint32_t a_addr = base + a_off + (2 * kk) * plane_bytes + (uint32_t)(r * p.seg_stride_px + s) * 16u;
-                    const uint32_t b_addr = base + b_off + (uint32_t)((tap * p.ksteps + kk) * 2) * b_tile;
-                    umma_bf16(tmem_base, make_desc_nosw(a_addr, plane_bytes, 128u), make_desc_nosw(b_addr, b_tile, 128u),
-                              idesc, (tap | kk) ? 1u : 0u);
+                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
+                              (tap | kk) ? 1u : 0u);
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
                 }
             }
             umma_commit(mma_done);
@@ -266,9 +315,17 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         if (valid) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN, add);      // in flight while the MMAs run
         mbar_wait(mma_done, 0);
         tc_fence_after();
+        HALO_STAMP(5);
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+            const int nsteps = p.ntaps * p.ksteps;
+            for (int sl = 1; sl < NA && sl < nsteps; ++sl) {      // fold the other accumulators (slots never written stay out)
+                uint32_t v2[16];
+                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sl * p.BN + c0), v2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+            }
             float f[16];
             if (valid) {
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
@@ -276,6 +333,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             }
             if (p.epi.sums_out) tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, red);
         }
+        HALO_STAMP(6);
         tc_fence_before();
     }
     __syncthreads();
@@ -283,7 +341,11 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+    HALO_STAMP(7);
 }
+
+static long long* g_halo_dbg = nullptr;
+static size_t g_halo_dbg_ctas = 0;
 
 // ------------------------------------------------------------------------------------------ host side
 static int halo_plane_px(int ntaps, int W) {
@@ -334,10 +396,11 @@ __global__ void pack_halo_weight_kernel(const float* __restrict__ w, __nv_bfloat
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int j = (int)(r % 8); r /= 8;
-        const int n = (int)(r % npad); r /= npad;
+        const int row = (int)(r % 16); r /= 16;
         const int plane = (int)(r % 2); r /= 2;
         const int kk = (int)(r % (cin / 16)); r /= (cin / 16);
-        const int tap = (int)r;
+        const int tap = (int)(r % ntaps); r /= ntaps;
+        const int n = (int)r * 16 + row;
         const int c = kk * 16 + plane * 8 + j;
         const float v = n < cout ? w[((size_t)n * cin + c) * ntaps + tap] : 0.f;
         out[i] = __float2bfloat16_rn(v);
@@ -384,7 +447,40 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
     p.div_wp = make_fastdiv((uint32_t)p.Wp);
     p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
+    {
+        // 3-D view of the packed weights [block][tap*kstep*plane][16 rows x 8 ch = 128 bf16]
+        static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+        if (!enc) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            DS_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            DS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+            enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        }
+        const cuuint64_t tkp = (cuuint64_t)p.ntaps * p.ksteps * 2;
+        cuuint64_t dims[3] = {128, (cuuint64_t)(p.Npad / 16), tkp};
+        cuuint64_t strides[2] = {tkp * 256, 256};                     // bytes: next 16-channel block, next plane image
+        cuuint32_t box[3] = {128, (cuuint32_t)(p.BN / 16), (cuuint32_t)tkp};
+        cuuint32_t es[3] = {1, 1, 1};
+        DS_REQUIRE(tkp <= 256, "halo conv: %d taps x %d k-steps exceed one TMA box", p.ntaps, p.ksteps);
+        CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint8_t*>(w_packed), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("halo conv: cuTensorMapEncodeTiled for the weights failed (%d)", (int)r);
+            return DS_ERR_CUDA;
+        }
+    }
     const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp);
+    if (getenv("DIFFSPLIT_B200_HALO_DBG")) {
+        const size_t ctas = (size_t)m_tiles * p.n_tiles;
+        if (!g_halo_dbg || g_halo_dbg_ctas < ctas) {
+            if (g_halo_dbg) cudaFree(g_halo_dbg);
+            DS_CHECK_CUDA(cudaMalloc(&g_halo_dbg, ctas * 8 * sizeof(long long)));
+            g_halo_dbg_ctas = ctas;
+        }
+        p.dbg = g_halo_dbg;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
@@ -395,3 +491,18 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
 }
 
 }  // namespace ds
+
+// debugging aid: average per-phase cycle counts of the last conv_halo launch (DIFFSPLIT_B200_HALO_DBG=1)
+extern "C" int ds_debug_halo_phases(double* out7, int* n_ctas) {
+    using namespace ds;
+    DS_REQUIRE(g_halo_dbg && out7 && n_ctas, "halo debug buffer not active");
+    std::vector<long long> h(g_halo_dbg_ctas * 8);
+    DS_CHECK_CUDA(cudaDeviceSynchronize());
+    DS_CHECK_CUDA(cudaMemcpy(h.data(), g_halo_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 7; ++i) out7[i] = 0;
+    for (size_t c = 0; c < g_halo_dbg_ctas; ++c)
+        for (int i = 0; i < 7; ++i) out7[i] += (double)(h[c * 8 + i + 1] - h[c * 8 + i]);
+    for (int i = 0; i < 7; ++i) out7[i] /= (double)g_halo_dbg_ctas;
+    *n_ctas = (int)g_halo_dbg_ctas;
+    return DS_OK;
+}

@@ -138,6 +138,9 @@ int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const f
                    void* d_out_b16, float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch,
                    size_t scratch_bytes, void* stream);
 size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ksize);
+/* debugging aid (DIFFSPLIT_B200_HALO_DBG=1): mean clock64 cycles of the 7 phases of the last fused-conv launch:
+ * setup | wait for predecessor | loads + scale table | transform + stage | MMA | epilogue | teardown */
+int ds_debug_halo_phases(double* h_out7, int* n_ctas);
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]
  * (softmax(q k^T / sqrt(C)) v, unet.py:132-139) */
 int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream);

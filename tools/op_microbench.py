@@ -55,6 +55,13 @@ def main():
                                         out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sp()))
         us = timed_graph(fn)
         print(f"gnconv (pack + gn_stats + conv_halo) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (3 kernels)")
+        if os.environ.get("DIFFSPLIT_B200_HALO_DBG"):
+            fn()
+            ph = (C.c_double * 7)()
+            n = C.c_int()
+            _lib.check(L.ds_debug_halo_phases(ph, C.byref(n)))
+            names = ["setup", "wait_prev", "loads+table", "transform+stage", "mma", "epilogue", "teardown"]
+            print("  phases (mean cycles over", n.value, "CTAs):", {k: round(v) for k, v in zip(names, ph)}, "sum", round(sum(ph)))
     elif kind == "conv_tc":
         xa = xa32.bfloat16()
         xb = xb32.bfloat16() if cb else None
