@@ -1,6 +1,7 @@
 // Miscellaneous C-ABI entry points: error text, device info, and the standalone operator wrappers that the
 // parity tests call one by one.
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -28,6 +29,49 @@ bool pdl_enabled() {
     return v == 1;
 }
 }  // namespace ds
+
+namespace ds {
+constexpr int TRACE_MAX = 8192;
+static unsigned long long* g_trace = nullptr;
+static int g_trace_n = 0;
+static int g_trace_kind[TRACE_MAX];
+TraceSlot trace_next(int kind) {
+    static int on = -1;
+    if (on < 0) on = getenv("DIFFSPLIT_B200_TRACE") ? 1 : 0;
+    TraceSlot t = {nullptr, 0};
+    if (!on) return t;
+    if (!g_trace) {
+        if (cudaMalloc(&g_trace, TRACE_MAX * 2 * sizeof(unsigned long long)) != cudaSuccess) return t;
+        cudaMemset(g_trace, 0, TRACE_MAX * 2 * sizeof(unsigned long long));
+    }
+    if (g_trace_n >= TRACE_MAX) return t;
+    g_trace_kind[g_trace_n] = kind;
+    t.buf = g_trace;
+    t.id = g_trace_n++;
+    return t;
+}
+}  // namespace ds
+
+// timeline debugging: forget all ids / (re)arm the slots recorded so far / read them back
+extern "C" int ds_debug_trace_reset(int forget_ids) {
+    using namespace ds;
+    if (!g_trace) return DS_OK;
+    if (forget_ids) g_trace_n = 0;
+    std::vector<unsigned long long> init(TRACE_MAX * 2);
+    for (int i = 0; i < TRACE_MAX; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+    DS_CHECK_CUDA(cudaDeviceSynchronize());
+    DS_CHECK_CUDA(cudaMemcpy(g_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    return DS_OK;
+}
+extern "C" int ds_debug_trace_read(unsigned long long* h_start_end, int* h_kind, int max_n) {
+    using namespace ds;
+    if (!g_trace) return 0;
+    cudaDeviceSynchronize();
+    const int n = g_trace_n < max_n ? g_trace_n : max_n;
+    cudaMemcpy(h_start_end, g_trace, (size_t)n * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i) h_kind[i] = g_trace_kind[i];
+    return n;
+}
 
 using namespace ds;
 

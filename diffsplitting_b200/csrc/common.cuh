@@ -47,6 +47,23 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+// ---- optional kernel timeline (DIFFSPLIT_B200_TRACE=1): every traced launch gets an id; its CTAs atomically record the
+// earliest start / latest end in nanoseconds of the GPU global timer.  Works inside CUDA-graph replays.
+struct TraceSlot { unsigned long long* buf; int id; };
+TraceSlot trace_next(int kind);                 // host: {nullptr, 0} when tracing is off
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(const TraceSlot& t) {
+    if (t.buf && threadIdx.x == 0) atomicMin(t.buf + 2 * t.id, gtime_ns());
+}
+__device__ __forceinline__ void trace_end(const TraceSlot& t) {
+    if (t.buf && threadIdx.x == 0) atomicMax(t.buf + 2 * t.id + 1, gtime_ns());
+}
+#endif
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

@@ -17,6 +17,7 @@ namespace ds {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_SPLIT = 64;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_SUM_COPIES = 8;      // == TC_SUM_COPIES (tc_ptx.cuh): replicated statistics accumulators
 
 int gn_nsplit(int B, int HW, int C) {
     int64_t per = (int64_t)HW * C;
@@ -195,25 +196,39 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
     __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
     pdl_wait();
     pdl_trigger();
-    if (t < G) {
-        if (sums_a) {        // per-channel fp64 (sum, sumsq) emitted by the producers' epilogues
+    if (sums_a) {        // per-channel fp64 (sum, sumsq) emitted by the producers' epilogues, replicated GN_SUM_COPIES times
+        __shared__ double g_s[GN_MAX_GROUPS], g_q[GN_MAX_GROUPS];
+        if (t < G) { g_s[t] = 0.0; g_q[t] = 0.0; }
+        __syncthreads();
+        // one thread per channel adds the copies (independent loads), then one shared-memory atomic pair per channel
+        for (int c = t; c < C; c += GN_THREADS) {
+            const bool first = c < ca;
+            const double2* src = reinterpret_cast<const double2*>(first ? sums_a + ((size_t)bi * ca + c) * 2
+                                                                        : sums_b + ((size_t)bi * cb + (c - ca)) * 2);
+            const size_t cstride = (size_t)gridDim.y * (first ? ca : cb);      // gridDim.y = B
             double sm = 0.0, sq = 0.0;
-            for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
-                const double* src = c < ca ? sums_a + ((size_t)bi * ca + c) * 2 : sums_b + ((size_t)bi * cb + (c - ca)) * 2;
-                sm += src[0];
-                sq += src[1];
+#pragma unroll
+            for (int k = 0; k < GN_SUM_COPIES; ++k) {
+                const double2 v = src[k * cstride];
+                sm += v.x;
+                sq += v.y;
             }
+            atomicAdd(&g_s[c / cpg], sm);
+            atomicAdd(&g_q[c / cpg], sq);
+        }
+        __syncthreads();
+        if (t < G) {
             const double n = (double)HW * cpg;
-            const double mean = sm / n;
-            double var = sq / n - mean * mean;
+            const double mean = g_s[t] / n;
+            double var = g_q[t] / n - mean * mean;
             if (var < 0.0) var = 0.0;
             s_mean[t] = (float)mean;
             s_rstd[t] = (float)(1.0 / sqrt(var + 1e-5));
-        } else {
-            const float2 st = stats[(size_t)bi * G + t];
-            s_mean[t] = st.x;
-            s_rstd[t] = st.y;
         }
+    } else if (t < G) {
+        const float2 st = stats[(size_t)bi * G + t];
+        s_mean[t] = st.x;
+        s_rstd[t] = st.y;
     }
     __syncthreads();
     const size_t base = (size_t)bi * HW;

@@ -42,6 +42,7 @@ struct TcParams {
     int stages;
     int8_t tap_dx[4][TC_MAX_TAPS], tap_dy[4][TC_MAX_TAPS], tap_view[4][TC_MAX_TAPS];   // per class
     int up;                           // output pixel = (2y + class/2, 2x + class%2)
+    TraceSlot trace;
 };
 
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int NA = 1;       // (several accumulators were measured slower: the MMAs are operand-fetch bound, not latency bound)
     const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
 
+    trace_begin(p.trace);
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tfull_bar, 1);
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, n_base + c0, add);
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, n_base + c0, f);
             }
-            if (p.epi.sums_out) tc_epilogue_stats(p.epi, f, valid, b, n_base + c0, m, (int)threadIdx.x - 64, red);
+            if (p.epi.sums_out)
+                tc_epilogue_stats(p.epi, f, valid, b, n_base + c0, m, (int)threadIdx.x - 64, b0, (int)(blockIdx.x % TC_SUM_COPIES), red);
         }
         tc_fence_before();
     }
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+    trace_end(p.trace);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -416,6 +420,8 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
     p.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16);
     p.epi.out_nchw = out_nchw;
     p.epi.sums_out = sums_out;
+    p.epi.sums_B = p.B;
+    p.trace = trace_next(4);
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

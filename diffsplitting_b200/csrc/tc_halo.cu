@@ -62,8 +62,14 @@ struct HaloParams {
     // operand buffer geometry: `contig` = the three filter-row segments overlap inside ONE contiguous run of the flat
     // padded index space (W + 2 <= 139): every pixel is staged exactly once; else three separate 136-pixel segments
     int contig, plane_px, seg_stride_px;
+    // A operand layout: rb == 0: no-swizzle [8-channel plane][pixel][16 B] (the tensor pipe reads it at ~32 B/clk);
+    // rb = 32 / 64 / 128: K-chunks of rb/2 channels, [chunk][pixel][rb bytes] with the matching UMMA swizzle, shifted
+    // windows addressed through the descriptor's base-offset field
+    int rb, base_off_mode;
+    uint32_t chunk_bytes;
     FastDiv div_hpwp, div_wp, div_planepx;
     long long* dbg;                             // optional per-CTA phase timestamps (clock64), 8 per CTA
+    TraceSlot trace;
 };
 #define HALO_STAMP(i) do { if (p.dbg && tid == (i >= 5 ? 64 : 0)) p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
@@ -76,12 +82,13 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo,
 __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 127u) & ~127u;
+    const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = p.C >> 3;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const uint32_t a_off = 0, b_off = P * plane_bytes;
+    const uint32_t a_bytes_total = p.rb ? (uint32_t)(p.C * 2 / p.rb) * p.chunk_bytes : P * plane_bytes;
+    const uint32_t a_off = 0, b_off = a_bytes_total;
     // weights of one 16-output-channel block: [tap][kstep][plane(2)][16 rows][16 B]; a CTA owns BN/16 consecutive blocks
     const uint32_t blk_bytes = (uint32_t)p.ntaps * p.ksteps * 512u;
     const uint32_t b_bytes = (uint32_t)(p.BN >> 4) * blk_bytes;
@@ -94,7 +101,9 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     int b_last = (q0 + 128 + p.Wp) / p.HpWp;
     if (b_last > p.B - 1) b_last = p.B - 1;
     const int nsamp = b_last - b_first + 1;
-    const uint32_t bar_off = (tab_off + (uint32_t)nsamp * p.C * 8u + 15u) & ~15u;
+    const uint32_t gst_off = tab_off + (uint32_t)nsamp * p.C * 8u;                 // (mean, rstd) per (sample, group)
+    const uint32_t chs_off = (gst_off + (uint32_t)nsamp * HALO_MAX_GROUPS * 8u + 15u) & ~15u;   // fp64 (sum, sq) per (sample, ch)
+    const uint32_t bar_off = (chs_off + (uint32_t)nsamp * p.C * 16u + 15u) & ~15u;
     const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
     uint8_t* red = gbase + bar_off + 32u;                                          // epilogue reduction buffer
     // NA independent accumulators: back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency
@@ -103,6 +112,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
 
     HALO_STAMP(0);
+    trace_begin(p.trace);
     if (tid == 0) {
         mbar_init(bfull, 1);
         mbar_init(mma_done, 1);
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     // global-memory round trips (statistics / affine parameters and pixels) overlap.
     float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
     const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
-    struct Pix { const float* a; const float* b; int tabi; uint32_t dst; };   // a == nullptr: zero padding
+    struct Pix { const float* a; const float* b; int tabi; uint32_t dst; int pxi; };   // a == nullptr: zero padding
     auto decode = [&](int px, Pix& px_) {
         int q;
         if (p.contig) {
@@ -146,6 +156,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         px_.b = nullptr;
         px_.tabi = 0;
         px_.dst = base + a_off + px * 16;
+        px_.pxi = px;
         if (q >= 0 && q < p.total_q) {
             const int b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
@@ -193,7 +204,16 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             }
             val = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        const uint32_t dst = px_.dst + kp * plane_bytes;
+        uint32_t dst;
+        if (p.rb) {
+            const int per = p.rb >> 4;                                 // 16-byte chunks per row
+            const int kc = kp / per, kq = kp - kc * per;
+            const uint32_t off = (uint32_t)px_.pxi * p.rb + kq * 16;
+            const uint32_t mask = p.rb == 128 ? 7u : (p.rb == 64 ? 3u : 1u);
+            dst = base + a_off + kc * p.chunk_bytes + (off ^ (((off >> 7) & mask) << 4));
+        } else {
+            dst = px_.dst + kp * plane_bytes;
+        }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
     };
 
@@ -223,34 +243,50 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     {
         const bool norm = p.stats || p.sums_a;
         const int cpg = norm ? p.C / p.G : 1;
-        const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
+        float2* gst = reinterpret_cast<float2*>(gbase + gst_off);
+        if (p.sums_a) {
+            // fold the producers' replicated per-channel fp64 sums into (mean, rstd) per (sample, group); a group may
+            // straddle the two sources of a concat.  Stage 1: one thread per (sample, channel) adds the replicated copies
+            // (all loads independent: ONE round trip); stage 2: one thread per (sample, group) adds its channels from smem.
+            double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
+            for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
+                const int s = i / p.C, cc = i - s * p.C, b = b_first + s;
+                const bool first = cc < p.ca;
+                const double2* src = reinterpret_cast<const double2*>(
+                    first ? p.sums_a + ((size_t)b * p.ca + cc) * 2 : p.sums_b + ((size_t)b * p.cb + (cc - p.ca)) * 2);
+                const size_t cstride = (size_t)p.B * (first ? p.ca : p.cb);
+                double2 v[TC_SUM_COPIES];
+#pragma unroll
+                for (int k = 0; k < TC_SUM_COPIES; ++k) v[k] = src[k * cstride];
+                double sm = 0.0, sq = 0.0;
+#pragma unroll
+                for (int k = 0; k < TC_SUM_COPIES; ++k) { sm += v[k].x; sq += v[k].y; }
+                chs[i] = make_double2(sm, sq);
+            }
+            __syncthreads();
+            const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
+            for (int i = tid; i < nsamp * p.G; i += HALO_THREADS) {
+                const int s = i / p.G, g = i - s * p.G;
+                double sm = 0.0, sq = 0.0;
+                for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+                    const double2 v = chs[s * p.C + cc];
+                    sm += v.x;
+                    sq += v.y;
+                }
+                const double mu = sm * inv_cnt;
+                double var = sq * inv_cnt - mu * mu;
+                if (var < 0.0) var = 0.0;
+                gst[i] = make_float2((float)mu, rsqrtf((float)var + 1e-5f));
+            }
+            __syncthreads();
+        }
         for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
-            const int s = i / p.C, c = i - s * p.C, b = b_first + s;
+            const int s = i / p.C, c = i - s * p.C;
             float a = 1.f, sh = 0.f;
             if (norm) {
-                float mean, rstd;
-                if (p.sums_a) {
-                    // fold the producers' per-channel fp64 sums of this channel's group (it may straddle the two sources)
-                    const int g = c / cpg;
-                    double sm = 0.0, sq = 0.0;
-                    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-                        const double* src = cc < p.ca ? p.sums_a + ((size_t)b * p.ca + cc) * 2
-                                                      : p.sums_b + ((size_t)b * p.cb + (cc - p.ca)) * 2;
-                        sm += src[0];
-                        sq += src[1];
-                    }
-                    const double mu = sm * inv_cnt;
-                    double var = sq * inv_cnt - mu * mu;
-                    if (var < 0.0) var = 0.0;
-                    mean = (float)mu;
-                    rstd = rsqrtf((float)var + 1e-5f);
-                } else {
-                    const float2 st = p.stats[(size_t)b * p.G + c / cpg];
-                    mean = st.x;
-                    rstd = st.y;
-                }
-                a = rstd * p.gamma[c];
-                sh = p.beta[c] - mean * a;
+                const float2 st = p.sums_a ? gst[s * p.G + c / cpg] : p.stats[(size_t)(b_first + s) * p.G + c / cpg];
+                a = st.y * p.gamma[c];
+                sh = p.beta[c] - st.x * a;
             }
             tab[i] = make_float2(a, sh);
         }
@@ -283,15 +319,40 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             const uint32_t a_kstep = (2u * plane_bytes) >> 4;
             const uint32_t b_kstep = (uint32_t)p.BN * 2u;                                              // 2 planes of BN * 16 B
             uint32_t b_lo = b_lo0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int r = p.ntaps == 9 ? tap / 3 : 0;
-                const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
-                uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
-                for (int kk = 0; kk < p.ksteps; ++kk) {
-                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
-                              (tap | kk) ? 1u : 0u);
-                    a_lo += a_kstep;
-                    b_lo += b_kstep;
+            if (p.rb == 0) {
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int r = p.ntaps == 9 ? tap / 3 : 0;
+                    const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
+                    uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
+                    for (int kk = 0; kk < p.ksteps; ++kk) {
+                        umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
+                                  (tap | kk) ? 1u : 0u);
+                        a_lo += a_kstep;
+                        b_lo += b_kstep;
+                    }
+                }
+            } else {
+                // swizzled A: start = chunk + shift * rb + kstep-in-row * 32; SBO = 8 rows; the window does not start on a
+                // swizzle-atom boundary -> base offset = (start >> 7) & 7
+                const uint32_t layout = p.rb == 128 ? 2u : (p.rb == 64 ? 4u : 6u);
+                const uint32_t a_hi_fixed = ((8u * p.rb) >> 4) | (1u << 14) | (layout << 29);
+                const int kpr = p.rb >> 5;                                  // K steps per row
+                const int nchunk = p.ksteps / kpr;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int r = p.ntaps == 9 ? tap / 3 : 0;
+                    const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
+                    const uint32_t shift = (uint32_t)(r * p.seg_stride_px + sx) * p.rb;
+                    for (int kc = 0; kc < nchunk; ++kc) {
+                        const uint32_t row0 = base + a_off + kc * p.chunk_bytes + shift;
+                        const uint32_t boff = p.base_off_mode ? ((row0 >> 7) & 7u) : 0u;
+                        const uint32_t a_hi = a_hi_fixed | (boff << 17);
+                        for (int kk = 0; kk < kpr; ++kk) {
+                            const uint32_t a_lo = (((row0 + kk * 32u) & 0x3FFFFu) >> 4) | (1u << 16);
+                            umma_bf16(tmem_base, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
+                                      (tap | kc | kk) ? 1u : 0u);
+                            b_lo += b_kstep;
+                        }
+                    }
                 }
             }
             umma_commit(mma_done);
@@ -331,7 +392,8 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
             }
-            if (p.epi.sums_out) tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, red);
+            if (p.epi.sums_out)
+                tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, fdiv(q0, p.div_hpwp), (int)(blockIdx.x % TC_SUM_COPIES), red);
         }
         HALO_STAMP(6);
         tc_fence_before();
@@ -342,6 +404,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
         tmem_dealloc(tmem_base, tmem_cols);
     }
     HALO_STAMP(7);
+    trace_end(p.trace);
 }
 
 static long long* g_halo_dbg = nullptr;
@@ -354,9 +417,35 @@ static int halo_plane_px(int ntaps, int W) {
     return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
 }
 
+// A-operand layout: 0 (default): no-swizzle [8-channel plane][pixel][16 B]; 2: swizzled [K chunk][pixel][32|64|128 B]
+// with descriptor base offset 0; 1: swizzled with base offset = (start >> 7) & 7.
+// Measured on B200 (tests/test_gpu_parity.py::test_fused_gn_swish_conv_operator under DIFFSPLIT_B200_HALO_SWZ=...):
+// mode 2 is CORRECT for windows that start anywhere inside a swizzle atom - the tensor core's swizzle is a pure function of
+// the shared-memory address bits - while mode 1 gives wrong results.  Mode 2 is not faster here (the MMA phase is bound by
+// the ~100 cycles per K=16 step that fetching the 128-row A operand costs in either layout, and the swizzled staging
+// stores conflict), so the simpler layout stays the default.
+static int halo_swizzle_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DIFFSPLIT_B200_HALO_SWZ");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+static int halo_row_bytes(int C) {
+    if (!halo_swizzle_mode()) return 0;
+    return C % 64 == 0 ? 128 : (C % 32 == 0 ? 64 : 32);
+}
+static size_t halo_a_bytes(int C, int ntaps, int W) {
+    const int rb = halo_row_bytes(C);
+    const int px = halo_plane_px(ntaps, W);
+    if (!rb) return (size_t)(C / 8) * px * 16;
+    return (size_t)(C * 2 / rb) * align_up((size_t)px * rb, 1024);
+}
+
 static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp) {
-    return (size_t)(C / 8) * halo_plane_px(ntaps, W) * 16 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
-           64 + TC_RED_BYTES + 128;
+    return halo_a_bytes(C, ntaps, W) + 1024 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
+           (size_t)nsamp * HALO_MAX_GROUPS * 8 + (size_t)nsamp * C * 16 + 96 + TC_RED_BYTES + 128;
 }
 
 static int halo_samples_per_tile(int H, int W) {
@@ -428,6 +517,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.gamma = norm.gamma; p.beta = norm.beta; p.G = norm.G > 0 ? norm.G : 1; p.swish = norm.swish;
     DS_REQUIRE(p.G <= HALO_MAX_GROUPS, "halo conv: %d groups > %d", p.G, HALO_MAX_GROUPS);
     p.epi.sums_out = sums_out;
+    p.epi.sums_B = B;
     p.w = w_packed;
     p.epi.bias = epi.bias; p.epi.temb = epi.temb; p.epi.temb_off = epi.temb_off; p.epi.temb_stride = epi.temb_stride;
     p.epi.temb_bcast = epi.temb_bcast; p.epi.residual = epi.residual;
@@ -447,6 +537,9 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
     p.div_wp = make_fastdiv((uint32_t)p.Wp);
     p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
+    p.rb = halo_row_bytes(p.C);
+    p.base_off_mode = halo_swizzle_mode() == 1 ? 1 : 0;
+    p.chunk_bytes = p.rb ? (uint32_t)align_up((size_t)p.plane_px * p.rb, 1024) : 0;
     {
         // 3-D view of the packed weights [block][tap*kstep*plane][16 rows x 8 ch = 128 bf16]
         static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
@@ -472,6 +565,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
         }
     }
     const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp);
+    p.trace = trace_next(6);
     if (getenv("DIFFSPLIT_B200_HALO_DBG")) {
         const size_t ctas = (size_t)m_tiles * p.n_tiles;
         if (!g_halo_dbg || g_halo_dbg_ctas < ctas) {

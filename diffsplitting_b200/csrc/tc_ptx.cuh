@@ -99,8 +99,10 @@ struct TcEpi {
     float* out_f32;                   // fp32 NHWC or null   (consumers: GroupNorm statistics, residual adds)
     __nv_bfloat16* out_b16;           // bf16 NHWC or null   (consumers: TMA-fed convolutions, attention)
     float* out_nchw;                  // fp32 NCHW or null   (the network output)
-    double* sums_out;                 // [B][Cout][2] (sum, sum of squares) accumulators of the OUTPUT tensor or null:
-                                      // the GroupNorm statistics of the consumer, produced here instead of by a pass over HBM
+    double* sums_out;                 // [TC_SUM_COPIES][B][Cout][2] (sum, sum of squares) accumulators of the OUTPUT tensor
+                                      // or null: the GroupNorm statistics of the consumer, produced here instead of by a
+                                      // pass over HBM
+    int sums_B;                       // batch size (stride of the replicated accumulators)
     int Cout, Ho, Wo;
 };
 
@@ -179,42 +181,67 @@ __device__ __forceinline__ void tc_epilogue_write(const TcEpi& p, const uint32_t
 }
 
 // Per-channel (sum, sum of squares) of one 128-row x 16-channel epilogue chunk, per sample, accumulated into sums_out.
-// Called by the 128 epilogue threads (te = 0..127, row m of the tile); `red` = TC_RED_BYTES of shared memory.
-// Transposed pass: thread (channel c = te & 15, row group te >> 4) walks 16 consecutive rows in fp32 and flushes one
-// fp64 atomic pair per sample it meets (rows are ordered by sample), so the summation tree is fixed up to the order of
-// the fp64 atomics.
+// Called by the 128 epilogue threads (te = 0..127, row m of the tile); `red` = TC_RED_BYTES of shared memory; `b_tile0` =
+// sample of the tile's first row (rows are ordered by sample).
+//  1. transposed pass: thread (channel c = te & 15, row group te >> 4) walks 16 consecutive rows in fp32;
+//  2. the 8 row groups of the two first samples of the tile are folded through shared memory -> ONE fp64 atomic pair per
+//     (sample, channel) and CTA (further samples of tiny images: direct atomics);
+//  3. the accumulators are replicated TC_SUM_COPIES times (copy = CTA index mod copies): same-address L2 atomics
+//     serialise, 34 CTAs x 8 row groups hammering one address cost ~20 us per layer before this.
+constexpr int TC_SUM_COPIES = 8;
+__device__ __forceinline__ void tc_stats_atomic(const TcEpi& p, int copy, int b, int ch, float s, float q) {
+    double* dst = p.sums_out + (((size_t)copy * p.sums_B + b) * p.Cout + ch) * 2;
+    atomicAdd(dst, (double)s);
+    atomicAdd(dst + 1, (double)q);
+}
 __device__ __forceinline__ void tc_epilogue_stats(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int m, int te,
-                                                  uint8_t* red_raw) {
+                                                  int b_tile0, int copy, uint8_t* red_raw) {
     float* red = reinterpret_cast<float*>(red_raw);
     int* sb = reinterpret_cast<int*>(red_raw + 128 * TC_RED_LD * 4);
 #pragma unroll
     for (int j = 0; j < 16; ++j) red[m * TC_RED_LD + j] = valid ? f[j] : 0.f;
     sb[m] = valid ? b : -1;
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int c = te & 15, rg = te >> 4, r0 = rg * 16;
+    const bool cok = n0 + c < p.Cout;
+    float ps[2] = {0.f, 0.f}, pq[2] = {0.f, 0.f};          // partials of the tile's first two samples
     {
-        const int c = te & 15, r0 = (te >> 4) * 16;
-        const bool cok = n0 + c < p.Cout;
         int cur = -1;
         float s = 0.f, q = 0.f;
+        auto flush = [&]() {
+            if (cur < 0) return;
+            const int rel = cur - b_tile0;
+            if (rel == 0 || rel == 1) { ps[rel] = s; pq[rel] = q; }
+            else if (cok) tc_stats_atomic(p, copy, cur, n0 + c, s, q);
+        };
         for (int r = r0; r < r0 + 16; ++r) {
             const int bb = sb[r];
             if (bb < 0) continue;
-            if (bb != cur) {
-                if (cur >= 0 && cok) {
-                    double* dst = p.sums_out + ((size_t)cur * p.Cout + n0 + c) * 2;
-                    atomicAdd(dst, (double)s);
-                    atomicAdd(dst + 1, (double)q);
-                }
-                cur = bb; s = 0.f; q = 0.f;
-            }
+            if (bb != cur) { flush(); cur = bb; s = 0.f; q = 0.f; }
             const float v = red[r * TC_RED_LD + c];
             s += v;
             q = fmaf(v, v, q);
         }
-        if (cur >= 0 && cok) {
-            double* dst = p.sums_out + ((size_t)cur * p.Cout + n0 + c) * 2;
-            atomicAdd(dst, (double)s);
-            atomicAdd(dst + 1, (double)q);
+        flush();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done reading `red`: reuse it for the fold
+    // fold[rel][kind (sum|sq)][c][rg]
+    red[((0 * 2 + 0) * 16 + c) * 8 + rg] = ps[0];
+    red[((0 * 2 + 1) * 16 + c) * 8 + rg] = pq[0];
+    red[((1 * 2 + 0) * 16 + c) * 8 + rg] = ps[1];
+    red[((1 * 2 + 1) * 16 + c) * 8 + rg] = pq[1];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (te < 32) {
+        const int rel = te >> 4, cc = te & 15;
+        const int bb = b_tile0 + rel;
+        if (n0 + cc < p.Cout && bb < p.sums_B) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s += red[((rel * 2 + 0) * 16 + cc) * 8 + k];
+                q += red[((rel * 2 + 1) * 16 + cc) * 8 + k];
+            }
+            if (s != 0.f || q != 0.f) tc_stats_atomic(p, copy, bb, n0 + cc, s, q);
         }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");

@@ -82,6 +82,9 @@ struct Op {
     // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
     int64_t sums_out = NONE;             // slot the producer's epilogue accumulates into
     int64_t sums_a = NONE, sums_b = NONE;   // slots of the (two) sources a fused / apply-only GroupNorm reads
+    // fork / join: `side` ops run on the handle's side stream concurrently with the main chain (the 1x1 res_conv of a
+    // block is independent of conv1); the op flagged `join` waits for it
+    int side = 0, join = 0;
     // attn
     int N = 0, C = 0;
 };
@@ -177,6 +180,8 @@ struct ds_unet {
     bool weights_ready = false;
     std::vector<Plan*> plans;
     bool keep_taps = false;
+    cudaStream_t side_stream = nullptr;  // fork / join partner of the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int skip_mask = 0;                   // timing experiments only (DIFFSPLIT_B200_SKIP): bit OpKind = do not launch
 
     const float* wp(int i) const { return d_arena + specs[i].off; }
@@ -384,7 +389,7 @@ struct Planner {
         if (!tc) fmt = F32;
         if (tc && (fmt & F32) && want_sums) {       // a GroupNorm will read this tensor: its producer emits the statistics
             a.sums = (int64_t)stats_top;
-            stats_top += align_up((size_t)B * C * 2 * sizeof(double), 256);
+            stats_top += align_up((size_t)8 /* TC_SUM_COPIES */ * B * C * 2 * sizeof(double), 256);
         }
         if (fmt & F32) a.f32 = arena.alloc((size_t)B * H * W * C * 4);
         if (fmt & B16) a.b16 = arena.alloc((size_t)B * H * W * C * 2);
@@ -452,17 +457,22 @@ struct Planner {
     Act resblock(const Layer& L, Act x, const Act* skip) {
         const ResW& r = L.res;
         const int H = x.H, W = x.W;
-        Act h = make(r.cout, H, W, F32);
-        gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act resid = x;
         Act rbuf;
-        if (r.has_res) {
+        if (r.has_res) {            // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
             rbuf = make(r.cout, H, W, F32, false);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
+            p->ops.back().side = tc ? 1 : 0;
             resid = rbuf;
         }
+        Act h = make(r.cout, H, W, F32);
+        gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act out = make(r.cout, H, W, F32 | B16);
         gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, &resid, out);
+        if (r.has_res && tc) {
+            for (size_t i = p->ops.size(); i-- > 0;)
+                if (p->ops[i].kind == OP_CONV && p->ops[i].cw == &r.conv2) { p->ops[i].join = 1; break; }
+        }
         release(h);
         if (r.has_res) release(rbuf);
         if (r.attn) {
@@ -605,6 +615,9 @@ extern "C" void ds_unet_destroy(ds_unet* n) {
     if (!n) return;
     if (n->d_arena) cudaFree(n->d_arena);
     if (n->d_arena_bf16) cudaFree(n->d_arena_bf16);
+    if (n->side_stream) cudaStreamDestroy(n->side_stream);
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
     for (Plan* p : n->plans) delete p;
     delete n;
 }
@@ -698,6 +711,11 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
         unsigned* counters = nullptr;
         int rc2 = gn_counters(&counters);     // first use allocates: must not happen inside a graph capture
         if (rc2 != DS_OK) return rc2;
+    }
+    if (!n->side_stream) {
+        DS_CHECK_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking));
+        DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+        DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
     }
     n->weights_ready = true;
     return DS_OK;
@@ -861,6 +879,15 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 rc = launch_gn_stats(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, B, o.HW, n->d.norm_groups, gn_scratch, counters, st);
                 break;
             case OP_CONV: {
+                cudaStream_t st_main = st;
+                const bool on_side = o.side && !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr;
+                if (on_side) {
+                    DS_CHECK_CUDA(cudaEventRecord(n->ev_fork, st_main));
+                    DS_CHECK_CUDA(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0));
+                }
+                if (o.join && !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr)
+                    DS_CHECK_CUDA(cudaStreamWaitEvent(st_main, n->ev_join, 0));
+                cudaStream_t st = on_side ? n->side_stream : st_main;
                 ConvSrc s;
                 s.a = ptr(o.src_a); s.b = ptr(o.src_b);
                 s.ca = o.src_nchw ? ca : o.ca; s.cb = o.src_nchw ? cb : o.cb;
@@ -890,6 +917,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
                                          ptr(o.dst), st);
                 }
+                if (on_side && rc == DS_OK) DS_CHECK_CUDA(cudaEventRecord(n->ev_join, n->side_stream));
                 break;
             }
             case OP_ATTN:

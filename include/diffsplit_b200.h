@@ -141,6 +141,10 @@ size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ks
 /* debugging aid (DIFFSPLIT_B200_HALO_DBG=1): mean clock64 cycles of the 7 phases of the last fused-conv launch:
  * setup | wait for predecessor | loads + scale table | transform + stage | MMA | epilogue | teardown */
 int ds_debug_halo_phases(double* h_out7, int* n_ctas);
+/* debugging aid (DIFFSPLIT_B200_TRACE=1): GPU-timer (ns) start / end of every tensor-core conv launch, also inside
+ * CUDA-graph replays.  reset(1) forgets the launch ids, reset(0) re-arms the recorded ones; read returns the count. */
+int ds_debug_trace_reset(int forget_ids);
+int ds_debug_trace_read(unsigned long long* h_start_end, int* h_kind, int max_n);
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]
  * (softmax(q k^T / sqrt(C)) v, unet.py:132-139) */
 int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream);
