@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     pdl_trigger();
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const size_t blk16 = (size_t)16 * p.KC * 2;
             const uint8_t* wsrc = p.w + ((size_t)cls * U * p.nb16 + (size_t)nt * (p.BN / 16)) * blk16;
             for (int u = 0; u < U; ++u) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t row_bytes = p.KC * 2u;

@@ -106,14 +106,12 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     const uint32_t bar_off = (chs_off + (uint32_t)nsamp * p.C * 16u + 15u) & ~15u;
     const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
     uint8_t* red = gbase + bar_off + 32u;                                          // epilogue reduction buffer
-    // NA independent accumulators: back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency
-    // (~150 cycles each, measured); rotating over NA column ranges lets them pipeline, the epilogue adds them up
-    const int NA = 1;       // (rotating over several accumulators was measured slower: the MMAs are operand-fetch bound)
+    const int NA = 1;       // one accumulator (rotating over several column ranges was measured slower)
     const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
 
     HALO_STAMP(0);
     trace_begin(p.trace);
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         mbar_init(bfull, 1);
         mbar_init(mma_done, 1);
         fence_barrier_init();
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     HALO_STAMP(4);
 
     if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_wait(bfull, 0);
             tc_fence_after();
             // Descriptors differ only in the 14-bit start-address field: 32-bit adds.  B image of (tap, kstep): two planes of

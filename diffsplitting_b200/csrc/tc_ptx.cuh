@@ -36,6 +36,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// One lane of a fully converged warp.  Selecting the issuing thread with elect.sync (instead of `lane == 0`) lets ptxas prove
+// that a single thread is active: without it every UTCHMMA / UTMALDG is wrapped in an ELECT / R2UR / BRA.U.ANY loop over
+// the "possibly several" active lanes, which alone costs more than a small-N MMA (tools/mma_probe.cu: 52 vs 39 cycles).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
