@@ -22,7 +22,8 @@
 
 namespace ds {
 
-constexpr int HALO_THREADS = 192;
+constexpr int HALO_THREADS = 192;        // base block: TMA/setup warp, MMA warp, 4 epilogue warps (all of them stage)
+constexpr int HALO_MAX_THREADS = 512;    // wide block for layers that fit one CTA per SM anyway: extra warps only stage
 constexpr int HALO_SEG_PX = 136;           // 128 outputs + 2 halo pixels, padded to a multiple of 8
 constexpr int HALO_MAX_SAMPLES = 12;
 constexpr int HALO_MAX_GROUPS = 64;
@@ -79,12 +80,13 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo,
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
     const int P = p.C >> 3;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const uint32_t a_bytes_total = p.rb ? (uint32_t)(p.C * 2 / p.rb) * p.chunk_bytes : P * plane_bytes;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
     };
     Item it0, it1;
     issue(tid, it0);
-    issue(tid + HALO_THREADS, it1);
+    issue(tid + nthr, it1);
 
     // ---- per (sample in tile, channel) scale / shift of the fused GroupNorm: a = rstd * gamma, sh = beta - mean * a
     {
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             // straddle the two sources of a concat.  Stage 1: one thread per (sample, channel) adds the replicated copies
             // (all loads independent: ONE round trip); stage 2: one thread per (sample, group) adds its channels from smem.
             double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
-            for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
+            for (int i = tid; i < nsamp * p.C; i += nthr) {
                 const int s = i / p.C, cc = i - s * p.C, b = b_first + s;
                 const bool first = cc < p.ca;
                 const double2* src = reinterpret_cast<const double2*>(
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             }
             __syncthreads();
             const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
-            for (int i = tid; i < nsamp * p.G; i += HALO_THREADS) {
+            for (int i = tid; i < nsamp * p.G; i += nthr) {
                 const int s = i / p.G, g = i - s * p.G;
                 double sm = 0.0, sq = 0.0;
                 for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             }
             __syncthreads();
         }
-        for (int i = tid; i < nsamp * p.C; i += HALO_THREADS) {
+        for (int i = tid; i < nsamp * p.C; i += nthr) {
             const int s = i / p.C, c = i - s * p.C;
             float a = 1.f, sh = 0.f;
             if (norm) {
@@ -294,9 +296,9 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
 
     finish(it0);
     finish(it1);
-    for (int i0 = tid + 2 * HALO_THREADS; i0 < items; i0 += 2 * HALO_THREADS) {
+    for (int i0 = tid + 2 * nthr; i0 < items; i0 += 2 * nthr) {
         issue(i0, it0);
-        issue(i0 + HALO_THREADS, it1);
+        issue(i0 + nthr, it1);
         finish(it0);
         finish(it1);
     }
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(HALO_THREADS) conv_halo_kernel(const __grid_co
             umma_commit(mma_done);
         }
         __syncwarp();
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 6) {
         const int qd = warp & 3;
         const int m = qd * 32 + lane;
         const int q = q0 + m;
@@ -575,10 +577,21 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
-    DS_CHECK_CUDA(launch_pdl(conv_halo_kernel, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(HALO_THREADS), smem, st, p));
+    // Staging is latency bound (global loads of the raw activations): single-wave grids whose shared-memory footprint leaves
+    // one or two CTAs per SM anyway get extra warps that only stage.
+    static int thr_env = -1;
+    if (thr_env < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_THREADS"); thr_env = e ? atoi(e) : 0; }
+    const size_t n_ctas = (size_t)m_tiles * p.n_tiles;
+    int threads = (n_ctas <= 2 * 148 && smem >= 48 * 1024) ? HALO_MAX_THREADS : HALO_THREADS;
+    if (thr_env >= HALO_THREADS && thr_env <= HALO_MAX_THREADS && thr_env % 32 == 0) threads = thr_env;
+    if (threads == HALO_THREADS)
+        DS_CHECK_CUDA(launch_pdl(conv_halo_kernel<HALO_THREADS>, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(threads), smem, st, p));
+    else
+        DS_CHECK_CUDA(launch_pdl(conv_halo_kernel<HALO_MAX_THREADS>, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(threads), smem, st, p));
     return DS_OK;
 }
 
