@@ -84,6 +84,7 @@ _SIGS = {
     "ds_debug_trace_reset": (C.c_int, [C.c_int]),
     "ds_debug_trace_read": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_int]),
     "ds_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ds_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ds_sampler_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "ds_randn_axpy": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p,
                                 C.c_uint64, C.c_int, C.c_void_p]),

@@ -161,6 +161,14 @@ extern "C" int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, 
     return launch_attention(d_qkv, d_out, B, N, C, 0, (cudaStream_t)stream);
 }
 
+extern "C" int ds_attention_bf16(const void* d_qkv, void* d_out, int B, int N, int C, void* stream) {
+    DS_REQUIRE(d_qkv && d_out, "attention (bf16): null argument");
+    AttnTcPlan plan;
+    int rc = attn_tc_build(&plan, d_qkv, d_out, B, N, C);
+    if (rc != DS_OK) return rc;
+    return attn_tc_launch(&plan, (cudaStream_t)stream);
+}
+
 extern "C" size_t ds_conv2d_bf16_scratch_bytes(int cin, int cout, int ksize) {
     return align_up(tc_packed_weight_bytes(cout, cin, ksize), 1024);
 }

@@ -38,4 +38,13 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
                      int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
                      double* sums_out, cudaStream_t st);
 
+// ---- bf16 tensor-core self-attention (attention_tc.cu): qkv bf16 [B,N,3C] -> out bf16 [B,N,C]
+struct AttnTcPlan {
+    alignas(64) uint8_t params[512];      // an AttnTcParams (tensor map + geometry), filled by attn_tc_build
+    int smem_bytes, grid_x, grid_y, grid_z;
+};
+bool attn_tc_supported(int N, int C);                              // C a multiple of 64
+int attn_tc_build(AttnTcPlan* plan, const void* qkv, void* out, int B, int N, int C);
+int attn_tc_launch(const AttnTcPlan* plan, cudaStream_t st);
+
 }  // namespace ds

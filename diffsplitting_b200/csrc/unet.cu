@@ -98,6 +98,7 @@ struct Plan {
     int B, H, W, prec;
     std::vector<Op> ops;
     std::vector<TcConvPlan> tc;          // per op (bf16 mode): TMA descriptors + launch geometry
+    std::vector<AttnTcPlan> attn;        // per op (bf16 mode, attention ops whose channel count is a multiple of 64)
     const void* tc_ws = nullptr;         // workspace base the descriptors were encoded for
     size_t bytes = 0;
     int64_t temb_buf = NONE, gn_scratch = NONE;
@@ -834,8 +835,13 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
     if (tc && p->tc_ws != d_ws) {
         // (re)encode the TMA descriptors for this workspace address
         p->tc.assign(p->ops.size(), TcConvPlan());
+        p->attn.assign(p->ops.size(), AttnTcPlan());
         for (size_t i = 0; i < p->ops.size(); ++i) {
             const Op& o = p->ops[i];
+            if (o.kind == OP_ATTN && attn_tc_supported(o.N, o.C)) {
+                rc = attn_tc_build(&p->attn[i], ptr(o.src_a), ptr(o.dst_b16), B, o.N, o.C);
+                if (rc != DS_OK) return rc;
+            }
             if (o.kind != OP_CONV || o.src_nchw || o.halo) continue;
             if (!n->specs[o.cw->w].tc_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws)) {
                 set_error("unet_forward: bf16 mode needs channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
@@ -921,7 +927,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 break;
             }
             case OP_ATTN:
-                rc = launch_attention(ptr(o.src_a), tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
+                if (tc && attn_tc_supported(o.N, o.C) && !getenv("DIFFSPLIT_B200_ATTN_CUDA_CORES"))
+                    rc = attn_tc_launch(&p->attn[oi], st);
+                else
+                    rc = launch_attention(ptr(o.src_a), tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
                 break;
             default:
                 rc = DS_OK;

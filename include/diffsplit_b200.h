@@ -148,6 +148,9 @@ int ds_debug_trace_read(unsigned long long* h_start_end, int* h_kind, int max_n)
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]
  * (softmax(q k^T / sqrt(C)) v, unet.py:132-139) */
 int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void* stream);
+/* the same on the tensor cores (tcgen05 / TMEM / TMA, precision mode DS_PREC_BF16): qkv and out are bf16, scores and
+ * the output accumulate in fp32, the probabilities are rounded to bf16.  C must be a multiple of 64. */
+int ds_attention_bf16(const void* d_qkv, void* d_out, int B, int N, int C, void* stream);
 
 /* ------------------------------------------------------------------ sampler updates
  * One fused elementwise kernel per reverse step (replaces p_sample / inference_one_step:

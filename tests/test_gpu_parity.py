@@ -229,6 +229,26 @@ def test_attention_operator(B, N, Cc):
     assert relerr(out, ref) <= 1e-5
 
 
+@pytest.mark.parametrize("B,N,Cc,scale", [(16, 64, 128, 1.0), (2, 16, 128, 1.0), (2, 256, 512, 1.0), (1, 300, 128, 3.0), (1, 1024, 256, 1.0),
+                                          (2, 100, 64, 4.0), (1, 4096, 128, 2.0), (1, 1024, 1024, 1.0)])
+def test_attention_tensor_core_operator(B, N, Cc, scale):
+    """tcgen05 attention (bf16 operands, fp32 scores / accumulator) vs float64 softmax attention of the SAME bf16-rounded
+    q, k, v.  Error budget: P and the output are rounded to bf16 (2^-9 relative each).  `scale` > 1 sharpens the softmax so
+    that the max-subtraction and the two-pass denominator matter."""
+    g = torch.Generator().manual_seed(N + Cc)
+    qkv = (torch.randn((B, N, 3 * Cc), generator=g) * scale).to(torch.bfloat16)
+    q, k, v = qkv.double().split(Cc, dim=2)
+    ref = torch.softmax(q @ k.transpose(1, 2) / Cc ** 0.5, dim=-1) @ v
+    qd = qkv.to(DEV)
+    out = torch.full((B, N, Cc), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ds_attention_bf16(qd.data_ptr(), out.data_ptr(), B, N, Cc, sptr()))
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    rms = ((out.double().cpu() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
+    print(f"[attention tc B{B} N{N} C{Cc}] max-rel {err:.3e} rel-rms {rms:.3e}")
+    assert err <= 1e-2 and rms <= 5e-3
+
+
 # ------------------------------------------------------------------------------------------------ UNet
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", list(UNET_CASES))
