@@ -382,7 +382,16 @@ def main():
         else:
             ach = a["bytes"] / a["ms"] / 1e6
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-        roof.update({"traffic": None, "kernel": top, "share_of_step": a["ms"] / tot, "peak_source": pk["src"],
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_halo_traffic.json")
+        if top == "gn_swish_conv_tc" and args.workload == DEFAULT_WORKLOAD and args.precision == "bf16" and os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic = tj["traffic_bytes_per_launch"]
+            traffic_src = ("profiles/r1_halo_traffic.json: dram read+write bytes per launch, mean over the %d launches of one step, "
+                           "ncu --set full (caches flushed per replay); algorithmic bytes per launch = %.0f"
+                           % (tj["launches_captured"], a["bytes"] / a["launches"]))
+        roof.update({"traffic": traffic, "traffic_source": traffic_src, "kernel": top, "share_of_step": a["ms"] / tot, "peak_source": pk["src"],
                      "per_launch_us": a["ms"] / a["launches"] * 1e3,
                      "note": "algorithmic bytes|flops of all launches of this kernel in one step / their summed CUDA-event time "
                              "(each operator timed as 20 back-to-back launches after 1 warm-up, L2 warm as in the real chain)"})
