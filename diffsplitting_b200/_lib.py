@@ -84,6 +84,9 @@ _SIGS = {
     "ds_debug_trace_reset": (C.c_int, [C.c_int]),
     "ds_debug_trace_read": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_int]),
     "ds_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ds_chain2_bf16_scratch_bytes": (C.c_size_t, [C.c_int] * 8),
+    "ds_chain2_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p, C.c_void_p]
+                       + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "ds_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ds_sampler_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "ds_randn_axpy": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p,

@@ -161,6 +161,66 @@ extern "C" int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, 
     return launch_attention(d_qkv, d_out, B, N, C, 0, (cudaStream_t)stream);
 }
 
+// Two chained fused ops in ONE per-sample persistent kernel (tc_chain.cu), shaped like a ResnetBlock:
+//   h = conv1(swish(GN1(cat[xa, xb]))) + b1 ;  y = conv2(swish(GN2(h))) + b2 [+ residual]
+// GN2 reads the statistics op 1's epilogue emitted inside the same launch.
+static size_t chain2_layout(int B, int H, int W, int cin, int cmid, int cout, int ks, size_t* off_w2, size_t* off_sa, size_t* off_sb,
+                            size_t* off_sh, size_t* off_h, int ca, int cb) {
+    size_t o = 0;
+    o += align_up(chain_packed_weight_bytes(cmid, cin, ks), 1024);
+    *off_w2 = o; o += align_up(chain_packed_weight_bytes(cout, cmid, ks), 1024);
+    *off_sa = o; o += align_up((size_t)TC_SUM_COPIES * B * ca * 16, 256);
+    *off_sb = o; o += align_up((size_t)TC_SUM_COPIES * B * (cb > 0 ? cb : 1) * 16, 256);
+    *off_sh = o; o += align_up((size_t)TC_SUM_COPIES * B * cmid * 16, 256);
+    *off_h = o; o += align_up((size_t)B * H * W * cmid * 4, 256);
+    return o;
+}
+
+extern "C" size_t ds_chain2_bf16_scratch_bytes(int B, int H, int W, int ca, int cb, int cmid, int cout, int ksize) {
+    size_t a, b, c, d, e;
+    return chain2_layout(B, H, W, ca + cb, cmid, cout, ksize, &a, &b, &c, &d, &e, ca, cb);
+}
+
+extern "C" int ds_chain2_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma1, const float* d_beta1,
+                              const float* d_w1_oihw, const float* d_b1, const float* d_gamma2, const float* d_beta2,
+                              const float* d_w2_oihw, const float* d_b2, const float* d_residual, int groups, float* d_out_f32,
+                              void* d_out_b16, int B, int H, int W, int cmid, int cout, int ksize, void* d_scratch,
+                              size_t scratch_bytes, void* stream) {
+    DS_REQUIRE(d_xa && d_w1_oihw && d_w2_oihw && d_scratch && (d_out_f32 || d_out_b16) && groups > 0, "chain2_bf16: null argument");
+    size_t off_w2, off_sa, off_sb, off_sh, off_h;
+    const size_t need = chain2_layout(B, H, W, ca + cb, cmid, cout, ksize, &off_w2, &off_sa, &off_sb, &off_sh, &off_h, ca, cb);
+    DS_REQUIRE(scratch_bytes >= need, "chain2_bf16: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* sc = (uint8_t*)d_scratch;
+    int rc = chain_pack_conv_weight(d_w1_oihw, sc, cmid, ca + cb, ksize, st);
+    if (rc != DS_OK) return rc;
+    rc = chain_pack_conv_weight(d_w2_oihw, sc + off_w2, cout, cmid, ksize, st);
+    if (rc != DS_OK) return rc;
+    DS_CHECK_CUDA(cudaMemsetAsync(sc + off_sa, 0, off_h - off_sa, st));
+    rc = launch_ch_sums(d_xa, ca, B, H * W, (double*)(sc + off_sa), st);
+    if (rc != DS_OK) return rc;
+    if (cb > 0) {
+        rc = launch_ch_sums(d_xb, cb, B, H * W, (double*)(sc + off_sb), st);
+        if (rc != DS_OK) return rc;
+    }
+    ChainOpDesc ops[2];
+    memset(ops, 0, sizeof(ops));
+    ops[0].src_a = d_xa; ops[0].src_b = cb > 0 ? d_xb : nullptr; ops[0].ca = ca; ops[0].cb = cb;
+    ops[0].norm = 1; ops[0].swish = 1; ops[0].G = groups;
+    ops[0].sums_a = (const double*)(sc + off_sa); ops[0].sums_b = cb > 0 ? (const double*)(sc + off_sb) : nullptr;
+    ops[0].gamma = d_gamma1; ops[0].beta = d_beta1; ops[0].w = sc; ops[0].cout = cmid; ops[0].ks = ksize;
+    ops[0].epi.bias = d_b1; ops[0].out_f32 = (float*)(sc + off_h); ops[0].sums_out = (double*)(sc + off_sh);
+    ops[1].src_a = sc + off_h; ops[1].ca = cmid;
+    ops[1].norm = 1; ops[1].swish = 1; ops[1].G = groups;
+    ops[1].sums_a = (const double*)(sc + off_sh);
+    ops[1].gamma = d_gamma2; ops[1].beta = d_beta2; ops[1].w = sc + off_w2; ops[1].cout = cout; ops[1].ks = ksize;
+    ops[1].epi.bias = d_b2; ops[1].epi.residual = d_residual; ops[1].out_f32 = d_out_f32; ops[1].out_b16 = d_out_b16;
+    ChainPlan plan;
+    rc = chain_build(&plan, ops, 2, B, H, W);
+    if (rc != DS_OK) return rc;
+    return chain_launch(&plan, st);
+}
+
 extern "C" int ds_attention_bf16(const void* d_qkv, void* d_out, int B, int N, int C, void* stream) {
     DS_REQUIRE(d_qkv && d_out, "attention (bf16): null argument");
     AttnTcPlan plan;

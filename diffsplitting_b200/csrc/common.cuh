@@ -79,6 +79,9 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// replication factor of the per-channel fp64 (sum, sumsq) GroupNorm accumulators [copies][B][C][2] (contention spreading)
+constexpr int TC_SUM_COPIES = 8;
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -47,4 +47,30 @@ bool attn_tc_supported(int N, int C);                              // C a multip
 int attn_tc_build(AttnTcPlan* plan, const void* qkv, void* out, int B, int N, int C);
 int attn_tc_launch(const AttnTcPlan* plan, cudaStream_t st);
 
+// ---- per-sample persistent chain of [GroupNorm(+Swish) ->] 3x3 / 1x1 convs for the low-resolution levels (tc_chain.cu)
+constexpr int CHAIN_MAX_OPS = 16;
+constexpr int CHAIN_MAX_MTILES = 3;           // 128-row tiles per sample: (H+2)(W+2) <= 384, i.e. up to 17x17
+struct ChainOpDesc {
+    const void* src_a; const void* src_b;     // fp32 NHWC sources (concat), or bf16 NHWC when src_b16 (then no normalisation)
+    int ca, cb, src_b16;
+    int norm, swish, G;                       // fused GroupNorm of the concat input, statistics from sums_a / sums_b
+    const double* sums_a; const double* sums_b;
+    const float* gamma; const float* beta;
+    const uint8_t* w;                         // chain_pack_conv_weight() image
+    int cout, ks;
+    ConvEpi epi;                              // bias / temb / residual (fp32 NHWC)
+    float* out_f32; void* out_b16;            // fp32 and/or bf16 NHWC outputs
+    double* sums_out;                         // statistics of the output (replicated slots) or null
+};
+struct ChainPlan {
+    alignas(64) uint8_t params[4096];         // a ChainParams
+    int smem_bytes, B;
+};
+bool chain_level_supported(int H, int W);
+bool chain_conv_supported(int ca, int cb, int cout, int ks, int H, int W);
+size_t chain_packed_weight_bytes(int cout, int cin, int ks);
+int chain_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);
+int chain_build(ChainPlan* plan, const ChainOpDesc* ops, int nops, int B, int H, int W);
+int chain_launch(const ChainPlan* plan, cudaStream_t st);
+
 }  // namespace ds

@@ -120,6 +120,9 @@ constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD * 4 + 128 * 4;   // [128 rows]
 // one thread = one output pixel (b, oy, ox), 16 consecutive output channels starting at n0, accumulators in v[16]
 // Everything the epilogue ADDS to the accumulators of one (pixel, 16-channel chunk): bias + conditioning vector + fp32
 // residual.  Split from the store so that these global loads are issued BEFORE the thread waits for the MMAs.
+// COHERENT: the residual may have been written earlier by the SAME kernel (tc_chain.cu): ld.global.cg instead of the
+// non-coherent path.
+template <bool COHERENT = false>
 __device__ __forceinline__ void tc_epilogue_addend(const TcEpi& p, int b, int oy, int ox, int n0, float (&add)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) add[j] = 0.f;
@@ -138,12 +141,12 @@ __device__ __forceinline__ void tc_epilogue_addend(const TcEpi& p, int b, int oy
             const float4* r = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 rv = __ldg(r + j);
+                const float4 rv = COHERENT ? __ldcg(r + j) : __ldg(r + j);
                 add[4 * j] += rv.x; add[4 * j + 1] += rv.y; add[4 * j + 2] += rv.z; add[4 * j + 3] += rv.w;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += __ldg(p.residual + off + j);
+            for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += COHERENT ? __ldcg(p.residual + off + j) : __ldg(p.residual + off + j);
         }
     }
 }
@@ -196,7 +199,6 @@ __device__ __forceinline__ void tc_epilogue_write(const TcEpi& p, const uint32_t
 //     (sample, channel) and CTA (further samples of tiny images: direct atomics);
 //  3. the accumulators are replicated TC_SUM_COPIES times (copy = CTA index mod copies): same-address L2 atomics
 //     serialise, 34 CTAs x 8 row groups hammering one address cost ~20 us per layer before this.
-constexpr int TC_SUM_COPIES = 8;
 __device__ __forceinline__ void tc_stats_atomic(const TcEpi& p, int copy, int b, int ch, float s, float q) {
     double* dst = p.sums_out + (((size_t)copy * p.sums_B + b) * p.Cout + ch) * 2;
     atomicAdd(dst, (double)s);

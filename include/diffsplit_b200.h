@@ -151,6 +151,15 @@ int ds_attention_f32(const float* d_qkv, float* d_out, int B, int N, int C, void
 /* the same on the tensor cores (tcgen05 / TMEM / TMA, precision mode DS_PREC_BF16): qkv and out are bf16, scores and
  * the output accumulate in fp32, the probabilities are rounded to bf16.  C must be a multiple of 64. */
 int ds_attention_bf16(const void* d_qkv, void* d_out, int B, int N, int C, void* stream);
+/* two chained fused ops in ONE per-sample persistent kernel (the low-resolution path of the bf16 UNet), shaped like a
+ * ResnetBlock (unet.py:94-123):  h = conv1(swish(GN1(cat[xa, xb]))) + b1 ;  y = conv2(swish(GN2(h))) + b2 [+ residual].
+ * fp32 NHWC in / out; (H+2)(W+2) <= 384; channel counts multiples of 8 (16 in total), <= 256. */
+size_t ds_chain2_bf16_scratch_bytes(int B, int H, int W, int ca, int cb, int cmid, int cout, int ksize);
+int ds_chain2_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma1, const float* d_beta1,
+                   const float* d_w1_oihw, const float* d_b1, const float* d_gamma2, const float* d_beta2,
+                   const float* d_w2_oihw, const float* d_b2, const float* d_residual, int groups, float* d_out_f32,
+                   void* d_out_b16, int B, int H, int W, int cmid, int cout, int ksize, void* d_scratch, size_t scratch_bytes,
+                   void* stream);
 
 /* ------------------------------------------------------------------ sampler updates
  * One fused elementwise kernel per reverse step (replaces p_sample / inference_one_step:

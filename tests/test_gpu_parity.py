@@ -195,6 +195,54 @@ def test_fused_gn_swish_conv_operator(ca, cb, cout, ks, G, swish, B, H, W, resid
     assert e32 <= 2e-3 and e16 <= 6e-3
 
 
+@pytest.mark.parametrize("ca,cb,cmid,cout,ks,G,B,H,W,residual", [
+    (128, 0, 128, 128, 3, 16, 16, 8, 8, 1), (64, 0, 128, 128, 3, 16, 2, 8, 8, 0), (128, 128, 128, 128, 3, 16, 3, 8, 8, 0),
+    (128, 64, 128, 128, 3, 16, 2, 8, 8, 1), (64, 32, 64, 64, 3, 16, 2, 16, 16, 1), (32, 0, 64, 64, 3, 16, 1, 16, 16, 0),
+    (128, 0, 128, 256, 1, 16, 2, 8, 8, 0), (16, 16, 32, 16, 3, 8, 5, 4, 4, 0), (64, 0, 64, 48, 3, 16, 2, 12, 10, 0)])
+def test_persistent_chain_operator(ca, cb, cmid, cout, ks, G, B, H, W, residual):
+    """conv_chain_kernel: two fused GN+Swish->conv ops of one sample in ONE persistent CTA (the second GroupNorm reads the
+    statistics the first op's epilogue produced inside the same launch) vs the same math in float64 with bf16-rounded
+    conv operands."""
+    g = torch.Generator().manual_seed(ca + cb + cout + H)
+    cin = ca + cb
+    x = torch.randn((B, cin, H, W), generator=g) * 1.5 + 0.3
+    g1, b1 = 1 + 0.3 * torch.randn(cin, generator=g), 0.3 * torch.randn(cin, generator=g)
+    g2, b2 = 1 + 0.3 * torch.randn(cmid, generator=g), 0.3 * torch.randn(cmid, generator=g)
+    w1 = torch.randn((cmid, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5
+    w2 = torch.randn((cout, cmid, ks, ks), generator=g) / (cmid * ks * ks) ** 0.5
+    c1, c2 = torch.randn((cmid,), generator=g), torch.randn((cout,), generator=g)
+
+    def block(a, gam, bet, w, bias):
+        a = F.group_norm(a, G, gam.double(), bet.double(), eps=1e-5)
+        a = a * torch.sigmoid(a)
+        return F.conv2d(a.float().bfloat16().double(), w.bfloat16().double(), bias.double(), padding=ks // 2)
+
+    h = block(x.double(), g1, b1, w1, c1)
+    ref = block(h.float().double(), g2, b2, w2, c2)       # h is stored as fp32
+    res = None
+    if residual:
+        res = torch.randn((B, cout, H, W), generator=g)
+        ref = ref + res.double()
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV)
+    xa, xb = nhwc(x[:, :ca]), (nhwc(x[:, ca:]) if cb else None)
+    rd = nhwc(res) if residual else None
+    out32 = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    out16 = torch.full((B, H, W, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    L = _lib.lib()
+    nb = L.ds_chain2_bf16_scratch_bytes(B, H, W, ca, cb, cmid, cout, ks)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+    dv = [t.to(DEV) for t in (g1, b1, w1, c1, g2, b2, w2, c2)]
+    _lib.check(L.ds_chain2_bf16(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, dv[0].data_ptr(), dv[1].data_ptr(),
+                                dv[2].data_ptr(), dv[3].data_ptr(), dv[4].data_ptr(), dv[5].data_ptr(), dv[6].data_ptr(),
+                                dv[7].data_ptr(), None if rd is None else rd.data_ptr(), G, out32.data_ptr(), out16.data_ptr(),
+                                B, H, W, cmid, cout, ks, scratch.data_ptr(), nb, sptr()))
+    torch.cuda.synchronize()
+    e32 = relerr(out32.permute(0, 3, 1, 2), ref.float())
+    e16 = relerr(out16.float().permute(0, 3, 1, 2), ref.float())
+    print(f"[chain {ca}+{cb}->{cmid}->{cout} k{ks} G{G} {B}x{H}x{W}] rel err fp32 out {e32:.3e} bf16 out {e16:.3e}")
+    assert e32 <= 4e-3 and e16 <= 8e-3      # two ops: twice the 1-ulp bf16 re-rounding budget of the single fused op
+
+
 @pytest.mark.parametrize("ca,cb,G,B,HW,swish", [(16, 0, 16, 2, (16, 16), 1), (16, 32, 16, 1, (12, 20), 1), (128, 0, 16, 3, (8, 8), 0),
                                                  (512, 256, 32, 1, (4, 4), 1), (32, 0, 8, 16, (64, 64), 1), (2048, 0, 16, 1, (8, 8), 1)])
 def test_groupnorm_swish_operator(ca, cb, G, B, HW, swish):
