@@ -375,7 +375,7 @@ def main():
         top = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[top]
         ai = a["flops"] / max(a["bytes"], 1.0)
-        tensor_bound = top in ("conv_tc", "gn_swish_conv_tc", "conv_f32", "attention") and ai * pk["hbm"] * 1e9 > pk["tf_sustained"] * 1e12
+        tensor_bound = top in ("conv_tc", "gn_swish_conv_tc", "conv_chain_tc", "conv_f32", "attention") and ai * pk["hbm"] * 1e9 > pk["tf_sustained"] * 1e12
         if tensor_bound:
             ach = a["flops"] / a["ms"] / 1e9
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"]}

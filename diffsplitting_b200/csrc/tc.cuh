@@ -64,9 +64,11 @@ struct ChainOpDesc {
 };
 struct ChainPlan {
     alignas(64) uint8_t params[4096];         // a ChainParams
-    int smem_bytes, B;
+    int smem_bytes, B, CL;                    // CL = CTAs per cluster = per sample
 };
 bool chain_level_supported(int H, int W);
+int chain_slice_rows(int cout);               // output channels per CTA (16 or 32)
+int chain_cluster_size(int cout);             // CTAs per sample; all ops of one chain must agree on both
 bool chain_conv_supported(int ca, int cb, int cout, int ks, int H, int W);
 size_t chain_packed_weight_bytes(int cout, int cin, int ks);
 int chain_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);

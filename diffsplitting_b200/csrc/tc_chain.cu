@@ -3,19 +3,26 @@
 // At 8x8 (and 16x16) a layer of the splitting networks is 1..3 tiles of 128 output rows per sample: launched one layer per
 // kernel it occupies a third of the SMs for ~10 us of which most is launch / drain / dependency latency (profiles/README.md).
 // But GroupNorm, the convolutions and the residual adds never mix samples (model/sr3_modules/unet.py:80-123), so the whole
-// run of consecutive low-resolution layers of ONE sample needs no grid-wide dependency: one CTA per sample walks the ops
-// of the run, with CTA barriers where a kernel boundary used to be.
+// run of consecutive low-resolution layers of ONE sample needs no grid-wide dependency.
 //
-//   warp 0        weight producer: cp.async.bulk of (tap, 64-channel chunk) slabs [plane][Cout][16 B] through an mbarrier
+// One thread-block CLUSTER per sample walks the ops of the run; the CTAs of the cluster split the OUTPUT channels
+// (slices of `ns` = 16 or 32): an SM can only ingest ~25-30 B/clk from L2 (measured: one CTA streaming the 295 KB of a
+// 128x128x3x3 layer took 12k cycles), so the weights of a layer must be spread over several SMs.  Every CTA stages the
+// full A operand (all input channels of its sample), multiplies it with its weight slice, writes its output channels and
+// their statistics to global memory, and the cluster meets at an mbarrier-based cluster barrier where a kernel boundary
+// used to be.
+//
+//   warp 0        weight producer: cp.async.bulk of (tap, 128-channel chunk) slabs [plane][ns][16 B] through an mbarrier
 //                 ring; runs ahead across op boundaries (weights are constants), also before griddepcontrol.wait
-//   warp 1        MMA issuer: tcgen05.mma M=128, N=Cout (<= 256), accumulators in TMEM
+//   warp 1        MMA issuer: tcgen05.mma M=128, N=ns, accumulators in TMEM
 //   warps 2..15   workers: build the scale/shift table from the producers' fp64 (sum, sumsq), stage the A operand
 //                 (fp32 -> normalise -> Swish -> bf16, flat zero-padded index space exactly as tc_halo.cu, so a filter
 //                 tap is a shift of the descriptor start address); warps 2..5 also run the epilogue (bias, time vector,
 //                 fp32 residual, fp32 / bf16 stores, statistics of the output for the next GroupNorm)
 //
 // Activations stay in the planner's global buffers (L2 resident); tensors written earlier in the same launch are read with
-// ld.global.cg (never the non-coherent path).  Statistics go to the same replicated fp64 slots the other kernels use.
+// ld.global.cg (never the non-coherent path).  Statistics go to copy 0 of the replicated fp64 slots the other kernels use
+// (plain stores: every channel has exactly one owner CTA).
 #include <cuda.h>
 
 #include "tc.cuh"
@@ -28,61 +35,158 @@ constexpr int CH_WORKERS = CH_THREADS - 64;       // warps 2..15
 constexpr int CH_MAX_GROUPS = 64;
 constexpr int CH_MAX_C = 256;                     // input channels (concat) and output channels
 constexpr int CH_INFLIGHT = 4;                    // staged work items in flight per worker thread
-constexpr int CH_KC = 64;                         // channels per weight slab
+constexpr int CH_KC = 128;                        // channels per weight slab
+constexpr int CH_MAX_PX = 176;                    // staged pixels per tile: 130 + 2 (W + 2), W <= 20
 constexpr size_t CH_SMEM_LIMIT = 208 * 1024;
 
 struct ChainDev {                                 // device view of one op
     const void* src_a; const void* src_b;         // fp32 NHWC (src_b16 = 0) or bf16 NHWC (src_b16 = 1, no normalisation)
     const double* sums_a; const double* sums_b;   // replicated per-channel fp64 (sum, sumsq) of the sources (norm = 1)
     const float* gamma; const float* beta;
-    const uint8_t* w;                             // bf16 [tap][chunk][plane][Npad][8]
+    const uint8_t* w;                             // bf16 [slice][tap][plane][ns][8]
     TcEpi epi;
-    int ca, cb, G, swish, norm, ntaps, Npad, src_b16;
+    int ca, cb, G, swish, norm, ntaps, src_b16;
 };
 
 struct ChainParams {
-    int nops, B, H, W, Wp, HpWp, mtiles, plane_px, stages;
-    uint32_t stage_bytes, a_bytes, tmem_cols;
+    int nops, B, H, W, Wp, HpWp, mtiles, plane_px, stages, CL, ns;
+    uint32_t stage_bytes, a_bytes;
+    FastDiv div_px, div_wp;
     TraceSlot trace;
+    long long* dbg;                               // optional: clock64 stamps of CTA 0, 6 per op (first tile)
     ChainDev ops[CHAIN_MAX_OPS];
 };
 static_assert(sizeof(ChainParams) <= 4000, "ChainParams must stay a by-value kernel parameter");
+#define CH_STAMP(k) do { if (p.dbg && blockIdx.x == 0 && wt == 0 && t == 0) p.dbg[oi * 6 + (k)] = clock64(); } while (0)
 
 __device__ __forceinline__ void ch_bar_workers() { asm volatile("bar.sync 2, %0;" ::"n"(CH_WORKERS) : "memory"); }
 __device__ __forceinline__ void ch_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void cluster_mbar_arrive(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(local_bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// column sums of a 32-row x 16-column block held as v[16] per lane: recursive halving, 16 shuffles; afterwards lane l holds
+// the sum of column  8 b4 + 4 b3 + 2 b2 + b1  (b_k = bit k of l), duplicated in the lane pair (l, l ^ 1)
+__device__ __forceinline__ float ch_colsum16(const float (&v)[16], int lane) {
+    float a[8];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float mine = hi ? v[j + 8] : v[j], other = hi ? v[j] : v[j + 8];
+            a[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        }
+    }
+    float b4[4];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mine = hi ? a[j + 4] : a[j], other = hi ? a[j] : a[j + 4];
+            b4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+        }
+    }
+    float c2[2];
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float mine = hi ? b4[j + 2] : b4[j], other = hi ? b4[j] : b4[j + 2];
+            c2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+        }
+    }
+    const bool hi = lane & 2;
+    const float mine = hi ? c2[1] : c2[0], other = hi ? c2[0] : c2[1];
+    float d = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// bias + conditioning vector + fp32 residual of one (pixel, 16-channel chunk); the chunk lies inside Cout or is a tail
+__device__ __forceinline__ void ch_addend(const TcEpi& e, int b, int oy, int ox, int n0, float (&add)[16]) {
+    if (n0 + 16 > e.Cout) { tc_epilogue_addend<true>(e, b, oy, ox, n0, add); return; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) add[j] = 0.f;
+    if (e.bias) {
+        const float4* s = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 v = __ldg(s + j); add[4 * j] = v.x; add[4 * j + 1] = v.y; add[4 * j + 2] = v.z; add[4 * j + 3] = v.w; }
+    }
+    if (e.temb) {
+        const float4* s = reinterpret_cast<const float4*>(e.temb + (size_t)(e.temb_bcast ? 0 : b) * e.temb_stride + e.temb_off + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 v = __ldg(s + j); add[4 * j] += v.x; add[4 * j + 1] += v.y; add[4 * j + 2] += v.z; add[4 * j + 3] += v.w; }
+    }
+    if (e.residual) {
+        const float4* s = reinterpret_cast<const float4*>(e.residual + (((size_t)b * e.Ho + oy) * e.Wo + ox) * e.Cout + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 v = __ldcg(s + j); add[4 * j] += v.x; add[4 * j + 1] += v.y; add[4 * j + 2] += v.z; add[4 * j + 3] += v.w; }
+    }
+}
 
 __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_constant__ ChainParams p) {
     extern __shared__ uint8_t ch_smem[];
     const uint32_t raw = smem_u32(ch_smem);
-    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t base = (raw + 1023u) & ~1023u;      // identical offset in every CTA of the cluster (same kernel, same layout)
     uint8_t* gbase = ch_smem + (base - raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / p.CL, slice = blockIdx.x - b * p.CL;       // cluster = CL consecutive CTAs = one sample
+    const int ncol0 = slice * p.ns;                                       // first output channel of this CTA
 
     const uint32_t a_off = 0;
     const uint32_t ring_off = p.a_bytes;
     const uint32_t tab_off = ring_off + (uint32_t)p.stages * p.stage_bytes;        // float2 [CH_MAX_C]
     const uint32_t gst_off = tab_off + CH_MAX_C * 8u;                              // float2 [CH_MAX_GROUPS]
     const uint32_t chs_off = gst_off + CH_MAX_GROUPS * 8u;                         // double2 [CH_MAX_C]
-    const uint32_t bar_off = chs_off + CH_MAX_C * 16u;
+    const uint32_t pix_off = chs_off + CH_MAX_C * 16u;                             // int [CH_MAX_PX]
+    const uint32_t stat_off = pix_off + CH_MAX_PX * 4u;                            // double2 [4 quadrants][32 columns]
+    const uint32_t bar_off = stat_off + 4u * 32u * 16u;
     auto full_bar = [&](int s) { return base + bar_off + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return base + bar_off + 64u + 8u * (uint32_t)s; };
-    const uint32_t a_full = base + bar_off + 128u, mma_done = a_full + 8u, tmem_slot = a_full + 16u;
-    uint8_t* red = gbase + bar_off + 160u;
+    const uint32_t a_full = base + bar_off + 128u, mma_done = a_full + 8u, xbar = a_full + 16u, tmem_slot = a_full + 24u;
 
     trace_begin(p.trace);
     if (warp == 0 && elect_one()) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(a_full, 1);
         mbar_init(mma_done, 1);
+        mbar_init(xbar, (uint32_t)p.CL);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, 32);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.CL > 1) cluster_sync_all();             // every CTA's cluster barrier is initialised before anyone arrives on it
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -94,12 +198,13 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
             for (int oi = 0; oi < p.nops; ++oi) {
                 const ChainDev& o = p.ops[oi];
                 const int C = o.ca + o.cb;
+                const uint8_t* wslice = o.w + (size_t)slice * o.ntaps * C * p.ns * 2;
                 for (int t = 0; t < p.mtiles; ++t) {
-                    const uint8_t* src = o.w;
+                    const uint8_t* src = wslice;
                     for (int tap = 0; tap < o.ntaps; ++tap) {
                         for (int c0 = 0; c0 < C; c0 += CH_KC, ++u) {
                             const int kc = min(CH_KC, C - c0);
-                            const uint32_t bytes = (uint32_t)kc * o.Npad * 2u;
+                            const uint32_t bytes = (uint32_t)kc * p.ns * 2u;
                             const int s = u % p.stages;
                             mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
                             mbar_expect_tx(full_bar(s), bytes);
@@ -118,14 +223,16 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
             const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
             const uint32_t a_lo0 = (((base + a_off) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ns >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_lbo = (uint32_t)p.ns;                                  // (ns * 16 B) >> 4: between the two planes of a K step
+            const uint32_t a_kstep = (2u * plane_bytes) >> 4, b_kstep = 2u * b_lbo;
             for (int oi = 0; oi < p.nops; ++oi) {
                 const ChainDev& o = p.ops[oi];
                 const int C = o.ca + o.cb;
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(o.Npad >> 3) << 17) | ((128u >> 4) << 24);
-                const uint32_t b_lbo = ((uint32_t)o.Npad * 16u) >> 4;                // between the two 8-channel planes of a K step
                 for (int t = 0; t < p.mtiles; ++t, ++it) {
                     mbar_wait(a_full, (uint32_t)it & 1u);
                     tc_fence_after();
+                    long long wait_full = 0;
                     uint32_t first = 1;
                     for (int tap = 0; tap < o.ntaps; ++tap) {
                         const int r = o.ntaps == 9 ? tap / 3 : 1;
@@ -134,20 +241,26 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                         for (int c0 = 0; c0 < C; c0 += CH_KC, ++u) {
                             const int kc = min(CH_KC, C - c0);
                             const int s = u % p.stages;
+                            const long long w0 = p.dbg ? clock64() : 0;
                             mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
+                            if (p.dbg) wait_full += clock64() - w0;
                             tc_fence_after();
-                            uint32_t a_lo = a_tap + (uint32_t)(c0 >> 3) * (plane_bytes >> 4);
-                            uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
-                            for (int k = 0; k < kc; k += 16) {
-                                umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first ? 0u : 1u);
-                                first = 0;
-                                a_lo += (2u * plane_bytes) >> 4;
-                                b_lo += 2u * b_lbo;
+                            const uint32_t a_lo = a_tap + (uint32_t)(c0 >> 3) * (plane_bytes >> 4);
+                            const uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
+                            const int ksteps = kc >> 4;
+                            // all descriptors of the slab are independent adds: the up-to-8 MMAs issue back to back
+#pragma unroll
+                            for (int k = 0; k < CH_KC / 16; ++k) {
+                                if (k < ksteps)
+                                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)k * a_kstep),
+                                              ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, (first && k == 0) ? 0u : 1u);
                             }
+                            first = 0;
                             umma_commit(empty_bar(s));
                         }
                     }
                     umma_commit(mma_done);
+                    if (p.dbg && blockIdx.x == 0 && t == 0) p.dbg[oi * 6 + 5] = wait_full;
                 }
             }
         }
@@ -157,13 +270,16 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
         const int wt = tid - 64;
         pdl_wait();
         float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
-        float2* gst = reinterpret_cast<float2*>(gbase + gst_off);
-        double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
+            double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
+        int* pixinfo = reinterpret_cast<int*>(gbase + pix_off);
+        double2* stat = reinterpret_cast<double2*>(gbase + stat_off);
         const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
         int it = 0;
+        int pix_tile = -1;                        // tile the pixel table currently describes
         for (int oi = 0; oi < p.nops; ++oi) {
             const ChainDev& o = p.ops[oi];
             const int C = o.ca + o.cb;
+            { const int t = 0; CH_STAMP(0); }
             // ---- scale / shift table of the fused GroupNorm (a = rstd * gamma, sh = beta - mean * a)
             if (o.norm) {
                 const int cpg = C / o.G;
@@ -182,27 +298,39 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 }
                 ch_bar_workers();
                 const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
-                for (int g = wt; g < o.G; g += CH_WORKERS) {
+                for (int cc = wt; cc < C; cc += CH_WORKERS) {       // every channel folds its own group (cpg smem reads)
+                    const int g0 = cc / cpg * cpg;
                     double sm = 0.0, sq = 0.0;
-                    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) { sm += chs[cc].x; sq += chs[cc].y; }
+                    for (int k = g0; k < g0 + cpg; ++k) { sm += chs[k].x; sq += chs[k].y; }
                     const double mu = sm * inv_cnt;
                     double var = sq * inv_cnt - mu * mu;
                     if (var < 0.0) var = 0.0;
-                    gst[g] = make_float2((float)mu, rsqrtf((float)var + 1e-5f));
+                    const float a = rsqrtf((float)var + 1e-5f) * __ldg(o.gamma + cc);
+                    tab[cc] = make_float2(a, __ldg(o.beta + cc) - (float)mu * a);
                 }
-                ch_bar_workers();
-                for (int cc = wt; cc < C; cc += CH_WORKERS) {
-                    const float2 st = gst[cc / cpg];
-                    const float a = st.y * __ldg(o.gamma + cc);
-                    tab[cc] = make_float2(a, __ldg(o.beta + cc) - st.x * a);
-                }
-                ch_bar_workers();
             }
+            if (o.epi.sums_out && wt < 128) stat[wt] = make_double2(0.0, 0.0);
             for (int t = 0; t < p.mtiles; ++t, ++it) {
-                // ---- stage the A operand of this tile: flat padded positions [128 t - Wp - 1, 128 t + 128 + Wp + 1)
+                // ---- pixel table of this tile: staged position -> pixel index inside the sample, or -1 = zero padding
                 const int q_first = t * 128 - p.Wp - 1;
+                if (pix_tile != t) {
+                    for (int px = wt; px < p.plane_px; px += CH_WORKERS) {
+                        const int q = q_first + px;
+                        int v = -1;
+                        if (q >= 0 && q < p.HpWp) {
+                            const int yy = fdiv(q, p.div_wp), xx = q - yy * p.Wp;
+                            if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) v = (yy - 1) * p.W + (xx - 1);
+                        }
+                        pixinfo[px] = v;
+                    }
+                    pix_tile = t;
+                }
+                ch_bar_workers();                  // table + pixel table visible
+                CH_STAMP(1);
+                // ---- stage the A operand of this tile: flat padded positions [128 t - Wp - 1, 128 t + 128 + Wp + 1)
                 const int npl = C >> 3;
                 const int items = p.plane_px * npl;
+                const size_t pix0 = (size_t)b * p.H * p.W;
                 // work item = (8-channel plane, pixel); CH_INFLIGHT items in flight per thread (the loads are L2 round trips)
                 for (int i0 = wt; i0 < items; i0 += CH_INFLIGHT * CH_WORKERS) {
                     uint4 raw0[CH_INFLIGHT], raw1[CH_INFLIGHT];
@@ -214,14 +342,12 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                         okv[e] = false;
                         kpv[e] = -1;
                         if (i >= items) continue;
-                        const int kp = i / p.plane_px, px = i - kp * p.plane_px;
+                        const int kp = fdiv(i, p.div_px), px = i - kp * p.plane_px;
                         kpv[e] = kp; pxv[e] = px;
-                        const int q = q_first + px;
-                        if (q < 0 || q >= p.HpWp) continue;
-                        const int yy = q / p.Wp, xx = q - yy * p.Wp;
-                        if (yy < 1 || yy > p.H || xx < 1 || xx > p.W) continue;
+                        const int pi = pixinfo[px];
+                        if (pi < 0) continue;
                         okv[e] = true;
-                        const size_t pix = ((size_t)b * p.H + (yy - 1)) * p.W + (xx - 1);
+                        const size_t pix = pix0 + (size_t)pi;
                         const int c0 = kp * 8;
                         if (o.src_b16) {
                             const __nv_bfloat16* src = c0 < o.ca ? reinterpret_cast<const __nv_bfloat16*>(o.src_a) + pix * o.ca + c0
@@ -279,7 +405,8 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 fence_proxy_async();
                 ch_bar_workers();
                 if (wt == 0) ch_mbar_arrive(a_full);
-                // ---- epilogue (warps 2..5: TMEM lane quadrant = warp & 3)
+                CH_STAMP(2);
+                // ---- epilogue (warps 2..5: TMEM lane quadrant = warp & 3): this CTA's ns output channels
                 if (warp < 6) {
                     const int qd = warp & 3;
                     const int m = qd * 32 + lane;
@@ -287,29 +414,66 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                     bool valid = q < p.HpWp;
                     int oy = 0, ox = 0;
                     if (valid) {
-                        const int yy = q / p.Wp, xx = q - yy * p.Wp;
+                        const int yy = fdiv(q, p.div_wp), xx = q - yy * p.Wp;
                         valid = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
                         oy = yy - 1;
                         ox = xx - 1;
                     }
-                    float add[16];
-                    if (valid) tc_epilogue_addend<true>(o.epi, b, oy, ox, 0, add);
+                    float add0[16], add1[16];                  // both chunks' addends are in flight while the MMAs run
+                    const bool two = p.ns > 16;
+                    if (valid) {
+                        ch_addend(o.epi, b, oy, ox, ncol0, add0);
+                        if (two) ch_addend(o.epi, b, oy, ox, ncol0 + 16, add1);
+                    }
                     mbar_wait(mma_done, (uint32_t)it & 1u);
                     tc_fence_after();
-                    for (int c0 = 0; c0 < o.Npad; c0 += 16) {
+                    CH_STAMP(3);
+#pragma unroll
+                    for (int ck = 0; ck < 2; ++ck) {
+                        if (ck == 1 && !two) break;
                         uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+                        tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ck * 16), v);
                         float f[16];
-                        if (valid) {
-                            if (c0) tc_epilogue_addend<true>(o.epi, b, oy, ox, c0, add);
-                            tc_epilogue_write(o.epi, v, add, b, oy, ox, c0, f);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+                        if (valid) tc_epilogue_write(o.epi, v, ck ? add1 : add0, b, oy, ox, ncol0 + ck * 16, f);
+                        if (o.epi.sums_out) {
+                            float sq[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) sq[j] = f[j] * f[j];
+                            const float s1 = ch_colsum16(f, lane), s2 = ch_colsum16(sq, lane);
+                            if (!(lane & 1)) {
+                                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                double2& d = stat[qd * 32 + ck * 16 + col];       // owned by this lane for the whole op
+                                d.x += (double)s1;
+                                d.y += (double)s2;
+                            }
                         }
-                        if (o.epi.sums_out) tc_epilogue_stats(o.epi, f, valid, b, c0, m, wt, b, b % TC_SUM_COPIES, red);
                     }
                     tc_fence_before();
+                    // ---- after the last tile: statistics of this CTA's output channels -> copy 0 of the replicated slots
+                    // (plain stores: every channel has one owner CTA)
+                    if (o.epi.sums_out && t == p.mtiles - 1) {
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (wt < p.ns && ncol0 + wt < o.epi.Cout) {
+                            double sm = 0.0, sq = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { sm += stat[k * 32 + wt].x; sq += stat[k * 32 + wt].y; }
+                            double* dst = o.epi.sums_out + ((size_t)b * o.epi.Cout + ncol0 + wt) * 2;
+                            __stcg(reinterpret_cast<double2*>(dst), make_double2(sm, sq));
+                        }
+                    }
                     __threadfence();
+                    CH_STAMP(4);
                 }
-                ch_bar_workers();          // outputs + statistics of this tile are visible to the CTA; A buffer and TMEM are free
+                ch_bar_workers();          // outputs (and statistics) are fenced; A buffer and TMEM are free
+            }
+            // ---- cluster barrier: every CTA of the sample has written (and fenced) its channels of this op
+            if (p.CL > 1) {
+                if (wt == 0) {
+                    for (int r = 0; r < p.CL; ++r) cluster_mbar_arrive(xbar, (uint32_t)r);
+                }
+                cluster_mbar_wait(xbar, (uint32_t)oi & 1u);
             }
         }
     }
@@ -318,39 +482,48 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
     trace_end(p.trace);
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        tmem_dealloc(tmem_base, 32);
     }
+    if (p.CL > 1) cluster_sync_all();             // nobody exits while a peer may still arrive on its barrier
 }
 
 // ------------------------------------------------------------------------------------------ host side
 static int chain_plane_px(int W) { return (130 + 2 * (W + 2) + 7) / 8 * 8; }
 
-bool chain_level_supported(int H, int W) { return (H + 2) * (W + 2) <= 128 * CHAIN_MAX_MTILES; }
+bool chain_level_supported(int H, int W) { return (H + 2) * (W + 2) <= 128 * CHAIN_MAX_MTILES && chain_plane_px(W) <= CH_MAX_PX; }
+
+int chain_slice_rows(int cout) {
+    const int npad = (cout + 15) / 16 * 16;
+    return npad % 32 == 0 ? 32 : 16;
+}
+
+int chain_cluster_size(int cout) { return (cout + 15) / 16 * 16 / chain_slice_rows(cout); }
 
 bool chain_conv_supported(int ca, int cb, int cout, int ks, int H, int W) {
     const int C = ca + cb;
     if (!chain_level_supported(H, W)) return false;
     if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > CH_MAX_C) return false;
-    if (cout <= 0 || (cout + 15) / 16 * 16 > CH_MAX_C) return false;
+    const int npad = (cout + 15) / 16 * 16;
+    if (cout <= 0 || npad > CH_MAX_C || chain_cluster_size(cout) > 8) return false;
     return ks == 1 || ks == 3;
 }
 
 size_t chain_packed_weight_bytes(int cout, int cin, int ks) { return (size_t)ks * ks * cin * ((cout + 15) / 16 * 16) * 2; }
 
-// w_oihw fp32 [cout][cin][ks][ks] -> bf16 [tap][chunk of <= 64 channels][8-channel plane][Npad rows][8]
+// w_oihw fp32 [cout][cin][ks][ks] -> bf16 [slice of ns output channels][tap][8-channel plane][ns rows][8]
 __global__ void pack_chain_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int ks,
-                                         int npad) {
+                                         int npad, int ns) {
     const int ntaps = ks * ks;
     const size_t total = (size_t)ntaps * cin * npad;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        // planes are contiguous over the whole K range of a tap, so [chunk][plane] == [global plane]
         size_t r = i;
         const int j = (int)(r % 8); r /= 8;
-        const int row = (int)(r % npad); r /= npad;
+        const int row = (int)(r % ns); r /= ns;
         const int plane = (int)(r % (cin / 8)); r /= (cin / 8);
-        const int tap = (int)r;
+        const int tap = (int)(r % ntaps); r /= ntaps;
+        const int n = (int)r * ns + row;
         const int c = plane * 8 + j;
-        const float v = row < cout ? w[((size_t)row * cin + c) * ntaps + tap] : 0.f;
+        const float v = n < cout ? w[((size_t)n * cin + c) * ntaps + tap] : 0.f;
         out[i] = __float2bfloat16_rn(v);
     }
 }
@@ -360,7 +533,8 @@ int chain_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int c
     const int npad = (cout + 15) / 16 * 16;
     const size_t total = (size_t)ks * ks * cin * npad;
     int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
-    pack_chain_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, ks, npad);
+    pack_chain_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, ks, npad,
+                                                     chain_slice_rows(cout));
     DS_CHECK_LAUNCH("pack_chain_weight");
     return DS_OK;
 }
@@ -374,11 +548,17 @@ int chain_build(ChainPlan* plan, const ChainOpDesc* ops, int nops, int B, int H,
     p->nops = nops; p->B = B; p->H = H; p->W = W; p->Wp = W + 2; p->HpWp = (H + 2) * (W + 2);
     p->mtiles = (p->HpWp + 127) / 128;
     p->plane_px = chain_plane_px(W);
-    int cmax = 0, nmax = 0;
+    p->div_px = make_fastdiv((uint32_t)p->plane_px);
+    p->div_wp = make_fastdiv((uint32_t)p->Wp);
+    p->ns = chain_slice_rows(ops[0].cout);
+    p->CL = chain_cluster_size(ops[0].cout);
+    int cmax = 0;
     for (int i = 0; i < nops; ++i) {
         const ChainOpDesc& d = ops[i];
         DS_REQUIRE(chain_conv_supported(d.ca, d.cb, d.cout, d.ks, H, W), "chain: op %d has an unsupported shape (%d+%d -> %d, k%d)", i,
                    d.ca, d.cb, d.cout, d.ks);
+        DS_REQUIRE(chain_slice_rows(d.cout) == p->ns && chain_cluster_size(d.cout) == p->CL,
+                   "chain: op %d (%d output channels) does not split like op 0 (%d slices of %d)", i, d.cout, p->CL, p->ns);
         DS_REQUIRE(!d.norm || (d.G > 0 && d.G <= CH_MAX_GROUPS && (d.ca + d.cb) % d.G == 0 && d.sums_a && (d.cb == 0 || d.sums_b)),
                    "chain: op %d has an invalid GroupNorm (G=%d)", i, d.G);
         DS_REQUIRE(!(d.src_b16 && (d.norm || d.swish)), "chain: op %d normalises a bf16 source", i);
@@ -386,26 +566,28 @@ int chain_build(ChainPlan* plan, const ChainOpDesc* ops, int nops, int B, int H,
         o.src_a = d.src_a; o.src_b = d.src_b; o.ca = d.ca; o.cb = d.cb;
         o.sums_a = d.sums_a; o.sums_b = d.sums_b; o.gamma = d.gamma; o.beta = d.beta;
         o.G = d.G > 0 ? d.G : 1; o.swish = d.swish; o.norm = d.norm; o.src_b16 = d.src_b16;
-        o.w = d.w; o.ntaps = d.ks * d.ks; o.Npad = (d.cout + 15) / 16 * 16;
+        o.w = d.w; o.ntaps = d.ks * d.ks;
         o.epi.bias = d.epi.bias; o.epi.temb = d.epi.temb; o.epi.temb_off = d.epi.temb_off; o.epi.temb_stride = d.epi.temb_stride;
         o.epi.temb_bcast = d.epi.temb_bcast; o.epi.residual = d.epi.residual;
         o.epi.out_f32 = d.out_f32; o.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(d.out_b16); o.epi.out_nchw = nullptr;
         o.epi.sums_out = d.sums_out; o.epi.sums_B = B;
         o.epi.Cout = d.cout; o.epi.Ho = H; o.epi.Wo = W;
         cmax = cmax > d.ca + d.cb ? cmax : d.ca + d.cb;
-        nmax = nmax > o.Npad ? nmax : o.Npad;
     }
     p->a_bytes = (uint32_t)align_up((size_t)(cmax / 8) * p->plane_px * 16, 1024);
-    p->stage_bytes = (uint32_t)align_up((size_t)nmax * CH_KC * 2, 1024);
-    const size_t fixed = p->a_bytes + CH_MAX_C * 8 + CH_MAX_GROUPS * 8 + CH_MAX_C * 16 + 160 + TC_RED_BYTES + 1024 + 64;
+    p->stage_bytes = (uint32_t)align_up((size_t)p->ns * CH_KC * 2, 1024);
+    const size_t fixed = p->a_bytes + CH_MAX_C * 8 + CH_MAX_GROUPS * 8 + CH_MAX_C * 16 + CH_MAX_PX * 4 + 4 * 32 * 16 + 192 + 1024 + 64;
     DS_REQUIRE(fixed + 2 * (size_t)p->stage_bytes <= CH_SMEM_LIMIT, "chain: shared memory (A %u B + 2 x %u B)", p->a_bytes, p->stage_bytes);
     int stages = (int)((CH_SMEM_LIMIT - fixed) / p->stage_bytes);
     p->stages = stages > 8 ? 8 : stages;
-    p->tmem_cols = nmax <= 32 ? 32u : (nmax <= 64 ? 64u : (nmax <= 128 ? 128u : 256u));
     plan->smem_bytes = (int)(fixed + (size_t)p->stages * p->stage_bytes);
     plan->B = B;
+    plan->CL = p->CL;
     return DS_OK;
 }
+
+static long long* g_chain_dbg = nullptr;
+static int g_chain_dbg_nops = 0;
 
 int chain_launch(const ChainPlan* plan, cudaStream_t st) {
     static bool attr_set = false;
@@ -415,8 +597,43 @@ int chain_launch(const ChainPlan* plan, cudaStream_t st) {
     }
     ChainParams p = *reinterpret_cast<const ChainParams*>(plan->params);
     p.trace = trace_next(7);
-    DS_CHECK_CUDA(launch_pdl(conv_chain_kernel, dim3(plan->B), dim3(CH_THREADS), (size_t)plan->smem_bytes, st, p));
+    if (getenv("DIFFSPLIT_B200_CHAIN_DBG")) {
+        if (!g_chain_dbg) DS_CHECK_CUDA(cudaMalloc(&g_chain_dbg, CHAIN_MAX_OPS * 6 * sizeof(long long)));
+        DS_CHECK_CUDA(cudaMemsetAsync(g_chain_dbg, 0, CHAIN_MAX_OPS * 6 * sizeof(long long), st));
+        p.dbg = g_chain_dbg;
+        g_chain_dbg_nops = p.nops;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(plan->B * plan->CL));
+    cfg.blockDim = dim3(CH_THREADS);
+    cfg.dynamicSmemBytes = (size_t)plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)plan->CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    DS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, p));
     return DS_OK;
 }
 
 }  // namespace ds
+
+// debugging aid (DIFFSPLIT_B200_CHAIN_DBG=1): clock64 stamps of CTA 0 for every op of the LAST chain launch:
+// [op][0 start, 1 table built, 2 operand staged, 3 MMAs done, 4 epilogue done, 5 = cycles the MMA issuer waited for weight slabs]
+extern "C" int ds_debug_chain_phases(long long* out, int max_ops, int* n_ops) {
+    using namespace ds;
+    DS_REQUIRE(g_chain_dbg && out && n_ops, "chain debug buffer not active");
+    DS_CHECK_CUDA(cudaDeviceSynchronize());
+    const int n = g_chain_dbg_nops < max_ops ? g_chain_dbg_nops : max_ops;
+    DS_CHECK_CUDA(cudaMemcpy(out, g_chain_dbg, (size_t)n * 6 * sizeof(long long), cudaMemcpyDeviceToHost));
+    *n_ops = n;
+    return DS_OK;
+}

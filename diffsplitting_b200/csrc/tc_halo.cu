@@ -29,23 +29,6 @@ constexpr int HALO_MAX_SAMPLES = 12;
 constexpr int HALO_MAX_GROUPS = 64;
 constexpr size_t HALO_SMEM_LIMIT = 200 * 1024;
 
-// n / d for 0 <= n < 2^31 with a precomputed multiplier (CUTLASS FastDivmod scheme): no integer division on device
-struct FastDiv {
-    uint32_t d, mul, shr;
-};
-static FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    f.d = d;
-    if (d == 1) { f.mul = 0; f.shr = 0; return f; }
-    uint32_t lg = 0;
-    while ((1u << lg) < d) ++lg;
-    const uint32_t p = 31 + lg;
-    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
-    f.shr = p - 32;
-    return f;
-}
-__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
-
 struct HaloParams {
     CUtensorMap wmap;                           // packed weights as a 3-D tensor (128 bf16 = one 16-row x 8-channel plane
                                                 // of a block, 16-channel block, (tap, kstep, plane)): one TMA load lands the

@@ -29,6 +29,8 @@ struct WeightSpec {
     int tc_kc, tc_up;  // tensor-core pack variant (tc_kc == 0: layer has no bf16 pack)
     bool halo;         // additionally packed for the fused GroupNorm+Swish->conv kernel (tc_halo.cu)
     size_t off_halo;   // byte offset of that pack in the bf16 arena
+    bool chain;        // additionally packed for the per-sample persistent chain kernel (tc_chain.cu)
+    size_t off_chain;
     bool loaded;
 };
 
@@ -79,6 +81,8 @@ struct Op {
     int halo = 0;
     const GNW* fgn = nullptr;
     int fswish = 0;
+    // conv executed inside a per-sample persistent chain launch (tc_chain.cu): consecutive chain ops form one launch
+    int chain = 0, chain_src_b16 = 0;
     // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
     int64_t sums_out = NONE;             // slot the producer's epilogue accumulates into
     int64_t sums_a = NONE, sums_b = NONE;   // slots of the (two) sources a fused / apply-only GroupNorm reads
@@ -99,6 +103,9 @@ struct Plan {
     std::vector<Op> ops;
     std::vector<TcConvPlan> tc;          // per op (bf16 mode): TMA descriptors + launch geometry
     std::vector<AttnTcPlan> attn;        // per op (bf16 mode, attention ops whose channel count is a multiple of 64)
+    std::vector<ChainPlan> chains;       // per op: the launch of the chain that STARTS at this op (chain_len[i] ops)
+    std::vector<int> chain_len;          // > 0 at the first op of a chain, 0 elsewhere
+    int chain_time_len = -1;
     const void* tc_ws = nullptr;         // workspace base the descriptors were encoded for
     size_t bytes = 0;
     int64_t temb_buf = NONE, gn_scratch = NONE;
@@ -205,6 +212,8 @@ static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initia
     s.tc_up = 0;
     s.halo = false;
     s.off_halo = 0;
+    s.chain = false;
+    s.off_chain = 0;
     size_t elems = 1;
     if (kind == WK_CONV) elems = (size_t)s.shape[1] * s.shape[2] * s.shape[3] * npad;
     else if (kind == WK_VEC) elems = (size_t)(npad ? npad : s.shape[0]);
@@ -243,6 +252,11 @@ static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int k
         n->specs[c.w].halo = true;
         n->specs[c.w].off_halo = n->arena_bf16_bytes;
         n->arena_bf16_bytes += align_up(halo_packed_weight_bytes(cout, cin, ks), 1024);
+    }
+    if (tc && !up && cin % 16 == 0 && cin <= 256 && (cout + 15) / 16 * 16 <= 256) {
+        n->specs[c.w].chain = true;
+        n->specs[c.w].off_chain = n->arena_bf16_bytes;
+        n->arena_bf16_bytes += align_up(chain_packed_weight_bytes(cout, cin, ks), 1024);
     }
     if (bias) c.b = add_spec(n, p + ".bias", WK_VEC, {cout}, c.npad);
     return c;
@@ -418,7 +432,34 @@ struct Planner {
         if (b) o.sums_b = b->sums;
         p->ops.push_back(o);
     }
+    // per-sample persistent chain (tc_chain.cu): every stride-1 conv of a level whose padded sample fits `chain_mtiles`
+    // 128-row tiles
+    int chain_mtiles = 1;
+    bool chain_ok(const Act& a, const Act* b, const ConvW& w, int stride, int up) const {
+        if (!tc || chain_mtiles <= 0 || stride != 1 || up || !n->specs[w.w].chain) return false;
+        if ((a.H + 2) * (a.W + 2) > 128 * chain_mtiles) return false;
+        return chain_conv_supported(a.C, b ? b->C : 0, w.cout, w.ks, a.H, a.W);
+    }
+    void chain_conv(const Act& a, const Act* b, const GNW* g, int swish, const ConvW& w, int temb_off, const Act* residual,
+                    const Act& out) {
+        Op o; o.kind = OP_CONV;
+        o.chain = 1;
+        o.fgn = g; o.fswish = swish;
+        if (g) { o.sums_a = a.sums; if (b) o.sums_b = b->sums; }
+        o.chain_src_b16 = a.f32 == NONE ? 1 : 0;
+        o.src_a = o.chain_src_b16 ? a.b16 : a.f32; o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
+        if (b) { o.src_b = o.chain_src_b16 ? b->b16 : b->f32; o.cb = b->C; }
+        o.cw = &w; o.temb_off = temb_off; o.Ho = out.H; o.Wo = out.W;
+        if (residual) o.residual = residual->f32;
+        o.dst = out.f32; o.dst_b16 = out.b16;
+        o.sums_out = out.sums;
+        p->ops.push_back(o);
+    }
     void conv(const Act& a, const Act* b, const ConvW& w, int stride, int up, int temb_off, const Act* residual, const Act& out) {
+        if (chain_ok(a, b, w, stride, up) && ((a.f32 != NONE && (!b || b->f32 != NONE)) || (a.f32 == NONE && a.b16 != NONE && !b))) {
+            chain_conv(a, b, nullptr, 0, w, temb_off, residual, out);
+            return;
+        }
         Op o; o.kind = OP_CONV;
         o.src_a = conv_src(a); o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
         if (b) { o.src_b = conv_src(*b); o.cb = b->C; }
@@ -435,6 +476,10 @@ struct Planner {
     void gn_conv(const Act& a, const Act* b, const GNW& g, int swish, const ConvW& w, int temb_off, const Act* residual,
                  const Act& out) {
         const int cb = b ? b->C : 0;
+        if (chain_ok(a, b, w, 1, 0) && a.f32 != NONE && (!b || b->f32 != NONE) && a.sums != NONE && (!b || b->sums != NONE)) {
+            chain_conv(a, b, &g, swish, w, temb_off, residual, out);
+            return;
+        }
         if (tc && n->specs[w.w].halo && halo_conv_supported(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
             Op o; o.kind = OP_CONV;
             o.sums_a = a.sums;
@@ -460,17 +505,19 @@ struct Planner {
         const int H = x.H, W = x.W;
         Act resid = x;
         Act rbuf;
+        bool res_side = false;
         if (r.has_res) {            // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
             rbuf = make(r.cout, H, W, F32, false);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
-            p->ops.back().side = tc ? 1 : 0;
+            p->ops.back().side = (tc && !p->ops.back().chain) ? 1 : 0;
+            res_side = p->ops.back().side != 0;
             resid = rbuf;
         }
         Act h = make(r.cout, H, W, F32);
         gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act out = make(r.cout, H, W, F32 | B16);
         gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, &resid, out);
-        if (r.has_res && tc) {
+        if (r.has_res && tc && res_side) {
             for (size_t i = p->ops.size(); i-- > 0;)
                 if (p->ops[i].kind == OP_CONV && p->ops[i].cw == &r.conv2) { p->ops[i].join = 1; break; }
         }
@@ -506,6 +553,11 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     Planner P(n, p, !n->keep_taps);
     P.B = B;
     P.tc = prec == DS_PREC_BF16;
+    {
+        const char* e = getenv("DIFFSPLIT_B200_CHAIN_MTILES");      // 0 disables the per-sample persistent chains
+        P.chain_mtiles = e ? atoi(e) : 1;
+        if (P.chain_mtiles > CHAIN_MAX_MTILES) P.chain_mtiles = CHAIN_MAX_MTILES;
+    }
     if (d.with_time_emb) p->temb_buf = P.arena.alloc((size_t)B * n->temb_total * sizeof(float));
     p->gn_scratch = P.arena.alloc(gn_scratch_bytes(B, d.norm_groups));
 
@@ -566,6 +618,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
         Act ext;                       // the network output: external fp32 NCHW
         ext.f32 = EXT_OUT; ext.C = n->final_conv.cout; ext.H = x.H; ext.W = x.W;
         const size_t first_new = p->ops.size();
+        P.chain_mtiles = 0;                  // the final conv writes the caller's NCHW tensor: never part of a chain
         P.gn_conv(x, nullptr, n->final_gn, 1, n->final_conv, -1, nullptr, ext);
         for (size_t i = first_new; i < p->ops.size(); ++i)
             if (p->ops[i].kind == OP_CONV) p->ops[i].out_nchw = 1;
@@ -575,7 +628,20 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     p->stats_bytes = P.stats_top;
     p->bytes = p->stats_base + p->stats_bytes;
     int launches = d.with_time_emb ? 1 : 0;
-    for (auto& o : p->ops) launches += (o.kind == OP_GN && !P.tc) ? 2 : 1;      // fp32 GroupNorm = statistics + apply
+    int run = 0;                                                                 // ops of the current persistent chain
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        const Op& o = p->ops[i];
+        if (o.kind == OP_CONV && o.chain) {
+            const bool cont = run > 0 && run < CHAIN_MAX_OPS && p->ops[i - 1].Hs == o.Hs && p->ops[i - 1].Ws == o.Ws &&
+                              chain_cluster_size(p->ops[i - 1].cw->cout) == chain_cluster_size(o.cw->cout) &&
+                              chain_slice_rows(p->ops[i - 1].cw->cout) == chain_slice_rows(o.cw->cout);
+            if (!cont) { ++launches; run = 0; }
+            ++run;
+            continue;
+        }
+        run = 0;
+        launches += (o.kind == OP_GN && !P.tc) ? 2 : 1;                          // fp32 GroupNorm = statistics + apply
+    }
     if (P.tc && p->stats_bytes) ++launches;                                      // the statistics-arena memset
     p->launches = launches;
     *out = p;
@@ -672,6 +738,10 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
             }
             if (s.halo) {
                 rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
+                if (rc != DS_OK) return rc;
+            }
+            if (s.chain) {
+                rc = chain_pack_conv_weight(src, n->d_arena_bf16 + s.off_chain, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
                 if (rc != DS_OK) return rc;
             }
         } else {
@@ -842,7 +912,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 rc = attn_tc_build(&p->attn[i], ptr(o.src_a), ptr(o.dst_b16), B, o.N, o.C);
                 if (rc != DS_OK) return rc;
             }
-            if (o.kind != OP_CONV || o.src_nchw || o.halo) continue;
+            if (o.kind != OP_CONV || o.src_nchw || o.halo || o.chain) continue;
             if (!n->specs[o.cw->w].tc_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws)) {
                 set_error("unet_forward: bf16 mode needs channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
                           n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
@@ -855,11 +925,51 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 return DS_ERR_INVALID;
             }
         }
-        p->tc_ws = d_ws;
     }
     auto sums = [&](int64_t off) -> double* {
         return off == NONE ? nullptr : reinterpret_cast<double*>(base + p->stats_base + off);
     };
+    if (tc && (p->tc_ws != d_ws || p->chain_time_len != time_len)) {
+        // per-sample persistent chains: maximal runs of consecutive chain ops at one resolution -> one launch each
+        p->chains.assign(p->ops.size(), ChainPlan());
+        p->chain_len.assign(p->ops.size(), 0);
+        size_t i = 0;
+        while (i < p->ops.size()) {
+            if (!(p->ops[i].kind == OP_CONV && p->ops[i].chain)) { ++i; continue; }
+            size_t j = i;
+            std::vector<ChainOpDesc> descs;
+            while (j < p->ops.size() && p->ops[j].kind == OP_CONV && p->ops[j].chain && p->ops[j].Hs == p->ops[i].Hs &&
+                   p->ops[j].Ws == p->ops[i].Ws && (int)descs.size() < CHAIN_MAX_OPS &&
+                   chain_cluster_size(p->ops[j].cw->cout) == chain_cluster_size(p->ops[i].cw->cout) &&
+                   chain_slice_rows(p->ops[j].cw->cout) == chain_slice_rows(p->ops[i].cw->cout)) {
+                const Op& o = p->ops[j];
+                ChainOpDesc d;
+                memset(&d, 0, sizeof(d));
+                d.src_a = ptr(o.src_a); d.src_b = ptr(o.src_b); d.ca = o.ca; d.cb = o.cb; d.src_b16 = o.chain_src_b16;
+                d.norm = o.fgn ? 1 : 0; d.swish = o.fswish; d.G = n->d.norm_groups;
+                d.sums_a = sums(o.sums_a); d.sums_b = sums(o.sums_b);
+                d.gamma = o.fgn ? n->wp(o.fgn->w) : nullptr; d.beta = o.fgn ? n->wp(o.fgn->b) : nullptr;
+                d.w = n->d_arena_bf16 + n->specs[o.cw->w].off_chain;
+                d.cout = o.cw->cout; d.ks = o.cw->ks;
+                d.epi.bias = o.cw->b >= 0 ? n->wp(o.cw->b) : nullptr;
+                d.epi.temb = o.temb_off >= 0 ? temb : nullptr;
+                d.epi.temb_off = o.temb_off >= 0 ? o.temb_off : 0;
+                d.epi.temb_stride = n->temb_total;
+                d.epi.temb_bcast = (time_len == 1);
+                d.epi.residual = ptr(o.residual);
+                d.out_f32 = ptr(o.dst); d.out_b16 = ptr(o.dst_b16);
+                d.sums_out = sums(o.sums_out);
+                descs.push_back(d);
+                ++j;
+            }
+            rc = chain_build(&p->chains[i], descs.data(), (int)descs.size(), B, p->ops[i].Hs, p->ops[i].Ws);
+            if (rc != DS_OK) return rc;
+            p->chain_len[i] = (int)descs.size();
+            i = j;
+        }
+        p->chain_time_len = time_len;
+    }
+    if (tc) p->tc_ws = d_ws;
     if (tc && p->stats_bytes) DS_CHECK_CUDA(cudaMemsetAsync(base + p->stats_base, 0, p->stats_bytes, st));
     size_t op_index = 0;
     for (const Op& o : p->ops) {
@@ -907,7 +1017,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.residual = ptr(o.residual);
                 e.out_nchw = o.out_nchw;
                 e.out2_bf16 = ptr(o.dst_b16);
-                if (o.halo) {
+                if (o.chain) {
+                    used_tc = true;
+                    rc = p->chain_len[oi] > 0 ? chain_launch(&p->chains[oi], st) : DS_OK;   // later ops of a chain: nothing to do
+                } else if (o.halo) {
                     used_tc = true;
                     HaloNorm nm;
                     nm.stats = nullptr; nm.sums_a = sums(o.sums_a); nm.sums_b = sums(o.sums_b);
@@ -947,7 +1060,8 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
             r.launches = 1;
             if (o.kind == OP_CONV) {
                 const int cin = o.src_nchw ? ca + cb : o.ca + o.cb;
-                r.kind = o.halo ? 6 : (used_tc ? 4 : 1);
+                r.kind = o.chain ? 7 : (o.halo ? 6 : (used_tc ? 4 : 1));
+                if (o.chain && p->chain_len[oi] == 0) r.launches = 0;
                 r.cin = cin; r.cout = o.cw->cout; r.ksize = o.cw->ks; r.h = o.Ho; r.w = o.Wo;
                 r.flops = 2.0 * B * o.Ho * o.Wo * (double)o.cw->ks * o.cw->ks * cin * o.cw->cout;
                 r.bytes = 4.0 * B * ((double)o.Hs * o.Ws * cin + (double)o.Ho * o.Wo * o.cw->cout *

@@ -231,7 +231,7 @@ class UNet(nn.Module):
             None if time is None else time.data_ptr(), 0 if time is None else time.numel(), out.data_ptr(),
             B, H, W, prec, ws.data_ptr(), ws.numel(), _lib.stream_ptr(), ops, max_ops, C.byref(n)))
         names = {0: "temb", 1: "conv_f32", 2: "groupnorm_swish", 3: "attention", 4: "conv_tc", 5: "gn_stats",
-                 6: "gn_swish_conv_tc"}
+                 6: "gn_swish_conv_tc", 7: "conv_chain_tc"}
         return [dict(kind=names[o.kind], cin=o.cin, cout=o.cout, ksize=o.ksize, h=o.h, w=o.w, launches=o.launches,
                      ms=o.ms, flops=o.flops, bytes=o.bytes) for o in ops[:n.value]]
 

@@ -89,7 +89,8 @@ double ds_unet_flops(const ds_unet* net, int H, int W);
 int  ds_unet_launches(ds_unet* net, int B, int H, int W, int precision);
 /* measurement: the same forward with a CUDA-event pair around every operator (synchronises; not capturable).
  * kind: 0 conditioning MLP, 1 conv fp32 (CUDA cores), 2 group-norm(+swish) (2 launches), 3 attention, 4 conv bf16
- * (tcgen05, TMA-fed), 5 group-norm statistics only, 6 fused group-norm-apply + swish + conv bf16 (tcgen05, staged).
+ * (tcgen05, TMA-fed), 5 group-norm statistics only, 6 fused group-norm-apply + swish + conv bf16 (tcgen05, staged),
+ * 7 the same inside a per-sample persistent chain launch (time reported on the chain's first operator, launches = 0 on the rest).
  * flops / bytes are the ALGORITHMIC figures of that operator for the whole batch. */
 typedef struct ds_op_profile {
     int32_t kind, cin, cout, ksize, h, w, launches;
@@ -143,6 +144,7 @@ size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ks
 int ds_debug_halo_phases(double* h_out7, int* n_ctas);
 /* debugging aid (DIFFSPLIT_B200_TRACE=1): GPU-timer (ns) start / end of every tensor-core conv launch, also inside
  * CUDA-graph replays.  reset(1) forgets the launch ids, reset(0) re-arms the recorded ones; read returns the count. */
+int ds_debug_chain_phases(long long* h_out, int max_ops, int* n_ops);   /* DIFFSPLIT_B200_CHAIN_DBG=1, see tc_chain.cu */
 int ds_debug_trace_reset(int forget_ids);
 int ds_debug_trace_read(unsigned long long* h_start_end, int* h_kind, int max_n);
 /* single-head attention over N=H*W tokens: qkv [B,N,3C] (q|k|v along C) -> out [B,N,C]

@@ -198,7 +198,8 @@ def test_fused_gn_swish_conv_operator(ca, cb, cout, ks, G, swish, B, H, W, resid
 @pytest.mark.parametrize("ca,cb,cmid,cout,ks,G,B,H,W,residual", [
     (128, 0, 128, 128, 3, 16, 16, 8, 8, 1), (64, 0, 128, 128, 3, 16, 2, 8, 8, 0), (128, 128, 128, 128, 3, 16, 3, 8, 8, 0),
     (128, 64, 128, 128, 3, 16, 2, 8, 8, 1), (64, 32, 64, 64, 3, 16, 2, 16, 16, 1), (32, 0, 64, 64, 3, 16, 1, 16, 16, 0),
-    (128, 0, 128, 256, 1, 16, 2, 8, 8, 0), (16, 16, 32, 16, 3, 8, 5, 4, 4, 0), (64, 0, 64, 48, 3, 16, 2, 12, 10, 0)])
+    (128, 0, 256, 256, 1, 16, 2, 8, 8, 0), (16, 16, 32, 32, 3, 8, 5, 4, 4, 0), (64, 0, 64, 64, 3, 16, 2, 12, 10, 0),
+    (32, 0, 48, 40, 3, 8, 3, 8, 8, 1), (16, 0, 16, 16, 3, 16, 2, 16, 16, 0)])
 def test_persistent_chain_operator(ca, cb, cmid, cout, ks, G, B, H, W, residual):
     """conv_chain_kernel: two fused GN+Swish->conv ops of one sample in ONE persistent CTA (the second GroupNorm reads the
     statistics the first op's epilogue produced inside the same launch) vs the same math in float64 with bf16-rounded
