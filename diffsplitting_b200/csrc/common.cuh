@@ -110,6 +110,11 @@ int launch_conv_f32(const ConvSrc& src, const float* w_packed /*[K][Npad]*/, int
 int launch_pack_conv_weight_f32(const float* w_oihw, float* w_packed, int Cout, int Cin, int ks, int Npad,
                                 cudaStream_t st);
 
+// entry conv (conv_entry.cu): 3x3, <= 16 input channels read from fp32 NCHW, <= 64 output channels, statistics epilogue
+bool entry_conv_supported(int ca, int cb, int cout, int ks);
+int launch_conv_entry(const float* xa, int ca, const float* xb, int cb, const float* w_packed, int npad, const float* bias, int cout,
+                      int B, int H, int W, float* out_f32, void* out_b16, double* sums_out, cudaStream_t st);
+
 int gn_nsplit(int B, int HW, int C);
 size_t gn_scratch_bytes(int B, int G);
 constexpr int GN_MAX_BATCH = 4096;

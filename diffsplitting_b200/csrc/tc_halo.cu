@@ -443,7 +443,9 @@ static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_
         if (npad % c == 0) { bn = c; break; }
     // every N tile re-stages (and re-normalises) the same operand pixels: only split N for shared memory or when the
     // grid would leave most SMs idle
-    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < 48)) bn >>= 1;
+    static int min_ctas = -1;
+    if (min_ctas < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_MIN_CTAS"); min_ctas = e ? atoi(e) : 48; }
+    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < min_ctas)) bn >>= 1;
     return bn;
 }
 

@@ -83,6 +83,8 @@ struct Op {
     int fswish = 0;
     // conv executed inside a per-sample persistent chain launch (tc_chain.cu): consecutive chain ops form one launch
     int chain = 0, chain_src_b16 = 0;
+    // the network's first conv on the dedicated small-Cin kernel (conv_entry.cu), which also emits the statistics
+    int entry = 0;
     // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
     int64_t sums_out = NONE;             // slot the producer's epilogue accumulates into
     int64_t sums_a = NONE, sums_b = NONE;   // slots of the (two) sources a fused / apply-only GroupNorm reads
@@ -571,8 +573,11 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
                 Op op; op.kind = OP_CONV;
                 op.src_a = EXT_XA; op.src_b = EXT_XB; op.src_nchw = 1; op.Hs = h; op.Ws = w;
                 op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.f32; op.dst_b16 = o.b16;
+                const bool entry_kernel = P.tc && entry_conv_supported(d.in_channel, 0, L.conv.cout, L.conv.ks) &&
+                                          getenv("DIFFSPLIT_B200_NO_ENTRY_KERNEL") == nullptr;
+                if (entry_kernel) { op.entry = 1; op.sums_out = o.sums; }
                 p->ops.push_back(op);
-                if (P.tc) {       // the CUDA-core entry conv does not emit statistics: one small pass over its output
+                if (P.tc && !entry_kernel) {   // the generic CUDA-core conv does not emit statistics: one pass over its output
                     Op cs; cs.kind = OP_CH_SUMS;
                     cs.src_a = o.f32; cs.ca = o.C; cs.HW = h * w; cs.sums_out = o.sums;
                     p->ops.push_back(cs);
@@ -1017,7 +1022,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 e.residual = ptr(o.residual);
                 e.out_nchw = o.out_nchw;
                 e.out2_bf16 = ptr(o.dst_b16);
-                if (o.chain) {
+                if (o.entry) {
+                    rc = launch_conv_entry(d_xa, ca, d_xb, cb, n->wp(o.cw->w), o.cw->npad, e.bias, o.cw->cout, B, o.Ho, o.Wo, ptr(o.dst),
+                                           ptr(o.dst_b16), sums(o.sums_out), st);
+                } else if (o.chain) {
                     used_tc = true;
                     rc = p->chain_len[oi] > 0 ? chain_launch(&p->chains[oi], st) : DS_OK;   // later ops of a chain: nothing to do
                 } else if (o.halo) {
