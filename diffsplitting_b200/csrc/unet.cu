@@ -191,7 +191,7 @@ struct ds_unet {
     std::vector<Plan*> plans;
     bool keep_taps = false;
     cudaStream_t side_stream = nullptr;  // fork / join partner of the caller's stream
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_temb = nullptr;
     int skip_mask = 0;                   // timing experiments only (DIFFSPLIT_B200_SKIP): bit OpKind = do not launch
 
     const float* wp(int i) const { return d_arena + specs[i].off; }
@@ -690,6 +690,7 @@ extern "C" void ds_unet_destroy(ds_unet* n) {
     if (n->side_stream) cudaStreamDestroy(n->side_stream);
     if (n->ev_fork) cudaEventDestroy(n->ev_fork);
     if (n->ev_join) cudaEventDestroy(n->ev_join);
+    if (n->ev_temb) cudaEventDestroy(n->ev_temb);
     for (Plan* p : n->plans) delete p;
     delete n;
 }
@@ -792,6 +793,7 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
         DS_CHECK_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking));
         DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
         DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+        DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_temb, cudaEventDisableTiming));
     }
     n->weights_ready = true;
     return DS_OK;
@@ -872,6 +874,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         return reinterpret_cast<float*>(base + off);
     };
     float* temb = nullptr;
+    bool temb_pending = false;               // the conditioning kernel is in flight on the side stream
     if (n->d.with_time_emb) {
         TembParams tp;
         tp.variant = n->d.variant;
@@ -887,9 +890,20 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
             if (rc != DS_OK) return rc;
             cudaEventRecord(prof->e0, st);
         }
+        // the conditioning vectors depend only on the noise level: their kernel runs on the forked stream beside the entry
+        // conv; the first consumer waits for it
+        const bool temb_side = !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr;
+        if (temb_side) {
+            DS_CHECK_CUDA(cudaEventRecord(n->ev_fork, st));
+            DS_CHECK_CUDA(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0));
+        }
         for (int rep_i = 0; rep_i < (prof ? prof->reps : 1); ++rep_i) {
-            rc = launch_temb_f32(tp, d_time, time_len, temb, st);
+            rc = launch_temb_f32(tp, d_time, time_len, temb, temb_side ? n->side_stream : st);
             if (rc != DS_OK) return rc;
+        }
+        if (temb_side) {
+            DS_CHECK_CUDA(cudaEventRecord(n->ev_temb, n->side_stream));
+            temb_pending = true;
         }
         if (prof && prof->n < prof->max_ops) {
             cudaEventRecord(prof->e1, st);
@@ -1001,6 +1015,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 break;
             case OP_CONV: {
                 cudaStream_t st_main = st;
+                if (temb_pending && (o.temb_off >= 0 || o.chain)) {
+                    DS_CHECK_CUDA(cudaStreamWaitEvent(st_main, n->ev_temb, 0));
+                    temb_pending = false;
+                }
                 const bool on_side = o.side && !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr;
                 if (on_side) {
                     DS_CHECK_CUDA(cudaEventRecord(n->ev_fork, st_main));
@@ -1091,6 +1109,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
             }
         }
     }
+    if (temb_pending) DS_CHECK_CUDA(cudaStreamWaitEvent(st, n->ev_temb, 0));      // no consumer: still join the fork
     return DS_OK;
 }
 
