@@ -31,6 +31,12 @@ def _use_graphs() -> bool:
     return os.environ.get("DIFFSPLIT_B200_GRAPH", "1") != "0"
 
 
+def _graph_steps() -> int:
+    """Reverse steps captured into ONE CUDA graph for runs of steps without a snapshot in between (the loop state - step
+    counter, Philox offset, time level - lives on the device, so a graph of G steps is G copies of the step's nodes)."""
+    return max(1, int(os.environ.get("DIFFSPLIT_B200_GRAPH_STEPS", "8")))
+
+
 # --------------------------------------------------------------------------------------------- schedules
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
     """float64 beta table; same families as the reference (sr3 diffusion.py:19-49)."""
@@ -112,6 +118,7 @@ class _Engine:
         self.cap = 0
         self.coef = self.ttab = None
         self.graph = None
+        self.multi = None                           # (G, graph of G consecutive steps)
         self.numel = self.x.numel()
         if self.eps.numel() != self.numel:
             raise ValueError(f"UNet out_channel {net.out_channel} != sampler state channels {C_state}")
@@ -125,6 +132,7 @@ class _Engine:
             self.coef = torch.zeros((self.cap, 5), dtype=torch.float32, device=self.device)
             self.ttab = torch.zeros((self.cap + 1,), dtype=torch.float32, device=self.device)
             self.graph = None                       # table pointers are baked into the captured kernel arguments
+            self.multi = None
         self.T = T
         self.coef[:T].copy_(coef, non_blocking=False)
         self.ttab[:T].copy_(ttab[:T], non_blocking=False)
@@ -165,6 +173,27 @@ class _Engine:
             with torch.cuda.graph(g):
                 self._enqueue_step()
             self.graph = g
+
+    def run(self, n):
+        """n consecutive reverse steps; whole multiples of G go through the G-step graph."""
+        if n <= 0:
+            return
+        if self.graph is None:
+            self.step()
+            n -= 1
+        G = _graph_steps()
+        if self.graph is not None and G > 1 and n >= G:
+            if self.multi is None or self.multi[0] != G:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(G):
+                        self._enqueue_step()
+                self.multi = (G, g)
+            while n >= G:
+                self.multi[1].replay()
+                n -= G
+        for _ in range(n):
+            self.step()
 
     def launches_per_step(self):
         return self.net.launches(self.B, self.H, self.W) + 1
@@ -326,11 +355,18 @@ class _GaussianDiffusion(_SamplerBase):
                 ret = torch.empty(((len(snaps) + 1) * B, Cs, H, W), dtype=torch.float32, device=dev)
                 ret[:B].copy_(first)
             slot = 1
-            for i in reversed(range(T)):
-                eng.step()
-                if continous and i % inter == 0:
-                    ret[slot * B:(slot + 1) * B].copy_(eng.x)
-                    slot += 1
+            if continous:
+                pending = 0
+                for i in reversed(range(T)):
+                    pending += 1
+                    if i % inter == 0:
+                        eng.run(pending)
+                        pending = 0
+                        ret[slot * B:(slot + 1) * B].copy_(eng.x)
+                        slot += 1
+                eng.run(pending)
+            else:
+                eng.run(T)
             draws = T if self._ddpm else T - 1
             _finish(gen, off0, eng.rng_inc * (1 + draws))
             if self._ddpm and not self.conditional:
@@ -400,6 +436,10 @@ class InDI(_SamplerBase):
     def _tables(self, T, t_start):
         """(T,5) coefficient rows and the (T+1,) time table, built with the reference's own fp32 expressions
         (indi.py:62-69: python-float t cast to an fp32 tensor each step, python-float delta)."""
+        key = (int(T), float(t_start), float(self.e))
+        cache = self.__dict__.setdefault("_table_cache", {})
+        if key in cache:                    # T python-level iterations of small tensor ops: ~25 ms at T=1000, per call
+            return cache[key]
         delta = t_start / T
         cur = t_start
         rows, times = [], []
@@ -412,6 +452,9 @@ class InDI(_SamplerBase):
             cur -= delta
         coef = torch.cat(rows, dim=0).contiguous()
         ttab = torch.cat(times + [times[-1]])
+        if len(cache) >= 8:
+            cache.clear()
+        cache[key] = (coef, ttab)
         return coef, ttab
 
     @torch.no_grad()
@@ -472,11 +515,18 @@ class InDI(_SamplerBase):
                 ret = torch.empty(((len(snaps) + 1) * B, Cs, H, W), dtype=torch.float32, device=dev)
                 ret[:B].copy_(eng.x)
             slot = 1
-            for idx in range(T):
-                eng.step()
-                if continuous and (idx % inter == 0 or idx == T - 1):
-                    ret[slot * B:(slot + 1) * B].copy_(eng.x)
-                    slot += 1
+            if continuous:
+                pending = 0
+                for idx in range(T):
+                    pending += 1
+                    if idx % inter == 0 or idx == T - 1:
+                        eng.run(pending)
+                        pending = 0
+                        ret[slot * B:(slot + 1) * B].copy_(eng.x)
+                        slot += 1
+                eng.run(pending)
+            else:
+                eng.run(T)
             _finish(gen, off0, eng.rng_inc * (1 + T))
             if continuous:
                 return ret
