@@ -1,5 +1,5 @@
 """Warm micro-benchmark of single operators through the C ABI (CUDA-graph of 50 launches, replayed): real per-launch
-GPU time without host launch overhead.  Usage: python tools/op_microbench.py [gnconv|conv_tc|gn] ca cb cout ks B H W"""
+GPU time without host launch overhead.  Usage: python tools/op_microbench.py [gnconv|conv_tc|gn|sampler] ca cb cout ks B H W"""
 import ctypes as C
 import os
 import sys
@@ -74,6 +74,24 @@ def main():
                                         scratch.data_ptr(), nb, sp()))
         us = timed_graph(fn)
         print(f"conv_tc (pack + conv_tc) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (2 kernels)")
+    elif kind == "sampler":
+        # fused posterior update + in-register Philox noise: 12 B per element (read x_t, read eps, write x_{t-1})
+        from diffsplitting_b200.model import samplers as SM
+        x = torch.randn((B, cin, H, W), generator=g).to(DEV)
+        eps = torch.randn((B, cin, H, W), generator=g).to(DEV)
+        out = torch.empty_like(x)
+        coef = torch.tensor([[1.01, 0.1, 0.4, 0.6, 0.05]], dtype=torch.float32, device=DEV)
+        threads, inc = SM._rng_geometry(x.numel(), 0)
+        a = _lib.StepArgs()
+        a.d_x = x.data_ptr(); a.d_net = eps.data_ptr(); a.d_out = out.data_ptr(); a.numel = x.numel()
+        a.mode = 0; a.clip = 1; a.d_coef = coef.data_ptr(); a.n_steps = 1; a.step = 0; a.d_state = None
+        a.seed = 1234; a.offset = 0; a.offset_inc = inc; a.rng_threads = threads; a.skip_rng_if_zero = 0
+
+        def fn():
+            _lib.check(L.ds_sampler_step(C.byref(a), sp()))
+        us = timed_graph(fn, n=10, reps=10)
+        gb = x.numel() * 12 / 1e9
+        print(f"sampler_step (posterior + Philox noise) {B}x{cin}x{H}x{W}: {us:.2f} us per call, {gb / (us * 1e-6):.0f} GB/s algorithmic")
     else:
         nb = L.ds_groupnorm_scratch_bytes(B, 16)
         scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
@@ -82,8 +100,10 @@ def main():
         def fn():
             _lib.check(L.ds_groupnorm_swish_f32(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
                                                 beta.data_ptr(), out.data_ptr(), B, H, W, 16, 1, scratch.data_ptr(), nb, sp()))
-        us = timed_graph(fn)
-        print(f"groupnorm (stats + apply, fp32 out) C={cin} {B}x{H}x{W}: {us:.2f} us per call (2 kernels)")
+        us = timed_graph(fn, n=10, reps=10)
+        gb = B * H * W * cin * 4 * 3 / 1e9
+        print(f"groupnorm (stats + apply, fp32 out) C={cin} {B}x{H}x{W}: {us:.2f} us per call (2 kernels), "
+              f"{gb / (us * 1e-6):.0f} GB/s algorithmic (2 reads + 1 write)")
 
 
 if __name__ == "__main__":
