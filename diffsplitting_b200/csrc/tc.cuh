@@ -23,6 +23,7 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
 
 // ---- fused GroupNorm-apply + Swish -> conv, operands staged through registers (tc_halo.cu); sources fp32 NHWC
 bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W);
+bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W);   // supported AND faster than GN-apply + TMA conv
 size_t halo_packed_weight_bytes(int cout, int cin, int ks);
 int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);
 // GroupNorm statistics of the concat input: either `stats` = (mean, rstd) [B][G], or per-channel fp64 (sum, sumsq)

@@ -755,6 +755,27 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) 
     return halo_smem_bytes(C, ks * ks, W, 16, nsamp) <= HALO_SMEM_LIMIT;
 }
 
+// Is the fused kernel also the FASTER choice (vs GroupNorm-apply into a bf16 tensor + the TMA-fed conv)?  Each CTA stages
+// plane_px pixels for 128 outputs (1.2x at 8 x 8 ... 3.2x for wide images, whose three filter rows are separate segments)
+// and every N tile repeats that work.  For grids of at most a few waves the saved launch and HBM round trip win regardless;
+// for many waves, measured on B200 (8 x C x S x S, us, fused vs unfused): C=16 S=512 190 vs 249, C=32 S=512 458 vs 550,
+// C=64 S=256 257 vs 344, C=64 S=512 ~1850 vs 1360 (the re-reads spill from L2 to HBM), C=128 S=128 570 vs 166,
+// C=128 S=256 2260 vs 645.
+bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W) {
+    if (!halo_conv_supported(ca, cb, cout, ks, B, H, W)) return false;
+    const int C = ca + cb, ntaps = ks * ks;
+    const int64_t m_tiles = ((int64_t)B * (H + 2) * (W + 2) + 127) / 128;
+    const int nsamp = halo_samples_per_tile(H, W);
+    const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles);
+    const int n_tiles = (cout + 15) / 16 * 16 / bn;
+    if (m_tiles * n_tiles <= 4 * 148) return true;                           // latency regime
+    const double redo = (double)halo_plane_px(ntaps, W) / 128.0;             // staged pixels per output pixel
+    if (redo * n_tiles * C > 320.0) return false;
+    const double in_bytes = (double)B * H * W * C * 4.0;
+    if (redo > 1.5 && in_bytes > 400e6) return false;                        // 3x re-reads of a tensor that does not fit L2
+    return true;
+}
+
 size_t halo_packed_weight_bytes(int cout, int cin, int ks) {
     return (size_t)ks * ks * cin * ((cout + 15) / 16 * 16) * 2;
 }

@@ -482,7 +482,7 @@ struct Planner {
             chain_conv(a, b, &g, swish, w, temb_off, residual, out);
             return;
         }
-        if (tc && n->specs[w.w].halo && halo_conv_supported(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
+        if (tc && n->specs[w.w].halo && halo_conv_preferred(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
             Op o; o.kind = OP_CONV;
             o.sums_a = a.sums;
             if (b) o.sums_b = b->sums;
