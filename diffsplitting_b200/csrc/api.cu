@@ -269,7 +269,7 @@ extern "C" int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int 
     DS_REQUIRE(scratch_bytes >= ds_gnconv_bf16_scratch_bytes(B, groups > 0 ? groups : 1, ca + cb, cout, ksize),
                "gnconv_bf16: scratch too small");
     DS_REQUIRE(halo_conv_supported(ca, cb, cout, ksize, B, H, W),
-               "gnconv_bf16: unsupported shape (channel counts multiples of 8, total a multiple of 16 and <= 128)");
+               "gnconv_bf16: unsupported shape (channel counts multiples of 8, total a multiple of 16 and <= 224)");
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* wp = (uint8_t*)d_scratch;
     void* gscratch = wp + align_up(halo_packed_weight_bytes(cout, ca + cb, ksize), 1024);

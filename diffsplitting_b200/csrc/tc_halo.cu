@@ -747,7 +747,7 @@ static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_
 
 bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) {
     const int C = ca + cb;
-    if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 128) return false;
+    if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 224 || ks * ks * (C / 16) * 2 > 256) return false;
     if (!(ks == 1 || ks == 3)) return false;
     if ((int64_t)B * (H + 2) * (W + 2) >= (1ll << 31) - 4096) return false;
     const int nsamp = halo_samples_per_tile(H, W);

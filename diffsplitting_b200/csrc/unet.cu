@@ -250,7 +250,7 @@ static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int k
         n->specs[c.w].tc_kc = tc_pick_kc(ca, cb);
         n->specs[c.w].tc_up = up;
     }
-    if (halo && cin % 16 == 0 && cin <= 128) {
+    if (halo && cin % 16 == 0 && cin <= 224) {
         n->specs[c.w].halo = true;
         n->specs[c.w].off_halo = n->arena_bf16_bytes;
         n->arena_bf16_bytes += align_up(halo_packed_weight_bytes(cout, cin, ks), 1024);
