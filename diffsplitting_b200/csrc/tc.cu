@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, n_base + c0, add);
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, n_base + c0, f);
             }
-            if (p.epi.sums_out)
-                tc_epilogue_stats(p.epi, f, valid, b, n_base + c0, m, (int)threadIdx.x - 64, b0, (int)(blockIdx.x % TC_SUM_COPIES), red);
+            if (p.epi.sums_out) {
+                const int nsr = min(p.tb, p.B - b0);
+                if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, n_base + c0, (int)threadIdx.x - 64, b0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                else tc_epilogue_stats(p.epi, f, valid, b, n_base + c0, m, (int)threadIdx.x - 64, b0, (int)(blockIdx.x % TC_SUM_COPIES), red);
+            }
         }
         tc_fence_before();
     }

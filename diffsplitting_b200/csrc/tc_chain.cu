@@ -94,43 +94,6 @@ __device__ __forceinline__ void cluster_mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
-// column sums of a 32-row x 16-column block held as v[16] per lane: recursive halving, 16 shuffles; afterwards lane l holds
-// the sum of column  8 b4 + 4 b3 + 2 b2 + b1  (b_k = bit k of l), duplicated in the lane pair (l, l ^ 1)
-__device__ __forceinline__ float ch_colsum16(const float (&v)[16], int lane) {
-    float a[8];
-    {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float mine = hi ? v[j + 8] : v[j], other = hi ? v[j] : v[j + 8];
-            a[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
-        }
-    }
-    float b4[4];
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float mine = hi ? a[j + 4] : a[j], other = hi ? a[j] : a[j + 4];
-            b4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
-        }
-    }
-    float c2[2];
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float mine = hi ? b4[j + 2] : b4[j], other = hi ? b4[j] : b4[j + 2];
-            c2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
-        }
-    }
-    const bool hi = lane & 2;
-    const float mine = hi ? c2[1] : c2[0], other = hi ? c2[0] : c2[1];
-    float d = mine + __shfl_xor_sync(0xffffffffu, other, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;
-}
-
 // bias + conditioning vector + fp32 residual of one (pixel, 16-channel chunk); the chunk lies inside Cout or is a tail
 __device__ __forceinline__ void ch_addend(const TcEpi& e, int b, int oy, int ox, int n0, float (&add)[16]) {
     if (n0 + 16 > e.Cout) { tc_epilogue_addend<true>(e, b, oy, ox, n0, add); return; }
@@ -441,7 +404,7 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                             float sq[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) sq[j] = f[j] * f[j];
-                            const float s1 = ch_colsum16(f, lane), s2 = ch_colsum16(sq, lane);
+                            const float s1 = tc_colsum16(f, lane), s2 = tc_colsum16(sq, lane);
                             if (!(lane & 1)) {
                                 const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
                                 double2& d = stat[qd * 32 + ck * 16 + col];       // owned by this lane for the whole op

@@ -375,8 +375,11 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
             }
-            if (p.epi.sums_out)
-                tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, fdiv(q0, p.div_hpwp), (int)(blockIdx.x % TC_SUM_COPIES), red);
+            if (p.epi.sums_out) {
+                const int bt0 = fdiv(q0, p.div_hpwp), nsr = fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
+                if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, tid - 64, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
+            }
         }
         HALO_STAMP(6);
         tc_fence_before();
@@ -670,8 +673,11 @@ __global__ void __launch_bounds__(HP_THREADS, 2) conv_halo_persistent_kernel(con
                     if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
                     tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
                 }
-                if (p.epi.sums_out)
-                    tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, te, fdiv(q0, p.div_hpwp), (int)(blockIdx.x % TC_SUM_COPIES), red);
+                if (p.epi.sums_out) {
+                    const int bt0 = fdiv(q0, p.div_hpwp), nsr = fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
+                    if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, te, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                    else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, te, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                }
             }
             tc_fence_before();
             hp_mbar_arrive(t_empty(buf));

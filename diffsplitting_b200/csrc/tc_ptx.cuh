@@ -131,6 +131,43 @@ struct TcEpi {
     int Cout, Ho, Wo;
 };
 
+// column sums of a 32-row x 16-column block held as v[16] per lane: recursive halving, 16 shuffles; afterwards lane l holds
+// the sum of column  8 b4 + 4 b3 + 2 b2 + b1  (b_k = bit k of l), duplicated in the lane pair (l, l ^ 1)
+__device__ __forceinline__ float tc_colsum16(const float (&v)[16], int lane) {
+    float a[8];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float mine = hi ? v[j + 8] : v[j], other = hi ? v[j] : v[j + 8];
+            a[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+        }
+    }
+    float b4[4];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mine = hi ? a[j + 4] : a[j], other = hi ? a[j] : a[j + 4];
+            b4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+        }
+    }
+    float c2[2];
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float mine = hi ? b4[j + 2] : b4[j], other = hi ? b4[j] : b4[j + 2];
+            c2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+        }
+    }
+    const bool hi = lane & 2;
+    const float mine = hi ? c2[1] : c2[0], other = hi ? c2[0] : c2[1];
+    float d = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
 constexpr int TC_RED_LD = 17;                                   // padded row of the epilogue reduction buffer
 constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD * 4 + 128 * 4;   // [128 rows][17] fp32 + [128] sample ids
 
@@ -272,6 +309,41 @@ __device__ __forceinline__ void tc_epilogue_stats(const TcEpi& p, const float (&
         }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// The same statistics with warp shuffles instead of the transposed shared-memory pass, for tiles whose 128 rows belong to at
+// most two samples (`nsamp_rows`, uniform over the CTA): per sample a masked column sum (16 shuffles each for sum and sum of
+// squares), one 128-thread barrier to fold the four warps, one fp64 atomic pair per (sample, channel).
+__device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int te,
+                                                       int b_tile0, int nsamp_rows, int copy, uint8_t* red_raw) {
+    float* red = reinterpret_cast<float*>(red_raw);          // [warp 4][sample 2][kind 2][16]
+    const int lane = te & 31, w = te >> 5;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (s < nsamp_rows) {
+            const bool mine = valid && b == b_tile0 + s;
+            float v[16], q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = mine ? f[j] : 0.f; q[j] = v[j] * v[j]; }
+            const float s1 = tc_colsum16(v, lane), s2 = tc_colsum16(q, lane);
+            if (!(lane & 1)) {
+                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                red[((w * 2 + s) * 2 + 0) * 16 + col] = s1;
+                red[((w * 2 + s) * 2 + 1) * 16 + col] = s2;
+            }
+        }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (te < 32 * nsamp_rows) {
+        const int s = te >> 5, kind = (te >> 4) & 1, col = te & 15;
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot += red[((k * 2 + s) * 2 + kind) * 16 + col];
+        const int bb = b_tile0 + s;
+        if (n0 + col < p.Cout && bb < p.sums_B && tot != 0.f)
+            atomicAdd(p.sums_out + (((size_t)copy * p.sums_B + bb) * p.Cout + n0 + col) * 2 + kind, (double)tot);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // `red` may be reused
 }
 
 }  // namespace ds
