@@ -226,11 +226,9 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
     {
         const bool norm = p.stats || p.sums_a;
         const int cpg = norm ? p.C / p.G : 1;
-        float2* gst = reinterpret_cast<float2*>(gbase + gst_off);
         if (p.sums_a) {
-            // fold the producers' replicated per-channel fp64 sums into (mean, rstd) per (sample, group); a group may
-            // straddle the two sources of a concat.  Stage 1: one thread per (sample, channel) adds the replicated copies
-            // (all loads independent: ONE round trip); stage 2: one thread per (sample, group) adds its channels from smem.
+            // fold the producers' replicated per-channel fp64 sums; a group may straddle the two sources of a concat.
+            // Stage 1: one thread per (sample, channel) adds the replicated copies (all loads independent: ONE round trip).
             double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
             for (int i = tid; i < nsamp * p.C; i += nthr) {
                 const int s = i / p.C, cc = i - s * p.C, b = b_first + s;
@@ -247,27 +245,22 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
                 chs[i] = make_double2(sm, sq);
             }
             __syncthreads();
-            const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
-            for (int i = tid; i < nsamp * p.G; i += nthr) {
-                const int s = i / p.G, g = i - s * p.G;
-                double sm = 0.0, sq = 0.0;
-                for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-                    const double2 v = chs[s * p.C + cc];
-                    sm += v.x;
-                    sq += v.y;
-                }
-                const double mu = sm * inv_cnt;
-                double var = sq * inv_cnt - mu * mu;
-                if (var < 0.0) var = 0.0;
-                gst[i] = make_float2((float)mu, rsqrtf((float)var + 1e-5f));
-            }
-            __syncthreads();
         }
+        const double inv_cnt = norm ? 1.0 / ((double)p.H * p.W * cpg) : 0.0;
         for (int i = tid; i < nsamp * p.C; i += nthr) {
             const int s = i / p.C, c = i - s * p.C;
             float a = 1.f, sh = 0.f;
-            if (norm) {
-                const float2 st = p.sums_a ? gst[s * p.G + c / cpg] : p.stats[(size_t)(b_first + s) * p.G + c / cpg];
+            if (p.sums_a) {                       // every channel folds its own group (cpg reads of shared memory)
+                const double2* cs = reinterpret_cast<const double2*>(gbase + chs_off) + s * p.C + c / cpg * cpg;
+                double sm = 0.0, sq = 0.0;
+                for (int k = 0; k < cpg; ++k) { sm += cs[k].x; sq += cs[k].y; }
+                const double mu = sm * inv_cnt;
+                double var = sq * inv_cnt - mu * mu;
+                if (var < 0.0) var = 0.0;
+                a = rsqrtf((float)var + 1e-5f) * p.gamma[c];
+                sh = p.beta[c] - (float)mu * a;
+            } else if (norm) {
+                const float2 st = p.stats[(size_t)(b_first + s) * p.G + c / cpg];
                 a = st.y * p.gamma[c];
                 sh = p.beta[c] - st.x * a;
             }
