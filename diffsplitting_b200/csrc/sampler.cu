@@ -86,12 +86,23 @@ __global__ void __launch_bounds__(ST_THREADS) sampler_step_kernel(const ds_step_
         a.d_out[i] = __fadd_rn(mean, __fmul_rn(z, c4));
     };
 
+    // Launched with programmatic stream serialisation: everything above and the first Philox / Box-Muller evaluation (the
+    // bulk of this kernel's arithmetic; it needs only the loop state the PREVIOUS step's update left behind) overlap the
+    // tail of the UNet's last conv; x_t and the network output are touched only after the wait.
+    const int64_t items = rounds * T;
+    const int64_t w_first = blockIdx.x * (int64_t)ST_THREADS + threadIdx.x;
+    float4 z_first = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gen && w_first < items) {
+        const int64_t r = w_first / T, j = w_first - r * T;
+        z_first = normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
+    }
+    pdl_trigger();
+    pdl_wait();
     if (gen) {
         // work item = (round r, torch thread j): one Philox call -> 4 elements
-        const int64_t items = rounds * T;
-        for (int64_t w = blockIdx.x * (int64_t)ST_THREADS + threadIdx.x; w < items; w += (int64_t)gridDim.x * ST_THREADS) {
+        for (int64_t w = w_first; w < items; w += (int64_t)gridDim.x * ST_THREADS) {
             const int64_t r = w / T, j = w - r * T;
-            const float4 z = normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
+            const float4 z = w == w_first ? z_first : normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
             const int64_t i0 = j + 4 * T * r;
             if (i0 < a.numel) update(i0, z.x);
             if (i0 + T < a.numel) update(i0 + T, z.y);
@@ -175,8 +186,7 @@ extern "C" int ds_sampler_step(const ds_step_args* a, void* stream) {
     DS_REQUIRE(!a->d_time_out || (a->d_time_table && a->d_state), "sampler_step: d_time_out needs d_time_table and d_state");
     int64_t work = a->numel;
     if (!a->d_noise) work = ((a->numel - 1) / (4 * (int64_t)a->rng_threads) + 1) * (int64_t)a->rng_threads;
-    sampler_step_kernel<<<step_grid(work), ST_THREADS, 0, (cudaStream_t)stream>>>(*a);
-    DS_CHECK_LAUNCH("sampler_step");
+    DS_CHECK_CUDA(launch_pdl(sampler_step_kernel, dim3((unsigned)step_grid(work)), dim3(ST_THREADS), 0, (cudaStream_t)stream, *a));
     return DS_OK;
 }
 

@@ -210,6 +210,10 @@ typedef struct ds_step_args {
     float*       d_time_out;   /* [time_len] or NULL */
     int32_t      time_len;
 } ds_step_args;
+/* The kernel is launched with programmatic stream serialisation and reads *d_state and evaluates its first Philox block
+ * BEFORE waiting for its predecessor in the stream: the predecessor must not be the kernel that last wrote *d_state (in the
+ * sampling loop the whole UNet forward lies between two updates; after ds_randn_axpy(.., d_state, ..) run the forward or
+ * synchronise the stream first). */
 int ds_sampler_step(const ds_step_args* args, void* stream);
 /* out = (base ? base : 0) + z*scale, z ~ torch.randn stream (the initial draw of p_sample_loop :194 /
  * InDI.inference :82).  Seed/offset from d_state (offset advanced by the kernel) or the arguments. */
