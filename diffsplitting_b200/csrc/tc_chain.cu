@@ -35,7 +35,8 @@ constexpr int CH_WORKERS = CH_THREADS - 64;       // warps 2..15
 constexpr int CH_MAX_GROUPS = 64;
 constexpr int CH_MAX_C = 256;                     // input channels (concat) and output channels
 constexpr int CH_INFLIGHT = 4;                    // staged work items in flight per worker thread
-constexpr int CH_KC = 128;                        // channels per weight slab
+constexpr int CH_KC = 128;                        // channels per weight unit = (tap, channel chunk)
+constexpr int CH_UNITS_PER_STAGE = 3;             // full-size units per ring slot (fewer, larger copies and barrier waits)
 constexpr int CH_MAX_PX = 176;                    // staged pixels per tile: 130 + 2 (W + 2), W <= 20
 constexpr size_t CH_SMEM_LIMIT = 208 * 1024;
 
@@ -162,18 +163,22 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 const ChainDev& o = p.ops[oi];
                 const int C = o.ca + o.cb;
                 const uint8_t* wslice = o.w + (size_t)slice * o.ntaps * C * p.ns * 2;
+                const int upt = (C + CH_KC - 1) / CH_KC;                 // (tap, <=128-channel chunk) units per tap
+                const int U = o.ntaps * upt;
+                const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C, CH_KC) * p.ns * 2u)));   // units per ring slot
                 for (int t = 0; t < p.mtiles; ++t) {
                     const uint8_t* src = wslice;
-                    for (int tap = 0; tap < o.ntaps; ++tap) {
-                        for (int c0 = 0; c0 < C; c0 += CH_KC, ++u) {
-                            const int kc = min(CH_KC, C - c0);
-                            const uint32_t bytes = (uint32_t)kc * p.ns * 2u;
-                            const int s = u % p.stages;
-                            mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
-                            mbar_expect_tx(full_bar(s), bytes);
-                            bulk_load(base + ring_off + (uint32_t)s * p.stage_bytes, src, bytes, full_bar(s));
-                            src += bytes;
+                    for (int u0 = 0; u0 < U; u0 += upst, ++u) {
+                        uint32_t bytes = 0;
+                        for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
+                            const int c0 = (uu % upt) * CH_KC;
+                            bytes += (uint32_t)min(CH_KC, C - c0) * p.ns * 2u;
                         }
+                        const int s = u % p.stages;
+                        mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
+                        mbar_expect_tx(full_bar(s), bytes);
+                        bulk_load(base + ring_off + (uint32_t)s * p.stage_bytes, src, bytes, full_bar(s));
+                        src += bytes;
                     }
                 }
             }
@@ -197,21 +202,23 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                     tc_fence_after();
                     long long wait_full = 0;
                     uint32_t first = 1;
-                    for (int tap = 0; tap < o.ntaps; ++tap) {
-                        const int r = o.ntaps == 9 ? tap / 3 : 1;
-                        const int sx = o.ntaps == 9 ? tap - 3 * r : 1;
-                        const uint32_t a_tap = a_lo0 + (uint32_t)(r * p.Wp + sx);
-                        for (int c0 = 0; c0 < C; c0 += CH_KC, ++u) {
-                            const int kc = min(CH_KC, C - c0);
-                            const int s = u % p.stages;
-                            const long long w0 = p.dbg ? clock64() : 0;
-                            mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
-                            if (p.dbg) wait_full += clock64() - w0;
-                            tc_fence_after();
-                            const uint32_t a_lo = a_tap + (uint32_t)(c0 >> 3) * (plane_bytes >> 4);
-                            const uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
-                            const int ksteps = kc >> 4;
-                            // all descriptors of the slab are independent adds: the up-to-8 MMAs issue back to back
+                    const int upt = (C + CH_KC - 1) / CH_KC;
+                    const int U = o.ntaps * upt;
+                    const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C, CH_KC) * p.ns * 2u)));
+                    for (int u0 = 0; u0 < U; u0 += upst, ++u) {
+                        const int s = u % p.stages;
+                        const long long w0 = p.dbg ? clock64() : 0;
+                        mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
+                        if (p.dbg) wait_full += clock64() - w0;
+                        tc_fence_after();
+                        uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
+                        for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
+                            const int tap = uu / upt, c0 = (uu - tap * upt) * CH_KC;
+                            const int r = o.ntaps == 9 ? tap / 3 : 1;
+                            const int sx = o.ntaps == 9 ? tap - 3 * r : 1;
+                            const uint32_t a_lo = a_lo0 + (uint32_t)(r * p.Wp + sx) + (uint32_t)(c0 >> 3) * (plane_bytes >> 4);
+                            const int ksteps = min(CH_KC, C - c0) >> 4;
+                            // all descriptors of the unit are independent adds: the up-to-8 MMAs issue back to back
 #pragma unroll
                             for (int k = 0; k < CH_KC / 16; ++k) {
                                 if (k < ksteps)
@@ -219,8 +226,9 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                                               ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, (first && k == 0) ? 0u : 1u);
                             }
                             first = 0;
-                            umma_commit(empty_bar(s));
+                            b_lo += (uint32_t)ksteps * b_kstep;
                         }
+                        umma_commit(empty_bar(s));
                     }
                     umma_commit(mma_done);
                     if (p.dbg && blockIdx.x == 0 && t == 0) p.dbg[oi * 6 + 5] = wait_full;
@@ -538,7 +546,7 @@ int chain_build(ChainPlan* plan, const ChainOpDesc* ops, int nops, int B, int H,
         cmax = cmax > d.ca + d.cb ? cmax : d.ca + d.cb;
     }
     p->a_bytes = (uint32_t)align_up((size_t)(cmax / 8) * p->plane_px * 16, 1024);
-    p->stage_bytes = (uint32_t)align_up((size_t)p->ns * CH_KC * 2, 1024);
+    p->stage_bytes = (uint32_t)align_up((size_t)p->ns * CH_KC * 2 * CH_UNITS_PER_STAGE, 1024);
     const size_t fixed = p->a_bytes + CH_MAX_C * 8 + CH_MAX_GROUPS * 8 + CH_MAX_C * 16 + CH_MAX_PX * 4 + 4 * 32 * 16 + 192 + 1024 + 64;
     DS_REQUIRE(fixed + 2 * (size_t)p->stage_bytes <= CH_SMEM_LIMIT, "chain: shared memory (A %u B + 2 x %u B)", p->a_bytes, p->stage_bytes);
     int stages = (int)((CH_SMEM_LIMIT - fixed) / p->stage_bytes);
