@@ -59,6 +59,11 @@ struct ChainOpDesc {
     const float* gamma; const float* beta;
     const uint8_t* w;                         // chain_pack_conv_weight() image
     int cout, ks;
+    // optional second operand, raw (no normalisation), applied as a 1x1 conv and accumulated into the same output:
+    // the res_conv of a ResnetBlock folded into its conv2 (unet.py:118-122:  block2(h) + res_conv(x))
+    const float* xsrc_a; const float* xsrc_b; int xca, xcb;
+    const uint8_t* wx;                        // chain_pack_conv_weight() image of the 1x1 weights
+    const float* bias2;
     ConvEpi epi;                              // bias / temb / residual (fp32 NHWC)
     float* out_f32; void* out_b16;            // fp32 and/or bf16 NHWC outputs
     double* sums_out;                         // statistics of the output (replicated slots) or null

@@ -47,6 +47,9 @@ struct ChainDev {                                 // device view of one op
     const uint8_t* w;                             // bf16 [slice][tap][plane][ns][8]
     TcEpi epi;
     int ca, cb, G, swish, norm, ntaps, src_b16;
+    const float* xsrc_a; const float* xsrc_b;     // optional raw second operand (folded 1x1 res_conv), fp32 NHWC
+    const uint8_t* wx;                            // its weights, bf16 [slice][plane][ns][8]
+    int xca, xcb;
 };
 
 struct ChainParams {
@@ -97,13 +100,25 @@ __device__ __forceinline__ void cluster_mbar_wait(uint32_t bar, uint32_t parity)
 
 // bias + conditioning vector + fp32 residual of one (pixel, 16-channel chunk); the chunk lies inside Cout or is a tail
 __device__ __forceinline__ void ch_addend(const TcEpi& e, int b, int oy, int ox, int n0, float (&add)[16]) {
-    if (n0 + 16 > e.Cout) { tc_epilogue_addend<true>(e, b, oy, ox, n0, add); return; }
+    if (n0 + 16 > e.Cout) {
+        tc_epilogue_addend<true>(e, b, oy, ox, n0, add);
+        if (e.bias2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + j < e.Cout) add[j] += __ldg(e.bias2 + n0 + j);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) add[j] = 0.f;
     if (e.bias) {
         const float4* s = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float4 v = __ldg(s + j); add[4 * j] = v.x; add[4 * j + 1] = v.y; add[4 * j + 2] = v.z; add[4 * j + 3] = v.w; }
+    }
+    if (e.bias2) {
+        const float4* s = reinterpret_cast<const float4*>(e.bias2 + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 v = __ldg(s + j); add[4 * j] += v.x; add[4 * j + 1] += v.y; add[4 * j + 2] += v.z; add[4 * j + 3] += v.w; }
     }
     if (e.temb) {
         const float4* s = reinterpret_cast<const float4*>(e.temb + (size_t)(e.temb_bcast ? 0 : b) * e.temb_stride + e.temb_off + n0);
@@ -163,22 +178,28 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 const ChainDev& o = p.ops[oi];
                 const int C = o.ca + o.cb;
                 const uint8_t* wslice = o.w + (size_t)slice * o.ntaps * C * p.ns * 2;
-                const int upt = (C + CH_KC - 1) / CH_KC;                 // (tap, <=128-channel chunk) units per tap
-                const int U = o.ntaps * upt;
-                const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C, CH_KC) * p.ns * 2u)));   // units per ring slot
+                const int Cx = o.xca + o.xcb;
+                const uint8_t* xslice = o.wx ? o.wx + (size_t)slice * Cx * p.ns * 2 : nullptr;
+                // stream the (tap, <=128-channel chunk) units of the weight image(s), several units per ring slot
                 for (int t = 0; t < p.mtiles; ++t) {
-                    const uint8_t* src = wslice;
-                    for (int u0 = 0; u0 < U; u0 += upst, ++u) {
-                        uint32_t bytes = 0;
-                        for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
-                            const int c0 = (uu % upt) * CH_KC;
-                            bytes += (uint32_t)min(CH_KC, C - c0) * p.ns * 2u;
+                    for (int img = 0; img < (xslice ? 2 : 1); ++img) {
+                        const uint8_t* src = img ? xslice : wslice;
+                        const int C_ = img ? Cx : C, ntaps_ = img ? 1 : o.ntaps;
+                        const int upt = (C_ + CH_KC - 1) / CH_KC;
+                        const int U = ntaps_ * upt;
+                        const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C_, CH_KC) * p.ns * 2u)));
+                        for (int u0 = 0; u0 < U; u0 += upst, ++u) {
+                            uint32_t bytes = 0;
+                            for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
+                                const int c0 = (uu % upt) * CH_KC;
+                                bytes += (uint32_t)min(CH_KC, C_ - c0) * p.ns * 2u;
+                            }
+                            const int s = u % p.stages;
+                            mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
+                            mbar_expect_tx(full_bar(s), bytes);
+                            bulk_load(base + ring_off + (uint32_t)s * p.stage_bytes, src, bytes, full_bar(s));
+                            src += bytes;
                         }
-                        const int s = u % p.stages;
-                        mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
-                        mbar_expect_tx(full_bar(s), bytes);
-                        bulk_load(base + ring_off + (uint32_t)s * p.stage_bytes, src, bytes, full_bar(s));
-                        src += bytes;
                     }
                 }
             }
@@ -202,33 +223,37 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                     tc_fence_after();
                     long long wait_full = 0;
                     uint32_t first = 1;
-                    const int upt = (C + CH_KC - 1) / CH_KC;
-                    const int U = o.ntaps * upt;
-                    const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C, CH_KC) * p.ns * 2u)));
-                    for (int u0 = 0; u0 < U; u0 += upst, ++u) {
-                        const int s = u % p.stages;
-                        const long long w0 = p.dbg ? clock64() : 0;
-                        mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
-                        if (p.dbg) wait_full += clock64() - w0;
-                        tc_fence_after();
-                        uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
-                        for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
-                            const int tap = uu / upt, c0 = (uu - tap * upt) * CH_KC;
-                            const int r = o.ntaps == 9 ? tap / 3 : 1;
-                            const int sx = o.ntaps == 9 ? tap - 3 * r : 1;
-                            const uint32_t a_lo = a_lo0 + (uint32_t)(r * p.Wp + sx) + (uint32_t)(c0 >> 3) * (plane_bytes >> 4);
-                            const int ksteps = min(CH_KC, C - c0) >> 4;
-                            // all descriptors of the unit are independent adds: the up-to-8 MMAs issue back to back
+                    // the MMAs of the weight image(s): operand planes [plane0, plane0 + C_/8), all taps or (folded 1x1) the centre
+                    for (int img = 0; img < (o.wx ? 2 : 1); ++img) {
+                        const int C_ = img ? o.xca + o.xcb : C, ntaps_ = img ? 1 : o.ntaps, plane0 = img ? (C >> 3) : 0;
+                        const int upt = (C_ + CH_KC - 1) / CH_KC;
+                        const int U = ntaps_ * upt;
+                        const int upst = max(1, (int)(p.stage_bytes / ((uint32_t)min(C_, CH_KC) * p.ns * 2u)));
+                        for (int u0 = 0; u0 < U; u0 += upst, ++u) {
+                            const int s = u % p.stages;
+                            const long long w0 = p.dbg ? clock64() : 0;
+                            mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
+                            if (p.dbg) wait_full += clock64() - w0;
+                            tc_fence_after();
+                            uint32_t b_lo = (((base + ring_off + (uint32_t)s * p.stage_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
+                            for (int uu = u0; uu < min(u0 + upst, U); ++uu) {
+                                const int tap = uu / upt, c0 = (uu - tap * upt) * CH_KC;
+                                const int r = ntaps_ == 9 ? tap / 3 : 1;
+                                const int sx = ntaps_ == 9 ? tap - 3 * r : 1;
+                                const uint32_t a_lo = a_lo0 + (uint32_t)(r * p.Wp + sx) + (uint32_t)(plane0 + (c0 >> 3)) * (plane_bytes >> 4);
+                                const int ksteps = min(CH_KC, C_ - c0) >> 4;
+                                // all descriptors of the unit are independent adds: the up-to-8 MMAs issue back to back
 #pragma unroll
-                            for (int k = 0; k < CH_KC / 16; ++k) {
-                                if (k < ksteps)
-                                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)k * a_kstep),
-                                              ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, (first && k == 0) ? 0u : 1u);
+                                for (int k = 0; k < CH_KC / 16; ++k) {
+                                    if (k < ksteps)
+                                        umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)k * a_kstep),
+                                                  ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                                first = 0;
+                                b_lo += (uint32_t)ksteps * b_kstep;
                             }
-                            first = 0;
-                            b_lo += (uint32_t)ksteps * b_kstep;
+                            umma_commit(empty_bar(s));
                         }
-                        umma_commit(empty_bar(s));
                     }
                     umma_commit(mma_done);
                     if (p.dbg && blockIdx.x == 0 && t == 0) p.dbg[oi * 6 + 5] = wait_full;
@@ -298,79 +323,86 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 }
                 ch_bar_workers();                  // table + pixel table visible
                 CH_STAMP(1);
-                // ---- stage the A operand of this tile: flat padded positions [128 t - Wp - 1, 128 t + 128 + Wp + 1)
-                const int npl = C >> 3;
-                const int items = p.plane_px * npl;
+                // ---- stage the A operand of this tile: flat padded positions [128 t - Wp - 1, 128 t + 128 + Wp + 1).
+                // Segment 0 = the (normalised) conv input, segment 1 = the raw block input of a folded 1x1 res_conv.
+                // Work item = (8-channel plane, pixel); CH_INFLIGHT items (two 16-byte L2 loads each) in flight per thread.
                 const size_t pix0 = (size_t)b * p.H * p.W;
-                // work item = (8-channel plane, pixel); CH_INFLIGHT items in flight per thread (the loads are L2 round trips)
-                for (int i0 = wt; i0 < items; i0 += CH_INFLIGHT * CH_WORKERS) {
-                    uint4 raw0[CH_INFLIGHT], raw1[CH_INFLIGHT];
-                    int kpv[CH_INFLIGHT], pxv[CH_INFLIGHT];
-                    bool okv[CH_INFLIGHT];
+                for (int seg = 0; seg < (o.wx ? 2 : 1); ++seg) {
+                    const void* sa = seg ? (const void*)o.xsrc_a : o.src_a;
+                    const void* sb = seg ? (const void*)o.xsrc_b : o.src_b;
+                    const int sca = seg ? o.xca : o.ca, scb = seg ? o.xcb : o.cb;
+                    const bool snorm = !seg && o.norm, sswish = !seg && o.swish, sb16 = !seg && o.src_b16;
+                    const int plane0 = seg ? (C >> 3) : 0;
+                    const int items = p.plane_px * ((sca + scb) >> 3);
+                    for (int i0 = wt; i0 < items; i0 += CH_INFLIGHT * CH_WORKERS) {
+                        uint4 raw0[CH_INFLIGHT], raw1[CH_INFLIGHT];
+                        int kpv[CH_INFLIGHT], pxv[CH_INFLIGHT];
+                        bool okv[CH_INFLIGHT];
 #pragma unroll
-                    for (int e = 0; e < CH_INFLIGHT; ++e) {
-                        const int i = i0 + e * CH_WORKERS;
-                        okv[e] = false;
-                        kpv[e] = -1;
-                        if (i >= items) continue;
-                        const int kp = fdiv(i, p.div_px), px = i - kp * p.plane_px;
-                        kpv[e] = kp; pxv[e] = px;
-                        const int pi = pixinfo[px];
-                        if (pi < 0) continue;
-                        okv[e] = true;
-                        const size_t pix = pix0 + (size_t)pi;
-                        const int c0 = kp * 8;
-                        if (o.src_b16) {
-                            const __nv_bfloat16* src = c0 < o.ca ? reinterpret_cast<const __nv_bfloat16*>(o.src_a) + pix * o.ca + c0
-                                                                 : reinterpret_cast<const __nv_bfloat16*>(o.src_b) + pix * o.cb + (c0 - o.ca);
-                            raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
-                        } else {
-                            const float* src = c0 < o.ca ? reinterpret_cast<const float*>(o.src_a) + pix * o.ca + c0
-                                                         : reinterpret_cast<const float*>(o.src_b) + pix * o.cb + (c0 - o.ca);
-                            raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
-                            raw1[e] = __ldcg(reinterpret_cast<const uint4*>(src) + 1);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < CH_INFLIGHT; ++e) {
-                        if (kpv[e] < 0) continue;
-                        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                        if (okv[e]) {
-                            if (o.src_b16) {
-                                val = raw0[e];
+                        for (int e = 0; e < CH_INFLIGHT; ++e) {
+                            const int i = i0 + e * CH_WORKERS;
+                            okv[e] = false;
+                            kpv[e] = -1;
+                            if (i >= items) continue;
+                            const int kp = fdiv(i, p.div_px), px = i - kp * p.plane_px;
+                            kpv[e] = kp; pxv[e] = px;
+                            const int pi = pixinfo[px];
+                            if (pi < 0) continue;
+                            okv[e] = true;
+                            const size_t pix = pix0 + (size_t)pi;
+                            const int c0 = kp * 8;
+                            if (sb16) {
+                                const __nv_bfloat16* src = c0 < sca ? reinterpret_cast<const __nv_bfloat16*>(sa) + pix * sca + c0
+                                                                    : reinterpret_cast<const __nv_bfloat16*>(sb) + pix * scb + (c0 - sca);
+                                raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
                             } else {
-                                float x[8] = {__uint_as_float(raw0[e].x), __uint_as_float(raw0[e].y), __uint_as_float(raw0[e].z),
-                                              __uint_as_float(raw0[e].w), __uint_as_float(raw1[e].x), __uint_as_float(raw1[e].y),
-                                              __uint_as_float(raw1[e].z), __uint_as_float(raw1[e].w)};
-                                if (o.norm) {
-                                    const float4* tb = reinterpret_cast<const float4*>(tab + kpv[e] * 8);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float4 sc = tb[j];
-                                        x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
-                                        x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
-                                    }
-                                }
-                                if (o.swish) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {           // y * sigmoid(y) = h * tanh(h) + h, h = y / 2
-                                        const float h = 0.5f * x[j];
-                                        float th;
-                                        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                                        x[j] = fmaf(h, th, h);
-                                    }
-                                }
-                                uint32_t w[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                                    w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                                }
-                                val = make_uint4(w[0], w[1], w[2], w[3]);
+                                const float* src = c0 < sca ? reinterpret_cast<const float*>(sa) + pix * sca + c0
+                                                            : reinterpret_cast<const float*>(sb) + pix * scb + (c0 - sca);
+                                raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
+                                raw1[e] = __ldcg(reinterpret_cast<const uint4*>(src) + 1);
                             }
                         }
-                        const uint32_t dst = base + a_off + (uint32_t)kpv[e] * plane_bytes + (uint32_t)pxv[e] * 16u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+#pragma unroll
+                        for (int e = 0; e < CH_INFLIGHT; ++e) {
+                            if (kpv[e] < 0) continue;
+                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                            if (okv[e]) {
+                                if (sb16) {
+                                    val = raw0[e];
+                                } else {
+                                    float x[8] = {__uint_as_float(raw0[e].x), __uint_as_float(raw0[e].y), __uint_as_float(raw0[e].z),
+                                                  __uint_as_float(raw0[e].w), __uint_as_float(raw1[e].x), __uint_as_float(raw1[e].y),
+                                                  __uint_as_float(raw1[e].z), __uint_as_float(raw1[e].w)};
+                                    if (snorm) {
+                                        const float4* tb = reinterpret_cast<const float4*>(tab + kpv[e] * 8);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float4 sc = tb[j];
+                                            x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
+                                            x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
+                                        }
+                                    }
+                                    if (sswish) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) {           // y * sigmoid(y) = h * tanh(h) + h, h = y / 2
+                                            const float h = 0.5f * x[j];
+                                            float th;
+                                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                                            x[j] = fmaf(h, th, h);
+                                        }
+                                    }
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                                    }
+                                    val = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
+                            }
+                            const uint32_t dst = base + a_off + (uint32_t)(plane0 + kpv[e]) * plane_bytes + (uint32_t)pxv[e] * 16u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -538,6 +570,15 @@ int chain_build(ChainPlan* plan, const ChainOpDesc* ops, int nops, int B, int H,
         o.sums_a = d.sums_a; o.sums_b = d.sums_b; o.gamma = d.gamma; o.beta = d.beta;
         o.G = d.G > 0 ? d.G : 1; o.swish = d.swish; o.norm = d.norm; o.src_b16 = d.src_b16;
         o.w = d.w; o.ntaps = d.ks * d.ks;
+        if (d.wx) {
+            const int Cx = d.xca + d.xcb;
+            DS_REQUIRE(d.xsrc_a && d.xca > 0 && d.xca % 8 == 0 && d.xcb % 8 == 0 && Cx % 16 == 0 && (d.xcb == 0 || d.xsrc_b) &&
+                           d.ca + d.cb + Cx <= CH_MAX_C + 256,
+                       "chain: op %d has an invalid folded 1x1 operand (%d+%d channels)", i, d.xca, d.xcb);
+            o.xsrc_a = d.xsrc_a; o.xsrc_b = d.xsrc_b; o.xca = d.xca; o.xcb = d.xcb; o.wx = d.wx;
+            o.epi.bias2 = d.bias2;
+            cmax = cmax > d.ca + d.cb + Cx ? cmax : d.ca + d.cb + Cx;
+        }
         o.epi.bias = d.epi.bias; o.epi.temb = d.epi.temb; o.epi.temb_off = d.epi.temb_off; o.epi.temb_stride = d.epi.temb_stride;
         o.epi.temb_bcast = d.epi.temb_bcast; o.epi.residual = d.epi.residual;
         o.epi.out_f32 = d.out_f32; o.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(d.out_b16); o.epi.out_nchw = nullptr;

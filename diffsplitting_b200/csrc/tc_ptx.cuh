@@ -118,6 +118,7 @@ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ?
 // ------------------------------------------------------------------------------------------ shared epilogue
 struct TcEpi {
     const float* bias;                // [Cout] or null
+    const float* bias2;               // second bias (the folded 1x1 res_conv of tc_chain.cu) or null; chain kernel only
     const float* temb;                // conditioning vectors or null
     int temb_off, temb_stride, temb_bcast;
     const float* residual;            // fp32 NHWC [B,Ho,Wo,Cout] or null (the residual stream stays fp32)

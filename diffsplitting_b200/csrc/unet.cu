@@ -83,6 +83,10 @@ struct Op {
     int fswish = 0;
     // conv executed inside a per-sample persistent chain launch (tc_chain.cu): consecutive chain ops form one launch
     int chain = 0, chain_src_b16 = 0;
+    // chain conv2 with the block's 1x1 res_conv folded in: raw second operand (fp32 copies) and its weights
+    int64_t xsrc_a = NONE, xsrc_b = NONE;
+    int xca = 0, xcb = 0;
+    const ConvW* xw = nullptr;
     // the network's first conv on the dedicated small-Cin kernel (conv_entry.cu), which also emits the statistics
     int entry = 0;
     // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
@@ -389,6 +393,8 @@ static int build_arch(ds_unet* n) {
 // ------------------------------------------------------------------------------------------ planning
 enum Fmt { F32 = 1, B16 = 2 };
 
+#define DS_ASSERT_CHAIN(op) do { if (!((op).kind == OP_CONV && (op).chain)) { fprintf(stderr, "diffsplit_b200: internal error, res fold on a non-chain op\n"); abort(); } } while (0)
+
 struct Planner {
     ds_unet* n;
     Plan* p;
@@ -508,7 +514,12 @@ struct Planner {
         Act resid = x;
         Act rbuf;
         bool res_side = false;
-        if (r.has_res) {            // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
+        // per-sample chain: the 1x1 res_conv becomes an extra K range of conv2 (one op less in the chain)
+        Act hprobe; hprobe.C = r.cout; hprobe.H = H; hprobe.W = W;
+        const bool fold_res = r.has_res && getenv("DIFFSPLIT_B200_NO_RES_FOLD") == nullptr && x.f32 != NONE &&
+                              (!skip || skip->f32 != NONE) && chain_ok(x, skip, r.res, 1, 0) && chain_ok(hprobe, nullptr, r.conv2, 1, 0) &&
+                              chain_ok(x, skip, r.conv1, 1, 0);
+        if (r.has_res && !fold_res) {   // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
             rbuf = make(r.cout, H, W, F32, false);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
             p->ops.back().side = (tc && !p->ops.back().chain) ? 1 : 0;
@@ -518,13 +529,20 @@ struct Planner {
         Act h = make(r.cout, H, W, F32);
         gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act out = make(r.cout, H, W, F32 | B16);
-        gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, &resid, out);
+        gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, fold_res ? nullptr : &resid, out);
+        if (fold_res) {
+            Op& o2 = p->ops.back();
+            DS_ASSERT_CHAIN(o2);
+            o2.xsrc_a = x.f32; o2.xca = x.C;
+            if (skip) { o2.xsrc_b = skip->f32; o2.xcb = skip->C; }
+            o2.xw = &r.res;
+        }
         if (r.has_res && tc && res_side) {
             for (size_t i = p->ops.size(); i-- > 0;)
                 if (p->ops[i].kind == OP_CONV && p->ops[i].cw == &r.conv2) { p->ops[i].join = 1; break; }
         }
         release(h);
-        if (r.has_res) release(rbuf);
+        if (r.has_res && !fold_res) release(rbuf);
         if (r.attn) {
             Act qkv = make(3 * r.cout, H, W, B16);
             gn_conv(out, nullptr, r.agn, 0, r.qkv, -1, nullptr, qkv);
@@ -970,6 +988,11 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 d.gamma = o.fgn ? n->wp(o.fgn->w) : nullptr; d.beta = o.fgn ? n->wp(o.fgn->b) : nullptr;
                 d.w = n->d_arena_bf16 + n->specs[o.cw->w].off_chain;
                 d.cout = o.cw->cout; d.ks = o.cw->ks;
+                if (o.xw) {
+                    d.xsrc_a = ptr(o.xsrc_a); d.xsrc_b = ptr(o.xsrc_b); d.xca = o.xca; d.xcb = o.xcb;
+                    d.wx = n->d_arena_bf16 + n->specs[o.xw->w].off_chain;
+                    d.bias2 = o.xw->b >= 0 ? n->wp(o.xw->b) : nullptr;
+                }
                 d.epi.bias = o.cw->b >= 0 ? n->wp(o.cw->b) : nullptr;
                 d.epi.temb = o.temb_off >= 0 ? temb : nullptr;
                 d.epi.temb_off = o.temb_off >= 0 ? o.temb_off : 0;
