@@ -25,6 +25,8 @@ namespace ds {
 constexpr int HALO_THREADS = 192;        // base block: TMA/setup warp, MMA warp, 4 epilogue warps (all of them stage)
 constexpr int HALO_MAX_THREADS = 512;    // wide block for layers that fit one CTA per SM anyway: extra warps only stage
 constexpr int HALO_SEG_PX = 136;           // 128 outputs + 2 halo pixels, padded to a multiple of 8
+constexpr int HALO_TW = 16, HALO_TH = 7, HALO_PW = HALO_TW + 2;      // 2-D tiles: 7 x 16 outputs, patch 9 x 18
+constexpr int HALO_2D_PX = ((HALO_TH + 2) * HALO_PW + 2 + 7) / 8 * 8;   // 168 staged positions
 constexpr int HALO_MAX_SAMPLES = 12;
 constexpr int HALO_MAX_GROUPS = 64;
 constexpr size_t HALO_SMEM_LIMIT = 200 * 1024;
@@ -46,6 +48,12 @@ struct HaloParams {
     // operand buffer geometry: `contig` = the three filter-row segments overlap inside ONE contiguous run of the flat
     // padded index space (W + 2 <= 139): every pixel is staged exactly once; else three separate 136-pixel segments
     int contig, plane_px, seg_stride_px;
+    // 2-D tile geometry (tile2d = 1): a tile is HALO_TH rows x HALO_TW columns of ONE sample; the staged patch has
+    // (HALO_TH + 2) rows of pitch HALO_PW = HALO_TW + 2, so a tap is still a constant shift (r * HALO_PW + s) and the 128 MMA
+    // rows are patch positions 0..127 (columns HALO_TW, HALO_TW + 1 of every row are computed and discarded).  Stages
+    // 1.5 pixels per output instead of 1.2 + 2 (W + 2) / 128 (flat tiles) or 3.2 (wide images).
+    int tile2d, tiles_x, tiles_y;
+    FastDiv div_tiles_x, div_tiles_xy;
     // A operand layout: rb == 0: no-swizzle [8-channel plane][pixel][16 B] (the tensor pipe reads it at ~32 B/clk);
     // rb = 32 / 64 / 128: K-chunks of rb/2 channels, [chunk][pixel][rb bytes] with the matching UMMA swizzle, shifted
     // windows addressed through the descriptor's base-offset field
@@ -64,7 +72,7 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo,
 }
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -85,6 +93,15 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
     if (q0 - p.Wp - 1 < 0) b_first = 0;
     int b_last = (q0 + 128 + p.Wp) / p.HpWp;
     if (b_last > p.B - 1) b_last = p.B - 1;
+    int tile_x0 = 0, tile_y0 = 0;                   // 2-D tiles: first output column / row of this tile
+    if (p.tile2d) {
+        const int tb = fdiv((int)blockIdx.x, p.div_tiles_xy);
+        const int rem = (int)blockIdx.x - tb * p.tiles_x * p.tiles_y;
+        const int ty = fdiv(rem, p.div_tiles_x);
+        tile_y0 = ty * HALO_TH;
+        tile_x0 = (rem - ty * p.tiles_x) * HALO_TW;
+        b_first = b_last = tb;
+    }
     const int nsamp = b_last - b_first + 1;
     const uint32_t gst_off = tab_off + (uint32_t)nsamp * p.C * 8u;                 // (mean, rstd) per (sample, group)
     const uint32_t chs_off = (gst_off + (uint32_t)nsamp * HALO_MAX_GROUPS * 8u + 15u) & ~15u;   // fp64 (sum, sq) per (sample, ch)
@@ -128,6 +145,21 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
     const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
     struct Pix { const float* a; const float* b; int tabi; uint32_t dst; int pxi; };   // a == nullptr: zero padding
     auto decode = [&](int px, Pix& px_) {
+        px_.a = nullptr;
+        px_.b = nullptr;
+        px_.tabi = 0;
+        px_.dst = base + a_off + px * 16;
+        px_.pxi = px;
+        if (p.tile2d) {
+            const int pr = px / HALO_PW, pc = px - pr * HALO_PW;
+            const int yy = tile_y0 + pr - 1, xx = tile_x0 + pc - 1;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                const size_t pix = ((size_t)b_first * p.H + yy) * p.W + xx;
+                px_.a = p.src_a + pix * p.ca;
+                px_.b = p.src_b ? p.src_b + pix * p.cb : nullptr;
+            }
+            return;
+        }
         int q;
         if (p.contig) {
             q = q_first + px;
@@ -135,11 +167,6 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
             const int seg = px / HALO_SEG_PX;
             q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
         }
-        px_.a = nullptr;
-        px_.b = nullptr;
-        px_.tabi = 0;
-        px_.dst = base + a_off + px * 16;
-        px_.pxi = px;
         if (q >= 0 && q < p.total_q) {
             const int b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
             uint32_t b_lo = b_lo0;
             if (p.rb == 0) {
                 for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int r = p.ntaps == 9 ? tap / 3 : 0;
+                    const int r = p.ntaps == 9 ? tap / 3 : (p.tile2d ? 1 : 0);
                     const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
                     uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
                     for (int kk = 0; kk < p.ksteps; ++kk) {
@@ -340,7 +367,13 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
         const int q = q0 + m;
         bool valid = q < p.total_q;
         int b = 0, oy = 0, ox = 0;
-        if (valid) {
+        if (p.tile2d) {
+            const int pr = m / HALO_PW, pc = m - pr * HALO_PW;
+            b = b_first;
+            oy = tile_y0 + pr;
+            ox = tile_x0 + pc;
+            valid = pr < HALO_TH && pc < HALO_TW && oy < p.H && ox < p.W;
+        } else if (valid) {
             b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
             const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
@@ -369,7 +402,8 @@ __global__ void __launch_bounds__(MAXT) conv_halo_kernel(const __grid_constant__
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
             }
             if (p.epi.sums_out) {
-                const int bt0 = fdiv(q0, p.div_hpwp), nsr = fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
+                const int bt0 = p.tile2d ? b_first : fdiv(q0, p.div_hpwp);
+                const int nsr = p.tile2d ? 1 : fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
                 if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, tid - 64, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
                 else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
             }
@@ -689,7 +723,19 @@ static long long* g_halo_dbg = nullptr;
 static size_t g_halo_dbg_ctas = 0;
 
 // ------------------------------------------------------------------------------------------ host side
+// 2-D tiles from this image width on (DIFFSPLIT_B200_HALO_2D_MINW; the flat tiles stage 130 + 2 (W + 2) positions for 128
+// outputs, the 2-D ones 168 for 112)
+static bool halo_use_2d(int W) {
+    static int minw = -1;
+    if (minw < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_2D_MINW"); minw = e ? atoi(e) : 138; }
+    return W >= minw && !getenv("DIFFSPLIT_B200_HALO_SWZ");
+}
+static int64_t halo_m_tiles(int B, int H, int W) {
+    if (halo_use_2d(W)) return (int64_t)B * ((H + HALO_TH - 1) / HALO_TH) * ((W + HALO_TW - 1) / HALO_TW);
+    return ((int64_t)B * (H + 2) * (W + 2) + 127) / 128;
+}
 static int halo_plane_px(int ntaps, int W) {
+    if (halo_use_2d(W)) return HALO_2D_PX;
     if (ntaps == 1) return HALO_SEG_PX;
     const int contig = 130 + 2 * (W + 2);
     return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
@@ -727,6 +773,7 @@ static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp) {
 }
 
 static int halo_samples_per_tile(int H, int W) {
+    if (halo_use_2d(W)) return 1;
     const int Wp = W + 2, HpWp = (H + 2) * Wp;
     return (128 + 2 * Wp + 2) / HpWp + 2;
 }
@@ -763,12 +810,12 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) 
 bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W) {
     if (!halo_conv_supported(ca, cb, cout, ks, B, H, W)) return false;
     const int C = ca + cb, ntaps = ks * ks;
-    const int64_t m_tiles = ((int64_t)B * (H + 2) * (W + 2) + 127) / 128;
+    const int64_t m_tiles = halo_m_tiles(B, H, W);
     const int nsamp = halo_samples_per_tile(H, W);
     const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles);
     const int n_tiles = (cout + 15) / 16 * 16 / bn;
     if (m_tiles * n_tiles <= 4 * 148) return true;                           // latency regime
-    const double redo = (double)halo_plane_px(ntaps, W) / 128.0;             // staged pixels per output pixel
+    const double redo = (double)halo_plane_px(ntaps, W) / (halo_use_2d(W) ? (double)(HALO_TH * HALO_TW) : 128.0);   // staged per output pixel
     if (redo * n_tiles * C > 320.0) return false;
     const double in_bytes = (double)B * H * W * C * 4.0;
     if (redo > 1.5 && in_bytes > 400e6) return false;                        // 3x re-reads of a tensor that does not fit L2
@@ -829,12 +876,18 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.C = ca + cb; p.ksteps = p.C / 16; p.ntaps = ks * ks;
     p.Npad = (cout + 15) / 16 * 16;
     const int nsamp = halo_samples_per_tile(H, W);
-    const int64_t m_tiles = ((int64_t)p.total_q + 127) / 128;
+    const int64_t m_tiles = halo_m_tiles(B, H, W);
+    p.tile2d = halo_use_2d(W) ? 1 : 0;
+    p.tiles_x = (W + HALO_TW - 1) / HALO_TW;
+    p.tiles_y = (H + HALO_TH - 1) / HALO_TH;
+    p.div_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
+    p.div_tiles_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
     p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles);
     p.n_tiles = p.Npad / p.BN;
     p.plane_px = halo_plane_px(p.ntaps, W);
     p.contig = (p.ntaps == 1 || p.plane_px != 3 * HALO_SEG_PX) ? 1 : 0;
     p.seg_stride_px = p.ntaps == 1 ? 0 : (p.contig ? p.Wp : HALO_SEG_PX);
+    if (p.tile2d) { p.contig = 1; p.seg_stride_px = HALO_PW; }
     p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
     p.div_wp = make_fastdiv((uint32_t)p.Wp);
     p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
@@ -890,7 +943,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
         const size_t b_bytes = (size_t)p.ntaps * p.ksteps * 2 * p.BN * 16;
         const size_t psmem = 2 * a_bytes + b_bytes + (size_t)HP_MAX_SAMPLES * (p.C * 8 + HALO_MAX_GROUPS * 8 + p.C * 16) + 128 +
                              TC_RED_BYTES + 1024 + 64;
-        const bool can = p.rb == 0 && nsamp <= HP_MAX_SAMPLES && psmem <= HALO_SMEM_LIMIT && !p.dbg;
+        const bool can = p.rb == 0 && !p.tile2d && nsamp <= HP_MAX_SAMPLES && psmem <= HALO_SMEM_LIMIT && !p.dbg;
         const bool want = persist_env == 2 || (persist_env == 1 && p.C >= 64 && (size_t)m_tiles * p.n_tiles >= 8 * 148);
         if (can && want) {
             const int per_sm = psmem <= 100 * 1024 ? 2 : 1;
