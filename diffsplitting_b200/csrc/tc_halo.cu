@@ -723,19 +723,23 @@ static long long* g_halo_dbg = nullptr;
 static size_t g_halo_dbg_ctas = 0;
 
 // ------------------------------------------------------------------------------------------ host side
-// 2-D tiles from this image width on (DIFFSPLIT_B200_HALO_2D_MINW; the flat tiles stage 130 + 2 (W + 2) positions for 128
-// outputs, the 2-D ones 168 for 112)
-static bool halo_use_2d(int W) {
+// 2-D tiles for wide images (the flat tiles stage 130 + 2 (W + 2) positions for 128 outputs, or three separate segments of
+// 136; the 2-D ones 168 for 112) - always from DIFFSPLIT_B200_HALO_2D_MINW (138) columns on, and from 48 columns on when
+// the layer is many waves of tiles (throughput regime; in the latency regime of the 64 x 64 benchmark layers the 14 % extra
+// tiles cost more than the smaller patches save: 2017 vs 2097 steps/s)
+static bool halo_use_2d(int B, int H, int W) {
     static int minw = -1;
     if (minw < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_2D_MINW"); minw = e ? atoi(e) : 138; }
-    return W >= minw && !getenv("DIFFSPLIT_B200_HALO_SWZ");
+    if (getenv("DIFFSPLIT_B200_HALO_SWZ")) return false;
+    if (W >= minw) return true;
+    return minw == 138 && W >= 48 && ((int64_t)B * (H + 2) * (W + 2) + 127) / 128 >= 8 * 148;
 }
 static int64_t halo_m_tiles(int B, int H, int W) {
-    if (halo_use_2d(W)) return (int64_t)B * ((H + HALO_TH - 1) / HALO_TH) * ((W + HALO_TW - 1) / HALO_TW);
+    if (halo_use_2d(B, H, W)) return (int64_t)B * ((H + HALO_TH - 1) / HALO_TH) * ((W + HALO_TW - 1) / HALO_TW);
     return ((int64_t)B * (H + 2) * (W + 2) + 127) / 128;
 }
-static int halo_plane_px(int ntaps, int W) {
-    if (halo_use_2d(W)) return HALO_2D_PX;
+static int halo_plane_px(int ntaps, int W, bool two_d) {
+    if (two_d) return HALO_2D_PX;
     if (ntaps == 1) return HALO_SEG_PX;
     const int contig = 130 + 2 * (W + 2);
     return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
@@ -760,25 +764,25 @@ static int halo_row_bytes(int C) {
     if (!halo_swizzle_mode()) return 0;
     return C % 64 == 0 ? 128 : (C % 32 == 0 ? 64 : 32);
 }
-static size_t halo_a_bytes(int C, int ntaps, int W) {
+static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d) {
     const int rb = halo_row_bytes(C);
-    const int px = halo_plane_px(ntaps, W);
+    const int px = halo_plane_px(ntaps, W, two_d);
     if (!rb) return (size_t)(C / 8) * px * 16;
     return (size_t)(C * 2 / rb) * align_up((size_t)px * rb, 1024);
 }
 
-static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp) {
-    return halo_a_bytes(C, ntaps, W) + 1024 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
+static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp, bool two_d) {
+    return halo_a_bytes(C, ntaps, W, two_d) + 1024 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
            (size_t)nsamp * HALO_MAX_GROUPS * 8 + (size_t)nsamp * C * 16 + 96 + TC_RED_BYTES + 128;
 }
 
-static int halo_samples_per_tile(int H, int W) {
-    if (halo_use_2d(W)) return 1;
+static int halo_samples_per_tile(int H, int W, bool two_d) {
+    if (two_d) return 1;
     const int Wp = W + 2, HpWp = (H + 2) * Wp;
     return (128 + 2 * Wp + 2) / HpWp + 2;
 }
 
-static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_tiles) {
+static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_tiles, bool two_d) {
     const int npad = (cout + 15) / 16 * 16;
     int bn = 16;
     for (int c = 128; c >= 16; c >>= 1)
@@ -787,7 +791,7 @@ static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_
     // grid would leave most SMs idle
     static int min_ctas = -1;
     if (min_ctas < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_MIN_CTAS"); min_ctas = e ? atoi(e) : 48; }
-    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < min_ctas)) bn >>= 1;
+    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp, two_d) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < min_ctas)) bn >>= 1;
     return bn;
 }
 
@@ -796,9 +800,10 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) 
     if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 224 || ks * ks * (C / 16) * 2 > 256) return false;
     if (!(ks == 1 || ks == 3)) return false;
     if ((int64_t)B * (H + 2) * (W + 2) >= (1ll << 31) - 4096) return false;
-    const int nsamp = halo_samples_per_tile(H, W);
+    const bool two_d = halo_use_2d(B, H, W);
+    const int nsamp = halo_samples_per_tile(H, W, two_d);
     if (nsamp > HALO_MAX_SAMPLES) return false;
-    return halo_smem_bytes(C, ks * ks, W, 16, nsamp) <= HALO_SMEM_LIMIT;
+    return halo_smem_bytes(C, ks * ks, W, 16, nsamp, two_d) <= HALO_SMEM_LIMIT;
 }
 
 // Is the fused kernel also the FASTER choice (vs GroupNorm-apply into a bf16 tensor + the TMA-fed conv)?  Each CTA stages
@@ -811,11 +816,12 @@ bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W) 
     if (!halo_conv_supported(ca, cb, cout, ks, B, H, W)) return false;
     const int C = ca + cb, ntaps = ks * ks;
     const int64_t m_tiles = halo_m_tiles(B, H, W);
-    const int nsamp = halo_samples_per_tile(H, W);
-    const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles);
+    const bool two_d = halo_use_2d(B, H, W);
+    const int nsamp = halo_samples_per_tile(H, W, two_d);
+    const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles, two_d);
     const int n_tiles = (cout + 15) / 16 * 16 / bn;
     if (m_tiles * n_tiles <= 4 * 148) return true;                           // latency regime
-    const double redo = (double)halo_plane_px(ntaps, W) / (halo_use_2d(W) ? (double)(HALO_TH * HALO_TW) : 128.0);   // staged per output pixel
+    const double redo = (double)halo_plane_px(ntaps, W, two_d) / (two_d ? (double)(HALO_TH * HALO_TW) : 128.0);   // staged per output pixel
     if (redo * n_tiles * C > 320.0) return false;
     const double in_bytes = (double)B * H * W * C * 4.0;
     if (redo > 1.5 && in_bytes > 400e6) return false;                        // 3x re-reads of a tensor that does not fit L2
@@ -875,16 +881,17 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.total_q = B * p.HpWp;
     p.C = ca + cb; p.ksteps = p.C / 16; p.ntaps = ks * ks;
     p.Npad = (cout + 15) / 16 * 16;
-    const int nsamp = halo_samples_per_tile(H, W);
+    const bool two_d = halo_use_2d(B, H, W);
+    const int nsamp = halo_samples_per_tile(H, W, two_d);
     const int64_t m_tiles = halo_m_tiles(B, H, W);
-    p.tile2d = halo_use_2d(W) ? 1 : 0;
+    p.tile2d = two_d ? 1 : 0;
     p.tiles_x = (W + HALO_TW - 1) / HALO_TW;
     p.tiles_y = (H + HALO_TH - 1) / HALO_TH;
     p.div_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
     p.div_tiles_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
-    p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles);
+    p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles, two_d);
     p.n_tiles = p.Npad / p.BN;
-    p.plane_px = halo_plane_px(p.ntaps, W);
+    p.plane_px = halo_plane_px(p.ntaps, W, two_d);
     p.contig = (p.ntaps == 1 || p.plane_px != 3 * HALO_SEG_PX) ? 1 : 0;
     p.seg_stride_px = p.ntaps == 1 ? 0 : (p.contig ? p.Wp : HALO_SEG_PX);
     if (p.tile2d) { p.contig = 1; p.seg_stride_px = HALO_PW; }
@@ -918,7 +925,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
             return DS_ERR_CUDA;
         }
     }
-    const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp);
+    const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp, two_d);
     p.trace = trace_next(6);
     if (getenv("DIFFSPLIT_B200_HALO_DBG")) {
         const size_t ctas = (size_t)m_tiles * p.n_tiles;
