@@ -171,6 +171,178 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     trace_end(p.trace);
 }
 
+// ------------------------------------------------------------------------------------------ tall-patch variant
+// For 3x3 stride-1 convolutions on large images the kernel above is bound by what an SM can pull from L2 (~25-30 B/clk): it
+// fetches every input pixel once per filter tap and the whole weight tile per 128-pixel tile.  Here a CTA owns MT
+// vertically adjacent tiles of 7 x 16 outputs and, per 64-channel chunk, loads ONE patch of (7 MT + 2) x 18 pixels with a
+// single TMA box (out-of-bounds rows / columns zero-filled = the padding).  In that patch (row pitch 18) a filter tap is a
+// constant row shift, so the A operand of (tile t, tap r,s) is just the descriptor start  patch + (126 t + 18 r + s) rows:
+// the tensor core's swizzle is a pure function of the shared-memory address, a window may start on any row of a swizzle
+// atom (profiles/README.md, finding 3).  Every weight stage is applied to all MT tiles (MT accumulators in TMEM), so the
+// weights are fetched once per 7 MT x 16 pixels.  Ingest per 64-channel chunk at 128 -> 128, MT = 3: 53 KB of pixels +
+// 147 KB of weights for 6.9k cycles of MMAs instead of 288 KB for 2.3k.
+constexpr int TP_TW = 16, TP_TH = 7, TP_PW = TP_TW + 2;
+constexpr int TP_MAX_MT = 3;
+constexpr int TP_THREADS = 64 + 256;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quadrant)
+
+struct TcpParams {
+    CUtensorMap pmap[2];              // sources a / b as (C, W, H, B), box {KC, 18, 7 MT + 2, 1}
+    const uint8_t* w;                 // the same packed weights as conv_tc_kernel (class 0)
+    TcEpi epi;
+    int nb16, B, H, W, BN, n_tiles, KC, chunks_a, chunks_b, MT, tiles_x, tiles_y, wstages;
+    uint32_t patch_bytes;
+    TraceSlot trace;
+};
+
+__global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_constant__ TcpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+    const uint32_t w_bytes = (uint32_t)p.BN * row_bytes;                    // one (tap, chunk) weight tile
+    const uint32_t wstage_bytes = (w_bytes + 1023u) & ~1023u;
+    const uint32_t wring = base + 2u * p.patch_bytes;
+    const uint32_t bar_base = wring + (uint32_t)p.wstages * wstage_bytes;
+    auto wfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto wempty = [&](int s) { return bar_base + 8u * (uint32_t)(p.wstages + s); };
+    const uint32_t pfull0 = bar_base + 16u * (uint32_t)p.wstages;          // pfull[2], pempty[2], tfull, tmem slot
+    auto pfull = [&](int i) { return pfull0 + 8u * (uint32_t)i; };
+    auto pempty = [&](int i) { return pfull0 + 16u + 8u * (uint32_t)i; };
+    const uint32_t tfull = pfull0 + 32u, tmem_slot = pfull0 + 40u;
+    uint8_t* red = smem_raw + (tmem_slot + 16u - smem_u32(smem_raw));
+
+    int bid = blockIdx.x;
+    const int tx_i = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty_i = bid % p.tiles_y; bid /= p.tiles_y;
+    const int b = bid;
+    const int x0 = tx_i * TP_TW, y0 = ty_i * TP_TH * p.MT;
+    const int nt = blockIdx.y;
+    const int nchunks = p.chunks_a + p.chunks_b;
+    const uint32_t ncols = (uint32_t)(p.MT * p.BN);
+    const uint32_t tmem_cols = ncols <= 32u ? 32u : (ncols <= 64u ? 64u : (ncols <= 128u ? 128u : (ncols <= 256u ? 256u : 512u)));
+
+    trace_begin(p.trace);
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.wstages; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(pfull(i), 1); mbar_init(pempty(i), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const size_t blk16 = (size_t)16 * p.KC * 2;
+            const uint8_t* wsrc = p.w + (size_t)nt * (p.BN / 16) * blk16;
+            const uint32_t box_bytes = (uint32_t)(TP_PW * (TP_TH * p.MT + 2)) * row_bytes;
+            int u = 0;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                const int pb = cc & 1;
+                mbar_wait(pempty(pb), (((uint32_t)(cc >> 1)) & 1u) ^ 1u);
+                const int src = cc < p.chunks_a ? 0 : 1;
+                const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
+                mbar_expect_tx(pfull(pb), box_bytes);
+                tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.pmap[src], pfull(pb), c0, x0 - 1, y0 - 1, b);
+                for (int tap = 0; tap < 9; ++tap, ++u) {
+                    const int s = u % p.wstages;
+                    mbar_wait(wempty(s), (((uint32_t)(u / p.wstages)) & 1u) ^ 1u);
+                    mbar_expect_tx(wfull(s), w_bytes);
+                    bulk_load(wring + (uint32_t)s * wstage_bytes, wsrc + (size_t)(tap * nchunks + cc) * p.nb16 * blk16, w_bytes, wfull(s));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            int u = 0;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                const int pb = cc & 1;
+                mbar_wait(pfull(pb), ((uint32_t)(cc >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t patch = base + (uint32_t)pb * p.patch_bytes;
+                for (int tap = 0; tap < 9; ++tap, ++u) {
+                    const int s = u % p.wstages;
+                    mbar_wait(wfull(s), ((uint32_t)(u / p.wstages)) & 1u);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_smem_desc(wring + (uint32_t)s * wstage_bytes, row_bytes);
+                    const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
+                    for (int t = 0; t < p.MT; ++t) {
+                        const uint64_t adesc = make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
+                        for (int k = 0; k < p.KC / 16; ++k)
+                            umma_bf16(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                      (cc | tap | k) ? 1u : 0u);
+                    }
+                    umma_commit(wempty(s));
+                }
+                umma_commit(pempty(pb));
+            }
+            umma_commit(tfull);
+        }
+        __syncwarp();
+    } else {
+        // two groups of four warps: group g takes the 16-column chunks with (chunk index & 1) == g of every tile; the
+        // addend (bias / time vector / residual) of the next chunk is loaded while the current one is processed
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int m = q * 32 + lane;
+        const int te = (int)threadIdx.x - 64 - grp * 128;
+        uint8_t* redg = red + (size_t)grp * TC_RED_BYTES;
+        const int pr = m / TP_PW, pc = m - pr * TP_PW;
+        const int x = x0 + pc;
+        const int cpt = p.BN >> 4;                                   // chunks per tile
+        const int nwork = (p.MT * cpt + 1 - grp) >> 1;                // chunks of this group: global chunk ids grp, grp + 2, ...
+        auto where = [&](int i, int& t, int& c0, int& y, bool& valid) {
+            const int g = grp + 2 * i;
+            t = g / cpt;
+            c0 = (g - t * cpt) * 16;
+            y = y0 + t * TP_TH + pr;
+            valid = pr < TP_TH && pc < TP_TW && y < p.H && x < p.W;
+        };
+        float add_next[16];
+        {
+            int t, c0, y; bool valid;
+            if (nwork > 0) { where(0, t, c0, y, valid); if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, add_next); }
+        }
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int i = 0; i < nwork; ++i) {
+            int t, c0, y; bool valid;
+            where(i, t, c0, y, valid);
+            float add[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) add[j] = add_next[j];
+            if (i + 1 < nwork) {
+                int t2, c2, y2; bool v2;
+                where(i + 1, t2, c2, y2, v2);
+                if (v2) tc_epilogue_addend(p.epi, b, y2, x, nt * p.BN + c2, add_next);
+            }
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.BN + c0), v);
+            float f[16];
+            if (valid) tc_epilogue_write(p.epi, v, add, b, y, x, nt * p.BN + c0, f);
+            if (p.epi.sums_out) {
+                if (grp == 0) tc_epilogue_stats_shfl<1>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, (int)(blockIdx.x % TC_SUM_COPIES), redg);
+                else tc_epilogue_stats_shfl<2>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, (int)(blockIdx.x % TC_SUM_COPIES), redg);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+    trace_end(p.trace);
+}
+
 // ------------------------------------------------------------------------------------------ weight packing
 // Swizzle<B,4,3> on byte offsets inside a tile whose rows are `row_bytes` wide (B = log2(row_bytes/16)).
 __host__ __device__ inline uint32_t swizzle_offset(uint32_t row, uint32_t byte_in_row, uint32_t row_bytes) {
@@ -312,10 +484,57 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     int rc = get_encoder();
     if (rc != DS_OK) return rc;
     DS_REQUIRE(tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws), "tc conv: unsupported shape");
+    plan->patch = 0;
+    const int kc = tc_pick_kc(ca, cb);
+    {
+        // tall-patch variant: 3x3 stride-1 layers in the throughput regime (DIFFSPLIT_B200_TC_PATCH: 0 never, 2 whenever possible)
+        static int patch_env = -1;
+        if (patch_env < 0) { const char* e = getenv("DIFFSPLIT_B200_TC_PATCH"); patch_env = e ? atoi(e) : 1; }
+        const int tiles_x = (Ws + TP_TW - 1) / TP_TW;
+        int mt = (Hs + TP_TH - 1) / TP_TH;
+        if (mt > TP_MAX_MT) mt = TP_MAX_MT;
+        const int bn = tc_bn(cout);
+        if (mt * bn > 512) mt = 512 / bn;
+        const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
+        const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
+        const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
+        if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 2 * 148 && ca + cb >= 64))) {
+            static_assert(sizeof(TcpParams) <= sizeof(plan->params), "TcConvPlan::params too small");
+            TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
+            memset(&q, 0, sizeof(q));
+            q.B = B; q.H = Hs; q.W = Ws; q.MT = mt; q.tiles_x = tiles_x; q.tiles_y = tiles_y;
+            q.epi.Ho = Hs; q.epi.Wo = Ws; q.epi.Cout = cout;
+            q.nb16 = (cout + 15) / 16;
+            q.BN = bn; q.n_tiles = (q.nb16 * 16) / bn;
+            q.KC = kc; q.chunks_a = ca / kc; q.chunks_b = cb / kc;
+            const int prows = TP_PW * (TP_TH * mt + 2) + 8;             // + the rows the last tile's window runs past the patch
+            q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * 2, 1024);
+            const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * 2, 1024);
+            int wst = (int)((196 * 1024 - 2 * (size_t)q.patch_bytes - 2048 - 2 * TC_RED_BYTES) / wstage);
+            if (wst > 9) wst = 9;
+            if (wst >= 2) {
+                q.wstages = wst;
+                for (int s_ = 0; s_ < 2; ++s_) {
+                    const void* ptr = s_ == 0 ? src_a : src_b;
+                    const int C = s_ == 0 ? ca : cb;
+                    if (!ptr || C == 0) continue;
+                    rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * 2, (size_t)Ws * C * 2, (size_t)Hs * Ws * C * 2, kc, TP_PW,
+                                    TP_TH * mt + 2, 1);
+                    if (rc != DS_OK) return rc;
+                }
+                plan->patch = 1;
+                plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 16 * wst + 64 + 1024 + 2 * TC_RED_BYTES);
+                plan->grid_x = tiles_x * tiles_y * B;
+                plan->grid_y = q.n_tiles;
+                plan->grid_z = 1;
+                plan->kc = kc;
+                return DS_OK;
+            }
+        }
+    }
     TcParams& p = *reinterpret_cast<TcParams*>(plan->params);
     static_assert(sizeof(TcParams) <= sizeof(plan->params), "TcConvPlan::params too small");
     memset(&p, 0, sizeof(p));
-    const int kc = tc_pick_kc(ca, cb);
     // tile space
     const int H = stride == 2 ? Hs / 2 : Hs, W = stride == 2 ? Ws / 2 : Ws;
     p.B = B; p.H = H; p.W = W;
@@ -411,6 +630,22 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
 
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
                    float* out_nchw, double* sums_out, cudaStream_t st) {
+    if (plan->patch) {
+        TcpParams q = *reinterpret_cast<const TcpParams*>(plan->params);
+        q.w = w_packed;
+        q.epi.bias = epi.bias; q.epi.temb = epi.temb; q.epi.temb_off = epi.temb_off; q.epi.temb_stride = epi.temb_stride;
+        q.epi.temb_bcast = epi.temb_bcast; q.epi.residual = epi.residual;
+        q.epi.out_f32 = out_f32; q.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); q.epi.out_nchw = out_nchw;
+        q.epi.sums_out = sums_out; q.epi.sums_B = q.B;
+        q.trace = trace_next(4);
+        static bool pattr = false;
+        if (!pattr) {
+            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            pattr = true;
+        }
+        DS_CHECK_CUDA(launch_pdl(conv_tcp_kernel, dim3(plan->grid_x, plan->grid_y, 1), dim3(TP_THREADS), (size_t)plan->smem_bytes, st, q));
+        return DS_OK;
+    }
     TcParams p = *reinterpret_cast<const TcParams*>(plan->params);
     p.w = w_packed;
     p.epi.bias = epi.bias;

@@ -7,6 +7,7 @@ namespace ds {
 struct TcConvPlan {
     alignas(64) uint8_t params[2048];     // a TcParams (tensor maps + geometry), filled by tc_build_conv
     int smem_bytes, grid_x, grid_y, grid_z, kc;
+    int patch;                            // 1: params hold a TcpParams (tall-patch kernel)
 };
 
 int tc_pick_kc(int ca, int cb);                                    // 64 / 32 / 16, or 0 if unsupported

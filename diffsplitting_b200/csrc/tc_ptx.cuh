@@ -315,6 +315,7 @@ __device__ __forceinline__ void tc_epilogue_stats(const TcEpi& p, const float (&
 // The same statistics with warp shuffles instead of the transposed shared-memory pass, for tiles whose 128 rows belong to at
 // most two samples (`nsamp_rows`, uniform over the CTA): per sample a masked column sum (16 shuffles each for sum and sum of
 // squares), one 128-thread barrier to fold the four warps, one fp64 atomic pair per (sample, channel).
+template <int BAR = 1>      // named barrier of the calling group of 128 epilogue threads
 __device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int te,
                                                        int b_tile0, int nsamp_rows, int copy, uint8_t* red_raw) {
     float* red = reinterpret_cast<float*>(red_raw);          // [warp 4][sample 2][kind 2][16]
@@ -334,7 +335,7 @@ __device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const flo
             }
         }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
     if (te < 32 * nsamp_rows) {
         const int s = te >> 5, kind = (te >> 4) & 1, col = te & 15;
         float tot = 0.f;
@@ -344,7 +345,7 @@ __device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const flo
         if (n0 + col < p.Cout && bb < p.sums_B && tot != 0.f)
             atomicAdd(p.sums_out + (((size_t)copy * p.sums_B + bb) * p.Cout + n0 + col) * 2 + kind, (double)tot);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");            // `red` may be reused
+    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");            // `red` may be reused
 }
 
 }  // namespace ds

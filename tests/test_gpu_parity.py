@@ -111,7 +111,9 @@ TC_CASES = [
     (128, 0, 128, 3, 1, 1, 1, 16, 16, 0, 0), (16, 0, 1, 3, 1, 0, 2, 16, 16, 0, 1), (16, 0, 6, 3, 1, 0, 1, 32, 32, 0, 1),
     (128, 0, 384, 1, 1, 0, 2, 8, 8, 0, 0), (16, 0, 16, 3, 1, 0, 1, 24, 20, 1, 0), (256, 0, 256, 3, 1, 0, 1, 4, 4, 0, 0),
     (16, 0, 16, 3, 1, 0, 16, 64, 64, 1, 0), (48, 0, 16, 3, 1, 0, 1, 128, 128, 0, 0), (192, 0, 64, 3, 1, 0, 2, 16, 16, 0, 0),
-    (512, 0, 512, 3, 1, 0, 1, 16, 16, 1, 0)]
+    (512, 0, 512, 3, 1, 0, 1, 16, 16, 1, 0),
+    # enough tiles for the tall-patch variant (>= 296 CTAs, >= 64 channels): one TMA patch per chunk, taps = row shifts
+    (64, 0, 64, 3, 1, 0, 8, 128, 128, 1, 0), (64, 64, 32, 3, 1, 0, 6, 100, 90, 0, 0)]
 
 
 @pytest.mark.parametrize("ca,cb,cout,ks,stride,up,B,H,W,residual,out_nchw", TC_CASES)
