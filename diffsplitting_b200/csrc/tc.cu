@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // 147 KB of weights for 6.9k cycles of MMAs instead of 288 KB for 2.3k.
 constexpr int TP_TW = 16, TP_TH = 7, TP_PW = TP_TW + 2;
 constexpr int TP_MAX_MT = 3;
-constexpr int TP_THREADS = 64 + 256;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quadrant)
+constexpr int TP_GROUPS = 4;               // epilogue groups of four warps (one warp per TMEM lane quadrant each)
+constexpr int TP_THREADS = 64 + 128 * TP_GROUPS;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
 
 struct TcpParams {
     CUtensorMap pmap[2];              // sources a / b as (C, W, H, B), box {KC, 18, 7 MT + 2, 1}
@@ -288,8 +289,9 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
         }
         __syncwarp();
     } else {
-        // two groups of four warps: group g takes the 16-column chunks with (chunk index & 1) == g of every tile; the
-        // addend (bias / time vector / residual) of the next chunk is loaded while the current one is processed
+        // TP_GROUPS groups of four warps: group g takes the 16-column chunks g, g + TP_GROUPS, ... of the CTA's MT tiles.  The
+        // epilogue is bound by the latency of the residual loads (HBM), so the addends of the next TWO chunks are in flight
+        // while one is processed, and the groups multiply the loads in flight per SM.
         const int q = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int m = q * 32 + lane;
@@ -298,40 +300,48 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
         const int pr = m / TP_PW, pc = m - pr * TP_PW;
         const int x = x0 + pc;
         const int cpt = p.BN >> 4;                                   // chunks per tile
-        const int nwork = (p.MT * cpt + 1 - grp) >> 1;                // chunks of this group: global chunk ids grp, grp + 2, ...
+        const int G = p.MT * cpt;
+        const int nwork = (G - grp + TP_GROUPS - 1) / TP_GROUPS;
         auto where = [&](int i, int& t, int& c0, int& y, bool& valid) {
-            const int g = grp + 2 * i;
+            const int g = grp + TP_GROUPS * i;
             t = g / cpt;
             c0 = (g - t * cpt) * 16;
             y = y0 + t * TP_TH + pr;
             valid = pr < TP_TH && pc < TP_TW && y < p.H && x < p.W;
         };
-        float add_next[16];
+        float addA[16], addB[16];
         {
             int t, c0, y; bool valid;
-            if (nwork > 0) { where(0, t, c0, y, valid); if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, add_next); }
+            if (nwork > 0) { where(0, t, c0, y, valid); if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, addA); }
+            if (nwork > 1) { where(1, t, c0, y, valid); if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, addB); }
         }
         mbar_wait(tfull, 0);
         tc_fence_after();
-        for (int i = 0; i < nwork; ++i) {
+        auto work = [&](int i, float (&add)[16]) {
             int t, c0, y; bool valid;
             where(i, t, c0, y, valid);
-            float add[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) add[j] = add_next[j];
-            if (i + 1 < nwork) {
-                int t2, c2, y2; bool v2;
-                where(i + 1, t2, c2, y2, v2);
-                if (v2) tc_epilogue_addend(p.epi, b, y2, x, nt * p.BN + c2, add_next);
-            }
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.BN + c0), v);
             float f[16];
             if (valid) tc_epilogue_write(p.epi, v, add, b, y, x, nt * p.BN + c0, f);
-            if (p.epi.sums_out) {
-                if (grp == 0) tc_epilogue_stats_shfl<1>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, (int)(blockIdx.x % TC_SUM_COPIES), redg);
-                else tc_epilogue_stats_shfl<2>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, (int)(blockIdx.x % TC_SUM_COPIES), redg);
+            if (i + 2 < nwork) {                                       // refill this slot with the addend of chunk i + 2
+                int t2, c2, y2; bool v2;
+                where(i + 2, t2, c2, y2, v2);
+                if (v2) tc_epilogue_addend(p.epi, b, y2, x, nt * p.BN + c2, add);
             }
+            if (p.epi.sums_out) {
+                const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
+                switch (grp) {
+                    case 0: tc_epilogue_stats_shfl<1>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, redg); break;
+                    case 1: tc_epilogue_stats_shfl<2>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, redg); break;
+                    case 2: tc_epilogue_stats_shfl<3>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, redg); break;
+                    default: tc_epilogue_stats_shfl<4>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, redg); break;
+                }
+            }
+        };
+        for (int i = 0; i < nwork; i += 2) {
+            work(i, addA);
+            if (i + 1 < nwork) work(i + 1, addB);
         }
         tc_fence_before();
     }
@@ -510,7 +520,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             const int prows = TP_PW * (TP_TH * mt + 2) + 8;             // + the rows the last tile's window runs past the patch
             q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * 2, 1024);
             const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * 2, 1024);
-            int wst = (int)((196 * 1024 - 2 * (size_t)q.patch_bytes - 2048 - 2 * TC_RED_BYTES) / wstage);
+            int wst = (int)((196 * 1024 - 2 * (size_t)q.patch_bytes - 2048 - TP_GROUPS * TC_RED_BYTES) / wstage);
             if (wst > 9) wst = 9;
             if (wst >= 2) {
                 q.wstages = wst;
@@ -523,7 +533,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                     if (rc != DS_OK) return rc;
                 }
                 plan->patch = 1;
-                plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 16 * wst + 64 + 1024 + 2 * TC_RED_BYTES);
+                plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 16 * wst + 64 + 1024 + TP_GROUPS * TC_RED_BYTES);
                 plan->grid_x = tiles_x * tiles_y * B;
                 plan->grid_y = q.n_tiles;
                 plan->grid_z = 1;
