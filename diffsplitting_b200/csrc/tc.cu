@@ -508,7 +508,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
         const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
         const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
-        if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 2 * 148 && ca + cb >= 64))) {
+        if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 148 && ca + cb >= 64))) {
             static_assert(sizeof(TcpParams) <= sizeof(plan->params), "TcConvPlan::params too small");
             TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
             memset(&q, 0, sizeof(q));
