@@ -17,7 +17,7 @@ namespace ds {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_SPLIT = 64;
 constexpr int GN_MAX_GROUPS = 64;
-constexpr int GN_SUM_COPIES = 8;      // == TC_SUM_COPIES (tc_ptx.cuh): replicated statistics accumulators
+constexpr int GN_SUM_COPIES = TC_SUM_COPIES;      // replicated statistics accumulators (common.cuh)
 
 int gn_nsplit(int B, int HW, int C) {
     int64_t per = (int64_t)HW * C;

@@ -412,7 +412,7 @@ struct Planner {
         if (!tc) fmt = F32;
         if (tc && (fmt & F32) && want_sums) {       // a GroupNorm will read this tensor: its producer emits the statistics
             a.sums = (int64_t)stats_top;
-            stats_top += align_up((size_t)8 /* TC_SUM_COPIES */ * B * C * 2 * sizeof(double), 256);
+            stats_top += align_up((size_t)TC_SUM_COPIES * B * C * 2 * sizeof(double), 256);
         }
         if (fmt & F32) a.f32 = arena.alloc((size_t)B * H * W * C * 4);
         if (fmt & B16) a.b16 = arena.alloc((size_t)B * H * W * C * 2);
