@@ -421,304 +421,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
 }
 
 
-// ------------------------------------------------------------------------------------------ persistent, pipelined variant
-// For grids of many waves (512 x 512 tiles: 16k tiles per layer) the one-tile-per-CTA kernel above is latency bound: a CTA
-// walks load -> normalise -> MMA -> epilogue once (~10k cycles) and four of them per SM overlap only by accident.  Here
-// every CTA owns a CONTIGUOUS run of tiles and three warp-specialised roles run a software pipeline over them:
-//   warps 0..5   stagers  : raw fp32 pixels -> normalise -> Swish -> bf16 -> A[buf]          (double buffered)
-//   warp  6      MMA      : A[buf] x resident weights -> TMEM[tb]                              (double buffered)
-//   warps 7..10  epilogue : TMEM[tb] -> bias / time vector / residual -> stores + statistics
-// The weights of the CTA's output-channel block are fetched once and stay in shared memory for all its tiles (for >= 64
-// channels they are most of what a one-tile CTA pulls through the SM's ~25 B/clk L2 port: 74 KB of weights vs 39 KB of
-// pixels per tile at 64 -> 64), the scale/shift table is rebuilt only when the run crosses into another sample.
-// Measured (8 x 256 x 256, 64 -> 64): 410 -> 265 us.  With <= 48 channels the two 192-thread stager groups per SM keep
-// fewer loads in flight than four one-tile CTAs and the variant is slower (a cp.async ring of raw tiles did not help: for
-// wide images the three filter rows are staged as three separate segments, 3x the pixels), so it is used from 64
-// channels up.
-constexpr int HP_STAGERS = 192;
-constexpr int HP_THREADS = HP_STAGERS + 32 + 128;
-constexpr int HP_MAX_SAMPLES = 3;
-
-__device__ __forceinline__ void hp_bar_stagers() { asm volatile("bar.sync 3, %0;" ::"n"(HP_STAGERS) : "memory"); }
-__device__ __forceinline__ void hp_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__global__ void __launch_bounds__(HP_THREADS, 2) conv_halo_persistent_kernel(const __grid_constant__ HaloParams p, int tiles_per_cta,
-                                                                            int m_tiles) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* gbase = smem_raw + (base - raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int P = p.C >> 3;
-    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const uint32_t a_bytes = (uint32_t)P * plane_bytes;
-    const uint32_t blk_bytes = (uint32_t)p.ntaps * p.ksteps * 512u;
-    const uint32_t b_bytes = (uint32_t)(p.BN >> 4) * blk_bytes;
-    const uint32_t b_off = 2u * a_bytes;
-    const uint32_t tab_off = b_off + b_bytes;                                       // float2 [HP_MAX_SAMPLES][C]
-    const uint32_t gst_off = tab_off + (uint32_t)HP_MAX_SAMPLES * p.C * 8u;         // float2 [HP_MAX_SAMPLES][G]
-    const uint32_t chs_off = (gst_off + (uint32_t)HP_MAX_SAMPLES * HALO_MAX_GROUPS * 8u + 15u) & ~15u;   // double2 [samples][C]
-    const uint32_t bar_off = (chs_off + (uint32_t)HP_MAX_SAMPLES * p.C * 16u + 15u) & ~15u;
-    const uint32_t bfull = base + bar_off;
-    auto a_full = [&](int i) { return bfull + 8u + 8u * (uint32_t)i; };
-    auto a_empty = [&](int i) { return bfull + 24u + 8u * (uint32_t)i; };
-    auto t_full = [&](int i) { return bfull + 40u + 8u * (uint32_t)i; };
-    auto t_empty = [&](int i) { return bfull + 56u + 8u * (uint32_t)i; };
-    const uint32_t tmem_slot = bfull + 72u;
-    uint8_t* red = gbase + bar_off + 96u;
-    const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : 256u));
-    const int nt = blockIdx.y;
-    const int tile0 = blockIdx.x * tiles_per_cta;
-    const int ntile = min(tiles_per_cta, m_tiles - tile0);
-
-    trace_begin(p.trace);
-    if (warp == 0 && elect_one()) {
-        mbar_init(bfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); mbar_init(t_full(i), 1); mbar_init(t_empty(i), 128); }
-        fence_barrier_init();
-        mbar_expect_tx(bfull, b_bytes);
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                base + b_off),
-            "l"(reinterpret_cast<uint64_t>(&p.wmap)), "r"(bfull), "r"(0), "r"(nt * (p.BN >> 4)), "r"(0)
-            : "memory");
-    }
-    if (warp == 6) tmem_alloc(tmem_slot, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    pdl_wait();
-    pdl_trigger();
-
-    if (warp < 6) {
-        // ------------------------------------------------------------------ stagers
-        float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
-        float2* gst = reinterpret_cast<float2*>(gbase + gst_off);
-        double2* chs = reinterpret_cast<double2*>(gbase + chs_off);
-        const bool norm = p.stats || p.sums_a;
-        const int cpg = norm ? p.C / p.G : 1;
-        int tab_first = -1, tab_n = 0;                           // samples the table currently covers
-        const int npairs = P >> 1;
-        const int items = npairs * p.plane_px;
-        for (int i = 0; i < ntile; ++i) {
-            const int buf = i & 1;
-            const int q0 = (tile0 + i) * 128;
-            int b_first = (q0 - p.Wp - 1) / p.HpWp;
-            if (q0 - p.Wp - 1 < 0) b_first = 0;
-            int b_last = (q0 + 128 + p.Wp) / p.HpWp;
-            if (b_last > p.B - 1) b_last = p.B - 1;
-            if (b_first < tab_first || b_last >= tab_first + tab_n || tab_first < 0) {
-                // ---- (re)build the scale / shift table for samples [b_first, b_last]
-                hp_bar_stagers();                                // nobody still reads the old table
-                tab_first = b_first;
-                tab_n = b_last - b_first + 1;
-                if (p.sums_a) {
-                    for (int k = tid; k < tab_n * p.C; k += HP_STAGERS) {
-                        const int s_ = k / p.C, cc = k - s_ * p.C, bb = b_first + s_;
-                        const bool first = cc < p.ca;
-                        const double2* src = reinterpret_cast<const double2*>(
-                            first ? p.sums_a + ((size_t)bb * p.ca + cc) * 2 : p.sums_b + ((size_t)bb * p.cb + (cc - p.ca)) * 2);
-                        const size_t cstride = (size_t)p.B * (first ? p.ca : p.cb);
-                        double2 v[TC_SUM_COPIES];
-#pragma unroll
-                        for (int c = 0; c < TC_SUM_COPIES; ++c) v[c] = src[c * cstride];
-                        double sm = 0.0, sq = 0.0;
-#pragma unroll
-                        for (int c = 0; c < TC_SUM_COPIES; ++c) { sm += v[c].x; sq += v[c].y; }
-                        chs[k] = make_double2(sm, sq);
-                    }
-                    hp_bar_stagers();
-                    const double inv_cnt = 1.0 / ((double)p.H * p.W * cpg);
-                    for (int k = tid; k < tab_n * p.G; k += HP_STAGERS) {
-                        const int s_ = k / p.G, g = k - s_ * p.G;
-                        double sm = 0.0, sq = 0.0;
-                        for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) { sm += chs[s_ * p.C + cc].x; sq += chs[s_ * p.C + cc].y; }
-                        const double mu = sm * inv_cnt;
-                        double var = sq * inv_cnt - mu * mu;
-                        if (var < 0.0) var = 0.0;
-                        gst[k] = make_float2((float)mu, rsqrtf((float)var + 1e-5f));
-                    }
-                    hp_bar_stagers();
-                }
-                for (int k = tid; k < tab_n * p.C; k += HP_STAGERS) {
-                    const int s_ = k / p.C, c = k - s_ * p.C;
-                    float a = 1.f, sh = 0.f;
-                    if (norm) {
-                        const float2 st = p.sums_a ? gst[s_ * p.G + c / cpg] : p.stats[(size_t)(b_first + s_) * p.G + c / cpg];
-                        a = st.y * p.gamma[c];
-                        sh = p.beta[c] - st.x * a;
-                    }
-                    tab[k] = make_float2(a, sh);
-                }
-                hp_bar_stagers();
-            }
-            mbar_wait(a_empty(buf), (((uint32_t)(i >> 1)) & 1u) ^ 1u);
-            const uint32_t abase = base + (uint32_t)buf * a_bytes;
-            const int q_first = p.ntaps == 9 ? q0 - p.Wp - 1 : q0 - 1;
-            // work item = (pixel, pair of 8-channel planes): four 16-byte loads; two items in flight per thread
-            for (int i0 = tid; i0 < items; i0 += 2 * HP_STAGERS) {
-                float4 v[2][4];
-                int tabi[2], pxi[2], kp[2];
-                bool on[2], real[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int idx = i0 + e * HP_STAGERS;
-                    on[e] = idx < items;
-                    real[e] = false;
-                    if (!on[e]) continue;
-                    const int pp = fdiv(idx, p.div_planepx);
-                    const int px = idx - pp * p.plane_px;
-                    pxi[e] = px; kp[e] = 2 * pp;
-                    int q;
-                    if (p.contig) q = q_first + px;
-                    else { const int seg = px / HALO_SEG_PX; q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX); }
-                    if (q >= 0 && q < p.total_q) {
-                        const int bb = fdiv(q, p.div_hpwp);
-                        const int rq = q - bb * p.HpWp;
-                        const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
-                        if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
-                            real[e] = true;
-                            const size_t pix = ((size_t)bb * p.H + (yy - 1)) * p.W + (xx - 1);
-                            tabi[e] = (bb - tab_first) * p.C;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int c0 = (kp[e] + h) * 8;
-                                const float* src = c0 < p.ca ? p.src_a + pix * p.ca + c0 : p.src_b + pix * p.cb + (c0 - p.ca);
-                                v[e][2 * h] = __ldg(reinterpret_cast<const float4*>(src));
-                                v[e][2 * h + 1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (!on[e]) continue;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                        if (real[e]) {
-                            const float4* tb = reinterpret_cast<const float4*>(tab + tabi[e] + (kp[e] + h) * 8);
-                            const float4 v0 = v[e][2 * h], v1 = v[e][2 * h + 1];
-                            float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 sc = tb[j];
-                                x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
-                                x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
-                            }
-                            if (p.swish) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float hh = 0.5f * x[j];
-                                    float th;
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
-                                    x[j] = fmaf(hh, th, hh);
-                                }
-                            }
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                                w[j] = *reinterpret_cast<const uint32_t*>(&hb);
-                            }
-                            val = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                        const uint32_t dst = abase + (uint32_t)(kp[e] + h) * plane_bytes + (uint32_t)pxi[e] * 16u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-                    }
-                }
-            }
-            fence_proxy_async();
-            hp_bar_stagers();
-            if (tid == 0) hp_mbar_arrive(a_full(buf));
-        }
-    } else if (warp == 6) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (elect_one()) {
-            mbar_wait(bfull, 0);
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-            const uint32_t b_lo0 = (((base + b_off) & 0x3FFFFu) >> 4) | ((uint32_t)p.BN << 16);
-            const uint32_t a_kstep = (2u * plane_bytes) >> 4;
-            const uint32_t b_kstep = (uint32_t)p.BN * 2u;
-            for (int i = 0; i < ntile; ++i) {
-                const int buf = i & 1;
-                const uint32_t ph = ((uint32_t)(i >> 1)) & 1u;
-                mbar_wait(a_full(buf), ph);
-                mbar_wait(t_empty(buf), ph ^ 1u);
-                tc_fence_after();
-                const uint32_t a_lo0 = (((base + (uint32_t)buf * a_bytes) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-                uint32_t b_lo = b_lo0;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int r = p.ntaps == 9 ? tap / 3 : 0;
-                    const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
-                    uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
-                    for (int kk = 0; kk < p.ksteps; ++kk) {
-                        umma_bf16(tacc, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
-                        a_lo += a_kstep;
-                        b_lo += b_kstep;
-                    }
-                }
-                umma_commit(a_empty(buf));
-                umma_commit(t_full(buf));
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------------------------ epilogue (warps 7..10)
-        const int qd = warp & 3;
-        const int m = qd * 32 + lane;
-        const int te = tid - (HP_STAGERS + 32);
-        for (int i = 0; i < ntile; ++i) {
-            const int buf = i & 1;
-            const int q0 = (tile0 + i) * 128;
-            const int q = q0 + m;
-            bool valid = q < p.total_q;
-            int b = 0, oy = 0, ox = 0;
-            if (valid) {
-                b = fdiv(q, p.div_hpwp);
-                const int rq = q - b * p.HpWp;
-                const int yy = fdiv(rq, p.div_wp), xx = rq - yy * p.Wp;
-                valid = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-                oy = yy - 1;
-                ox = xx - 1;
-            }
-            float add[16];
-            if (valid) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN, add);
-            mbar_wait(t_full(buf), ((uint32_t)(i >> 1)) & 1u);
-            tc_fence_after();
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * p.BN + c0), v);
-                float f[16];
-                if (valid) {
-                    if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
-                    tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
-                }
-                if (p.epi.sums_out) {
-                    const int bt0 = fdiv(q0, p.div_hpwp), nsr = fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
-                    if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, te, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
-                    else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, te, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
-                }
-            }
-            tc_fence_before();
-            hp_mbar_arrive(t_empty(buf));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    trace_end(p.trace);
-    if (warp == 6) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
-    }
-}
-
 static long long* g_halo_dbg = nullptr;
 static size_t g_halo_dbg_ctas = 0;
 
@@ -941,33 +643,6 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
-    }
-    // ---- many waves of tiles: the persistent, software-pipelined variant
-    {
-        static int persist_env = -1;
-        if (persist_env < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_PERSIST"); persist_env = e ? atoi(e) : 1; }
-        const size_t a_bytes = (size_t)(p.C / 8) * p.plane_px * 16;
-        const size_t b_bytes = (size_t)p.ntaps * p.ksteps * 2 * p.BN * 16;
-        const size_t psmem = 2 * a_bytes + b_bytes + (size_t)HP_MAX_SAMPLES * (p.C * 8 + HALO_MAX_GROUPS * 8 + p.C * 16) + 128 +
-                             TC_RED_BYTES + 1024 + 64;
-        const bool can = p.rb == 0 && !p.tile2d && nsamp <= HP_MAX_SAMPLES && psmem <= HALO_SMEM_LIMIT && !p.dbg;
-        const bool want = persist_env == 2 || (persist_env == 1 && p.C >= 64 && (size_t)m_tiles * p.n_tiles >= 8 * 148);
-        if (can && want) {
-            const int per_sm = psmem <= 100 * 1024 ? 2 : 1;
-            int ctas_x = per_sm * 148 / p.n_tiles;
-            if (ctas_x < 1) ctas_x = 1;
-            if (ctas_x > m_tiles) ctas_x = (int)m_tiles;
-            const int tiles_per_cta = (int)((m_tiles + ctas_x - 1) / ctas_x);
-            const int grid_x = (int)((m_tiles + tiles_per_cta - 1) / tiles_per_cta);
-            static bool pattr = false;
-            if (!pattr) {
-                DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-                pattr = true;
-            }
-            DS_CHECK_CUDA(launch_pdl(conv_halo_persistent_kernel, dim3((unsigned)grid_x, p.n_tiles, 1), dim3(HP_THREADS), psmem, st, p,
-                                     tiles_per_cta, (int)m_tiles));
-            return DS_OK;
-        }
     }
     // Staging is latency bound (global loads of the raw activations): single-wave grids whose shared-memory footprint leaves
     // one or two CTAs per SM anyway get extra warps that only stage.

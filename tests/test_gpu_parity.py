@@ -158,7 +158,9 @@ def test_conv_tc_operator(ca, cb, cout, ks, stride, up, B, H, W, residual, out_n
     (32, 0, 32, 3, 8, 1, 3, 32, 32, 1), (64, 32, 32, 3, 16, 1, 1, 32, 32, 0), (64, 0, 64, 3, 16, 1, 2, 16, 16, 1),
     (128, 0, 128, 3, 16, 1, 4, 8, 8, 1), (128, 0, 384, 1, 16, 0, 2, 8, 8, 0), (16, 0, 1, 3, 16, 1, 2, 32, 32, 0),
     (16, 0, 16, 3, 0, 0, 1, 24, 20, 0), (64, 64, 128, 3, 32, 1, 5, 4, 4, 0), (48, 0, 16, 3, 16, 1, 1, 128, 96, 0),
-    (128, 64, 64, 3, 16, 1, 3, 16, 16, 1), (128, 96, 48, 3, 16, 1, 2, 12, 12, 0)])
+    (128, 64, 64, 3, 16, 1, 3, 16, 16, 1), (128, 96, 48, 3, 16, 1, 2, 12, 12, 0),
+    # wide images: 2-D tiles of 7 x 16 outputs (ragged in both directions), 3x3 and 1x1, concat
+    (16, 0, 16, 3, 16, 1, 2, 40, 150, 1), (32, 16, 16, 3, 16, 1, 1, 33, 141, 0), (32, 0, 48, 1, 8, 0, 1, 20, 160, 0)])
 def test_fused_gn_swish_conv_operator(ca, cb, cout, ks, G, swish, B, H, W, residual):
     """conv_halo_kernel: GroupNorm statistics pass + ONE tensor-core kernel (normalise + Swish in the operand staging)
     vs fp64 conv of the bf16-rounded normalised activations and weights."""
