@@ -54,11 +54,10 @@ struct HaloParams {
     // 1.5 pixels per output instead of 1.2 + 2 (W + 2) / 128 (flat tiles) or 3.2 (wide images).
     int tile2d, tiles_x, tiles_y;
     FastDiv div_tiles_x, div_tiles_xy;
-    // A operand layout: rb == 0: no-swizzle [8-channel plane][pixel][16 B] (the tensor pipe reads it at ~32 B/clk);
-    // rb = 32 / 64 / 128: K-chunks of rb/2 channels, [chunk][pixel][rb bytes] with the matching UMMA swizzle, shifted
-    // windows addressed through the descriptor's base-offset field
-    int rb, base_off_mode;
-    uint32_t chunk_bytes;
+    // A operand layout: no-swizzle [8-channel plane][pixel][16 B].  (The swizzled layouts [64-channel chunk][pixel][128 B]
+    // also work for the shifted windows - the tensor core's swizzle is a pure function of the shared-memory address, the
+    // descriptor base offset stays 0 - but were slower here: profiles/README.md, findings 3 and 7; conv_tcp_kernel in tc.cu
+    // uses them because its patches come from TMA.)
     FastDiv div_hpwp, div_wp, div_planepx;
     long long* dbg;                             // optional per-CTA phase timestamps (clock64), 8 per CTA
     TraceSlot trace;
@@ -80,7 +79,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
     const int P = p.C >> 3;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const uint32_t a_bytes_total = p.rb ? (uint32_t)(p.C * 2 / p.rb) * p.chunk_bytes : P * plane_bytes;
+    const uint32_t a_bytes_total = P * plane_bytes;
     const uint32_t a_off = 0, b_off = a_bytes_total;
     // weights of one 16-output-channel block: [tap][kstep][plane(2)][16 rows][16 B]; a CTA owns BN/16 consecutive blocks
     const uint32_t blk_bytes = (uint32_t)p.ntaps * p.ksteps * 512u;
@@ -214,16 +213,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             }
             val = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        uint32_t dst;
-        if (p.rb) {
-            const int per = p.rb >> 4;                                 // 16-byte chunks per row
-            const int kc = kp / per, kq = kp - kc * per;
-            const uint32_t off = (uint32_t)px_.pxi * p.rb + kq * 16;
-            const uint32_t mask = p.rb == 128 ? 7u : (p.rb == 64 ? 3u : 1u);
-            dst = base + a_off + kc * p.chunk_bytes + (off ^ (((off >> 7) & mask) << 4));
-        } else {
-            dst = px_.dst + kp * plane_bytes;
-        }
+        const uint32_t dst = px_.dst + kp * plane_bytes;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
     };
 
@@ -322,40 +312,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             const uint32_t a_kstep = (2u * plane_bytes) >> 4;
             const uint32_t b_kstep = (uint32_t)p.BN * 2u;                                              // 2 planes of BN * 16 B
             uint32_t b_lo = b_lo0;
-            if (p.rb == 0) {
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int r = p.ntaps == 9 ? tap / 3 : (p.tile2d ? 1 : 0);
-                    const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
-                    uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
-                    for (int kk = 0; kk < p.ksteps; ++kk) {
-                        umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
-                                  (tap | kk) ? 1u : 0u);
-                        a_lo += a_kstep;
-                        b_lo += b_kstep;
-                    }
-                }
-            } else {
-                // swizzled A: start = chunk + shift * rb + kstep-in-row * 32; SBO = 8 rows; the window does not start on a
-                // swizzle-atom boundary -> base offset = (start >> 7) & 7
-                const uint32_t layout = p.rb == 128 ? 2u : (p.rb == 64 ? 4u : 6u);
-                const uint32_t a_hi_fixed = ((8u * p.rb) >> 4) | (1u << 14) | (layout << 29);
-                const int kpr = p.rb >> 5;                                  // K steps per row
-                const int nchunk = p.ksteps / kpr;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int r = p.ntaps == 9 ? tap / 3 : 0;
-                    const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
-                    const uint32_t shift = (uint32_t)(r * p.seg_stride_px + sx) * p.rb;
-                    for (int kc = 0; kc < nchunk; ++kc) {
-                        const uint32_t row0 = base + a_off + kc * p.chunk_bytes + shift;
-                        const uint32_t boff = p.base_off_mode ? ((row0 >> 7) & 7u) : 0u;
-                        const uint32_t a_hi = a_hi_fixed | (boff << 17);
-                        for (int kk = 0; kk < kpr; ++kk) {
-                            const uint32_t a_lo = (((row0 + kk * 32u) & 0x3FFFFu) >> 4) | (1u << 16);
-                            umma_bf16(tmem_base, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
-                                      (tap | kc | kk) ? 1u : 0u);
-                            b_lo += b_kstep;
-                        }
-                    }
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int r = p.ntaps == 9 ? tap / 3 : (p.tile2d ? 1 : 0);
+                const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
+                uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
+                for (int kk = 0; kk < p.ksteps; ++kk) {
+                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
                 }
             }
             umma_commit(mma_done);
@@ -432,7 +396,6 @@ static size_t g_halo_dbg_ctas = 0;
 static bool halo_use_2d(int B, int H, int W) {
     static int minw = -1;
     if (minw < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_2D_MINW"); minw = e ? atoi(e) : 138; }
-    if (getenv("DIFFSPLIT_B200_HALO_SWZ")) return false;
     if (W >= minw) return true;
     return minw == 138 && W >= 48 && ((int64_t)B * (H + 2) * (W + 2) + 127) / 128 >= 8 * 148;
 }
@@ -447,31 +410,7 @@ static int halo_plane_px(int ntaps, int W, bool two_d) {
     return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
 }
 
-// A-operand layout: 0 (default): no-swizzle [8-channel plane][pixel][16 B]; 2: swizzled [K chunk][pixel][32|64|128 B]
-// with descriptor base offset 0; 1: swizzled with base offset = (start >> 7) & 7.
-// Measured on B200 (tests/test_gpu_parity.py::test_fused_gn_swish_conv_operator under DIFFSPLIT_B200_HALO_SWZ=...):
-// mode 2 is CORRECT for windows that start anywhere inside a swizzle atom - the tensor core's swizzle is a pure function of
-// the shared-memory address bits - while mode 1 gives wrong results.  Mode 2 is not faster here (the MMA phase is bound by
-// the ~100 cycles per K=16 step that fetching the 128-row A operand costs in either layout, and the swizzled staging
-// stores conflict), so the simpler layout stays the default.
-static int halo_swizzle_mode() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DIFFSPLIT_B200_HALO_SWZ");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
-static int halo_row_bytes(int C) {
-    if (!halo_swizzle_mode()) return 0;
-    return C % 64 == 0 ? 128 : (C % 32 == 0 ? 64 : 32);
-}
-static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d) {
-    const int rb = halo_row_bytes(C);
-    const int px = halo_plane_px(ntaps, W, two_d);
-    if (!rb) return (size_t)(C / 8) * px * 16;
-    return (size_t)(C * 2 / rb) * align_up((size_t)px * rb, 1024);
-}
+static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d) { return (size_t)(C / 8) * halo_plane_px(ntaps, W, two_d) * 16; }
 
 static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp, bool two_d) {
     return halo_a_bytes(C, ntaps, W, two_d) + 1024 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
@@ -600,9 +539,6 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
     p.div_wp = make_fastdiv((uint32_t)p.Wp);
     p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
-    p.rb = halo_row_bytes(p.C);
-    p.base_off_mode = halo_swizzle_mode() == 1 ? 1 : 0;
-    p.chunk_bytes = p.rb ? (uint32_t)align_up((size_t)p.plane_px * p.rb, 1024) : 0;
     {
         // 3-D view of the packed weights [block][tap*kstep*plane][16 rows x 8 ch = 128 bf16]
         static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
