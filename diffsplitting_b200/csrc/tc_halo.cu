@@ -70,7 +70,7 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo,
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-template <int MAXT>
+template <int MAXT, bool TILE2D>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
     int b_last = (q0 + 128 + p.Wp) / p.HpWp;
     if (b_last > p.B - 1) b_last = p.B - 1;
     int tile_x0 = 0, tile_y0 = 0;                   // 2-D tiles: first output column / row of this tile
-    if (p.tile2d) {
+    if (TILE2D) {
         const int tb = fdiv((int)blockIdx.x, p.div_tiles_xy);
         const int rem = (int)blockIdx.x - tb * p.tiles_x * p.tiles_y;
         const int ty = fdiv(rem, p.div_tiles_x);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
         px_.tabi = 0;
         px_.dst = base + a_off + px * 16;
         px_.pxi = px;
-        if (p.tile2d) {
+        if (TILE2D) {
             const int pr = px / HALO_PW, pc = px - pr * HALO_PW;
             const int yy = tile_y0 + pr - 1, xx = tile_x0 + pc - 1;
             if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             const uint32_t b_kstep = (uint32_t)p.BN * 2u;                                              // 2 planes of BN * 16 B
             uint32_t b_lo = b_lo0;
             for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int r = p.ntaps == 9 ? tap / 3 : (p.tile2d ? 1 : 0);
+                const int r = p.ntaps == 9 ? tap / 3 : (TILE2D ? 1 : 0);
                 const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
                 uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
                 for (int kk = 0; kk < p.ksteps; ++kk) {
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
         const int q = q0 + m;
         bool valid = q < p.total_q;
         int b = 0, oy = 0, ox = 0;
-        if (p.tile2d) {
+        if (TILE2D) {
             const int pr = m / HALO_PW, pc = m - pr * HALO_PW;
             b = b_first;
             oy = tile_y0 + pr;
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
                 tc_epilogue_write(p.epi, v, add, b, oy, ox, nt * p.BN + c0, f);
             }
             if (p.epi.sums_out) {
-                const int bt0 = p.tile2d ? b_first : fdiv(q0, p.div_hpwp);
-                const int nsr = p.tile2d ? 1 : fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
+                const int bt0 = TILE2D ? b_first : fdiv(q0, p.div_hpwp);
+                const int nsr = TILE2D ? 1 : fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
                 if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, tid - 64, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
                 else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
             }
@@ -576,8 +576,10 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     }
     static bool attr_set = false;
     if (!attr_set) {
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr_set = true;
     }
     // Staging is latency bound (global loads of the raw activations): single-wave grids whose shared-memory footprint leaves
@@ -587,10 +589,15 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     const size_t n_ctas = (size_t)m_tiles * p.n_tiles;
     int threads = (n_ctas <= 2 * 148 && smem >= 48 * 1024) ? HALO_MAX_THREADS : HALO_THREADS;
     if (thr_env >= HALO_THREADS && thr_env <= HALO_MAX_THREADS && thr_env % 32 == 0) threads = thr_env;
+    const dim3 grid((unsigned)m_tiles, p.n_tiles, 1);
+    cudaError_t err;
     if (threads == HALO_THREADS)
-        DS_CHECK_CUDA(launch_pdl(conv_halo_kernel<HALO_THREADS>, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(threads), smem, st, p));
+        err = two_d ? launch_pdl(conv_halo_kernel<HALO_THREADS, true>, grid, dim3(threads), smem, st, p)
+                    : launch_pdl(conv_halo_kernel<HALO_THREADS, false>, grid, dim3(threads), smem, st, p);
     else
-        DS_CHECK_CUDA(launch_pdl(conv_halo_kernel<HALO_MAX_THREADS>, dim3((unsigned)m_tiles, p.n_tiles, 1), dim3(threads), smem, st, p));
+        err = two_d ? launch_pdl(conv_halo_kernel<HALO_MAX_THREADS, true>, grid, dim3(threads), smem, st, p)
+                    : launch_pdl(conv_halo_kernel<HALO_MAX_THREADS, false>, grid, dim3(threads), smem, st, p);
+    DS_CHECK_CUDA(err);
     return DS_OK;
 }
 
