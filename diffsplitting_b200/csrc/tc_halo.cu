@@ -1,17 +1,18 @@
 // Fused  GroupNorm-apply + Swish -> 3x3 / 1x1 convolution  on the tensor cores, operands staged through registers.
 //
-// Why a second tensor-core conv kernel: for the 16..128-channel layers of the splitting UNets the TMA im2col path
+// Why a second tensor-core conv kernel: for the 16..224-channel layers of the splitting UNets the TMA im2col path
 // (tc.cu) fetches every input pixel 9 times in 32..128-byte rows and needs a separate normalisation pass before it.
 // Here each CTA
-//   1. loads the raw fp32 input pixels it needs ONCE per filter row (3 row segments of 130 pixels, 16-byte loads),
-//      applies the per-(sample, channel) GroupNorm scale/shift + Swish of the reference Block
-//      (model/sr3_modules/unet.py:80-91) in registers, converts to bf16 and writes the UMMA no-swizzle K-major layout
-//      [8-channel plane][pixel][16 B];
+//   1. loads the raw fp32 input pixels of its tile + halo ONCE (16-byte loads), applies the per-(sample, channel)
+//      GroupNorm scale/shift + Swish of the reference Block (model/sr3_modules/unet.py:80-91) in registers, converts to
+//      bf16 and writes the UMMA no-swizzle K-major layout [8-channel plane][pixel][16 B];
 //   2. issues all 9 taps x C/16 tcgen05.mma from that one copy: in the ZERO-PADDED, row-major flattened image
-//      (pitch W+2) a filter tap is a constant shift of the flat index, i.e. just a different descriptor start address;
-//   3. runs the common epilogue (bias, conditioning vector, fp32 residual, fp32 / bf16 stores).
-// One tile = 128 consecutive flat padded positions (border positions are computed and discarded: 6 % waste at 64^2).
-// The channel concat of the up path (unet.py:255) is two source pointers; weights arrive with cp.async.bulk.
+//      (pitch W+2) - or, for wide images, in a 9 x 18 patch around a tile of 7 x 16 outputs (pitch 18) - a filter tap is
+//      a constant shift of the flat index, i.e. just a different descriptor start address;
+//   3. runs the common epilogue (bias, conditioning vector, fp32 residual, fp32 / bf16 stores, GroupNorm statistics of
+//      its own output for the consumer).
+// Flat tiles = 128 consecutive padded positions (border positions are computed and discarded: 6 % waste at 64^2).
+// The channel concat of the up path (unet.py:255) is two source pointers; the weights arrive with one 3-D TMA load.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -45,9 +46,9 @@ struct HaloParams {
     TcEpi epi;
     int B, H, W, Wp, HpWp, total_q;
     int C, ksteps, ntaps, BN, n_tiles, Npad;
-    // operand buffer geometry: `contig` = the three filter-row segments overlap inside ONE contiguous run of the flat
-    // padded index space (W + 2 <= 139): every pixel is staged exactly once; else three separate 136-pixel segments
-    int contig, plane_px, seg_stride_px;
+    // operand buffer geometry, flat tiles: the 128 outputs and their three filter rows are ONE contiguous run of the flat
+    // padded index space (130 + 2 (W + 2) positions, W + 2 <= 139; wider images use the 2-D tiles below)
+    int plane_px, seg_stride_px;
     // 2-D tile geometry (tile2d = 1): a tile is HALO_TH rows x HALO_TW columns of ONE sample; the staged patch has
     // (HALO_TH + 2) rows of pitch HALO_PW = HALO_TW + 2, so a tap is still a constant shift (r * HALO_PW + s) and the 128 MMA
     // rows are patch positions 0..127 (columns HALO_TW, HALO_TW + 1 of every row are computed and discarded).  Stages
@@ -159,13 +160,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             }
             return;
         }
-        int q;
-        if (p.contig) {
-            q = q_first + px;
-        } else {
-            const int seg = px / HALO_SEG_PX;
-            q = q0 + (seg - 1) * p.Wp - 1 + (px - seg * HALO_SEG_PX);
-        }
+        const int q = q_first + px;
         if (q >= 0 && q < p.total_q) {
             const int b = fdiv(q, p.div_hpwp);
             const int rq = q - b * p.HpWp;
@@ -396,7 +391,7 @@ static size_t g_halo_dbg_ctas = 0;
 static bool halo_use_2d(int B, int H, int W) {
     static int minw = -1;
     if (minw < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_2D_MINW"); minw = e ? atoi(e) : 138; }
-    if (W >= minw) return true;
+    if (W >= minw || 130 + 2 * (W + 2) > 3 * HALO_SEG_PX) return true;       // the flat run is capped at 408 staged positions
     return minw == 138 && W >= 48 && ((int64_t)B * (H + 2) * (W + 2) + 127) / 128 >= 8 * 148;
 }
 static int64_t halo_m_tiles(int B, int H, int W) {
@@ -406,8 +401,7 @@ static int64_t halo_m_tiles(int B, int H, int W) {
 static int halo_plane_px(int ntaps, int W, bool two_d) {
     if (two_d) return HALO_2D_PX;
     if (ntaps == 1) return HALO_SEG_PX;
-    const int contig = 130 + 2 * (W + 2);
-    return contig <= 3 * HALO_SEG_PX ? (contig + 7) / 8 * 8 : 3 * HALO_SEG_PX;
+    return (130 + 2 * (W + 2) + 7) / 8 * 8;
 }
 
 static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d) { return (size_t)(C / 8) * halo_plane_px(ntaps, W, two_d) * 16; }
@@ -533,9 +527,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles, two_d);
     p.n_tiles = p.Npad / p.BN;
     p.plane_px = halo_plane_px(p.ntaps, W, two_d);
-    p.contig = (p.ntaps == 1 || p.plane_px != 3 * HALO_SEG_PX) ? 1 : 0;
-    p.seg_stride_px = p.ntaps == 1 ? 0 : (p.contig ? p.Wp : HALO_SEG_PX);
-    if (p.tile2d) { p.contig = 1; p.seg_stride_px = HALO_PW; }
+    p.seg_stride_px = p.tile2d ? HALO_PW : (p.ntaps == 1 ? 0 : p.Wp);
     p.div_hpwp = make_fastdiv((uint32_t)p.HpWp);
     p.div_wp = make_fastdiv((uint32_t)p.Wp);
     p.div_planepx = make_fastdiv((uint32_t)p.plane_px);
