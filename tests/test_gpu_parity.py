@@ -452,6 +452,32 @@ def test_seeded_loops_replay_the_reference_rng_stream(graph, monkeypatch):
     assert torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("T", [1, 2, 10, 21])
+def test_joint_indi_snapshot_count_and_multi_step_graphs(T):
+    """The intent of the reference's tests/test_joint_indi.py:9-25 (continuous=True returns n_timestep + 1 snapshots per
+    batch element for small T), run through JointIndi with two real UNets; T = 10 / 21 also cross the 8-step CUDA graphs
+    of `_Engine.run`, whose result must equal stepping one graph replay at a time."""
+    from diffsplitting_b200.model.samplers import JointIndi
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
+    nets = [build(cfg, U.random_state_dict(cfg, seed=s), "bf16") for s in (3, 4)]
+    joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=nets[0], denoise_fn_ch2=nets[1],
+                      val_schedule_opt={"n_timestep": T}).to(DEV)
+    joint.set_new_noise_schedule({"n_timestep": T}, DEV)
+    x = (torch.rand((2, 1, 32, 32), generator=torch.Generator().manual_seed(0)) * 2 - 1).to(DEV)
+    inter = 1 | (T // 20)
+    n_snap = len([i for i in range(T) if i % inter == 0 or i == T - 1])
+    torch.manual_seed(5)
+    y = joint.inference(x, continuous=True)
+    assert tuple(y.shape) == ((n_snap + 1) * 2, 2, 32, 32) and torch.isfinite(y).all()
+    os.environ["DIFFSPLIT_B200_GRAPH_STEPS"] = "1"
+    try:
+        torch.manual_seed(5)
+        y1 = joint.inference(x, continuous=True)
+    finally:
+        del os.environ["DIFFSPLIT_B200_GRAPH_STEPS"]
+    assert torch.equal(y, y1)
+
+
 def test_final_psnr_within_point1_db_of_oracle():
     """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 16 InDI chain;
     T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation)."""
