@@ -67,9 +67,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int nt = blockIdx.y, cls = blockIdx.z;
     const int units_per_tap = p.chunks_a + p.chunks_b;
     const int U = p.ntaps * units_per_tap;
-    // NA independent accumulators (see tc_halo.cu): dependent MMAs into one accumulator serialise on the pipe latency
-    const int NA = 1;       // (several accumulators were measured slower: the MMAs are operand-fetch bound, not latency bound)
-    const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
+    const uint32_t tmem_cols = (uint32_t)p.BN <= 32u ? 32u : ((uint32_t)p.BN <= 64u ? 64u : 128u);
 
     trace_begin(p.trace);
     if (threadIdx.x == 0) {
@@ -110,7 +108,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t row_bytes = p.KC * 2u;
-            int step = 0;
             for (int u = 0; u < U; ++u) {
                 const int s = u % p.stages;
                 const uint32_t ph = (u / p.stages) & 1;
@@ -118,9 +115,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 tc_fence_after();
                 const uint32_t sa = base + s * stage_bytes;
                 const uint64_t adesc = make_smem_desc(sa, row_bytes), bdesc = make_smem_desc(sa + a_bytes, row_bytes);
-                for (int k = 0; k < p.KC / 16; ++k, ++step)
-                    umma_bf16(tmem_base + (uint32_t)((step % NA) * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                              step >= NA ? 1u : 0u);
+                for (int k = 0; k < p.KC / 16; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
                 umma_commit(empty_bar(s));        // frees the smem slot once these MMAs have read it
             }
             umma_commit(tfull_bar);               // accumulator complete
@@ -143,13 +139,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int nsteps = U * (p.KC / 16);
-            for (int sl = 1; sl < NA && sl < nsteps; ++sl) {
-                uint32_t v2[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * p.BN + c0), v2);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-            }
             float f[16];
             if (valid) {
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, n_base + c0, add);

@@ -108,8 +108,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
     const uint32_t bar_off = (chs_off + (uint32_t)nsamp * p.C * 16u + 15u) & ~15u;
     const uint32_t bfull = base + bar_off, mma_done = bfull + 8u, tmem_slot = bfull + 16u;
     uint8_t* red = gbase + bar_off + 32u;                                          // epilogue reduction buffer
-    const int NA = 1;       // one accumulator (rotating over several column ranges was measured slower)
-    const uint32_t tmem_cols = (uint32_t)(NA * p.BN) <= 32u ? 32u : ((uint32_t)(NA * p.BN) <= 64u ? 64u : 128u);
+    const uint32_t tmem_cols = (uint32_t)p.BN <= 32u ? 32u : ((uint32_t)p.BN <= 64u ? 64u : 128u);
 
     HALO_STAMP(0);
     trace_begin(p.trace);
@@ -348,13 +347,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
-            const int nsteps = p.ntaps * p.ksteps;
-            for (int sl = 1; sl < NA && sl < nsteps; ++sl) {      // fold the other accumulators (slots never written stay out)
-                uint32_t v2[16];
-                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sl * p.BN + c0), v2);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-            }
             float f[16];
             if (valid) {
                 if (c0) tc_epilogue_addend(p.epi, b, oy, ox, nt * p.BN + c0, add);
