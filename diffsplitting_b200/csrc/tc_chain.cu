@@ -34,7 +34,7 @@ constexpr int CH_THREADS = 512;
 constexpr int CH_WORKERS = CH_THREADS - 64;       // warps 2..15
 constexpr int CH_MAX_GROUPS = 64;
 constexpr int CH_MAX_C = 256;                     // input channels (concat) and output channels
-constexpr int CH_INFLIGHT = 4;                    // staged work items in flight per worker thread
+constexpr int CH_INFLIGHT = 3;                    // staged work items in flight per worker thread
 constexpr int CH_KC = 128;                        // channels per weight unit = (tap, channel chunk)
 constexpr int CH_UNITS_PER_STAGE = 3;             // full-size units per ring slot (fewer, larger copies and barrier waits)
 constexpr int CH_MAX_PX = 176;                    // staged pixels per tile: 130 + 2 (W + 2), W <= 20
