@@ -327,81 +327,75 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
                 // Segment 0 = the (normalised) conv input, segment 1 = the raw block input of a folded 1x1 res_conv.
                 // Work item = (8-channel plane, pixel); CH_INFLIGHT items (two 16-byte L2 loads each) in flight per thread.
                 const size_t pix0 = (size_t)b * p.H * p.W;
+                // Coalesced mapping: the channel vector of a pixel is contiguous in NHWC, so the lanes of a warp take
+                // consecutive 16-byte chunks (4 fp32 / 8 bf16 channels) of ONE pixel (two pixels per warp when a pixel has <= 16
+                // chunks) - one request = whole 128-byte lines instead of 32 separate sectors -; warps stride over the pixels,
+                // CH_INFLIGHT pixels (loads) in flight per lane.
+                const int wwarp = warp - 2;                                    // 0..13
                 for (int seg = 0; seg < (o.wx ? 2 : 1); ++seg) {
                     const void* sa = seg ? (const void*)o.xsrc_a : o.src_a;
                     const void* sb = seg ? (const void*)o.xsrc_b : o.src_b;
                     const int sca = seg ? o.xca : o.ca, scb = seg ? o.xcb : o.cb;
                     const bool snorm = !seg && o.norm, sswish = !seg && o.swish, sb16 = !seg && o.src_b16;
                     const int plane0 = seg ? (C >> 3) : 0;
-                    const int items = p.plane_px * ((sca + scb) >> 3);
-                    for (int i0 = wt; i0 < items; i0 += CH_INFLIGHT * CH_WORKERS) {
-                        uint4 raw0[CH_INFLIGHT], raw1[CH_INFLIGHT];
-                        int kpv[CH_INFLIGHT], pxv[CH_INFLIGHT];
-                        bool okv[CH_INFLIGHT];
-#pragma unroll
-                        for (int e = 0; e < CH_INFLIGHT; ++e) {
-                            const int i = i0 + e * CH_WORKERS;
-                            okv[e] = false;
-                            kpv[e] = -1;
-                            if (i >= items) continue;
-                            const int kp = fdiv(i, p.div_px), px = i - kp * p.plane_px;
-                            kpv[e] = kp; pxv[e] = px;
-                            const int pi = pixinfo[px];
-                            if (pi < 0) continue;
-                            okv[e] = true;
-                            const size_t pix = pix0 + (size_t)pi;
-                            const int c0 = kp * 8;
-                            if (sb16) {
-                                const __nv_bfloat16* src = c0 < sca ? reinterpret_cast<const __nv_bfloat16*>(sa) + pix * sca + c0
-                                                                    : reinterpret_cast<const __nv_bfloat16*>(sb) + pix * scb + (c0 - sca);
-                                raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
-                            } else {
-                                const float* src = c0 < sca ? reinterpret_cast<const float*>(sa) + pix * sca + c0
-                                                            : reinterpret_cast<const float*>(sb) + pix * scb + (c0 - sca);
-                                raw0[e] = __ldcg(reinterpret_cast<const uint4*>(src));
-                                raw1[e] = __ldcg(reinterpret_cast<const uint4*>(src) + 1);
-                            }
+                    const int esz = sb16 ? 2 : 4, cpi = 16 / esz;               // bytes per element, channels per 16-byte chunk
+                    const int nchunk = (sca + scb) / cpi;                       // chunks per pixel
+                    const int ppw = nchunk <= 16 ? 2 : 1;                       // pixels per warp iteration
+                    const int lsub = ppw == 2 ? (lane & 15) : lane, psub = ppw == 2 ? (lane >> 4) : 0;
+                    for (int c0 = lsub; c0 < nchunk; c0 += (ppw == 2 ? 16 : 32)) {
+                        const int ch = c0 * cpi;                                // first channel of this lane's chunk
+                        const bool in_a = ch < sca;
+                        const uint8_t* sbase = reinterpret_cast<const uint8_t*>(in_a ? sa : sb) + (size_t)(in_a ? ch : ch - sca) * esz;
+                        const size_t pstride = (size_t)(in_a ? sca : scb) * esz;
+                        float4 t0 = make_float4(1.f, 0.f, 1.f, 0.f), t1 = t0;
+                        if (snorm) {
+                            const float4* tb = reinterpret_cast<const float4*>(tab + ch);
+                            t0 = tb[0];
+                            t1 = tb[1];
                         }
+                        for (int px0 = wwarp * ppw + psub; px0 < p.plane_px; px0 += CH_INFLIGHT * 14 * ppw) {
+                            uint4 raw[CH_INFLIGHT];
+                            int pi[CH_INFLIGHT];
 #pragma unroll
-                        for (int e = 0; e < CH_INFLIGHT; ++e) {
-                            if (kpv[e] < 0) continue;
-                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                            if (okv[e]) {
+                            for (int e = 0; e < CH_INFLIGHT; ++e) {
+                                const int px = px0 + e * 14 * ppw;
+                                pi[e] = px < p.plane_px ? pixinfo[px] : -2;
+                                if (pi[e] >= 0) raw[e] = __ldcg(reinterpret_cast<const uint4*>(sbase + (pix0 + (size_t)pi[e]) * pstride));
+                            }
+#pragma unroll
+                            for (int e = 0; e < CH_INFLIGHT; ++e) {
+                                if (pi[e] == -2) continue;
+                                const int px = px0 + e * 14 * ppw;
                                 if (sb16) {
-                                    val = raw0[e];
+                                    const uint4 val = pi[e] >= 0 ? raw[e] : make_uint4(0u, 0u, 0u, 0u);
+                                    const uint32_t dst = base + a_off + (uint32_t)(plane0 + c0) * plane_bytes + (uint32_t)px * 16u;
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
                                 } else {
-                                    float x[8] = {__uint_as_float(raw0[e].x), __uint_as_float(raw0[e].y), __uint_as_float(raw0[e].z),
-                                                  __uint_as_float(raw0[e].w), __uint_as_float(raw1[e].x), __uint_as_float(raw1[e].y),
-                                                  __uint_as_float(raw1[e].z), __uint_as_float(raw1[e].w)};
-                                    if (snorm) {
-                                        const float4* tb = reinterpret_cast<const float4*>(tab + kpv[e] * 8);
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            const float4 sc = tb[j];
-                                            x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
-                                            x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
+                                    uint32_t w0 = 0u, w1 = 0u;
+                                    if (pi[e] >= 0) {
+                                        float x[4] = {__uint_as_float(raw[e].x), __uint_as_float(raw[e].y), __uint_as_float(raw[e].z), __uint_as_float(raw[e].w)};
+                                        if (snorm) {
+                                            x[0] = fmaf(x[0], t0.x, t0.y); x[1] = fmaf(x[1], t0.z, t0.w);
+                                            x[2] = fmaf(x[2], t1.x, t1.y); x[3] = fmaf(x[3], t1.z, t1.w);
                                         }
-                                    }
-                                    if (sswish) {
+                                        if (sswish) {
 #pragma unroll
-                                        for (int j = 0; j < 8; ++j) {           // y * sigmoid(y) = h * tanh(h) + h, h = y / 2
-                                            const float h = 0.5f * x[j];
-                                            float th;
-                                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                                            x[j] = fmaf(h, th, h);
+                                            for (int j = 0; j < 4; ++j) {       // y * sigmoid(y) = h * tanh(h) + h, h = y / 2
+                                                const float h = 0.5f * x[j];
+                                                float th;
+                                                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                                                x[j] = fmaf(h, th, h);
+                                            }
                                         }
+                                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+                                        w0 = *reinterpret_cast<const uint32_t*>(&h0);
+                                        w1 = *reinterpret_cast<const uint32_t*>(&h1);
                                     }
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                                    }
-                                    val = make_uint4(w[0], w[1], w[2], w[3]);
+                                    // chunk c0 = channels 4 c0 .. 4 c0 + 3 = half (c0 & 1) of plane c0 / 2
+                                    const uint32_t dst = base + a_off + (uint32_t)(plane0 + (c0 >> 1)) * plane_bytes + (uint32_t)px * 16u + (uint32_t)(c0 & 1) * 8u;
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(w0), "r"(w1) : "memory");
                                 }
                             }
-                            const uint32_t dst = base + a_off + (uint32_t)(plane0 + kpv[e]) * plane_bytes + (uint32_t)pxv[e] * 16u;
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
                         }
                     }
                 }
@@ -491,7 +485,9 @@ __global__ void __launch_bounds__(CH_THREADS) conv_chain_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static int chain_plane_px(int W) { return (130 + 2 * (W + 2) + 7) / 8 * 8; }
+// staged positions per tile; the count is made == 1 (mod 8) so that the plane pitch is 16 B off a multiple of 128 B: the
+// lanes of a warp write the SAME pixel of consecutive planes and would otherwise all hit the same banks
+static int chain_plane_px(int W) { return (130 + 2 * (W + 2) + 7) / 8 * 8 + 1; }
 
 bool chain_level_supported(int H, int W) { return (H + 2) * (W + 2) <= 128 * CHAIN_MAX_MTILES && chain_plane_px(W) <= CH_MAX_PX; }
 
