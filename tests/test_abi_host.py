@@ -86,6 +86,9 @@ def test_flops_and_launch_count_from_library():
     assert abs(net.flops(64, 64) - U.count_flops(cfgD, 64, 64)) < 1
     assert abs(net.flops(512, 512) / 1e9 - 70.72) < 1e-2
     assert net.launches(16, 64, 64, "fp32") > 50
+    # the bf16 plan of the benchmark workload (host-side planning, no GPU needed): fused GN->conv kernels, two per-sample
+    # chains, entry kernel, attention, time MLP + the statistics memset = 40; the sampler update makes it 41 per reverse step
+    assert net.launches(16, 64, 64, "bf16") == 40
     assert _lib.lib().ds_unet_workspace_bytes(net._handle, 16, 64, 64, 0) > 0
     assert _lib.lib().ds_unet_workspace_bytes(net._handle, 16, 60, 64, 0) == 0      # not divisible by 8
     assert b"divisible" in _lib.lib().ds_last_error()
