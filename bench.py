@@ -420,6 +420,11 @@ def main():
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "clocks": clk, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
                 "wall_s_timed_region": t_wall}
+        if "joint" in args.workload:
+            # BASELINE.json's second metric: a tile of the joint split needs T steps of each of its two UNets; this workload
+            # times one of them on a batch of B tiles
+            line["tiles_per_sec_equiv"] = value * B / (2.0 * T)
+            line["tiles_note"] = f"steps/s x {B} tiles per batch / (2 UNets x T={T} steps per tile)"
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
