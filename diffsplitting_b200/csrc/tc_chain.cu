@@ -605,7 +605,8 @@ int chain_launch(const ChainPlan* plan, cudaStream_t st) {
     }
     ChainParams p = *reinterpret_cast<const ChainParams*>(plan->params);
     p.trace = trace_next(7);
-    if (getenv("DIFFSPLIT_B200_CHAIN_DBG")) {
+    static const bool chain_dbg = getenv("DIFFSPLIT_B200_CHAIN_DBG") != nullptr;
+    if (chain_dbg) {
         if (!g_chain_dbg) DS_CHECK_CUDA(cudaMalloc(&g_chain_dbg, CHAIN_MAX_OPS * 6 * sizeof(long long)));
         DS_CHECK_CUDA(cudaMemsetAsync(g_chain_dbg, 0, CHAIN_MAX_OPS * 6 * sizeof(long long), st));
         p.dbg = g_chain_dbg;

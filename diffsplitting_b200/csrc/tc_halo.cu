@@ -549,7 +549,8 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     }
     const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp, two_d);
     p.trace = trace_next(6);
-    if (getenv("DIFFSPLIT_B200_HALO_DBG")) {
+    static const bool halo_dbg = getenv("DIFFSPLIT_B200_HALO_DBG") != nullptr;
+    if (halo_dbg) {
         const size_t ctas = (size_t)m_tiles * p.n_tiles;
         if (!g_halo_dbg || g_halo_dbg_ctas < ctas) {
             if (g_halo_dbg) cudaFree(g_halo_dbg);

@@ -395,6 +395,13 @@ enum Fmt { F32 = 1, B16 = 2 };
 
 #define DS_ASSERT_CHAIN(op) do { if (!((op).kind == OP_CONV && (op).chain)) { fprintf(stderr, "diffsplit_b200: internal error, res fold on a non-chain op\n"); abort(); } } while (0)
 
+// environment switches read once per process
+static bool env_set(const char* name) {
+    return getenv(name) != nullptr;
+}
+static bool no_side_stream() { static const bool v = env_set("DIFFSPLIT_B200_NO_SIDE"); return v; }
+static bool attn_cuda_cores() { static const bool v = env_set("DIFFSPLIT_B200_ATTN_CUDA_CORES"); return v; }
+
 struct Planner {
     ds_unet* n;
     Plan* p;
@@ -910,7 +917,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         }
         // the conditioning vectors depend only on the noise level: their kernel runs on the forked stream beside the entry
         // conv; the first consumer waits for it
-        const bool temb_side = !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr;
+        const bool temb_side = !prof && n->side_stream && !no_side_stream();
         if (temb_side) {
             DS_CHECK_CUDA(cudaEventRecord(n->ev_fork, st));
             DS_CHECK_CUDA(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0));
@@ -1042,12 +1049,12 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     DS_CHECK_CUDA(cudaStreamWaitEvent(st_main, n->ev_temb, 0));
                     temb_pending = false;
                 }
-                const bool on_side = o.side && !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr;
+                const bool on_side = o.side && !prof && n->side_stream && !no_side_stream();
                 if (on_side) {
                     DS_CHECK_CUDA(cudaEventRecord(n->ev_fork, st_main));
                     DS_CHECK_CUDA(cudaStreamWaitEvent(n->side_stream, n->ev_fork, 0));
                 }
-                if (o.join && !prof && n->side_stream && getenv("DIFFSPLIT_B200_NO_SIDE") == nullptr)
+                if (o.join && !prof && n->side_stream && !no_side_stream())
                     DS_CHECK_CUDA(cudaStreamWaitEvent(st_main, n->ev_join, 0));
                 cudaStream_t st = on_side ? n->side_stream : st_main;
                 ConvSrc s;
@@ -1089,7 +1096,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 break;
             }
             case OP_ATTN:
-                if (tc && attn_tc_supported(o.N, o.C) && !getenv("DIFFSPLIT_B200_ATTN_CUDA_CORES"))
+                if (tc && attn_tc_supported(o.N, o.C) && !attn_cuda_cores())
                     rc = attn_tc_launch(&p->attn[oi], st);
                 else
                     rc = launch_attention(ptr(o.src_a), tc ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.N, o.C, tc ? 1 : 0, st);
