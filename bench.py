@@ -388,7 +388,7 @@ def main():
             with open(tpath) as fh:
                 tj = json.load(fh)
             traffic = tj["traffic_bytes_per_launch"]
-            traffic_src = ("profiles/r1_halo_traffic.json: dram read+write bytes per launch, mean over the %d launches of one step, "
+            traffic_src = ("profiles/r1_halo_traffic.json: dram read+write bytes per launch, mean over the %d fused-conv launches of one step, "
                            "ncu --set full (caches flushed per replay); algorithmic bytes per launch = %.0f"
                            % (tj["launches_captured"], a["bytes"] / a["launches"]))
         roof.update({"traffic": traffic, "traffic_source": traffic_src, "kernel": top, "share_of_step": a["ms"] / tot, "peak_source": pk["src"],
