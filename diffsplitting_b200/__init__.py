@@ -11,7 +11,7 @@ import sys
 import types
 
 from . import _lib  # noqa: F401
-from . import data, model  # noqa: F401
+from . import core, data, model  # noqa: F401
 
 __version__ = "0.1.0"
 

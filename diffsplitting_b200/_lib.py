@@ -46,6 +46,22 @@ class StepArgs(C.Structure):
                 ("time_len", C.c_int32)]
 
 
+class TileNorm(C.Structure):
+    _fields_ = [("mean_target", C.c_double * 2), ("std_target", C.c_double * 2), ("mean_input", C.c_double),
+                ("std_input", C.c_double), ("w0", C.c_float), ("w1", C.c_float),
+                ("input_from_normalized_target", C.c_int32)]
+
+
+class PsnrArgs(C.Structure):
+    _fields_ = [("d_gt", C.c_void_p), ("d_pred", C.c_void_p),
+                ("gt_frame_stride", C.c_int64), ("gt_channel_stride", C.c_int64), ("gt_pixel_stride", C.c_int64),
+                ("pred_frame_stride", C.c_int64), ("pred_channel_stride", C.c_int64), ("pred_pixel_stride", C.c_int64),
+                ("n_frames", C.c_int32), ("C", C.c_int32), ("npix", C.c_int64),
+                ("unnormalize", C.c_int32), ("quantize_u16", C.c_int32),
+                ("scale", C.POINTER(C.c_double)), ("offset", C.POINTER(C.c_double)),
+                ("d_out", C.c_void_p), ("d_workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 _I3 = C.c_int32 * 3
 _SIGS = {
     "ds_last_error": (C.c_char_p, []),
@@ -97,6 +113,10 @@ _SIGS = {
     "ds_crop_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _I3, _I3, _I3, C.c_int, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_void_p]),
     "ds_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_void_p, C.c_void_p]),
+    "ds_tile_batch": (C.c_int, [C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_int64, C.c_int64,
+                                C.POINTER(TileNorm), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_psnr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "ds_psnr": (C.c_int, [C.POINTER(PsnrArgs), C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

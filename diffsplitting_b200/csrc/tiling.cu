@@ -152,6 +152,179 @@ __global__ void __launch_bounds__(256) crop_kernel(const T* __restrict__ frames,
     }
 }
 
+
+// ---- fused tile loader: crop + normalise + mix (SplitDataset.__getitem__, data/split_dataset.py:237-278, without transforms)
+// patch_c = frames[c, f, y0:y0+P, x0:x0+P].astype(float32); target_c = float32((float64(patch_c) - mean_t[c]) / std_t[c])
+// (normalize_target :199-201: a float32 array against float64 constants promotes to float64, one rounding at the astype);
+// input = w0 * target_0 + w1 * target_1 in float32 (:268-269, python-scalar weights stay weak) or
+// float32((float64(w0 * patch_0 + w1 * patch_1) - mean_inp) / std_inp) (:270-272).  Every operation is a single IEEE
+// operation in the reference, so the intrinsics below (no FMA contraction) reproduce it bit for bit.
+struct TileNorm {
+    double mean_t[2], std_t[2], mean_i, std_i;
+    float w0, w1;
+    int from_norm_target;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) tile_batch_kernel(const T* __restrict__ frames, const TileGeom g, int64_t first,
+                                                         int64_t n, const TileNorm nm, float* __restrict__ inp,
+                                                         float* __restrict__ target) {
+    const int P1 = g.patch[1], P2 = g.patch[2];
+    const int H = g.data[1], W = g.data[2], F = g.data[0];
+    const int64_t plane = (int64_t)P1 * P2;
+    const int64_t chan = (int64_t)F * H * W;
+    const int xq = P2 >> 2;                                            // 4 pixels per thread (P2 % 4 == 0)
+    const int64_t total = n * P1 * (int64_t)xq;
+    for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t ti = i / ((int64_t)P1 * xq);
+        int64_t r = i - ti * (int64_t)P1 * xq;
+        const int py = (int)(r / xq), px = (int)(r - (int64_t)py * xq) * 4;
+        int64_t idx = first + ti;
+        const int kf = (int)(idx / g.strides[0]);
+        idx -= kf * g.strides[0];
+        const int ky = (int)(idx / g.strides[1]);
+        const int kx = (int)(idx - ky * g.strides[1]);
+        const int f = grid_start(g, 0, kf) - g.off[0];
+        const int y = grid_start(g, 1, ky) - g.off[1] + py;
+        const int x = grid_start(g, 2, kx) - g.off[2] + px;
+        float vi[4], v0[4], v1[4];
+        const bool row_in = f >= 0 && f < F && y >= 0 && y < H;
+        const T* src = frames + ((int64_t)f * H + y) * W + x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float p0 = 0.f, p1 = 0.f;
+            if (row_in && x + j >= 0 && x + j < W) {
+                p0 = (float)__ldg(src + j);
+                p1 = (float)__ldg(src + chan + j);
+            }
+            const float t0 = (float)__ddiv_rn(__dsub_rn((double)p0, nm.mean_t[0]), nm.std_t[0]);
+            const float t1 = (float)__ddiv_rn(__dsub_rn((double)p1, nm.mean_t[1]), nm.std_t[1]);
+            v0[j] = t0;
+            v1[j] = t1;
+            if (nm.from_norm_target) {
+                vi[j] = __fadd_rn(__fmul_rn(nm.w0, t0), __fmul_rn(nm.w1, t1));
+            } else {
+                const float mix = __fadd_rn(__fmul_rn(nm.w0, p0), __fmul_rn(nm.w1, p1));
+                vi[j] = (float)__ddiv_rn(__dsub_rn((double)mix, nm.mean_i), nm.std_i);
+            }
+        }
+        const int64_t o = (int64_t)py * P2 + px;
+        *reinterpret_cast<float4*>(inp + ti * plane + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+        if (target) {
+            *reinterpret_cast<float4*>(target + (ti * 2) * plane + o) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+            *reinterpret_cast<float4*>(target + (ti * 2 + 1) * plane + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+        }
+    }
+}
+
+// ---- PSNR / RangeInvariantPsnr of whole images (core/psnr.py:46-82) with the caller's un-normalisation
+// (split.py:198-203: v * std + mean in float64, prediction clamped to [0, 65535], both truncated to uint16) folded in.
+// One pass: per image the 5 shifted moments of (gt, pred), the sum of squared differences, min and max of gt, in
+// fp64; the two metrics follow in closed form (the zero-mean / rescale steps of RangeInvariantPsnr reduce to
+// 10 log10(range^2 n / (Sgg - Sgp^2 / Spp)); the standard deviation cancels).
+constexpr int PSNR_VALS = 8;        // sum dg, sum dg^2, sum dp, sum dp^2, sum dg dp, sum (g - p)^2, min g, max g
+struct PsnrView {
+    const float* gt;
+    const float* pred;
+    int64_t gt_fs, gt_cs, gt_es, pr_fs, pr_cs, pr_es;                 // frame / channel / pixel strides in elements
+    int C;
+    int64_t npix;
+    double scale[4], offset[4];
+    int unnorm, quantize;
+};
+
+__device__ __forceinline__ double psnr_value(const PsnrView& v, float raw, int c, bool clamp) {
+    double x = (double)raw;
+    if (v.unnorm) x = __dadd_rn(__dmul_rn(x, v.scale[c]), v.offset[c]);
+    if (v.quantize) {
+        if (clamp) x = fmin(fmax(x, 0.0), 65535.0);
+        x = trunc(x);
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256) psnr_partial_kernel(const PsnrView v, double* __restrict__ partial) {
+    const int img = blockIdx.y, f = img / v.C, c = img - f * v.C;
+    const float* g = v.gt + f * v.gt_fs + c * v.gt_cs;
+    const float* p = v.pred + f * v.pr_fs + c * v.pr_cs;
+    const double g0 = psnr_value(v, __ldg(g), c, false), p0 = psnr_value(v, __ldg(p), c, true);
+    double a[PSNR_VALS] = {0, 0, 0, 0, 0, 0, g0, g0};
+    for (int64_t k = blockIdx.x * 256LL + threadIdx.x; k < v.npix; k += (int64_t)gridDim.x * 256) {
+        const double gv = psnr_value(v, __ldg(g + k * v.gt_es), c, false);
+        const double pv = psnr_value(v, __ldg(p + k * v.pr_es), c, true);
+        const double dg = gv - g0, dp = pv - p0, d = gv - pv;
+        a[0] += dg;
+        a[1] = fma(dg, dg, a[1]);
+        a[2] += dp;
+        a[3] = fma(dp, dp, a[3]);
+        a[4] = fma(dg, dp, a[4]);
+        a[5] = fma(d, d, a[5]);
+        a[6] = fmin(a[6], gv);
+        a[7] = fmax(a[7], gv);
+    }
+    __shared__ double red[8][PSNR_VALS];
+#pragma unroll
+    for (int i = 0; i < PSNR_VALS; ++i) {
+        double x = a[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = i < 6 ? x + y : (i == 6 ? fmin(x, y) : fmax(x, y));
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < PSNR_VALS) {
+        const int i = threadIdx.x;
+        double x = red[0][i];
+        for (int w = 1; w < 8; ++w) x = i < 6 ? x + red[w][i] : (i == 6 ? fmin(x, red[w][i]) : fmax(x, red[w][i]));
+        partial[((int64_t)img * gridDim.x + blockIdx.x) * PSNR_VALS + i] = x;
+    }
+}
+
+// out[img] = (PSNR, RangeInvariantPsnr, mse, range)
+__global__ void __launch_bounds__(32) psnr_final_kernel(const double* __restrict__ partial, int nblk, int64_t npix,
+                                                        float* __restrict__ out) {
+    const int img = blockIdx.x, lane = threadIdx.x;
+    double a[PSNR_VALS];
+    const double* pp = partial + (int64_t)img * nblk * PSNR_VALS;
+#pragma unroll
+    for (int i = 0; i < PSNR_VALS; ++i) a[i] = i < 6 ? 0.0 : pp[i];
+    for (int b = lane; b < nblk; b += 32) {
+#pragma unroll
+        for (int i = 0; i < PSNR_VALS; ++i) {
+            const double y = pp[(int64_t)b * PSNR_VALS + i];
+            a[i] = i < 6 ? a[i] + y : (i == 6 ? fmin(a[i], y) : fmax(a[i], y));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PSNR_VALS; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, a[i], o);
+            a[i] = i < 6 ? a[i] + y : (i == 6 ? fmin(a[i], y) : fmax(a[i], y));
+        }
+    }
+    if (lane == 0) {
+        const double n = (double)npix;
+        const double sgg = a[1] - a[0] * a[0] / n, spp = a[3] - a[2] * a[2] / n, sgp = a[4] - a[0] * a[2] / n;
+        const double range = a[7] - a[6], mse = a[5] / n;
+        const double resid = sgg - sgp * sgp / spp;
+        out[img * 4 + 0] = (float)(20.0 * log10(range / sqrt(mse)));
+        out[img * 4 + 1] = (float)(10.0 * log10(range * range * n / resid));
+        out[img * 4 + 2] = (float)mse;
+        out[img * 4 + 3] = (float)range;
+    }
+}
+
+static int psnr_blocks(int n_images, int64_t npix) {
+    int64_t want = (npix + 256 * 8 - 1) / (256 * 8);
+    int64_t cap = (148 * 8 + n_images - 1) / n_images;
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    return (int)(want < 1 ? 1 : want);
+}
+
 }  // namespace ds
 
 extern "C" int ds_tile_counts(const int32_t data_shape[3], const int32_t grid_shape[3], const int32_t patch_shape[3],
@@ -225,5 +398,66 @@ extern "C" int ds_stitch_tiles(const float* d_tiles, int C, const int32_t data_s
     int blocks = (int)((npix + 255) / 256 > 148 * 16 ? 148 * 16 : (npix + 255) / 256);
     stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_tiles, C, g, d_out);
     DS_CHECK_LAUNCH("stitch_tiles");
+    return DS_OK;
+}
+
+extern "C" int ds_tile_batch(const void* d_frames, int elem_size, const int32_t data_shape[3], const int32_t grid_shape[3],
+                             const int32_t patch_shape[3], int mode, int64_t first, int64_t n, const ds_tile_norm* norm,
+                             float* d_input, float* d_target, void* stream) {
+    using namespace ds;
+    TileGeom g;
+    int rc = make_geom(data_shape, grid_shape, patch_shape, mode, &g);
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(d_frames && d_input && norm, "tile_batch: null argument");
+    DS_REQUIRE(elem_size == 4 || elem_size == 2, "tile_batch: elem_size %d (4 = fp32, 2 = uint16)", elem_size);
+    DS_REQUIRE(g.patch[0] == 1 && g.grid[0] == 1, "tile_batch: only (1,P,P) patches over (F,H,W) data are supported");
+    DS_REQUIRE(g.patch[2] % 4 == 0, "tile_batch: patch width %d is not a multiple of 4", g.patch[2]);
+    DS_REQUIRE(first >= 0 && n >= 0 && first + n <= g.total, "tile_batch: tile range outside [0, %lld)", (long long)g.total);
+    DS_REQUIRE(norm->std_target[0] != 0.0 && norm->std_target[1] != 0.0 && norm->std_input != 0.0, "tile_batch: zero std");
+    if (n == 0) return DS_OK;
+    TileNorm nm;
+    for (int c = 0; c < 2; ++c) { nm.mean_t[c] = norm->mean_target[c]; nm.std_t[c] = norm->std_target[c]; }
+    nm.mean_i = norm->mean_input;
+    nm.std_i = norm->std_input;
+    nm.w0 = norm->w0;
+    nm.w1 = norm->w1;
+    nm.from_norm_target = norm->input_from_normalized_target;
+    const int64_t total = n * g.patch[1] * (int64_t)(g.patch[2] / 4);
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (elem_size == 4)
+        tile_batch_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)d_frames, g, first, n, nm, d_input, d_target);
+    else
+        tile_batch_kernel<unsigned short><<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned short*)d_frames, g, first, n, nm, d_input, d_target);
+    DS_CHECK_LAUNCH("tile_batch");
+    return DS_OK;
+}
+
+extern "C" size_t ds_psnr_workspace_bytes(int n_frames, int C, int64_t npix) {
+    if (n_frames <= 0 || C <= 0 || npix <= 0) return 0;
+    return (size_t)n_frames * C * ds::psnr_blocks(n_frames * C, npix) * ds::PSNR_VALS * sizeof(double);
+}
+
+extern "C" int ds_psnr(const ds_psnr_args* a, void* stream) {
+    using namespace ds;
+    DS_REQUIRE(a && a->d_gt && a->d_pred && a->d_out && a->d_workspace, "psnr: null argument");
+    DS_REQUIRE(a->n_frames > 0 && a->C > 0 && a->C <= 4 && a->npix > 0, "psnr: %d frames x %d channels (1..4) x %lld pixels",
+               a->n_frames, a->C, (long long)a->npix);
+    DS_REQUIRE(a->workspace_bytes >= ds_psnr_workspace_bytes(a->n_frames, a->C, a->npix), "psnr: workspace too small");
+    DS_REQUIRE(!a->unnormalize || (a->scale && a->offset), "psnr: unnormalize without scale / offset");
+    PsnrView v;
+    v.gt = a->d_gt; v.pred = a->d_pred;
+    v.gt_fs = a->gt_frame_stride; v.gt_cs = a->gt_channel_stride; v.gt_es = a->gt_pixel_stride;
+    v.pr_fs = a->pred_frame_stride; v.pr_cs = a->pred_channel_stride; v.pr_es = a->pred_pixel_stride;
+    v.C = a->C; v.npix = a->npix; v.unnorm = a->unnormalize; v.quantize = a->quantize_u16;
+    for (int c = 0; c < 4; ++c) {
+        v.scale[c] = a->unnormalize && c < a->C ? a->scale[c] : 1.0;
+        v.offset[c] = a->unnormalize && c < a->C ? a->offset[c] : 0.0;
+    }
+    const int n_images = a->n_frames * a->C;
+    const int nblk = psnr_blocks(n_images, a->npix);
+    psnr_partial_kernel<<<dim3(nblk, n_images), 256, 0, (cudaStream_t)stream>>>(v, (double*)a->d_workspace);
+    DS_CHECK_LAUNCH("psnr_partial");
+    psnr_final_kernel<<<n_images, 32, 0, (cudaStream_t)stream>>>((const double*)a->d_workspace, nblk, a->npix, a->d_out);
+    DS_CHECK_LAUNCH("psnr_final");
     return DS_OK;
 }

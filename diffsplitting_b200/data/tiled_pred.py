@@ -85,19 +85,31 @@ class TiledFrames:
                                                 _lib.stream_ptr()))
         return tiles
 
-    def batch(self, first, n):
-        tiles = self.raw_tiles(first, n)
-        dev = tiles.device
-        # float64 arithmetic then one rounding to fp32, like numpy with float64 normalisation constants
-        mt = torch.as_tensor(np.asarray(self.norm["mean_target"], dtype=np.float64).reshape(1, -1, 1, 1), device=dev)
-        st = torch.as_tensor(np.asarray(self.norm["std_target"], dtype=np.float64).reshape(1, -1, 1, 1), device=dev)
-        target = ((tiles.double() - mt) / st).float()
+    def _tile_norm(self):
+        nd = self.norm
+        mt = np.asarray(nd["mean_target"], dtype=np.float64).reshape(-1)
+        st = np.asarray(nd["std_target"], dtype=np.float64).reshape(-1)
+        if mt.size != 2 or st.size != 2:
+            raise ValueError("TiledFrames.batch: mean_target / std_target must have one entry per channel (2)")
         w0, w1 = self.weights
-        if self.input_from_normalized_target:
-            inp = w0 * target[:, 0:1] + w1 * target[:, 1:2]
-        else:
-            mix = w0 * tiles[:, 0:1] + w1 * tiles[:, 1:2]
-            inp = ((mix.double() - float(self.norm["mean_input"])) / float(self.norm["std_input"])).float()
+        return _lib.TileNorm((_lib.C.c_double * 2)(*mt), (_lib.C.c_double * 2)(*st), float(nd["mean_input"]),
+                             float(nd["std_input"]), float(w0), float(w1), int(bool(self.input_from_normalized_target)))
+
+    def batch(self, first, n):
+        """Tiles [first, first+n) as the stacked ``SplitDatasetTiledPred[i]`` items: one fused kernel (crop, float64
+        normalisation with one rounding to fp32, channel mix) straight from the resident frames."""
+        if self.C != 2:
+            raise ValueError("TiledFrames.batch: the splitting data path has two channels")
+        P = self.patch_size
+        dev = self.frames.device
+        inp = torch.empty((n, 1, P, P), dtype=torch.float32, device=dev)
+        target = torch.empty((n, 2, P, P), dtype=torch.float32, device=dev)
+        d, g, p = self.tile_manager._c_shapes()
+        nm = self._tile_norm()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ds_tile_batch(self.frames.data_ptr(), self.elem_size, d, g, p,
+                                                int(self.tile_manager.tiling_mode), first, n, _lib.C.byref(nm),
+                                                inp.data_ptr(), target.data_ptr(), _lib.stream_ptr()))
         return inp, target
 
     def __getitem__(self, index):

@@ -239,6 +239,43 @@ int ds_crop_tiles(const void* d_frames, int elem_size, int C, const int32_t data
 int ds_stitch_tiles(const float* d_tiles, int C, const int32_t data_shape[3], const int32_t grid_shape[3],
                     const int32_t patch_shape[3], int mode, float* d_out, void* stream);
 
+/* Fused tile loader: crop + normalise + mix of tiles [first, first+n) from 2-channel frames (2,F,H,W) fp32|uint16
+ * (SplitDataset.__getitem__ without transforms, data/split_dataset.py:237-278; normalize_target / normalize_inp :195-201).
+ * d_input (n,1,P,P), d_target (n,2,P,P) or NULL; bit-exact with the reference's numpy arithmetic (float64 constants,
+ * python-scalar channel weights). */
+typedef struct {
+    double  mean_target[2], std_target[2];
+    double  mean_input, std_input;
+    float   w0, w1;                         /* channel_weights */
+    int32_t input_from_normalized_target;
+} ds_tile_norm;
+int ds_tile_batch(const void* d_frames, int elem_size, const int32_t data_shape[3], const int32_t grid_shape[3],
+                  const int32_t patch_shape[3], int mode, int64_t first, int64_t n, const ds_tile_norm* norm,
+                  float* d_input, float* d_target, void* stream);
+
+/* ------------------------------------------------------------------ metrics
+ * PSNR and RangeInvariantPsnr (core/psnr.py:46-82) of n_frames x C images of npix pixels, one pass over gt and pred.
+ * Image (f, c) starts at base + f*frame_stride + c*channel_stride, pixels pixel_stride apart (elements), so both
+ * (F,C,H,W) and the stitched (F,H,W,C) layout are read in place.  unnormalize: v*scale[c] + offset[c] in float64;
+ * quantize_u16: the caller's cast to uint16 (split.py:198-203; the prediction is clamped to [0,65535] first).
+ * d_out [n_frames*C][4] = PSNR, RangeInvariantPsnr, mse, range(gt).  fp64 accumulation. */
+typedef struct {
+    const float* d_gt;
+    const float* d_pred;
+    int64_t gt_frame_stride, gt_channel_stride, gt_pixel_stride;
+    int64_t pred_frame_stride, pred_channel_stride, pred_pixel_stride;
+    int32_t n_frames, C;
+    int64_t npix;
+    int32_t unnormalize, quantize_u16;
+    const double* scale;                    /* host [C] or NULL */
+    const double* offset;                   /* host [C] or NULL */
+    float*  d_out;
+    void*   d_workspace;
+    size_t  workspace_bytes;
+} ds_psnr_args;
+size_t ds_psnr_workspace_bytes(int n_frames, int C, int64_t npix);
+int ds_psnr(const ds_psnr_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,11 +322,80 @@ def gen_tiling(R):
     np.savez_compressed(os.path.join(GOLD, "tiling.npz"), **out)
 
 
+def gen_metrics(R):
+    """PSNR / RangeInvariantPsnr vectors from the reference's core/psnr.py, the un-normalisation of split.py:198-203,
+    and normalised tile batches through the reference's SplitDatasetTiledPred with a non-trivial normalisation dict."""
+    from oracle import metrics_ref as M
+    import contextlib
+    import io
+    rng = np.random.default_rng(7)
+    out = {}
+    cases = {
+        "unit": (rng.standard_normal((3, 24, 40)).astype(np.float32), 0.1),
+        "u16": (rng.integers(0, 4000, size=(2, 32, 32)).astype(np.float32), 25.0),
+        "offset": ((rng.standard_normal((2, 16, 48)) * 3 + 1000).astype(np.float32), 0.5),
+    }
+    for tag, (gt, noise) in cases.items():
+        pred = (gt * 0.8 + 0.3 + noise * rng.standard_normal(gt.shape)).astype(np.float32)
+        p_ref = R.psnr.PSNR(torch.from_numpy(gt), torch.from_numpy(pred)).numpy()
+        r_ref = R.psnr.RangeInvariantPsnr(torch.from_numpy(gt), torch.from_numpy(pred)).numpy()
+        assert np.allclose(M.psnr(gt, pred), p_ref, rtol=0, atol=2e-4), (tag, M.psnr(gt, pred), p_ref)
+        assert np.allclose(M.range_invariant_psnr(gt, pred), r_ref, rtol=0, atol=2e-4), (tag, M.range_invariant_psnr(gt, pred), r_ref)
+        out[f"{tag}_gt"], out[f"{tag}_pred"], out[f"{tag}_psnr"], out[f"{tag}_ripsnr"] = gt, pred, p_ref, r_ref
+    p_fixed = R.psnr.PSNR(torch.from_numpy(cases["unit"][0]), torch.from_numpy(out["unit_pred"]), range_=torch.tensor(2.0)).numpy()
+    assert np.allclose(M.psnr(cases["unit"][0], out["unit_pred"], 2.0), p_fixed, atol=2e-4)
+    out["unit_psnr_range2"] = p_fixed
+    # the validation loop's un-normalise + uint16 cast + PSNR, split.py:189-208, on one (2,H,W) normalised pair
+    mean_t, std_t = np.array([600.25, 610.75]), np.array([600.25, 610.75])
+    target = rng.uniform(-1, 1, size=(2, 40, 56)).astype(np.float32)
+    prediction = (target + 0.05 * rng.standard_normal(target.shape)).astype(np.float32)
+    prediction[0, :2] = -1.2                       # below 0 after un-normalisation: clamped
+    target_img = (target * std_t.reshape(-1, 1, 1) + mean_t.reshape(-1, 1, 1)).astype(np.uint16)
+    pred_img = prediction * std_t.reshape(-1, 1, 1) + mean_t.reshape(-1, 1, 1)
+    pred_img[pred_img < 0] = 0
+    pred_img[pred_img > 65535] = 65535
+    pred_img = pred_img.astype(np.uint16)
+    vals = np.array([R.psnr.PSNR(target_img[c:c + 1] * 1.0, pred_img[c:c + 1] * 1.0).mean().item() for c in range(2)])
+    assert np.array_equal(M.unnormalize_u16(target, mean_t, std_t, False), target_img * 1.0)
+    assert np.array_equal(M.unnormalize_u16(prediction, mean_t, std_t, True), pred_img * 1.0)
+    mine = np.array([M.psnr(M.unnormalize_u16(target, mean_t, std_t, False)[c:c + 1],
+                            M.unnormalize_u16(prediction, mean_t, std_t, True)[c:c + 1])[0] for c in range(2)])
+    assert np.allclose(mine, vals, atol=2e-4), (mine, vals)
+    out["val_target"], out["val_prediction"], out["val_mean"], out["val_std"], out["val_psnr"] = target, prediction, mean_t, std_t, vals
+    # normalised tile batches through the reference dataset class (split_dataset.py:237-278), both input modes
+    fr = rng.integers(0, 1994, size=(2, 3, 96, 128)).astype(np.uint16)
+
+    def get_data(*a, **k):
+        return {i: fr[i] for i in range(2)}
+    import data.split_dataset as sdmod
+    sdmod.load_data = get_data
+    nd = {'mean_input': np.float64(1210.4), 'std_input': np.float64(1207.3), 'mean_target': np.array([600.3, 610.7]),
+          'std_target': np.array([598.9, 611.1]), 'target0_max': 1, 'target1_max': 1, 'input_max': 1}
+    tg = TR.TileGrid((3, 96, 128), (1, 16, 16), (1, 32, 32), TR.SHIFT)
+    idx = [0, 5, 17, tg.total - 1]
+    for tag, kw in (("mix", dict(channel_weights=[0.7, 0.4])), ("normtar", dict(channel_weights=[0.5, 0.5], input_from_normalized_target=True))):
+        with contextlib.redirect_stdout(io.StringIO()):
+            dset = R.tp.SplitDatasetTiledPred('Hagen', None, 32, grid_size=16, upper_clip=False, normalization_dict=nd,
+                                              enable_transforms=False, uncorrelated_channels=False, random_patching=False, **kw)
+        assert len(dset) == tg.total
+        items = [dset[i] for i in idx]
+        inp_ref = np.stack([it['input'] for it in items])
+        tar_ref = np.stack([it['target'] for it in items])
+        inp, tar = TR.normalise_and_mix(TR.crop_tiles(fr, tg, idx), nd['mean_target'], nd['std_target'], nd['mean_input'],
+                                        nd['std_input'], kw['channel_weights'], kw.get('input_from_normalized_target', False))
+        assert inp_ref.dtype == np.float32 and np.array_equal(inp, inp_ref) and np.array_equal(tar, tar_ref), tag
+        out[f"tiles_{tag}_input"], out[f"tiles_{tag}_target"] = inp_ref, tar_ref
+    out["tiles_frames"], out["tiles_idx"] = fr, np.array(idx)
+    print("[metrics] PSNR / RangeInvariantPsnr / un-normalise agree with core/psnr.py; tile batches identical to the dataset class")
+    np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     R = _import_reference()
     gen_tiling(R)
+    gen_metrics(R)
     gen_keys(R)
     gen_unet(R)
     gen_samplers(R)

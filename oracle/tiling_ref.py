@@ -121,12 +121,20 @@ def crop_tiles(frames: np.ndarray, tg: TileGrid, idxs=None) -> np.ndarray:
     return np.stack(out)
 
 
-def normalise_and_mix(tiles: np.ndarray, mean_t, std_t, mean_in, std_in, weights=(1, 1)):
-    """target = (tile-mean_t)/std_t ; input = (w0*ch0 + w1*ch1 - mean_in)/std_in
-    (split_dataset.py:198-204, 262-272), float32 results."""
+def normalise_and_mix(tiles: np.ndarray, mean_t, std_t, mean_in, std_in, weights=(1, 1), input_from_normalized_target=False):
+    """target = (tile-mean_t)/std_t ; input = (w0*ch0 + w1*ch1 - mean_in)/std_in, or w0*target0 + w1*target1 when
+    ``input_from_normalized_target`` (split_dataset.py:195-201, 262-272), float32 results.  The normalisation constants are
+    numpy float64 in the reference (compute_normalization_dict :28-75: np.quantile(...)/2, np.array([...])), so the
+    float32 patches promote to float64 and are rounded once by ``astype``; the python-scalar channel weights do not
+    promote (float32 products and sum)."""
     mt = np.asarray(mean_t, dtype=np.float64).reshape(1, -1, 1, 1)
     st = np.asarray(std_t, dtype=np.float64).reshape(1, -1, 1, 1)
+    tiles = tiles.astype(np.float32)
     target = ((tiles - mt) / st).astype(np.float32)
-    inp = weights[0] * tiles[:, 0:1] + weights[1] * tiles[:, 1:2]
-    inp = ((inp - mean_in) / std_in).astype(np.float32)
+    w0, w1 = (np.float32(w) for w in weights)
+    if input_from_normalized_target:
+        inp = w0 * target[:, 0:1] + w1 * target[:, 1:2]
+    else:
+        inp = w0 * tiles[:, 0:1] + w1 * tiles[:, 1:2]
+        inp = ((inp - np.float64(mean_in)) / np.float64(std_in)).astype(np.float32)
     return inp, target

@@ -25,6 +25,7 @@ from diffsplitting_b200.data import TiledFrames, TileIndexManager, TilingMode, s
 from diffsplitting_b200.model import create_model
 from diffsplitting_b200.model.samplers import GaussianDiffusionDdpm, GaussianDiffusionSr3, InDI, JointIndi
 from diffsplitting_b200.model.unet import UNet
+from oracle import metrics_ref as M
 from oracle import philox_ref as PH
 from oracle import samplers_ref as S
 from oracle import tiling_ref as TR
@@ -559,6 +560,75 @@ def test_full_size_tiling_identity_uint16():
         assert np.array_equal(inp.cpu().numpy()[0], inp_ref[j]) and np.array_equal(tar.cpu().numpy()[0], tar_ref[j])
         item = tf[i]
         assert np.array_equal(item["input"], inp_ref[j])
+
+
+def test_fused_tile_batch_matches_reference_dataset_items(gold_dir):
+    """ds_tile_batch (crop + float64 normalise + mix in one kernel) vs items recorded from the reference's
+    SplitDatasetTiledPred, both input modes, uint16 and fp32 frames: bit-exact."""
+    g = np.load(os.path.join(gold_dir, "metrics.npz"))
+    fr, idx = g["tiles_frames"], [int(i) for i in g["tiles_idx"]]
+    nd = {"mean_input": np.float64(1210.4), "std_input": np.float64(1207.3), "mean_target": np.array([600.3, 610.7]),
+          "std_target": np.array([598.9, 611.1])}
+    for frames in (fr, fr.astype(np.float32)):
+        for tag, w, fn in (("mix", (0.7, 0.4), False), ("normtar", (0.5, 0.5), True)):
+            tf = TiledFrames(frames, 32, 16, normalization_dict=nd, channel_weights=w, input_from_normalized_target=fn)
+            for j, i in enumerate(idx):
+                inp, tar = tf.batch(i, 1)
+                assert np.array_equal(inp.cpu().numpy()[0], g[f"tiles_{tag}_input"][j])
+                assert np.array_equal(tar.cpu().numpy()[0], g[f"tiles_{tag}_target"][j])
+            n = len(tf)
+            inp, tar = tf.batch(0, n)                                                  # the whole range in one launch
+            tg = TR.TileGrid((3, 96, 128), (1, 16, 16), (1, 32, 32), TR.SHIFT)
+            inp_ref, tar_ref = TR.normalise_and_mix(TR.crop_tiles(fr, tg), nd["mean_target"], nd["std_target"],
+                                                    nd["mean_input"], nd["std_input"], w, fn)
+            assert np.array_equal(inp.cpu().numpy(), inp_ref) and np.array_equal(tar.cpu().numpy(), tar_ref)
+    with pytest.raises(RuntimeError):
+        TiledFrames(fr, 32, 16, normalization_dict=nd).batch(len(tf) - 1, 2)           # range past the last tile
+
+
+def test_psnr_kernel_matches_reference_golden(gold_dir):
+    """ds_psnr vs values recorded from core/psnr.py (float32 torch): <= 5e-4 dB; fixed range_; numpy inputs."""
+    from diffsplitting_b200.core.psnr import PSNR, RangeInvariantPsnr
+    g = np.load(os.path.join(gold_dir, "metrics.npz"))
+    for tag in ("unit", "u16", "offset"):
+        gt, pr = torch.from_numpy(g[f"{tag}_gt"]).to(DEV), torch.from_numpy(g[f"{tag}_pred"]).to(DEV)
+        assert np.allclose(PSNR(gt, pr).cpu().numpy(), g[f"{tag}_psnr"], rtol=0, atol=5e-4)
+        assert np.allclose(RangeInvariantPsnr(gt, pr).cpu().numpy(), g[f"{tag}_ripsnr"], rtol=0, atol=5e-4)
+    assert np.allclose(PSNR(g["unit_gt"], g["unit_pred"], range_=2.0).cpu().numpy(), g["unit_psnr_range2"], atol=5e-4)
+    gt = torch.from_numpy(g["unit_gt"]).to(DEV)
+    assert torch.isinf(PSNR(gt, gt)).all()
+    with pytest.raises(AssertionError):
+        PSNR(gt[0], gt[0])
+
+
+def test_psnr_frames_in_place_on_stitched_layout(gold_dir):
+    """Whole-frame metrics read from the stitched (F,H,W,C) layout with the validation loop's un-normalisation and uint16
+    cast folded in (split.py:198-208), vs the float64 oracle: <= 1e-4 dB; and the golden value of the reference's loop."""
+    from diffsplitting_b200.core.psnr import psnr_frames
+    g = np.load(os.path.join(gold_dir, "metrics.npz"))
+    mean, std = g["val_mean"], g["val_std"]
+    t = torch.from_numpy(g["val_target"]).to(DEV)[None]                               # (1,C,H,W)
+    p = torch.from_numpy(g["val_prediction"]).to(DEV)[None]
+    ps, _ = psnr_frames(t, p, mean, std, channels_last=False)
+    assert np.allclose(ps.cpu().numpy()[0], g["val_psnr"], atol=5e-4)
+    ps_cl, _ = psnr_frames(t.permute(0, 2, 3, 1).contiguous(), p.permute(0, 2, 3, 1).contiguous(), mean, std)
+    assert torch.equal(ps, ps_cl)
+    # full-size frames: 3 x 1024^2 x 2 channels, many CTAs per image
+    rng = np.random.default_rng(11)
+    tgt = rng.uniform(-1, 1, size=(3, 1024, 1024, 2)).astype(np.float32)
+    prd = (0.9 * tgt + 0.02 + 0.1 * rng.standard_normal(tgt.shape)).astype(np.float32)
+    ps, ri = psnr_frames(torch.from_numpy(tgt).to(DEV), torch.from_numpy(prd).to(DEV), mean, std)
+    ps_raw, ri_raw = psnr_frames(torch.from_numpy(tgt).to(DEV), torch.from_numpy(prd).to(DEV))
+    for f in range(3):
+        tu = M.unnormalize_u16(tgt[f].transpose(2, 0, 1), mean, std, False)
+        pu = M.unnormalize_u16(prd[f].transpose(2, 0, 1), mean, std, True)
+        assert np.allclose(ps[f].cpu().numpy(), M.psnr(tu, pu), rtol=0, atol=1e-4)
+        assert np.allclose(ri[f].cpu().numpy(), M.range_invariant_psnr(tu, pu), rtol=0, atol=1e-4)
+        assert np.allclose(ps_raw[f].cpu().numpy(), M.psnr(tgt[f].transpose(2, 0, 1), prd[f].transpose(2, 0, 1)), atol=1e-4)
+        assert np.allclose(ri_raw[f].cpu().numpy(), M.range_invariant_psnr(tgt[f].transpose(2, 0, 1), prd[f].transpose(2, 0, 1)), atol=1e-4)
+    # invariance property of RangeInvariantPsnr: affine changes of the prediction do not move it
+    _, ri2 = psnr_frames(torch.from_numpy(tgt).to(DEV), torch.from_numpy(3.0 * prd + 0.5).to(DEV))
+    assert torch.allclose(ri2, ri_raw, atol=1e-3)
 
 
 # ------------------------------------------------------------------------------------------------ wrapper

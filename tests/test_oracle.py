@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import metrics_ref as M
 from oracle import philox_ref as PH
 from oracle import samplers_ref as S
 from oracle import tiling_ref as TR
@@ -85,6 +86,35 @@ def test_psnr_oracles(gold_dir):
     gt, pr = torch.from_numpy(g["psnr_gt"]), torch.from_numpy(g["psnr_pred"])
     assert np.allclose(S.psnr(gt, pr).numpy(), g["psnr"], atol=1e-4)
     assert np.allclose(S.range_invariant_psnr(gt, pr).numpy(), g["ripsnr"], atol=1e-4)
+
+
+def test_metrics_oracle_matches_reference_golden(gold_dir):
+    """float64 restatement of core/psnr.py + the un-normalisation of split.py:198-203 vs values recorded from the reference."""
+    g = _load(gold_dir, "metrics.npz")
+    for tag in ("unit", "u16", "offset"):
+        assert np.allclose(M.psnr(g[f"{tag}_gt"], g[f"{tag}_pred"]), g[f"{tag}_psnr"], rtol=0, atol=2e-4)
+        assert np.allclose(M.range_invariant_psnr(g[f"{tag}_gt"], g[f"{tag}_pred"]), g[f"{tag}_ripsnr"], rtol=0, atol=2e-4)
+    assert np.allclose(M.psnr(g["unit_gt"], g["unit_pred"], 2.0), g["unit_psnr_range2"], atol=2e-4)
+    t = M.unnormalize_u16(g["val_target"], g["val_mean"], g["val_std"], False)
+    p = M.unnormalize_u16(g["val_prediction"], g["val_mean"], g["val_std"], True)
+    assert p.min() == 0.0                                   # the clamped rows
+    vals = [M.psnr(t[c:c + 1], p[c:c + 1])[0] for c in range(2)]
+    assert np.allclose(vals, g["val_psnr"], atol=2e-4)
+    same = M.psnr(g["unit_gt"], g["unit_gt"])
+    assert np.all(np.isinf(same))                           # identical images: mse 0, as the reference (log10 of inf)
+
+
+def test_tile_batch_oracle_matches_reference_dataset_items(gold_dir):
+    """crop + normalise + mix vs items of the reference's SplitDatasetTiledPred (both input modes), bit-exact."""
+    g = _load(gold_dir, "metrics.npz")
+    fr, idx = g["tiles_frames"], [int(i) for i in g["tiles_idx"]]
+    tg = TR.TileGrid((3, 96, 128), (1, 16, 16), (1, 32, 32), TR.SHIFT)
+    nd = dict(mean_t=[600.3, 610.7], std_t=[598.9, 611.1], mean_in=1210.4, std_in=1207.3)
+    raw = TR.crop_tiles(fr, tg, idx)
+    for tag, w, fn in (("mix", (0.7, 0.4), False), ("normtar", (0.5, 0.5), True)):
+        inp, tar = TR.normalise_and_mix(raw, nd["mean_t"], nd["std_t"], nd["mean_in"], nd["std_in"], w, fn)
+        assert inp.dtype == np.float32 and tar.dtype == np.float32
+        assert np.array_equal(inp, g[f"tiles_{tag}_input"]) and np.array_equal(tar, g[f"tiles_{tag}_target"])
 
 
 def test_tiling_oracle_matches_reference_tables(gold_dir):
