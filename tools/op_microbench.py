@@ -30,11 +30,39 @@ def timed_graph(fn, n=50, reps=20):
     return e0.elapsed_time(e1) * 1000 / (n * reps)
 
 
+def data_path(kind, F, H, W):
+    """psnr: F frames of HxW, 2 channels, stitched (F,H,W,C) layout, un-normalise + uint16 cast folded in.
+    tilebatch: all tiles of 512^2 (grid 256) from F uint16 frames of HxW."""
+    import numpy as np
+    from diffsplitting_b200.core.psnr import psnr_frames
+    from diffsplitting_b200.data import TiledFrames
+    if kind == "psnr":
+        t = torch.rand((F, H, W, 2), device=DEV) * 2 - 1
+        p = t + 0.05 * torch.randn_like(t)
+        mean = std = np.array([600.25, 610.75])
+        us = timed_graph(lambda: psnr_frames(t, p, mean, std), n=10, reps=10)
+        nbytes = 2 * t.numel() * 4
+        print(f"psnr_frames {F}x{H}x{W}x2 (2 kernels, both metrics, both channels): {us:.1f} us per call, "
+              f"{nbytes / us / 1e6:.2f} TB/s algorithmic (read target + prediction once)")
+    else:
+        fr = torch.randint(0, 2000, (2, F, H, W), dtype=torch.int32, device=DEV).to(torch.uint16)
+        nd = {"mean_input": 1210.5, "std_input": 1210.5, "mean_target": np.array([600.25, 610.25]),
+              "std_target": np.array([600.25, 610.25])}
+        tf = TiledFrames(fr, 512, 256, normalization_dict=nd)
+        n = len(tf)
+        us = timed_graph(lambda: tf.batch(0, n), n=5, reps=10)
+        nbytes = n * 512 * 512 * (2 * 2 + 3 * 4)
+        print(f"tile_batch {n} tiles of 512^2 from {F}x{H}x{W} uint16 frames: {us:.1f} us per call, "
+              f"{nbytes / us / 1e6:.2f} TB/s algorithmic (2 uint16 reads + 3 fp32 writes per tile pixel)")
+
+
 def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "gnconv"
     ca, cb, cout, ks, B, H, W = [int(v) for v in (sys.argv[2:9] if len(sys.argv) >= 9 else "16 0 16 3 16 64 64".split())]
     cin = ca + cb
     L = _lib.lib()
+    if kind in ("psnr", "tilebatch"):
+        return data_path(kind, B, H, W)
     sp = lambda: _lib.stream_ptr()
     g = torch.Generator().manual_seed(0)
     w = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5).to(DEV)
