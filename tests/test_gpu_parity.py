@@ -344,6 +344,28 @@ def test_unet_matches_oracle(name, cfg, B, H, W, cond, precision):
     assert e <= TOL[precision] and r <= TOL_RMS[precision]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,cfg,H,W,cond", [
+    ("hagen_512", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 512, 512, 0),
+    ("splitting_512", U.make_cfg("sr3", 3, 2, 16, 16, (1, 2, 4, 8), (), 1, 512), 512, 512, 1),
+    ("sr3_16_128", U.make_cfg("sr3", 6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 128), 128, 128, 3),
+    ("sr3_64_512", U.make_cfg("sr3", 6, 3, 64, 16, (1, 2, 4, 8, 16), (), 1, 512), 512, 512, 3)])
+def test_unet_baseline_configs_at_full_resolution(name, cfg, H, W, cond, precision):
+    """The BASELINE.json networks at their full resolution (one sample; the CPU oracle needs a few seconds each): the
+    large-shape kernel variants (2-D tiles of the fused conv, tall-patch TMA conv, 1024 / 2048-channel layers, attention at
+    N = 1024 x C = 1024 and N = 256 x C = 512) inside the whole network, same gates as the small cases."""
+    sd = U.random_state_dict(cfg, seed=33)
+    net = build(cfg, sd, precision)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn((1, cfg["in_channel"], H, W), generator=g)
+    t = torch.rand((1, 1), generator=g) * 0.9 + 0.05 if cfg["variant"] == "sr3" else torch.rand((1,), generator=g)
+    ref = U.unet_forward(sd, cfg, x, t)
+    y = net(x[:, cond:].to(DEV), t.to(DEV), cond=x[:, :cond].to(DEV)) if cond else net(x.to(DEV), t.to(DEV))
+    e, r = relerr(y, ref), relrms(y, ref)
+    print(f"[unet {name} {precision} full resolution] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
+    assert e <= TOL[precision] and r <= TOL_RMS[precision]
+
+
 # ------------------------------------------------------------------------------------------------ samplers
 SCHED = dict(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=0.3)
 
