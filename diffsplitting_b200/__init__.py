@@ -19,7 +19,7 @@ __version__ = "0.1.0"
 def install(override_existing=True):
     """Alias the reference's module names to this package (the duck-typed boundary of SURVEY.md section 8b)."""
     from .data import tile_stitcher, tiled_pred, tiling_manager
-    from .model import base_model, model as model_mod, networks, samplers, unet
+    from .model import base_model, model as model_mod, networks, samplers, time_predictor, unet
 
     def put(name, mod):
         if override_existing or name not in sys.modules:
@@ -29,6 +29,10 @@ def install(override_existing=True):
     put("model.model", model_mod)
     put("model.networks", networks)
     put("model.base_model", base_model)
+    dm = types.ModuleType("model.ddpm_modules")                   # only the inference-side classes live here
+    dm.time_predictor = time_predictor
+    put("model.ddpm_modules", dm)
+    put("model.ddpm_modules.time_predictor", time_predictor)
     # data.* : only the tiling modules are replaced; the TIFF/LMDB dataset classes stay the reference's own
     put("data.tiling_manager", tiling_manager)
     put("data.tile_stitcher", tile_stitcher)

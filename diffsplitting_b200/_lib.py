@@ -117,6 +117,8 @@ _SIGS = {
                                 C.POINTER(TileNorm), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_psnr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "ds_psnr": (C.c_int, [C.POINTER(PsnrArgs), C.c_void_p]),
+    "ds_time_head_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ds_time_head_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

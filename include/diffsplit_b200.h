@@ -276,6 +276,14 @@ typedef struct {
 size_t ds_psnr_workspace_bytes(int n_frames, int C, int64_t npix);
 int ds_psnr(const ds_psnr_args* args, void* stream);
 
+/* Tail of the time predictor (model/ddpm_modules/time_predictor.py:5-12, 38-45): d_out[b] = sum(relu(unet_out) * m) / sum(m),
+ * m = sigmoid(conv7x7(x) + bias), sums over (channel, pixel).  d_x (B,cin,H,W), d_unet_out (B,cout,H,W) fp32 NCHW,
+ * d_w_oihw (cout,cin,7,7); cin <= 8, cout <= 4.  The UNet part is ds_unet_forward with with_time_emb = 0. */
+size_t ds_time_head_workspace_bytes(int B, int H, int W);
+int ds_time_head_f32(const float* d_x, const float* d_unet_out, const float* d_w_oihw, const float* d_bias,
+                     int B, int cin, int cout, int H, int W, float* d_out, void* d_workspace, size_t workspace_bytes,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

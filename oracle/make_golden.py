@@ -44,12 +44,13 @@ def _import_reference():
     import model.ddpm_modules.diffusion as ddpm_diff
     import model.ddpm_modules.indi as indi
     import model.ddpm_modules.joint_indi as joint
+    import model.ddpm_modules.time_predictor as timepred
     import data.tiling_manager as tm
     import data.tile_stitcher as ts
     import data.split_dataset_tiledpred as tp
     import core.psnr as psnr
     return types.SimpleNamespace(sr3_unet=sr3_unet, sr3_diff=sr3_diff, ddpm_unet=ddpm_unet,
-                                 ddpm_diff=ddpm_diff, indi=indi, joint=joint, tm=tm, ts=ts, tp=tp, psnr=psnr)
+                                 ddpm_diff=ddpm_diff, indi=indi, joint=joint, tm=tm, ts=ts, tp=tp, psnr=psnr, timepred=timepred)
 
 
 def build_ref_unet(R, cfg):
@@ -390,12 +391,41 @@ def gen_metrics(R):
     np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
 
 
+TIMEPRED_CASES = {
+    "hagen": (U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 64, with_time_emb=False), 3, 64, 64),   # the shipped config
+    "multi": (U.make_cfg("ddpm", 3, 2, 16, 8, (1, 2), (8,), 2, 16, with_time_emb=False), 2, 16, 24),
+}
+
+
+def gen_time_predictor(R):
+    """TimePredictor (time_predictor.py:13-45) with seeded weights loaded through its own load_state_dict (strict: pins the
+    key names), inputs and outputs recorded."""
+    out = {}
+    for tag, (cfg, B, H, W) in TIMEPRED_CASES.items():
+        sd = U.time_predictor_state_dict(cfg, seed=41)
+        ref = R.timepred.TimePredictor(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"],
+                                       inner_channel=cfg["inner_channel"], norm_groups=cfg["norm_groups"],
+                                       channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+                                       res_blocks=cfg["res_blocks"], dropout=0, image_size=cfg["image_size"]).eval()
+        ref.load_state_dict(sd, strict=True)
+        x = torch.randn((B, cfg["in_channel"], H, W), generator=torch.Generator().manual_seed(5))
+        with torch.no_grad():
+            y_ref = ref(x)
+        y = U.time_predictor_forward(sd, cfg, x)
+        err = (y - y_ref).abs().max().item()
+        assert err < 2e-6, (tag, err)
+        out[f"{tag}_x"], out[f"{tag}_y"] = x.numpy(), y_ref.numpy()
+        print(f"[time predictor] {tag}: oracle vs reference {err:.2e}; values {y_ref.numpy()}")
+    np.savez_compressed(os.path.join(GOLD, "time_predictor.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     R = _import_reference()
     gen_tiling(R)
     gen_metrics(R)
+    gen_time_predictor(R)
     gen_keys(R)
     gen_unet(R)
     gen_samplers(R)

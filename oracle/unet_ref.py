@@ -178,6 +178,26 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, time, prefix: str 
     return _gn_swish_conv(sd, "final_conv", x, cfg["norm_groups"])
 
 
+def time_predictor_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor) -> Tensor:
+    """TimePredictor.forward (model/ddpm_modules/time_predictor.py:38-45): ``cfg`` describes the inner ddpm UNet
+    (with_time_emb False), ``sd`` has the reference keys ``unet.*`` and ``foreground_mask.layer.{weight,bias}``."""
+    out = F.relu(unet_forward(sd, cfg, x, None, prefix="unet."))                                    # :39-40
+    attention = torch.sigmoid(F.conv2d(x, sd["foreground_mask.layer.weight"], sd["foreground_mask.layer.bias"],
+                                       padding=3))                                                   # :5-12, :41
+    out = (out * attention).reshape(out.shape[0], -1)                                               # :42-43
+    return out.sum(dim=1) / attention.reshape(out.shape).sum(dim=1)                                 # :44
+
+
+def time_predictor_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
+    sd = {"unet." + k: v for k, v in random_state_dict(cfg, seed=seed).items()}
+    g = torch.Generator().manual_seed(seed + 1000)
+    cin, cout = cfg["in_channel"], cfg["out_channel"]
+    bound = 1.0 / math.sqrt(cin * 49)
+    sd["foreground_mask.layer.weight"] = (torch.rand((cout, cin, 7, 7), generator=g) * 2 - 1) * bound
+    sd["foreground_mask.layer.bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+    return sd
+
+
 def random_state_dict(cfg: dict, seed: int = 0, scale: float = 1.0) -> Dict[str, Tensor]:
     """Seeded random weights with PyTorch-default-like fan-in scaling, generated
     independently of any nn.Module so they travel to the GPU box.  GroupNorm

@@ -30,7 +30,7 @@ from oracle import philox_ref as PH
 from oracle import samplers_ref as S
 from oracle import tiling_ref as TR
 from oracle import unet_ref as U
-from oracle.make_golden import UNET_CASES, Replay
+from oracle.make_golden import TIMEPRED_CASES, UNET_CASES, Replay
 from tests.configs import make_opt
 
 DEV = "cuda"
@@ -364,6 +364,30 @@ def test_unet_baseline_configs_at_full_resolution(name, cfg, H, W, cond, precisi
     e, r = relerr(y, ref), relrms(y, ref)
     print(f"[unet {name} {precision} full resolution] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
     assert e <= TOL[precision] and r <= TOL_RMS[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", list(TIMEPRED_CASES))
+def test_time_predictor_matches_reference_golden(gold_dir, case, precision):
+    """TimePredictor (UNet without time embedding + fused mask / masked-mean tail) vs outputs recorded from the reference's
+    class; its state_dict has exactly the reference's keys.  rel-err of the scalar: <= 1e-5 fp32, <= 1e-2 bf16."""
+    from diffsplitting_b200.model.time_predictor import TimePredictor
+    cfg, B, H, W = TIMEPRED_CASES[case]
+    g = np.load(os.path.join(gold_dir, "time_predictor.npz"))
+    sd = U.time_predictor_state_dict(cfg, seed=41)
+    m = TimePredictor(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], inner_channel=cfg["inner_channel"],
+                      norm_groups=cfg["norm_groups"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+                      res_blocks=cfg["res_blocks"], dropout=0.2, image_size=cfg["image_size"], precision=precision)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    y = m(torch.from_numpy(g[f"{case}_x"]).to(DEV)).cpu().numpy()
+    ref = g[f"{case}_y"]
+    err = float(np.abs(y - ref).max() / np.abs(ref).max())
+    print(f"[time predictor {case} {precision}] rel-err {err:.3e}")
+    assert y.shape == (B,) and err <= (1e-5 if precision == "fp32" else 1e-2)
+    with pytest.raises(RuntimeError):
+        m(torch.from_numpy(g[f"{case}_x"]))                       # CPU tensor: no fallback
 
 
 # ------------------------------------------------------------------------------------------------ samplers

@@ -11,7 +11,7 @@ from oracle import philox_ref as PH
 from oracle import samplers_ref as S
 from oracle import tiling_ref as TR
 from oracle import unet_ref as U
-from oracle.make_golden import UNET_CASES, Replay
+from oracle.make_golden import TIMEPRED_CASES, UNET_CASES, Replay
 
 
 def _load(gold_dir, name):
@@ -102,6 +102,15 @@ def test_metrics_oracle_matches_reference_golden(gold_dir):
     assert np.allclose(vals, g["val_psnr"], atol=2e-4)
     same = M.psnr(g["unit_gt"], g["unit_gt"])
     assert np.all(np.isinf(same))                           # identical images: mse 0, as the reference (log10 of inf)
+
+
+@pytest.mark.parametrize("case", list(TIMEPRED_CASES))
+def test_time_predictor_oracle_matches_reference_golden(gold_dir, case):
+    cfg, B, H, W = TIMEPRED_CASES[case]
+    g = _load(gold_dir, "time_predictor.npz")
+    sd = U.time_predictor_state_dict(cfg, seed=41)
+    y = U.time_predictor_forward(sd, cfg, torch.from_numpy(g[f"{case}_x"]))
+    assert y.shape == (B,) and np.allclose(y.numpy(), g[f"{case}_y"], rtol=0, atol=2e-6)
 
 
 def test_tile_batch_oracle_matches_reference_dataset_items(gold_dir):
