@@ -525,6 +525,54 @@ def test_joint_indi_snapshot_count_and_multi_step_graphs(T):
     assert torch.equal(y, y1)
 
 
+def test_mmse_tiled_evaluation_follows_the_notebook_loop():
+    """evaluate_mmse == the loop of notebooks/EvaluateJointIndi.ipynb cells 55-62 written out literally (batch 1, both
+    full JointIndi.inference calls per tile, `mmse_pred += pred / mmse_count`, stitch, RangeInvariantPsnr): bit-identical
+    under the same seed with chunk=1 / replay_reference_rng, and the device metric agrees with the float64 oracle on the
+    stitched frames.  The batched fast path (chunk 4, only the two kept loops) gives the same shapes and finite values."""
+    from diffsplitting_b200.evaluate import evaluate_mmse
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2), (), 1, 32)
+    nets = [build(cfg, U.random_state_dict(cfg, seed=s), "bf16") for s in (3, 4)]
+    joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=nets[0], denoise_fn_ch2=nets[1],
+                      val_schedule_opt={"n_timestep": 2}).to(DEV)
+    joint.set_new_noise_schedule({"n_timestep": 2}, DEV)
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 2000, size=(2, 2, 64, 64)).astype(np.uint16)
+    nd = {"mean_input": np.float64(1000.0), "std_input": np.float64(1000.0), "mean_target": np.array([500.0, 500.0]),
+          "std_target": np.array([500.0, 500.0])}
+    tf = TiledFrames(frames, 32, 16, normalization_dict=nd)
+    W_, T_, M_ = 0.5, 2, 2
+    torch.manual_seed(11)
+    res = evaluate_mmse(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=M_, chunk=1, replay_reference_rng=True)
+    # the notebook loop
+    torch.manual_seed(11)
+    runs, targets = [], []
+    for m in range(M_):
+        preds = []
+        for i in range(len(tf)):
+            data = tf[i]
+            inp0 = data["target"][:1] * (1 - W_) + data["target"][1:2] * W_
+            inp1 = data["target"][1:2] * (1 - W_) + data["target"][:1] * W_
+            p0 = joint.inference(torch.Tensor(inp0[None]).to(DEV), continuous=False, t_float_start=W_, num_timesteps=T_)[:, 0]
+            p1 = joint.inference(torch.Tensor(inp1[None]).to(DEV), continuous=False, t_float_start=W_, num_timesteps=T_)[:, 1]
+            preds.append(torch.stack([p0, p1], dim=1).cpu().numpy())
+            if m == 0:
+                targets.append(data["target"][None])
+        runs.append(np.concatenate(preds, axis=0))
+    mmse = 0
+    for m in range(M_):
+        mmse += runs[m] / M_
+    pred_st = stitch_predictions(mmse, tf.tile_manager)
+    tar_st = stitch_predictions(np.concatenate(targets, axis=0), tf.tile_manager)
+    assert np.array_equal(res["prediction"].cpu().numpy(), pred_st) and np.array_equal(res["target"].cpu().numpy(), tar_st)
+    for c in range(2):
+        ref = M.range_invariant_psnr(tar_st[..., c], pred_st[..., c])
+        assert np.allclose(res["range_invariant_psnr"][:, c].cpu().numpy(), ref, rtol=0, atol=1e-4)
+    fast = evaluate_mmse(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=M_, chunk=4)
+    assert fast["prediction"].shape == res["prediction"].shape and torch.isfinite(fast["range_invariant_psnr"]).all()
+    assert torch.equal(fast["target"], res["target"])
+
+
 def test_final_psnr_within_point1_db_of_oracle():
     """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 16 InDI chain;
     T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation)."""
