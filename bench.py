@@ -145,7 +145,7 @@ def cpu_baseline(w, seconds=12.0):
         step()
         n += 1
         dt = time.perf_counter() - t0
-        if dt >= seconds or n >= 200:
+        if dt >= seconds or n >= 2000:
             break
     return {"value": n / dt, "unit": "steps/s", "cores": cores, "kind": "port",
             "sample": f"{n} full-batch reverse steps of the oracle (torch-CPU fp32 port of the reference) in {dt:.1f} s"}
