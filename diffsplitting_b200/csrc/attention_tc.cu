@@ -43,6 +43,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// 2^x for x <= 0 (scores minus their row maximum): the bare SFU instruction; exp2f() wraps it in range scaling that the
+// softmax does not need (a flushed denormal is 0 either way after the bf16 rounding / in a sum of values <= 1)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -173,19 +180,33 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
                     if (c * 16 + i < kvalid) bm = fmaxf(bm, __uint_as_float(v[i]));
             }
             const float m_new = fmaxf(m_run, bm);
-            float sum = 0.f;
+            const float mneg = -m_new * p.scale_log2;
+            // four independent partial sums: one dependent FADD chain over 128 SFU results made this loop latency bound
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             for (int c = 0; c < AT_BK / 16; ++c) {
                 if (c * 16 >= kvalid) break;
                 tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+                if (c * 16 + 16 <= kvalid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c * 16 + i < kvalid) sum += exp2f((__uint_as_float(v[i]) - m_new) * p.scale_log2);
+                    for (int i = 0; i < 16; i += 4) {
+                        s0 += ex2_fast(fmaf(__uint_as_float(v[i]), p.scale_log2, mneg));
+                        s1 += ex2_fast(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, mneg));
+                        s2 += ex2_fast(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, mneg));
+                        s3 += ex2_fast(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, mneg));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c * 16 + i < kvalid) s0 += ex2_fast(fmaf(__uint_as_float(v[i]), p.scale_log2, mneg));
+                }
             }
-            l_run = l_run * exp2f((m_run - m_new) * p.scale_log2) + sum;    // first block: exp2(-inf) = 0
+            const float sum = (s0 + s1) + (s2 + s3);
+            l_run = l_run * ex2_fast((m_run - m_new) * p.scale_log2) + sum;    // first block: 2^(-inf) = 0
             m_run = m_new;
             if (!single) { tc_fence_before(); mbar_arrive(s_free); }
         }
         const uint32_t prow = (uint32_t)m * 128u;
+        const float mneg_run = -m_run * p.scale_log2;
         for (int j = 0; j < nkb; ++j) {                                     // pass B: P = exp(s - max) -> smem
             if (!single) {
                 mbar_wait(s_full, (uint32_t)it & 1u);
@@ -197,12 +218,21 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
 #pragma unroll 1
             for (int c = 0; c < AT_BK / 16; ++c) {
                 uint32_t pk[8];
-                if (c * 16 < kvalid) {
+                if (c * 16 + 16 <= kvalid) {
                     tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float e0 = (c * 16 + 2 * i < kvalid) ? exp2f((__uint_as_float(v[2 * i]) - m_run) * p.scale_log2) : 0.f;
-                        const float e1 = (c * 16 + 2 * i + 1 < kvalid) ? exp2f((__uint_as_float(v[2 * i + 1]) - m_run) * p.scale_log2) : 0.f;
+                        const float e0 = ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run));
+                        const float e1 = ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, mneg_run));
+                        __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                } else if (c * 16 < kvalid) {
+                    tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float e0 = (c * 16 + 2 * i < kvalid) ? ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run)) : 0.f;
+                        const float e1 = (c * 16 + 2 * i + 1 < kvalid) ? ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, mneg_run)) : 0.f;
                         __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
                         pk[i] = *reinterpret_cast<uint32_t*>(&h);
                     }

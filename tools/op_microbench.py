@@ -63,6 +63,13 @@ def main():
     L = _lib.lib()
     if kind in ("psnr", "tilebatch"):
         return data_path(kind, B, H, W)
+    if kind == "attn":                      # attn 0 0 0 0 B N C
+        N, Cc = H, W
+        qkv = torch.randn((B, N, 3 * Cc), generator=torch.Generator().manual_seed(0)).to(DEV).to(torch.bfloat16)
+        o = torch.empty((B, N, Cc), dtype=torch.bfloat16, device=DEV)
+        us = timed_graph(lambda: _lib.check(L.ds_attention_bf16(qkv.data_ptr(), o.data_ptr(), B, N, Cc, _lib.stream_ptr())), n=10, reps=5)
+        print(f"attention_tc B={B} N={N} C={Cc}: {us:.1f} us, {4.0 * B * N * N * Cc / us / 1e6:.1f} TFLOP/s (4 B N^2 C)")
+        return
     sp = lambda: _lib.stream_ptr()
     g = torch.Generator().manual_seed(0)
     w = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5).to(DEV)
