@@ -16,7 +16,11 @@
 //                                as [key][channel] rows, which IS the canonical MN-major SW128 layout)
 //   warps 2..5  : softmax / epilogue, one thread per query row (tcgen05.ld 32x32b)
 //
-// TMEM: columns [0,128) scores, [128,128+CV) output accumulator.  Everything accumulates in fp32; P is rounded to bf16
+// For C <= 256 the query panels are loaded ONCE and stay resident (the ring then carries keys only); with more than one key
+// block the scores are double-buffered in TMEM, so the tensor core computes block j+1 while the softmax warps work on
+// block j (an SM ingests only ~25-30 B/clk from L2: reloading Q per key block and serialising MMA and softmax made the
+// N = 4096 case 2x slower).
+// TMEM: one key block: columns [0,128) scores, [128,128+CV) output; otherwise [0,128) and [128,256) scores, [256,256+CV) output.  Everything accumulates in fp32; P is rounded to bf16
 // (values in [0,1]); the normalisation 1/l is applied to the fp32 accumulator in the epilogue.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -33,7 +37,7 @@ constexpr uint32_t AT_PANEL = 128 * 128;         // one 64-channel (or 64-key) p
 struct AttnTcParams {
     CUtensorMap map;                             // qkv as [3C, N, B] bf16, box {64, 128, 1}, SWIZZLE_128B
     __nv_bfloat16* out;
-    int B, N, C, CV, stages;
+    int B, N, C, CV, stages, q_res;
     float scale_log2;                            // log2(e) / sqrt(C)
     TraceSlot trace;
 };
@@ -70,21 +74,25 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
     const int vpanels = p.CV >> 6;
 
     const uint32_t base = (smem_u32(at_smem) + 1023u) & ~1023u;
-    const uint32_t ring = base;                                   // stages x (Q panel | K panel)
-    const uint32_t vbuf = ring + (uint32_t)p.stages * 2u * AT_PANEL;
+    const uint32_t qbuf = base;                                   // resident Q panels (q_res)
+    const uint32_t ring = base + (p.q_res ? (uint32_t)nchunk * AT_PANEL : 0u);   // stages x (K panel) or (Q panel | K panel)
+    const uint32_t slot = p.q_res ? AT_PANEL : 2u * AT_PANEL;
+    const uint32_t vbuf = ring + (uint32_t)p.stages * slot;
     const uint32_t pbuf = vbuf + (uint32_t)vpanels * AT_PANEL;    // P: 2 key panels
     const uint32_t bars = pbuf + 2u * AT_PANEL;
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(4 + s); };
-    const uint32_t s_full = bars + 64, s_free = bars + 72, p_full = bars + 80, pv_done = bars + 88, v_full = bars + 96;
-    const uint32_t tmem_slot = bars + 104;
-    const uint32_t tmem_cols = p.CV <= 128 ? 256u : 512u;
+    auto s_full = [&](int i) { return bars + 64u + 8u * (uint32_t)i; };        // score buffer i written
+    auto s_free = [&](int i) { return bars + 80u + 8u * (uint32_t)i; };        // score buffer i consumed
+    const uint32_t p_full = bars + 96, pv_done = bars + 104, v_full = bars + 112, q_full = bars + 120;
+    const uint32_t tmem_slot = bars + 128;
+    const uint32_t tmem_cols = single && p.CV <= 128 ? 256u : 512u;
 
     trace_begin(p.trace);
     if (warp == 0 && elect_one()) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(s_free(i), 128); }
+        mbar_init(q_full, 1);
         mbar_init(p_full, 128);
         mbar_init(pv_done, 1);
         mbar_init(v_full, 1);
@@ -96,26 +104,31 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128u;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + (single ? 128u : 256u);
     pdl_wait();
     pdl_trigger();
 
     if (warp == 0) {
         if (elect_one()) {
+            if (p.q_res) {
+                mbar_expect_tx(q_full, (uint32_t)nchunk * AT_PANEL);
+                for (int cc = 0; cc < nchunk; ++cc) tma_load_3d(qbuf + (uint32_t)cc * AT_PANEL, &p.map, q_full, cc * 64, q0, b);
+            }
             int u = 0;
-            auto load_qk = [&](int j) {
+            auto load_k = [&](int j) {
                 for (int cc = 0; cc < nchunk; ++cc, ++u) {
                     const int s = u % p.stages;
                     mbar_wait(empty_bar(s), (((uint32_t)(u / p.stages)) & 1u) ^ 1u);
-                    const uint32_t dst = ring + (uint32_t)s * 2u * AT_PANEL;
-                    mbar_expect_tx(full_bar(s), 2u * AT_PANEL);
-                    tma_load_3d(dst, &p.map, full_bar(s), cc * 64, q0, b);
-                    tma_load_3d(dst + AT_PANEL, &p.map, full_bar(s), p.C + cc * 64, j * AT_BK, b);
+                    const uint32_t dst = ring + (uint32_t)s * slot;
+                    mbar_expect_tx(full_bar(s), slot);
+                    if (!p.q_res) tma_load_3d(dst, &p.map, full_bar(s), cc * 64, q0, b);
+                    tma_load_3d(dst + (p.q_res ? 0u : AT_PANEL), &p.map, full_bar(s), p.C + cc * 64, j * AT_BK, b);
                 }
             };
-            for (int j = 0; j < nkb; ++j) load_qk(j);                      // pass A
-            for (int j = 0; j < nkb; ++j) {                                // pass B
-                if (!single) load_qk(j);
+            for (int j = 0; j < nkb; ++j) load_k(j);                       // pass A
+            if (!single) load_k(0);                                        // pass B: keys run one block ahead of V
+            for (int j = 0; j < nkb; ++j) {
+                if (!single && j + 1 < nkb) load_k(j + 1);
                 if (j > 0) mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);     // V buffer free
                 mbar_expect_tx(v_full, (uint32_t)vpanels * AT_PANEL);
                 for (int pc = 0; pc < vpanels; ++pc)
@@ -129,24 +142,29 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(p.CV >> 3) << 17) | ((128u >> 4) << 24);
             int u = 0, it = 0;
+            if (p.q_res) { mbar_wait(q_full, 0u); tc_fence_after(); }
             auto scores = [&]() {
-                if (it > 0) { mbar_wait(s_free, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+                const int sb = single ? 0 : (it & 1);                       // score buffer of this block
+                if (it >= 2) { mbar_wait(s_free(sb), (uint32_t)((it >> 1) - 1) & 1u); tc_fence_after(); }
                 for (int cc = 0; cc < nchunk; ++cc, ++u) {
                     const int s = u % p.stages;
                     mbar_wait(full_bar(s), ((uint32_t)(u / p.stages)) & 1u);
                     tc_fence_after();
-                    const uint32_t sa = ring + (uint32_t)s * 2u * AT_PANEL;
-                    const uint64_t qd = at_desc(sa, 16), kd = at_desc(sa + AT_PANEL, 16);
+                    const uint32_t sa = ring + (uint32_t)s * slot;
+                    const uint64_t qd = at_desc(p.q_res ? qbuf + (uint32_t)cc * AT_PANEL : sa, 16);
+                    const uint64_t kd = at_desc(p.q_res ? sa : sa + AT_PANEL, 16);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, (cc | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_s + (uint32_t)sb * 128u, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, (cc | k) ? 1u : 0u);
                     umma_commit(empty_bar(s));
                 }
-                umma_commit(s_full);
+                umma_commit(s_full(sb));
                 ++it;
             };
             for (int j = 0; j < nkb; ++j) scores();                        // pass A
-            for (int j = 0; j < nkb; ++j) {                                // pass B
-                if (!single) scores();
+            if (!single) scores();                                         // pass B: scores run one block ahead of P V
+            for (int j = 0; j < nkb; ++j) {
+                if (!single && j + 1 < nkb) scores();
                 mbar_wait(p_full, (uint32_t)j & 1u);
                 mbar_wait(v_full, (uint32_t)j & 1u);
                 tc_fence_after();
@@ -168,13 +186,15 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
         int it = 0;
         uint32_t v[16];
         for (int j = 0; j < nkb; ++j, ++it) {                               // pass A: exact max and denominator
-            mbar_wait(s_full, (uint32_t)it & 1u);
+            const int sb = single ? 0 : (it & 1);
+            const uint32_t tmem_sj = tmem_s + lane_addr + (uint32_t)sb * 128u;
+            mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const int kvalid = min(AT_BK, p.N - j * AT_BK);
             float bm = -INFINITY;
             for (int c = 0; c < AT_BK / 16; ++c) {
                 if (c * 16 >= kvalid) break;
-                tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+                tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if (c * 16 + i < kvalid) bm = fmaxf(bm, __uint_as_float(v[i]));
@@ -185,7 +205,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             for (int c = 0; c < AT_BK / 16; ++c) {
                 if (c * 16 >= kvalid) break;
-                tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+                tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
                 if (c * 16 + 16 <= kvalid) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
@@ -203,13 +223,15 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             const float sum = (s0 + s1) + (s2 + s3);
             l_run = l_run * ex2_fast((m_run - m_new) * p.scale_log2) + sum;    // first block: 2^(-inf) = 0
             m_run = m_new;
-            if (!single) { tc_fence_before(); mbar_arrive(s_free); }
+            if (!single) { tc_fence_before(); mbar_arrive(s_free(sb)); }
         }
         const uint32_t prow = (uint32_t)m * 128u;
         const float mneg_run = -m_run * p.scale_log2;
         for (int j = 0; j < nkb; ++j) {                                     // pass B: P = exp(s - max) -> smem
+            const int sb = single ? 0 : (it & 1);
+            const uint32_t tmem_sj = tmem_s + lane_addr + (uint32_t)sb * 128u;
             if (!single) {
-                mbar_wait(s_full, (uint32_t)it & 1u);
+                mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
                 tc_fence_after();
                 ++it;
             }
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             for (int c = 0; c < AT_BK / 16; ++c) {
                 uint32_t pk[8];
                 if (c * 16 + 16 <= kvalid) {
-                    tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+                    tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float e0 = ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run));
@@ -228,7 +250,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
                         pk[i] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 } else if (c * 16 < kvalid) {
-                    tmem_ld16(tmem_s + lane_addr + (uint32_t)(c * 16), v);
+                    tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float e0 = (c * 16 + 2 * i < kvalid) ? ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run)) : 0.f;
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(p_full);
-            if (!single) mbar_arrive(s_free);
+            if (!single) mbar_arrive(s_free(sb));
         }
         mbar_wait(pv_done, (uint32_t)(nkb - 1) & 1u);
         tc_fence_after();
@@ -311,9 +333,17 @@ int attn_tc_build(AttnTcPlan* plan, const void* qkv, void* out, int B, int N, in
     p->out = reinterpret_cast<__nv_bfloat16*>(out);
     p->B = B; p->N = N; p->C = C;
     p->CV = attn_pick_cv(C);
-    p->stages = C / 64 < 3 ? C / 64 : 3;
+    p->q_res = C <= 256;
+    const size_t fixed = (size_t)(p->q_res ? (C / 64) * AT_PANEL : 0) + (size_t)(p->CV / 64) * AT_PANEL + 2 * AT_PANEL;
+    const size_t slot_bytes = p->q_res ? AT_PANEL : 2 * AT_PANEL;
+    int stages = (int)((200 * 1024 - fixed) / slot_bytes);
+    const int want = p->q_res ? 4 : 3;
+    if (stages > want) stages = want;
+    if (N <= AT_BK && stages > C / 64) stages = C / 64;                          // one key block: nothing to prefetch
+    DS_REQUIRE(stages >= 1, "attention (bf16): no room for the operand ring at C=%d", C);
+    p->stages = stages;
     p->scale_log2 = (float)(1.4426950408889634 / sqrt((double)C));
-    plan->smem_bytes = (int)((size_t)p->stages * 2 * AT_PANEL + (size_t)(p->CV / 64) * AT_PANEL + 2 * AT_PANEL + 128 + 1024);
+    plan->smem_bytes = (int)(fixed + (size_t)p->stages * slot_bytes + 256 + 1024);
     plan->grid_x = cdiv(N, 128); plan->grid_y = C / p->CV; plan->grid_z = B;
     return DS_OK;
 }
