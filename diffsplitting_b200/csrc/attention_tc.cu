@@ -185,40 +185,47 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
         float m_run = -INFINITY, l_run = 0.f;
         int it = 0;
         uint32_t v[16];
+        uint32_t sv[AT_BK];
         for (int j = 0; j < nkb; ++j, ++it) {                               // pass A: exact max and denominator
             const int sb = single ? 0 : (it & 1);
             const uint32_t tmem_sj = tmem_s + lane_addr + (uint32_t)sb * 128u;
             mbar_wait(s_full(sb), (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const int kvalid = min(AT_BK, p.N - j * AT_BK);
-            float bm = -INFINITY;
-            for (int c = 0; c < AT_BK / 16; ++c) {
-                if (c * 16 >= kvalid) break;
-                tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
+            // the whole 128-column row in registers: 8 pipelined TMEM loads, one wait, one read of the scores
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c * 16 + i < kvalid) bm = fmaxf(bm, __uint_as_float(v[i]));
+            for (int c = 0; c < AT_BK / 16; ++c) tmem_ld16_nowait(tmem_sj + (uint32_t)(c * 16), reinterpret_cast<uint32_t(&)[16]>(sv[c * 16]));
+            tmem_ld_wait();
+            float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+            if (kvalid == AT_BK) {
+#pragma unroll
+                for (int i = 0; i < AT_BK; i += 4) {
+                    b0 = fmaxf(b0, __uint_as_float(sv[i]));
+                    b1 = fmaxf(b1, __uint_as_float(sv[i + 1]));
+                    b2 = fmaxf(b2, __uint_as_float(sv[i + 2]));
+                    b3 = fmaxf(b3, __uint_as_float(sv[i + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < AT_BK; ++i)
+                    if (i < kvalid) b0 = fmaxf(b0, __uint_as_float(sv[i]));
             }
-            const float m_new = fmaxf(m_run, bm);
+            const float m_new = fmaxf(m_run, fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)));
             const float mneg = -m_new * p.scale_log2;
             // four independent partial sums: one dependent FADD chain over 128 SFU results made this loop latency bound
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            for (int c = 0; c < AT_BK / 16; ++c) {
-                if (c * 16 >= kvalid) break;
-                tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
-                if (c * 16 + 16 <= kvalid) {
+            if (kvalid == AT_BK) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        s0 += ex2_fast(fmaf(__uint_as_float(v[i]), p.scale_log2, mneg));
-                        s1 += ex2_fast(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, mneg));
-                        s2 += ex2_fast(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, mneg));
-                        s3 += ex2_fast(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, mneg));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c * 16 + i < kvalid) s0 += ex2_fast(fmaf(__uint_as_float(v[i]), p.scale_log2, mneg));
+                for (int i = 0; i < AT_BK; i += 4) {
+                    s0 += ex2_fast(fmaf(__uint_as_float(sv[i]), p.scale_log2, mneg));
+                    s1 += ex2_fast(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, mneg));
+                    s2 += ex2_fast(fmaf(__uint_as_float(sv[i + 2]), p.scale_log2, mneg));
+                    s3 += ex2_fast(fmaf(__uint_as_float(sv[i + 3]), p.scale_log2, mneg));
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < AT_BK; ++i)
+                    if (i < kvalid) s0 += ex2_fast(fmaf(__uint_as_float(sv[i]), p.scale_log2, mneg));
             }
             const float sum = (s0 + s1) + (s2 + s3);
             l_run = l_run * ex2_fast((m_run - m_new) * p.scale_log2) + sum;    // first block: 2^(-inf) = 0
@@ -237,30 +244,20 @@ __global__ void __launch_bounds__(AT_THREADS) attention_tc_kernel(const __grid_c
             }
             if (j > 0) mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);         // P buffer free
             const int kvalid = min(AT_BK, p.N - j * AT_BK);
-#pragma unroll 1
+#pragma unroll
+            for (int c = 0; c < AT_BK / 16; ++c) tmem_ld16_nowait(tmem_sj + (uint32_t)(c * 16), reinterpret_cast<uint32_t(&)[16]>(sv[c * 16]));
+            tmem_ld_wait();
+#pragma unroll
             for (int c = 0; c < AT_BK / 16; ++c) {
                 uint32_t pk[8];
-                if (c * 16 + 16 <= kvalid) {
-                    tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float e0 = ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run));
-                        const float e1 = ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, mneg_run));
-                        __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-                        pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                } else if (c * 16 < kvalid) {
-                    tmem_ld16(tmem_sj + (uint32_t)(c * 16), v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float e0 = (c * 16 + 2 * i < kvalid) ? ex2_fast(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, mneg_run)) : 0.f;
-                        const float e1 = (c * 16 + 2 * i + 1 < kvalid) ? ex2_fast(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, mneg_run)) : 0.f;
-                        __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-                        pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = 0u;
+                for (int i = 0; i < 8; ++i) {
+                    float e0 = ex2_fast(fmaf(__uint_as_float(sv[c * 16 + 2 * i]), p.scale_log2, mneg_run));
+                    float e1 = ex2_fast(fmaf(__uint_as_float(sv[c * 16 + 2 * i + 1]), p.scale_log2, mneg_run));
+                    if (c * 16 + 2 * i >= kvalid) e0 = 0.f;
+                    if (c * 16 + 2 * i + 1 >= kvalid) e1 = 0.f;
+                    __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 // keys [16c, 16c+16) of row m: panel c/4, 16-byte chunks 2(c%4), 2(c%4)+1, XOR-swizzled with the row
                 const uint32_t pan = pbuf + (uint32_t)(c >> 2) * AT_PANEL + prow;
