@@ -69,14 +69,14 @@ def swish(x: Tensor) -> Tensor:
 def noise_level_encoding(level: Tensor, dim: int) -> Tensor:
     """sr3 unet.py:23-31.  level: (B,1) -> (B,1,dim)."""
     half = dim // 2
-    step = torch.arange(half, dtype=level.dtype) / half
+    step = torch.arange(half, dtype=level.dtype, device=level.device) / half
     enc = level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     return torch.cat([enc.sin(), enc.cos()], dim=-1)
 
 
 def time_encoding(t: Tensor, dim: int) -> Tensor:
     """ddpm unet.py:19-34.  t: any shape -> (*shape, dim)."""
-    inv_freq = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * (-math.log(10000) / dim))
+    inv_freq = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32, device=t.device) * (-math.log(10000) / dim))
     s = torch.outer(t.reshape(-1).float(), inv_freq)
     return torch.cat([s.sin(), s.cos()], dim=-1).reshape(*t.shape, dim)
 

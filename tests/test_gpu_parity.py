@@ -573,6 +573,55 @@ def test_mmse_tiled_evaluation_follows_the_notebook_loop():
     assert torch.equal(fast["target"], res["target"])
 
 
+def test_step_rate_against_torch_eager_on_the_same_gpu():
+    """'the existing Blackwell path' = the reference's PyTorch ops run eagerly on the B200 (cuDNN convs with
+    TF32 allowed, native_group_norm, ~225 launches per step).  The oracle IS those ops, so it is moved to the GPU and timed
+    beside the engine on the bench workload (hagen InDI 64x64, batch 16).  Printed with -s; the engine must be >= 3x faster
+    (measured ~2200 vs ~270 steps/s)."""
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
+    sd = U.random_state_dict(cfg, seed=1)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    B, T = 16, 1000
+    x0 = (torch.rand((B, 1, 64, 64), generator=torch.Generator().manual_seed(0)) * 2 - 1).to(DEV)
+    den = lambda xx, tt: U.unet_forward(sd_dev, cfg, xx, tt)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        def eager_steps(n):
+            x, t = x0.clone(), 1.0
+            for _ in range(n):
+                t32 = torch.Tensor([t]).to(DEV)                       # indi.py:62-69 with the H2D of :65
+                d = 1.0 / T
+                x = d / t32 * den(x, t32) + (1 - d / t32) * x + torch.randn_like(x) * (0.01 * (t32 - d))
+                t -= d
+            return x
+        with torch.no_grad():
+            eager_steps(5)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eager_steps(40)
+            e1.record()
+            torch.cuda.synchronize()
+        eager_rate = 40 / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    net = build(cfg, sd, "bf16")
+    indi = InDI(net, 32, channels=1, out_channel=1, conditional=False, val_schedule_opt={"n_timestep": T}).to(DEV)
+    indi.set_new_noise_schedule({"n_timestep": T}, DEV)
+    indi.inference(x0, num_timesteps=400)                     # builds the step graphs
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    indi.inference(x0, num_timesteps=400)
+    e1.record()
+    torch.cuda.synchronize()
+    rate = 400 / (e0.elapsed_time(e1) * 1e-3)
+    print(f"[same-GPU baseline] torch eager (TF32) {eager_rate:.0f} steps/s, engine {rate:.0f} steps/s, x{rate / eager_rate:.1f}")
+    assert rate >= 3 * eager_rate
+
+
 def test_final_psnr_within_point1_db_of_oracle():
     """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 16 InDI chain;
     T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation)."""
