@@ -1,5 +1,6 @@
 """Warm micro-benchmark of single operators through the C ABI (CUDA-graph of 50 launches, replayed): real per-launch
-GPU time without host launch overhead.  Usage: python tools/op_microbench.py [gnconv|conv_tc|gn|sampler] ca cb cout ks B H W"""
+GPU time without host launch overhead.  Usage: python tools/op_microbench.py [gnconv|conv_tc|gn|sampler] ca cb cout ks B H W
+       python tools/op_microbench.py attn 0 0 0 0 B N C | psnr 0 0 0 0 F H W | tilebatch 0 0 0 0 F H W"""
 import ctypes as C
 import os
 import sys
