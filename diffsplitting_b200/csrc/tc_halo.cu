@@ -379,12 +379,15 @@ static size_t g_halo_dbg_ctas = 0;
 // 2-D tiles for wide images (the flat tiles stage 130 + 2 (W + 2) positions for 128 outputs, or three separate segments of
 // 136; the 2-D ones 168 for 112) - always from DIFFSPLIT_B200_HALO_2D_MINW (138) columns on, and from 48 columns on when
 // the layer is many waves of tiles (throughput regime; in the latency regime of the 64 x 64 benchmark layers the 14 % extra
-// tiles cost more than the smaller patches save: 2017 vs 2097 steps/s)
+// tiles cost more than the smaller patches save: 2017 vs 2097 steps/s), from 96 columns on already at 5 waves
 static bool halo_use_2d(int B, int H, int W) {
     static int minw = -1;
     if (minw < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_2D_MINW"); minw = e ? atoi(e) : 138; }
     if (W >= minw || 130 + 2 * (W + 2) > 3 * HALO_SEG_PX) return true;       // the flat run is capped at 408 staged positions
-    return minw == 138 && W >= 48 && ((int64_t)B * (H + 2) * (W + 2) + 127) / 128 >= 8 * 148;
+    const int64_t flat_tiles = ((int64_t)B * (H + 2) * (W + 2) + 127) / 128;
+    // W >= 96: the flat tiles stage >= 2.5x the outputs, and 5 waves are enough for the 2-D tiles to win
+    // (8 x 64 x 128 x 128, 64 -> 64: 125 -> 79 us; hagen_joint_512: 5.29 -> 5.09 ms per step)
+    return minw == 138 && ((W >= 48 && flat_tiles >= 8 * 148) || (W >= 96 && flat_tiles >= 5 * 148));
 }
 static int64_t halo_m_tiles(int B, int H, int W) {
     if (halo_use_2d(B, H, W)) return (int64_t)B * ((H + HALO_TH - 1) / HALO_TH) * ((W + HALO_TW - 1) / HALO_TW);
