@@ -41,6 +41,49 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.TensorView) == 8 + 8 + 8 + 32
 
 
+def test_struct_sizes_match_a_c_compiler(tmp_path):
+    """sizeof of every struct of include/diffsplit_b200.h as gcc sees it == the ctypes mirrors in _lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    pairs = [("ds_unet_desc", _lib.UNetDesc), ("ds_tensor_view", _lib.TensorView), ("ds_op_profile", _lib.OpProfile),
+             ("ds_sampler_state", _lib.SamplerState), ("ds_step_args", _lib.StepArgs), ("ds_tile_norm", _lib.TileNorm),
+             ("ds_psnr_args", _lib.PsnrArgs)]
+    src = tmp_path / "sizes.c"
+    body = "".join(f'  printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs)
+    src.write_text('#include <stdio.h>\n#include "diffsplit_b200.h"\nint main(void) {\n' + body + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    for (cname, ct), size in zip(pairs, out):
+        assert C.sizeof(ct) == int(size), (cname, C.sizeof(ct), size)
+
+
+def test_time_predictor_keys_and_no_cpu_fallback():
+    """TimePredictor has exactly the reference's state_dict keys (model/ddpm_modules/time_predictor.py:13-36; the oracle's
+    seeded dict was loaded strictly into the reference class by make_golden) and refuses CPU tensors."""
+    from diffsplitting_b200.model.time_predictor import TimePredictor
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 64, with_time_emb=False)
+    m = TimePredictor(in_channel=1, out_channel=1, inner_channel=16, norm_groups=16, channel_mults=(1, 2, 4, 8), attn_res=(),
+                      res_blocks=1, dropout=0.2, image_size=64)
+    sd = U.time_predictor_state_dict(cfg, seed=1)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    assert not m.unet.with_time_emb
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 64, 64))
+
+
+def test_evaluate_host_logic():
+    from diffsplitting_b200.evaluate import _clamp_t, mixed_inputs
+    t = torch.arange(2 * 2 * 3 * 3, dtype=torch.float32).reshape(2, 2, 3, 3)
+    a, b = mixed_inputs(t, 0.25)
+    assert torch.equal(a, t[:, :1] * 0.75 + t[:, 1:2] * 0.25) and torch.equal(b, t[:, 1:2] * 0.75 + t[:, :1] * 0.25)
+    assert _clamp_t(1e-9) == 0.0 and _clamp_t(1.5) == 1.0 and _clamp_t(0.3) == 0.3
+
+
 def test_error_reporting_without_device():
     d = _lib.UNetDesc()
     d.variant = 7
@@ -233,12 +276,15 @@ def test_install_aliases():
 
     import diffsplitting_b200 as dsb
     saved = {k: sys.modules.get(k) for k in ("model", "model.networks", "data.tile_stitcher", "predtiler", "predtiler.dataset",
-                                             "model.model", "model.base_model", "data.tiling_manager")}
+                                             "model.model", "model.base_model", "data.tiling_manager", "model.ddpm_modules",
+                                             "model.ddpm_modules.time_predictor")}
     try:
         dsb.install()
         import model as M
         from predtiler.dataset import get_tile_manager as gtm
         assert M.create_model is dsb.model.create_model and gtm is get_tile_manager
+        from model.ddpm_modules.time_predictor import TimePredictor as TP
+        assert TP is dsb.model.time_predictor.TimePredictor
     finally:
         for k, v in saved.items():
             if v is None:
