@@ -43,7 +43,7 @@ class StepArgs(C.Structure):
                 ("step", C.c_int32), ("d_state", C.c_void_p), ("d_noise", C.c_void_p), ("seed", C.c_uint64),
                 ("offset", C.c_uint64), ("offset_inc", C.c_uint64), ("rng_threads", C.c_int32),
                 ("skip_rng_if_zero", C.c_int32), ("d_time_table", C.c_void_p), ("d_time_out", C.c_void_p),
-                ("time_len", C.c_int32)]
+                ("time_len", C.c_int32), ("per_sample_numel", C.c_int64)]
 
 
 class TileNorm(C.Structure):

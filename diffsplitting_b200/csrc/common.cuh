@@ -128,7 +128,7 @@ int launch_gn_stats(const float* a, int ca, const float* b, int cb, int B, int H
 float2* gn_stats_ptr(void* scratch, int B, int G);
 int launch_gn_apply_sums(const float* a, int ca, const float* b, int cb, const double* sums_a, const double* sums_b,
                          const float* gamma, const float* beta, void* out, int B, int HW, int G, int swish, int out_bf16,
-                         cudaStream_t st);
+                         void* scratch, cudaStream_t st);
 int launch_ch_sums(const float* x, int C, int B, int HW, double* out /*[B][C][2], pre-zeroed*/, cudaStream_t st);
 int gn_counters(unsigned** out);     // per-device buffer, allocated on first use (never inside graph capture)
 

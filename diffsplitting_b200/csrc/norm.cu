@@ -343,27 +343,128 @@ int launch_groupnorm(const float* a, int ca, const float* b, int cb, const float
     return DS_OK;
 }
 
-// ---- bf16 mode: statistics arrive as per-channel fp64 sums from the producers' epilogues; only the apply pass runs
+// ---- bf16 mode: statistics arrive as per-channel fp64 sums from the producers' epilogues; only the apply pass runs.
+// (1) gn_fold_kernel: ONE CTA per sample folds the replicated per-channel sums into (mean, rstd) per group (before this
+//     every apply CTA repeated the fold: C x 8 copies x 16 B per 16 KB of data, 0.29 TB/s on a 1536-channel tensor);
+// (2) gn_apply_tab_kernel: a CTA builds the per-channel (scale, shift) table of its sample in shared memory once and walks
+//     >= 32 K elements with 16-byte loads / 8- or 16-byte stores (no per-element integer division, no per-element
+//     gamma / beta / mean / rstd fetches).
+__global__ void __launch_bounds__(GN_THREADS) gn_fold_kernel(const double* __restrict__ sums_a, int ca,
+                                                              const double* __restrict__ sums_b, int cb, int HW, int G,
+                                                              float2* __restrict__ stats) {
+    const int C = ca + cb, cpg = C / G, bi = blockIdx.x, t = threadIdx.x, B = gridDim.x;
+    __shared__ double g_s[GN_MAX_GROUPS], g_q[GN_MAX_GROUPS];
+    if (t < G) { g_s[t] = 0.0; g_q[t] = 0.0; }
+    pdl_wait();
+    pdl_trigger();
+    __syncthreads();
+    for (int c = t; c < C; c += GN_THREADS) {
+        const bool first = c < ca;
+        const double2* src = reinterpret_cast<const double2*>(first ? sums_a + ((size_t)bi * ca + c) * 2
+                                                                    : sums_b + ((size_t)bi * cb + (c - ca)) * 2);
+        const size_t cstride = (size_t)B * (first ? ca : cb);
+        double2 v[GN_SUM_COPIES];
+#pragma unroll
+        for (int k = 0; k < GN_SUM_COPIES; ++k) v[k] = src[k * cstride];
+        double sm = 0.0, sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < GN_SUM_COPIES; ++k) { sm += v[k].x; sq += v[k].y; }
+        atomicAdd(&g_s[c / cpg], sm);
+        atomicAdd(&g_q[c / cpg], sq);
+    }
+    __syncthreads();
+    if (t < G) {
+        const double n = (double)HW * cpg;
+        const double mean = g_s[t] / n;
+        double var = g_q[t] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[(size_t)bi * G + t] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+    }
+}
+
+constexpr int GN_TAB_MAX_C = 4096;
+
+template <typename Tout>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_tab_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
+                                                                   int cb, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, Tout* __restrict__ out, int HW,
+                                                                   int G, int nchunk, int swish, const float2* __restrict__ stats) {
+    extern __shared__ float2 gn_tab[];                 // [C] (scale, shift):  y = x * scale + shift
+    const int C = ca + cb, cpg = C / G, bi = blockIdx.y, t = threadIdx.x;
+    constexpr bool kFast = sizeof(Tout) == 2;
+    pdl_wait();
+    pdl_trigger();
+    for (int c = t; c < C; c += GN_THREADS) {
+        // the reference's order: ((x - mean) * rstd) * gamma + beta; folded into one fma per element (<= 2 ulp of the
+        // normalised value, far below the bf16 / tf32 operand rounding that follows)
+        const float2 st = stats[(size_t)bi * G + c / cpg];
+        const float sc = st.y * gamma[c];
+        gn_tab[c] = make_float2(sc, fmaf(-st.x, sc, beta[c]));
+    }
+    __syncthreads();
+    const size_t base = (size_t)bi * HW;
+    const int q = C >> 2;
+    const int64_t total = (int64_t)HW * q;
+    const int64_t v0 = total * blockIdx.x / nchunk, v1 = total * (blockIdx.x + 1) / nchunk;
+    auto one = [&](int64_t v) {
+        const int p = (int)(v / q), c = (int)(v - (int64_t)p * q) * 4;
+        const float4 x = load4(a, ca, b, cb, base + p, c);
+        const float4 t0 = *reinterpret_cast<const float4*>(gn_tab + c), t1 = *reinterpret_cast<const float4*>(gn_tab + c + 2);
+        float y[4] = {fmaf(x.x, t0.x, t0.y), fmaf(x.y, t0.z, t0.w), fmaf(x.z, t1.x, t1.y), fmaf(x.w, t1.z, t1.w)};
+        if (swish) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = swish_f(y[j], kFast);
+        }
+        Tout* o = out + (base + p) * C + c;
+        if constexpr (sizeof(Tout) == 2) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]), hi = __floats2bfloat162_rn(y[2], y[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(o) = pk;
+        } else {
+            *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    };
+    int64_t v = v0 + t;
+    for (; v + 3 * GN_THREADS < v1; v += 4 * GN_THREADS) {      // four independent 16-byte loads in flight
+        one(v); one(v + GN_THREADS); one(v + 2 * GN_THREADS); one(v + 3 * GN_THREADS);
+    }
+    for (; v < v1; v += GN_THREADS) one(v);
+}
+
 int launch_gn_apply_sums(const float* a, int ca, const float* b, int cb, const double* sums_a, const double* sums_b,
                          const float* gamma, const float* beta, void* out, int B, int HW, int G, int swish, int out_bf16,
-                         cudaStream_t st) {
+                         void* scratch, cudaStream_t st) {
     const int C = ca + cb;
     DS_REQUIRE(G >= 1 && G <= GN_MAX_GROUPS && C % G == 0, "groupnorm: %d channels not divisible into %d groups", C, G);
     DS_REQUIRE((int64_t)HW * C < (1ll << 31), "groupnorm: sample too large");
-    const bool vec = gn_vec_ok(a, ca, b, cb, gamma, beta);
+    DS_REQUIRE(scratch, "groupnorm: scratch missing");
+    float2* stats = gn_stats_ptr(scratch, B, G);
+    launch_pdl(gn_fold_kernel, dim3(B), dim3(GN_THREADS), 0, st, sums_a, ca, sums_b, cb, HW, G, stats);
+    DS_CHECK_LAUNCH("gn_fold");
     const int64_t total = (int64_t)HW * C;
+    typedef __nv_bfloat16 bf;
+    const bool tab = (ca % 4 == 0) && (cb % 4 == 0) && C <= GN_TAB_MAX_C && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                     (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    if (tab) {
+        // >= 32 K elements per CTA (the table costs C entries), at least ~4 CTAs per SM when the tensor allows it
+        int nchunk = (int)((total + 32767) / 32768);
+        if (nchunk < 1) nchunk = 1;
+        if (nchunk > 65535) nchunk = 65535;
+        const dim3 grid(nchunk, B);
+        const size_t smem = (size_t)C * sizeof(float2);
+        if (out_bf16) launch_pdl(gn_apply_tab_kernel<bf>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, (const float2*)stats);
+        else launch_pdl(gn_apply_tab_kernel<float>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, (const float2*)stats);
+        DS_CHECK_LAUNCH("gn_apply_tab");
+        return DS_OK;
+    }
     int nchunk = (int)((total + 4095) / 4096);
     if (nchunk > 65535) nchunk = 65535;
     if (nchunk < 1) nchunk = 1;
     const dim3 grid(nchunk, B);
-    typedef __nv_bfloat16 bf;
-    if (out_bf16) {
-        if (vec) launch_pdl(gn_apply_kernel<bf, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
-        else launch_pdl(gn_apply_kernel<bf, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
-    } else {
-        if (vec) launch_pdl(gn_apply_kernel<float, true>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
-        else launch_pdl(gn_apply_kernel<float, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, nullptr, sums_a, sums_b);
-    }
+    if (out_bf16) launch_pdl(gn_apply_kernel<bf, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, (const float2*)stats, nullptr, nullptr);
+    else launch_pdl(gn_apply_kernel<float, false>, grid, dim3(GN_THREADS), 0, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, (const float2*)stats, nullptr, nullptr);
     DS_CHECK_LAUNCH("gn_apply");
     return DS_OK;
 }

@@ -62,9 +62,30 @@ __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t subseq, uint64
 
 constexpr int ST_THREADS = 256;
 
+// one element of the update, every product / sum individually rounded in the reference's order
+__device__ __forceinline__ float step_update(float x, float n, float z, float c0, float c1, float c2, float c3, float c4, int mode,
+                                             int clip) {
+    float x0;
+    if (mode == 0) {
+        x0 = __fsub_rn(__fmul_rn(c0, x), __fmul_rn(c1, n));
+        if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    } else {
+        x0 = n;
+    }
+    const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, x));
+    return __fadd_rn(mean, __fmul_rn(z, c4));
+}
+
+// VEC: one CUDA thread = FOUR consecutive torch threads j .. j+3 (four Philox calls): for each of torch's four unrolled lanes
+// ii the four results are the consecutive elements j + T ii + 4 T r .. +3, i.e. one 16-byte load of x_t, one of the network
+// output and one 16-byte store, all eight loads of a work item in flight together (the scalar mapping issued 4-byte accesses
+// at stride T).  The element <-> (thread, lane, round) mapping and the arithmetic are unchanged: bit-identical results.
+template <bool VEC>
 __global__ void __launch_bounds__(ST_THREADS) sampler_step_kernel(const ds_step_args a) {
-    const int k = a.d_state ? a.d_state->step : a.step;
+    int k = a.d_state ? a.d_state->step : a.step;
+    if (k >= a.n_steps) k = a.n_steps - 1;                  // a loop run past its table repeats the last row instead of reading beyond it
     const float* cf = a.d_coef + (size_t)k * 5;
+    const bool per_sample = a.per_sample_numel > 0;         // rows indexed by sample (ddpm p_sample with unequal t)
     const float c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3], c4 = cf[4];
     const uint64_t offset = a.d_state ? a.d_state->offset : a.offset;
     const uint64_t seed = a.d_state ? a.d_state->seed : a.seed;
@@ -73,45 +94,111 @@ __global__ void __launch_bounds__(ST_THREADS) sampler_step_kernel(const ds_step_
     const int64_t rounds = gen ? (a.numel - 1) / (4 * T) + 1 : 0;
 
     auto update = [&](int64_t i, float z) {
-        const float x = a.d_x[i];
-        const float n = a.d_net[i];
-        float x0;
-        if (a.mode == 0) {
-            x0 = __fsub_rn(__fmul_rn(c0, x), __fmul_rn(c1, n));
-            if (a.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        if (per_sample) {
+            const float* r = a.d_coef + (size_t)(i / a.per_sample_numel) * 5;
+            a.d_out[i] = step_update(a.d_x[i], a.d_net[i], z, __ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), __ldg(r + 4), a.mode, a.clip);
         } else {
-            x0 = n;
+            a.d_out[i] = step_update(a.d_x[i], a.d_net[i], z, c0, c1, c2, c3, c4, a.mode, a.clip);
         }
-        const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, x));
-        a.d_out[i] = __fadd_rn(mean, __fmul_rn(z, c4));
     };
 
     // Launched with programmatic stream serialisation: everything above and the first Philox / Box-Muller evaluation (the
     // bulk of this kernel's arithmetic; it needs only the loop state the PREVIOUS step's update left behind) overlap the
     // tail of the UNet's last conv; x_t and the network output are touched only after the wait.
-    const int64_t items = rounds * T;
     const int64_t w_first = blockIdx.x * (int64_t)ST_THREADS + threadIdx.x;
-    float4 z_first = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gen && w_first < items) {
-        const int64_t r = w_first / T, j = w_first - r * T;
-        z_first = normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
-    }
-    pdl_trigger();
-    pdl_wait();
-    if (gen) {
-        // work item = (round r, torch thread j): one Philox call -> 4 elements
-        for (int64_t w = w_first; w < items; w += (int64_t)gridDim.x * ST_THREADS) {
-            const int64_t r = w / T, j = w - r * T;
-            const float4 z = w == w_first ? z_first : normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
-            const int64_t i0 = j + 4 * T * r;
-            if (i0 < a.numel) update(i0, z.x);
-            if (i0 + T < a.numel) update(i0 + T, z.y);
-            if (i0 + 2 * T < a.numel) update(i0 + 2 * T, z.z);
-            if (i0 + 3 * T < a.numel) update(i0 + 3 * T, z.w);
+    if (VEC) {
+        const int64_t Tq = T >> 2;                          // T = 256 * grid: a multiple of 4
+        const int64_t items = rounds * Tq;
+        float4 zf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) zf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gen && w_first < items) {
+            const int64_t r = w_first / Tq, q = w_first - r * Tq;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) zf[u] = normal4(seed, (uint64_t)(4 * q + u), offset / 4 + (uint64_t)r);
+        }
+        pdl_trigger();
+        pdl_wait();
+        if (gen) {
+            for (int64_t w = w_first; w < items; w += (int64_t)gridDim.x * ST_THREADS) {
+                const int64_t r = w / Tq, q = w - r * Tq;
+                float4 z[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) z[u] = w == w_first ? zf[u] : normal4(seed, (uint64_t)(4 * q + u), offset / 4 + (uint64_t)r);
+                const int64_t i0 = 4 * q + 4 * T * r;
+                float4 xv[4], nv[4];
+                bool full[4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int64_t i = i0 + ii * T;
+                    full[ii] = i + 3 < a.numel;
+                    if (full[ii]) {
+                        xv[ii] = *reinterpret_cast<const float4*>(a.d_x + i);
+                        nv[ii] = *reinterpret_cast<const float4*>(a.d_net + i);
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int64_t i = i0 + ii * T;
+                    const float zz[4] = {ii == 0 ? z[0].x : ii == 1 ? z[0].y : ii == 2 ? z[0].z : z[0].w,
+                                         ii == 0 ? z[1].x : ii == 1 ? z[1].y : ii == 2 ? z[1].z : z[1].w,
+                                         ii == 0 ? z[2].x : ii == 1 ? z[2].y : ii == 2 ? z[2].z : z[2].w,
+                                         ii == 0 ? z[3].x : ii == 1 ? z[3].y : ii == 2 ? z[3].z : z[3].w};
+                    if (full[ii]) {
+                        float4 o;
+                        o.x = step_update(xv[ii].x, nv[ii].x, zz[0], c0, c1, c2, c3, c4, a.mode, a.clip);
+                        o.y = step_update(xv[ii].y, nv[ii].y, zz[1], c0, c1, c2, c3, c4, a.mode, a.clip);
+                        o.z = step_update(xv[ii].z, nv[ii].z, zz[2], c0, c1, c2, c3, c4, a.mode, a.clip);
+                        o.w = step_update(xv[ii].w, nv[ii].w, zz[3], c0, c1, c2, c3, c4, a.mode, a.clip);
+                        *reinterpret_cast<float4*>(a.d_out + i) = o;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (i + u < a.numel) update(i + u, zz[u]);
+                    }
+                }
+            }
+        } else {
+            const int64_t n4 = a.numel >> 2;
+            for (int64_t v = w_first; v < n4; v += (int64_t)gridDim.x * ST_THREADS) {
+                const float4 xv = *reinterpret_cast<const float4*>(a.d_x + 4 * v);
+                const float4 nv = *reinterpret_cast<const float4*>(a.d_net + 4 * v);
+                float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.d_noise) zv = *reinterpret_cast<const float4*>(a.d_noise + 4 * v);
+                float4 o;
+                o.x = step_update(xv.x, nv.x, zv.x, c0, c1, c2, c3, c4, a.mode, a.clip);
+                o.y = step_update(xv.y, nv.y, zv.y, c0, c1, c2, c3, c4, a.mode, a.clip);
+                o.z = step_update(xv.z, nv.z, zv.z, c0, c1, c2, c3, c4, a.mode, a.clip);
+                o.w = step_update(xv.w, nv.w, zv.w, c0, c1, c2, c3, c4, a.mode, a.clip);
+                *reinterpret_cast<float4*>(a.d_out + 4 * v) = o;
+            }
+            if (w_first == 0)
+                for (int64_t i = n4 << 2; i < a.numel; ++i) update(i, a.d_noise ? a.d_noise[i] : 0.0f);
         }
     } else {
-        for (int64_t i = blockIdx.x * (int64_t)ST_THREADS + threadIdx.x; i < a.numel; i += (int64_t)gridDim.x * ST_THREADS)
-            update(i, a.d_noise ? a.d_noise[i] : 0.0f);
+        const int64_t items = rounds * T;
+        float4 z_first = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gen && w_first < items) {
+            const int64_t r = w_first / T, j = w_first - r * T;
+            z_first = normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
+        }
+        pdl_trigger();
+        pdl_wait();
+        if (gen) {
+            // work item = (round r, torch thread j): one Philox call -> 4 elements
+            for (int64_t w = w_first; w < items; w += (int64_t)gridDim.x * ST_THREADS) {
+                const int64_t r = w / T, j = w - r * T;
+                const float4 z = w == w_first ? z_first : normal4(seed, (uint64_t)j, offset / 4 + (uint64_t)r);
+                const int64_t i0 = j + 4 * T * r;
+                if (i0 < a.numel) update(i0, z.x);
+                if (i0 + T < a.numel) update(i0 + T, z.y);
+                if (i0 + 2 * T < a.numel) update(i0 + 2 * T, z.z);
+                if (i0 + 3 * T < a.numel) update(i0 + 3 * T, z.w);
+            }
+        } else {
+            for (int64_t i = w_first; i < a.numel; i += (int64_t)gridDim.x * ST_THREADS)
+                update(i, a.d_noise ? a.d_noise[i] : 0.0f);
+        }
     }
 
     // last block to finish advances the device-side loop state (graph replay needs no host scalars)
@@ -181,12 +268,23 @@ extern "C" int ds_sampler_step(const ds_step_args* a, void* stream) {
     using namespace ds;
     DS_REQUIRE(a && a->d_x && a->d_net && a->d_out && a->numel > 0 && a->d_coef, "sampler_step: null argument");
     DS_REQUIRE(a->mode == 0 || a->mode == 1, "sampler_step: mode %d", a->mode);
+    DS_REQUIRE(a->n_steps > 0, "sampler_step: n_steps %d", a->n_steps);
     DS_REQUIRE(a->d_state || (a->step >= 0 && a->step < a->n_steps), "sampler_step: step %d outside [0,%d)", a->step, a->n_steps);
     DS_REQUIRE(a->d_noise || a->rng_threads > 0, "sampler_step: rng_threads must be set when noise is generated");
     DS_REQUIRE(!a->d_time_out || (a->d_time_table && a->d_state), "sampler_step: d_time_out needs d_time_table and d_state");
-    int64_t work = a->numel;
-    if (!a->d_noise) work = ((a->numel - 1) / (4 * (int64_t)a->rng_threads) + 1) * (int64_t)a->rng_threads;
-    DS_CHECK_CUDA(launch_pdl(sampler_step_kernel, dim3((unsigned)step_grid(work)), dim3(ST_THREADS), 0, (cudaStream_t)stream, *a));
+    DS_REQUIRE(a->per_sample_numel == 0 || (!a->d_state && a->step == 0 && !a->skip_rng_if_zero && a->per_sample_numel > 0 &&
+                                            a->numel % a->per_sample_numel == 0 && a->numel / a->per_sample_numel <= a->n_steps),
+               "sampler_step: per-sample rows need d_state == NULL, step 0, skip_rng_if_zero 0 and numel = n_steps * per_sample_numel");
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = a->per_sample_numel == 0 && al16(a->d_x) && al16(a->d_net) && al16(a->d_out) && (!a->d_noise || al16(a->d_noise)) &&
+                     (a->d_noise || a->rng_threads % 4 == 0);
+    int64_t work;
+    if (a->d_noise) work = vec ? (a->numel + 3) / 4 : a->numel;
+    else work = ((a->numel - 1) / (4 * (int64_t)a->rng_threads) + 1) * (int64_t)(vec ? a->rng_threads / 4 : a->rng_threads);
+    if (vec)
+        DS_CHECK_CUDA(launch_pdl(sampler_step_kernel<true>, dim3((unsigned)step_grid(work)), dim3(ST_THREADS), 0, (cudaStream_t)stream, *a));
+    else
+        DS_CHECK_CUDA(launch_pdl(sampler_step_kernel<false>, dim3((unsigned)step_grid(work)), dim3(ST_THREADS), 0, (cudaStream_t)stream, *a));
     return DS_OK;
 }
 

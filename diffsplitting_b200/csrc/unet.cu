@@ -670,7 +670,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
             continue;
         }
         run = 0;
-        launches += (o.kind == OP_GN && !P.tc) ? 2 : 1;                          // fp32 GroupNorm = statistics + apply
+        launches += o.kind == OP_GN ? 2 : 1;                                      // GroupNorm = statistics (or their fold) + apply
     }
     if (P.tc && p->stats_bytes) ++launches;                                      // the statistics-arena memset
     p->launches = launches;
@@ -1032,7 +1032,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
             case OP_GN:
                 if (tc)
                     rc = launch_gn_apply_sums(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, sums(o.sums_a), sums(o.sums_b), n->wp(o.gw->w),
-                                              n->wp(o.gw->b), ptr(o.dst_b16), B, o.HW, n->d.norm_groups, o.swish, 1, st);
+                                              n->wp(o.gw->b), ptr(o.dst_b16), B, o.HW, n->d.norm_groups, o.swish, 1, gn_scratch, st);
                 else
                     rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
                                           n->d.norm_groups, o.swish, gn_scratch, counters, 0, st);

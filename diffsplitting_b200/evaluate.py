@@ -25,6 +25,18 @@ def _clamp_t(t, eps=1e-6):
     return 0.0 if t < eps else (1.0 if t > 1 else t)
 
 
+def _predict(sampler, inp, t, num_timesteps, channel):
+    """Channel ``channel`` of ``sampler.inference`` for every tile of the batch.  t <= 0 is the clean end of the InDI path
+    (the reference computes 0 / 0 there): the input already is the prediction."""
+    if hasattr(sampler, "indi1") and (t <= 0.0 or t >= 1.0):
+        # JointIndi at an end point: one of its two loops would start at t = 0; only the loop whose channel is kept runs
+        return _predict(sampler.indi1, inp, t, num_timesteps, 0) if channel == 0 else _predict(sampler.indi2, inp, 1 - t, num_timesteps, 0)
+    if t <= 0.0:
+        return inp[:, 0]
+    out = sampler.inference(inp, continuous=False, t_float_start=t, num_timesteps=num_timesteps, all_samples=True)
+    return out[:, channel]
+
+
 def mmse_predict_tiles(joint_model, tiled, mixing_t=0.5, num_timesteps=5, mmse_count=5, chunk=1, t_float_start=None,
                        replay_reference_rng=False):
     """Returns (mmse prediction, targets), both (N,2,P,P) CUDA fp32 for all N tiles of ``tiled``.
@@ -50,14 +62,16 @@ def mmse_predict_tiles(joint_model, tiled, mixing_t=0.5, num_timesteps=5, mmse_c
             else:
                 ts = tuple(t(i) if callable(t) else t for t, i in zip(t_float_start, (inp0, inp1)))
             t0, t1 = _clamp_t(ts[0]), _clamp_t(ts[1])
+            # continuous=False returns only the LAST batch element (the reference's `ret_img[-1:]`, indi.py:95): the batched
+            # path asks for every element's final state (`all_samples`), so chunk > 1 predicts every tile of the chunk
             if replay_reference_rng:
-                p0 = joint_model.inference(inp0, continuous=False, t_float_start=t0, num_timesteps=num_timesteps)[:, 0]
-                p1 = joint_model.inference(inp1, continuous=False, t_float_start=t1, num_timesteps=num_timesteps)[:, 1]
+                p0 = _predict(joint_model, inp0, t0, num_timesteps, 0)
+                p1 = _predict(joint_model, inp1, t1, num_timesteps, 1)
             else:       # JointIndi.inference :131-135: channel 0 = indi1 at t, channel 1 = indi2 at 1 - t
-                p0 = joint_model.indi1.inference(inp0, continuous=False, t_float_start=t0, num_timesteps=num_timesteps)[:, 0]
-                p1 = joint_model.indi2.inference(inp1, continuous=False, t_float_start=1 - t1, num_timesteps=num_timesteps)[:, 0]
-            pred[first:first + n, 0] += p0 / mmse_count
-            pred[first:first + n, 1] += p1 / mmse_count
+                p0 = _predict(joint_model.indi1, inp0, t0, num_timesteps, 0)
+                p1 = _predict(joint_model.indi2, inp1, 1 - t1, num_timesteps, 0)
+            pred[first:first + n, 0].add_(p0 / mmse_count)
+            pred[first:first + n, 1].add_(p1 / mmse_count)
     return pred, targets
 
 

@@ -124,6 +124,11 @@ class _Engine:
             raise ValueError(f"UNet out_channel {net.out_channel} != sampler state channels {C_state}")
         _, self.dev_index = _generator(device)
         self.rng_threads, self.rng_inc = _rng_geometry(self.numel, self.dev_index)
+        # the captured graphs bake the workspace address: the engine owns a reference, so the tensor outlives any eviction
+        # from the net's workspace cache
+        self.ws = net.workspace(B, H, W, None, device)
+        self.T = 0
+        self.steps_done = 0
 
     def load_tables(self, coef: torch.Tensor, ttab: torch.Tensor):
         T = coef.shape[0]
@@ -135,11 +140,13 @@ class _Engine:
             self.multi = None
         self.T = T
         self.coef[:T].copy_(coef, non_blocking=False)
-        self.ttab[:T].copy_(ttab[:T], non_blocking=False)
+        self.ttab[:T + 1].copy_(ttab[:T + 1], non_blocking=False)     # entry T = the time the last step leaves behind
         self.time.fill_(float(ttab[0]))
+        self.steps_done = 0
 
     def reset_state(self, seed, offset):
         st = _lib.SamplerState(seed=seed, offset=offset, step=0, done=0)
+        self.steps_done = 0
         # pageable source: the copy is staged before returning, so back-to-back calls cannot race on it
         self.state.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
 
@@ -151,9 +158,9 @@ class _Engine:
 
     def _enqueue_step(self):
         if self.cond is None:
-            self.net.forward_into(self.eps, self.x, None, self.time)
+            self.net.forward_into(self.eps, self.x, None, self.time, ws=self.ws)
         else:
-            self.net.forward_into(self.eps, self.cond, self.x, self.time)
+            self.net.forward_into(self.eps, self.cond, self.x, self.time, ws=self.ws)
         a = _lib.StepArgs()
         a.d_x = self.x.data_ptr(); a.d_net = self.eps.data_ptr(); a.d_out = self.x.data_ptr()
         a.numel = self.numel; a.mode = self.mode; a.clip = self.clip
@@ -163,7 +170,16 @@ class _Engine:
         a.d_time_table = self.ttab.data_ptr(); a.d_time_out = self.time.data_ptr(); a.time_len = self.time.numel()
         _lib.check(_lib.lib().ds_sampler_step(C.byref(a), _lib.stream_ptr()))
 
+    def _account(self, n):
+        self.steps_done += n
+        if self.steps_done > self.T:
+            raise RuntimeError(f"sampler engine: {self.steps_done} steps requested from a table of {self.T} rows")
+
     def step(self):
+        self._account(1)
+        self._step()
+
+    def _step(self):
         if self.graph is not None:
             self.graph.replay()
             return
@@ -178,8 +194,9 @@ class _Engine:
         """n consecutive reverse steps; whole multiples of G go through the G-step graph."""
         if n <= 0:
             return
+        self._account(n)
         if self.graph is None:
-            self.step()
+            self._step()
             n -= 1
         G = _graph_steps()
         if self.graph is not None and G > 1 and n >= G:
@@ -193,10 +210,53 @@ class _Engine:
                 self.multi[1].replay()
                 n -= G
         for _ in range(n):
-            self.step()
+            self._step()
 
     def launches_per_step(self):
         return self.net.launches(self.B, self.H, self.W) + 1
+
+
+class _PairEngine:
+    """Two independent engines (the two UNets of JointIndi, joint_indi.py:132-135) stepped together: every step forks the
+    second engine onto a side stream, so ONE CUDA graph holds both branches and the GPU runs them concurrently."""
+
+    def __init__(self, e1: _Engine, e2: _Engine):
+        self.e1, self.e2 = e1, e2
+        self.side = torch.cuda.Stream(device=e1.device)
+        self.graph = None
+        self.multi = None
+
+    def _enqueue_step(self):
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        self.e1._enqueue_step()
+        with torch.cuda.stream(self.side):
+            self.e2._enqueue_step()
+        main.wait_stream(self.side)
+
+    _step = _Engine._step
+
+    def run(self, n):
+        if n <= 0:
+            return
+        self.e1._account(n)
+        self.e2._account(n)
+        if self.graph is None:
+            self._step()
+            n -= 1
+        G = _graph_steps()
+        if self.graph is not None and G > 1 and n >= G:
+            if self.multi is None or self.multi[0] != G:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(G):
+                        self._enqueue_step()
+                self.multi = (G, g)
+            while n >= G:
+                self.multi[1].replay()
+                n -= G
+        for _ in range(n):
+            self._step()
 
 
 class _SamplerBase(nn.Module):
@@ -276,23 +336,36 @@ class _GaussianDiffusion(_SamplerBase):
 
     @torch.no_grad()
     def p_sample(self, x, t, clip_denoised=True, repeat_noise=False, condition_x=None, noise=None):
-        """One reverse step x_t -> x_{t-1}.  ``t``: python int (sr3) or a (B,) tensor of equal entries (ddpm).
+        """One reverse step x_t -> x_{t-1}.  ``t``: python int (sr3) or a (B,) tensor (ddpm: ``extract`` gathers the
+        buffers per sample, ddpm_modules/diffusion.py:64-67,195-203 - entries may differ within the batch).
         ``noise`` (extension): inject z instead of drawing it from the generator."""
         _lib.require_cuda(x, "p_sample input")
+        B = x.shape[0]
+        T = self.num_timesteps
+        per_sample = None
         if torch.is_tensor(t):
-            tv = t.reshape(-1)
-            if not bool((tv == tv[0]).all()):
-                raise NotImplementedError("per-sample timesteps differ within the batch")
-            t = int(tv[0])
+            tv = t.reshape(-1).to("cpu", torch.long)
+            if tv.numel() not in (1, B):
+                raise ValueError(f"p_sample: t must have 1 or {B} entries")
+            if bool((tv == tv[0]).all()):
+                t = int(tv[0])
+            else:
+                per_sample = tv
         net = self.denoise_fn
         net.commit()
-        B = x.shape[0]
         dev = x.device
-        T = self.num_timesteps
         coef, ttab = self._coef()
-        k = T - 1 - t
         x = x.float().contiguous()
-        tvec = torch.full((self._time_len(B),), float(ttab[k]), dtype=torch.float32, device=dev)
+        if per_sample is None:
+            k = T - 1 - t
+            tvec = torch.full((self._time_len(B),), float(ttab[k]), dtype=torch.float32, device=dev)
+            dcoef = coef[k:k + 1].to(dev)
+        else:
+            if int(per_sample.min()) < 0 or int(per_sample.max()) >= T:
+                raise ValueError("p_sample: t outside [0, num_timesteps)")
+            ks = T - 1 - per_sample
+            tvec = ttab[ks].to(dev)
+            dcoef = coef[ks].contiguous().to(dev)                 # one row per sample
         eps = torch.empty((B, net.out_channel) + tuple(x.shape[2:]), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             if condition_x is not None:
@@ -300,20 +373,22 @@ class _GaussianDiffusion(_SamplerBase):
             else:
                 net.forward_into(eps, x, None, tvec)
             out = torch.empty_like(x)
-            dcoef = coef[k:k + 1].to(dev)
             gen, idx = _generator(dev)
             threads, inc = _rng_geometry(x.numel(), idx)
             a = _lib.StepArgs()
             a.d_x = x.data_ptr(); a.d_net = eps.data_ptr(); a.d_out = out.data_ptr(); a.numel = x.numel()
-            a.mode = 0; a.clip = int(bool(clip_denoised)); a.d_coef = dcoef.data_ptr(); a.n_steps = 1; a.step = 0
+            a.mode = 0; a.clip = int(bool(clip_denoised)); a.d_coef = dcoef.data_ptr(); a.n_steps = dcoef.shape[0]; a.step = 0
             a.d_state = None
             a.seed = gen.initial_seed(); a.offset = gen.get_offset(); a.offset_inc = inc; a.rng_threads = threads
             a.skip_rng_if_zero = 0 if self._ddpm else 1
+            if per_sample is not None:
+                a.per_sample_numel = x.numel() // B
+                a.skip_rng_if_zero = 0
             if noise is not None:
                 noise = noise.to(dev).float().contiguous()
                 a.d_noise = noise.data_ptr()
             _lib.check(_lib.lib().ds_sampler_step(C.byref(a), _lib.stream_ptr()))
-            if noise is None and (self._ddpm or t > 0):
+            if noise is None and (self._ddpm or per_sample is not None or t > 0):
                 _finish(gen, a.offset, inc)
         return out
 
@@ -345,7 +420,6 @@ class _GaussianDiffusion(_SamplerBase):
                 eng.cond.copy_(x_in)
             eng.initial_noise(None, 1.0)
             snaps = [i for i in reversed(range(T)) if i % inter == 0]
-            keep_all = continous or self._ddpm and not self.conditional
             if self.conditional:
                 first = x_in.float().repeat((1, Cs // cc, 1, 1))
             else:
@@ -411,6 +485,44 @@ def _delta_ok(delta_t, t_cur):
     T=20 with t_start=1.0 (cur = 0.00099999999999912 < delta = 0.001).  Conscious fix: the check tolerates the
     accumulated rounding (1e-9 relative); every case the reference completes is unchanged."""
     return delta_t <= t_cur * (1 + 1e-9) + 1e-300
+
+
+def _run_snapshots(engines, T, snaps, continuous):
+    """Run T steps of one engine, or of two engines concurrently (JointIndi), copying every engine's state after the steps
+    listed in ``snaps`` when ``continuous``.  Returns the per-engine snapshot stacks (or None)."""
+    runner = engines[0] if len(engines) == 1 else _pair(engines[0], engines[1])
+    if not continuous:
+        runner.run(T)
+        return None
+    rets = []
+    for e in engines:
+        r = torch.empty(((len(snaps) + 1) * e.B, e.C, e.H, e.W), dtype=torch.float32, device=e.device)
+        r[:e.B].copy_(e.x)
+        rets.append(r)
+    slot, pending, snapset = 1, 0, set(snaps)
+    for idx in range(T):
+        pending += 1
+        if idx in snapset:
+            runner.run(pending)
+            pending = 0
+            for e, r in zip(engines, rets):
+                r[slot * e.B:(slot + 1) * e.B].copy_(e.x)
+            slot += 1
+    runner.run(pending)
+    return rets
+
+
+_pairs = {}
+
+
+def _pair(e1, e2):
+    key = (id(e1), id(e2))
+    p = _pairs.get(key)
+    if p is None or p.e1 is not e1 or p.e2 is not e2:
+        if len(_pairs) >= 4:
+            _pairs.clear()
+        p = _pairs[key] = _PairEngine(e1, e2)
+    return p
 
 
 class InDI(_SamplerBase):
@@ -487,50 +599,53 @@ class InDI(_SamplerBase):
                 _finish(gen, a.offset, inc)
         return out
 
-    @torch.no_grad()
-    def inference(self, x_in, continuous=False, num_timesteps=None, t_float_start=1.0, eps=1e-8):
-        if num_timesteps is None:
-            num_timesteps = self.num_timesteps
-        T = int(num_timesteps)
+    def _setup(self, x_in, T, t_float_start, seed, off0):
+        """Engine of this sampler loaded for one ``inference`` call: tables, loop state seeded at generator offset
+        ``off0``, x_t = x + e*t*z drawn (indi.py:80-83).  Returns the engine; it consumes ``rng_inc * (1 + T)`` of offset."""
         assert self.conditional is False
         _lib.require_cuda(x_in, "InDI input")
         dev = x_in.device
         net = self.denoise_fn
-        inter = 1 | (T // 20)
         x_cat = torch.cat([x_in.float()] * self.out_channel, dim=1).contiguous()
         B, Cs, H, W = x_cat.shape
+        net.commit()
+        eng = self._engine(net, B, Cs, H, W, 0, 1, dev, 1, False, 0)
+        coef, ttab = self._tables(T, t_float_start)
+        eng.load_tables(coef, ttab)
+        eng.reset_state(seed, off0)
+        scale = float((self.e * torch.Tensor([t_float_start]))[0])
+        eng.initial_noise(x_cat, scale)
+        return eng
+
+    @staticmethod
+    def _snapshots(T):
+        inter = 1 | (T // 20)
+        return [i for i in range(T) if i % inter == 0 or i == T - 1]
+
+    @torch.no_grad()
+    def inference(self, x_in, continuous=False, num_timesteps=None, t_float_start=1.0, eps=1e-8, all_samples=False):
+        """indi.py:71-95.  ``all_samples`` (extension): with ``continuous=False`` return the final state of EVERY batch
+        element ``(B,C,H,W)`` instead of the reference's ``ret_img[-1:]`` (last element only)."""
+        if num_timesteps is None:
+            num_timesteps = self.num_timesteps
+        T = int(num_timesteps)
+        if float(t_float_start) <= 0.0:
+            # t = 0 is the clean end of the InDI path: the reference divides 0 / 0 here (delta = t = 0) and returns NaNs
+            raise ValueError("InDI.inference: t_float_start must be > 0 (t = 0 means the input already is the prediction)")
+        _lib.require_cuda(x_in, "InDI input")
+        dev = x_in.device
         with torch.cuda.device(dev):
-            net.commit()
-            eng = self._engine(net, B, Cs, H, W, 0, 1, dev, 1, False, 0)
-            coef, ttab = self._tables(T, t_float_start)
-            eng.load_tables(coef, ttab)
             gen, _ = _generator(dev)
             seed, off0 = gen.initial_seed(), gen.get_offset()
-            eng.reset_state(seed, off0)
-            scale = float((self.e * torch.Tensor([t_float_start]))[0])
-            eng.initial_noise(x_cat, scale)
-            snaps = [i for i in range(T) if i % inter == 0 or i == T - 1]
-            ret = None
-            if continuous:
-                ret = torch.empty(((len(snaps) + 1) * B, Cs, H, W), dtype=torch.float32, device=dev)
-                ret[:B].copy_(eng.x)
-            slot = 1
-            if continuous:
-                pending = 0
-                for idx in range(T):
-                    pending += 1
-                    if idx % inter == 0 or idx == T - 1:
-                        eng.run(pending)
-                        pending = 0
-                        ret[slot * B:(slot + 1) * B].copy_(eng.x)
-                        slot += 1
-                eng.run(pending)
-            else:
-                eng.run(T)
+            eng = self._setup(x_in, T, t_float_start, seed, off0)
+            B = eng.B
+            out = _run_snapshots([eng], T, self._snapshots(T), continuous)
             _finish(gen, off0, eng.rng_inc * (1 + T))
             if continuous:
-                return ret
-            return eng.x[-1:].clone() if T > 0 else x_cat[-1:]          # `ret_img[-1:]` (indi.py:95)
+                return out[0]
+            if all_samples:
+                return eng.x.clone()
+            return eng.x[-1:].clone()                                   # `ret_img[-1:]` (indi.py:95)
 
     def launches_per_step(self, B, H, W):
         return self.denoise_fn.launches(B, H, W) + 1
@@ -590,9 +705,28 @@ class JointIndi(_SamplerBase):
         return self.indi1.num_timesteps
 
     @torch.no_grad()
-    def inference(self, x_in, continuous=False, num_timesteps=None, t_float_start=0.5, eps=1e-8):
-        ch1 = self.indi1.inference(x_in, continuous=continuous, num_timesteps=num_timesteps,
-                                   t_float_start=t_float_start, eps=eps)
-        ch2 = self.indi2.inference(x_in, continuous=continuous, num_timesteps=num_timesteps,
-                                   t_float_start=1 - t_float_start, eps=eps)
-        return torch.cat([ch1, ch2], dim=1)
+    def inference(self, x_in, continuous=False, num_timesteps=None, t_float_start=0.5, eps=1e-8, all_samples=False):
+        """joint_indi.py:131-135: two independent InDI loops (indi1 from t, indi2 from 1 - t), concatenated on dim 1.
+        The loops share nothing, so they run as the two branches of one CUDA graph (``DIFFSPLIT_B200_JOINT_SERIAL=1``:
+        one after the other, as the reference); the generator is consumed in the reference's order either way."""
+        T = int(self.indi1.num_timesteps if num_timesteps is None else num_timesteps)
+        t1, t2 = float(t_float_start), 1 - float(t_float_start)
+        serial = os.environ.get("DIFFSPLIT_B200_JOINT_SERIAL") is not None or not _use_graphs()
+        if serial or min(t1, t2) <= 0.0:
+            ch1 = self.indi1.inference(x_in, continuous=continuous, num_timesteps=T, t_float_start=t1, eps=eps, all_samples=all_samples)
+            ch2 = self.indi2.inference(x_in, continuous=continuous, num_timesteps=T, t_float_start=t2, eps=eps, all_samples=all_samples)
+            return torch.cat([ch1, ch2], dim=1)
+        _lib.require_cuda(x_in, "JointIndi input")
+        dev = x_in.device
+        with torch.cuda.device(dev):
+            gen, _ = _generator(dev)
+            seed, off0 = gen.initial_seed(), gen.get_offset()
+            e1 = self.indi1._setup(x_in, T, t1, seed, off0)
+            e2 = self.indi2._setup(x_in, T, t2, seed, off0 + e1.rng_inc * (1 + T))
+            out = _run_snapshots([e1, e2], T, InDI._snapshots(T), continuous)
+            _finish(gen, off0, (e1.rng_inc + e2.rng_inc) * (1 + T))
+            if continuous:
+                return torch.cat(out, dim=1)
+            if all_samples:
+                return torch.cat([e1.x, e2.x], dim=1)
+            return torch.cat([e1.x[-1:], e2.x[-1:]], dim=1)

@@ -6,8 +6,8 @@ Reference: ``model/sr3_modules/unet.py:161-259`` (``variant='sr3'``, ``time`` = 
 
 The parameter tree is generated from the native library's own weight registry
 (``ds_unet_weight_name/shape``), so the names the kernels look up and the names a reference checkpoint
-provides cannot drift apart; ``tests/test_boundary.py`` pins them against key lists recorded from the
-reference modules.
+provides cannot drift apart; ``tests/test_abi_host.py::test_state_dict_keys_match_reference`` pins them against
+key lists recorded from the reference modules (``tests/golden/state_dict_keys.json``).
 """
 import ctypes as C
 import math
@@ -171,24 +171,30 @@ class UNet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def workspace(self, B, H, W, prec, device):
-        key = (B, H, W, prec, device)
+        """Scratch tensor for one (shape, precision).  The cache only avoids re-allocation for eager callers: anything that
+        bakes the address into a CUDA graph (the sampler engines) keeps its own reference, so evicting an entry here never
+        frees memory a captured graph still uses."""
+        if prec is None:
+            prec = _PRECISIONS[self.precision]
+        key = (B, H, W, prec, torch.device(device))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.lib().ds_unet_workspace_bytes(self._handle, B, H, W, prec)
             if nbytes == 0:
                 _lib.check(-1)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            if len(self._ws) > 8:
-                self._ws.clear()
+            while len(self._ws) >= 8:
+                self._ws.pop(next(iter(self._ws)))          # oldest entry only
             self._ws[key] = ws
         return ws
 
-    def forward_into(self, out, xa, xb, time, precision=None):
+    def forward_into(self, out, xa, xb, time, precision=None, ws=None):
         """Raw entry: all tensors fp32 contiguous CUDA; ``xb`` may be None; ``time`` fp32 with 1 or B entries."""
         B, ca, H, W = xa.shape
         cb = 0 if xb is None else xb.shape[1]
         prec = _PRECISIONS[precision or self.precision]
-        ws = self.workspace(B, H, W, prec, xa.device)
+        if ws is None:
+            ws = self.workspace(B, H, W, prec, xa.device)
         _lib.check(_lib.lib().ds_unet_forward(
             self._handle, xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb,
             None if time is None else time.data_ptr(), 0 if time is None else time.numel(),

@@ -209,6 +209,9 @@ typedef struct ds_step_args {
     const float* d_time_table; /* [n_steps+1] UNet time input per step (entry n_steps unused) or NULL */
     float*       d_time_out;   /* [time_len] or NULL */
     int32_t      time_len;
+    int64_t      per_sample_numel; /* 0, or elements per sample: element i uses coefficient row i / per_sample_numel of d_coef
+                                    * [B,5] (ddpm p_sample with a different t per sample, ddpm_modules/diffusion.py:64-67,
+                                    * 195-203); needs d_state == NULL, step 0 */
 } ds_step_args;
 /* The kernel is launched with programmatic stream serialisation and reads *d_state and evaluates its first Philox block
  * BEFORE waiting for its predecessor in the stream: the predecessor must not be the kernel that last wrote *d_state (in the

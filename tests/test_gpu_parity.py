@@ -499,6 +499,96 @@ def test_seeded_loops_replay_the_reference_rng_stream(graph, monkeypatch):
     assert torch.equal(y, y2)
 
 
+def test_ddpm_p_sample_with_a_different_timestep_per_sample():
+    """ddpm_modules/diffusion.py:64-67,195-203: `extract` gathers every buffer with the (B,) tensor t, so the samples of a
+    batch may sit at different timesteps (incl. t == 0, whose noise is masked)."""
+    _, (cfgd, sdd), _ = _nets()
+    netD = GaussianDiffusionDdpm(build(cfgd, sdd), 16, channels=2, conditional=True).to(DEV)
+    netD.set_new_noise_schedule(SCHED, DEV)
+    g = torch.Generator().manual_seed(21)
+    cond = torch.rand((3, 1, 16, 16), generator=g) * 2 - 1
+    x = torch.randn((3, 2, 16, 16), generator=g)
+    z = torch.randn((3, 2, 16, 16), generator=g)
+    t = torch.tensor([4, 0, 2])
+    tab = S.schedule_tables(SCHED)
+    ref = S.ddpm_p_sample(tab, lambda a, tt: U.unet_forward(sdd, cfgd, a, tt), x, t, cond, True, z)
+    y = netD.p_sample(x.to(DEV), t.to(DEV), condition_x=cond.to(DEV), noise=z)
+    assert float((y.cpu() - ref).abs().max()) < 2e-5
+    # generated noise: the same draw torch.randn would produce, one generator increment consumed
+    gen = torch.cuda.default_generators[0]
+    zd = _cuda_draws(31, [(3, 2, 16, 16)])[0]
+    end = gen.get_offset()
+    torch.manual_seed(31)
+    y2 = netD.p_sample(x.to(DEV), t.to(DEV), condition_x=cond.to(DEV))
+    assert gen.get_offset() == end
+    ref2 = S.ddpm_p_sample(tab, lambda a, tt: U.unet_forward(sdd, cfgd, a, tt), x, t, cond, True, zd)
+    assert float((y2.cpu() - ref2).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("numel,offset_elems", [(1003, 0), (4096 + 5, 1), (3 * 512 * 512, 0), (1 << 20, 3)])
+def test_sampler_update_vectorised_and_scalar_paths_agree_bitwise(numel, offset_elems):
+    """ds_sampler_step: the 16-byte path (four torch threads per CUDA thread) and the scalar path (taken for unaligned
+    tensors) produce the same bits as the reference expression evaluated by torch on torch's own draw."""
+    gen = torch.cuda.default_generators[0]
+    sms, max_thr, _, _ = _lib.device_info(0)
+    grid = min(sms * (max_thr // 256), (numel + 255) // 256)
+    threads, inc = 256 * grid, ((numel - 1) // (256 * grid * 4) + 1) * 4
+    torch.manual_seed(99)
+    z = torch.randn(numel, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    buf_x = torch.randn(numel + 8, generator=g).to(DEV)
+    buf_n = torch.randn(numel + 8, generator=g).to(DEV)
+    x, n = buf_x[offset_elems:offset_elems + numel], buf_n[offset_elems:offset_elems + numel]
+    coef = torch.tensor([[1.25, 0.75, 0.3, 0.7, 0.11]], device=DEV)
+    for mode, clip in ((0, 1), (1, 0)):
+        x0 = (coef[0, 0] * x - coef[0, 1] * n).clamp(-1, 1) if mode == 0 else n
+        ref = (coef[0, 2] * x0 + coef[0, 3] * x) + z * coef[0, 4]
+        out = torch.empty(numel + 8, device=DEV)[offset_elems:offset_elems + numel]
+        a = _lib.StepArgs()
+        a.d_x = x.data_ptr(); a.d_net = n.data_ptr(); a.d_out = out.data_ptr(); a.numel = numel
+        a.mode = mode; a.clip = clip; a.d_coef = coef.data_ptr(); a.n_steps = 1; a.step = 0; a.d_state = None
+        torch.manual_seed(99)
+        a.seed = gen.initial_seed(); a.offset = gen.get_offset(); a.offset_inc = inc; a.rng_threads = threads
+        _lib.check(_lib.lib().ds_sampler_step(C.byref(a), sptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), (numel, offset_elems, mode)
+        # injected noise, same paths
+        a.d_noise = z.data_ptr()
+        out.zero_()
+        _lib.check(_lib.lib().ds_sampler_step(C.byref(a), sptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+
+
+def test_joint_indi_concurrent_branches_equal_the_serial_loops(monkeypatch):
+    """joint_indi.py:132-135 runs its two InDI loops one after the other; here they are the two branches of one CUDA graph.
+    Same seed -> same result as the serial order (DIFFSPLIT_B200_JOINT_SERIAL=1), same generator end state, and
+    `all_samples` returns every batch element where the reference's `ret_img[-1:]` keeps the last one."""
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
+    nets = [build(cfg, U.random_state_dict(cfg, seed=s), "fp32") for s in (3, 4)]
+    joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=nets[0], denoise_fn_ch2=nets[1],
+                      val_schedule_opt={"n_timestep": 5}).to(DEV)
+    joint.set_new_noise_schedule({"n_timestep": 5}, DEV)
+    x = (torch.rand((3, 1, 32, 32), generator=torch.Generator().manual_seed(0)) * 2 - 1).to(DEV)
+    gen = torch.cuda.default_generators[0]
+    torch.manual_seed(5)
+    y = joint.inference(x, continuous=True, t_float_start=0.3)
+    end = gen.get_offset()
+    torch.manual_seed(5)
+    ya = joint.inference(x, continuous=False, t_float_start=0.3, all_samples=True)
+    torch.manual_seed(5)
+    yl = joint.inference(x, continuous=False, t_float_start=0.3)
+    monkeypatch.setenv("DIFFSPLIT_B200_JOINT_SERIAL", "1")
+    torch.manual_seed(5)
+    ys = joint.inference(x, continuous=True, t_float_start=0.3)
+    assert gen.get_offset() == end
+    assert y.shape == ys.shape and float((y - ys).abs().max()) < 1e-5
+    assert ya.shape == (3, 2, 32, 32) and float((ya - ys[-3:]).abs().max()) < 1e-5
+    assert yl.shape == (1, 2, 32, 32) and torch.equal(yl, ya[-1:])
+    with pytest.raises(ValueError, match="t_float_start"):
+        joint.indi1.inference(x, t_float_start=0.0)
+
+
 @pytest.mark.parametrize("T", [1, 2, 10, 21])
 def test_joint_indi_snapshot_count_and_multi_step_graphs(T):
     """The intent of the reference's tests/test_joint_indi.py:9-25 (continuous=True returns n_timestep + 1 snapshots per
@@ -571,6 +661,17 @@ def test_mmse_tiled_evaluation_follows_the_notebook_loop():
     fast = evaluate_mmse(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=M_, chunk=4)
     assert fast["prediction"].shape == res["prediction"].shape and torch.isfinite(fast["range_invariant_psnr"]).all()
     assert torch.equal(fast["target"], res["target"])
+    # batched chunks predict EVERY tile of the chunk (continuous=False alone keeps only the last batch element): with the
+    # noise switched off (e = 0) the tile-by-tile result cannot depend on the chunk size
+    for ind in (joint.indi1, joint.indi2):
+        ind.e = 0.0
+    from diffsplitting_b200.evaluate import mmse_predict_tiles
+    p1, _ = mmse_predict_tiles(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=1, chunk=1)
+    p4, _ = mmse_predict_tiles(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=1, chunk=4)
+    p3, _ = mmse_predict_tiles(joint, tf, mixing_t=W_, num_timesteps=T_, mmse_count=1, chunk=3, replay_reference_rng=True)
+    scale = float(p1.abs().max())
+    assert float((p1 - p4).abs().max()) < 2e-2 * scale and float((p1 - p3).abs().max()) < 2e-2 * scale
+    assert float((p1[0] - p1[1]).abs().max()) > 0.05 * scale          # tiles do differ
 
 
 def test_step_rate_against_torch_eager_on_the_same_gpu():
