@@ -113,6 +113,10 @@ _SIGS = {
     "ds_crop_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _I3, _I3, _I3, C.c_int, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_void_p]),
     "ds_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_void_p, C.c_void_p]),
+    "ds_tile_regions": (C.c_int, [_I3, _I3, _I3, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int32)]),
+    "ds_pack_tile_regions": (C.c_int, [C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p]),
+    "ds_stitch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_void_p, C.c_void_p]),
     "ds_tile_batch": (C.c_int, [C.c_void_p, C.c_int, _I3, _I3, _I3, C.c_int, C.c_int64, C.c_int64,
                                 C.POINTER(TileNorm), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_psnr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),

@@ -124,6 +124,59 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ t
     }
 }
 
+// ---- multi-GPU exchange format: only the part of a predicted tile that the stitcher reads (its destination box: the inner
+// grid cell, widened to the frame edge where the patch touches it, tile_stitcher.py:28-57) is packed as [C][hy][hx] and
+// travels; 490 x 2 x 512^2 tiles = 1.03 GB shrink to the 335 MB of the stitched frames.  Tiles are addressed by their GLOBAL
+// index, so the packed buffers of any partition of the tiles stitch to the same bits.
+__global__ void __launch_bounds__(256) pack_regions_kernel(const float* __restrict__ tiles, int C, const TileGeom g,
+                                                           const int64_t* __restrict__ tile_ids, const int64_t* __restrict__ offsets,
+                                                           int64_t n, float* __restrict__ packed) {
+    const int P1 = g.patch[1], P2 = g.patch[2];
+    // one CTA walks one (tile, channel) region at a time: its geometry is CTA-uniform
+    for (int64_t job = blockIdx.x; job < n * C; job += gridDim.x) {
+        const int64_t ti = job / C;
+        const int c = (int)(job - ti * C);
+        int64_t idx = tile_ids[ti];
+        idx -= (idx / g.strides[0]) * g.strides[0];
+        const int ky = (int)(idx / g.strides[1]), kx = (int)(idx - (int64_t)ky * g.strides[1]);
+        int ylo, yhi, xlo, xhi;
+        dst_interval(g, 1, ky, &ylo, &yhi);
+        dst_interval(g, 2, kx, &xlo, &xhi);
+        const int hy = yhi - ylo, hx = xhi - xlo;
+        const int py0 = ylo - (grid_start(g, 1, ky) - g.off[1]), px0 = xlo - (grid_start(g, 2, kx) - g.off[2]);
+        const float* src = tiles + ((ti * C + c) * P1 + py0) * (int64_t)P2 + px0;
+        float* dst = packed + offsets[ti] + (int64_t)c * hy * hx;
+        for (int i = threadIdx.x; i < hy * hx; i += 256) {
+            const int y = i / hx, x = i - y * hx;
+            dst[i] = src[(int64_t)y * P2 + x];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) stitch_packed_kernel(const float* __restrict__ packed, const int64_t* __restrict__ tile_off,
+                                                            int C, const TileGeom g, float* __restrict__ out) {
+    const int W = g.data[2], H = g.data[1];
+    const int64_t npix = (int64_t)g.data[0] * H * W;
+    for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < npix; i += (int64_t)gridDim.x * 256) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const int f = (int)(i / ((int64_t)W * H));
+        const int kf = owner(g, 0, f), ky = owner(g, 1, y), kx = owner(g, 2, x);
+        float* dst = out + i * C;
+        if (kf < 0 || ky < 0 || kx < 0) {
+            for (int c = 0; c < C; ++c) dst[c] = 0.f;
+            continue;
+        }
+        const int64_t n = kf * g.strides[0] + ky * g.strides[1] + kx;
+        int ylo, yhi, xlo, xhi;
+        dst_interval(g, 1, ky, &ylo, &yhi);
+        dst_interval(g, 2, kx, &xlo, &xhi);
+        const int hy = yhi - ylo, hx = xhi - xlo;
+        const float* src = packed + tile_off[n] + (int64_t)(y - ylo) * hx + (x - xlo);
+        for (int c = 0; c < C; ++c) dst[c] = src[(int64_t)c * hy * hx];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) crop_kernel(const T* __restrict__ frames, int C, const TileGeom g, int64_t first,
                                                    int64_t n, float* __restrict__ tiles) {
@@ -412,6 +465,76 @@ extern "C" int ds_stitch_tiles(const float* d_tiles, int C, const int32_t data_s
     int blocks = (int)((npix + 255) / 256 > 148 * 16 ? 148 * 16 : (npix + 255) / 256);
     stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_tiles, C, g, d_out);
     DS_CHECK_LAUNCH("stitch_tiles");
+    return DS_OK;
+}
+
+static int stitch_geom(const int32_t data_shape[3], const int32_t grid_shape[3], const int32_t patch_shape[3], int mode, ds::TileGeom* g,
+                       const char* who) {
+    using namespace ds;
+    int rc = make_geom(data_shape, grid_shape, patch_shape, mode, g);
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(g->patch[0] == 1 && g->grid[0] == 1, "%s: only (1,P,P) patches over (F,H,W) data are supported", who);
+    if (mode != DS_TILE_SHIFT) {
+        for (int d = 0; d < 3; ++d) {
+            const int last = grid_start(*g, d, g->counts[d] - 1);
+            DS_REQUIRE(last + g->grid[d] <= g->data[d] && grid_start(*g, d, 0) >= 0,
+                       "%s: grid cell outside the data in dim %d (reference asserts)", who, d);
+        }
+    }
+    return DS_OK;
+}
+
+extern "C" int ds_tile_regions(const int32_t data_shape[3], const int32_t grid_shape[3], const int32_t patch_shape[3], int mode,
+                               int64_t first, int64_t n, int32_t* h_regions) {
+    using namespace ds;
+    TileGeom g;
+    int rc = stitch_geom(data_shape, grid_shape, patch_shape, mode, &g, "tile_regions");
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(h_regions && first >= 0 && n >= 0 && first + n <= g.total, "tile_regions: tile range outside [0, %lld)", (long long)g.total);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t idx = first + i;
+        const int kf = (int)(idx / g.strides[0]);
+        idx -= kf * g.strides[0];
+        const int ky = (int)(idx / g.strides[1]), kx = (int)(idx - (int64_t)ky * g.strides[1]);
+        int lo, hi;
+        dst_interval(g, 0, kf, &lo, &hi);
+        h_regions[i * 5 + 0] = lo;
+        dst_interval(g, 1, ky, &lo, &hi);
+        h_regions[i * 5 + 1] = lo; h_regions[i * 5 + 2] = hi;
+        dst_interval(g, 2, kx, &lo, &hi);
+        h_regions[i * 5 + 3] = lo; h_regions[i * 5 + 4] = hi;
+    }
+    return DS_OK;
+}
+
+extern "C" int ds_pack_tile_regions(const float* d_tiles, int C, const int32_t data_shape[3], const int32_t grid_shape[3],
+                                    const int32_t patch_shape[3], int mode, const int64_t* d_tile_ids, const int64_t* d_offsets,
+                                    int64_t n, float* d_packed, void* stream) {
+    using namespace ds;
+    TileGeom g;
+    int rc = stitch_geom(data_shape, grid_shape, patch_shape, mode, &g, "pack_tile_regions");
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(C > 0 && n >= 0, "pack_tile_regions: bad argument");
+    if (n == 0) return DS_OK;
+    DS_REQUIRE(d_tiles && d_tile_ids && d_offsets && d_packed, "pack_tile_regions: null argument");
+    const int64_t jobs = n * C;
+    const int blocks = (int)(jobs > 148 * 8 ? 148 * 8 : jobs);
+    pack_regions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_tiles, C, g, d_tile_ids, d_offsets, n, d_packed);
+    DS_CHECK_LAUNCH("pack_tile_regions");
+    return DS_OK;
+}
+
+extern "C" int ds_stitch_packed(const float* d_packed, const int64_t* d_tile_offsets, int C, const int32_t data_shape[3],
+                                const int32_t grid_shape[3], const int32_t patch_shape[3], int mode, float* d_out, void* stream) {
+    using namespace ds;
+    TileGeom g;
+    int rc = stitch_geom(data_shape, grid_shape, patch_shape, mode, &g, "stitch_packed");
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(d_packed && d_tile_offsets && d_out && C > 0, "stitch_packed: null argument");
+    const int64_t npix = (int64_t)g.data[0] * g.data[1] * g.data[2];
+    int blocks = (int)((npix + 255) / 256 > 148 * 16 ? 148 * 16 : (npix + 255) / 256);
+    stitch_packed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_packed, d_tile_offsets, C, g, d_out);
+    DS_CHECK_LAUNCH("stitch_packed");
     return DS_OK;
 }
 

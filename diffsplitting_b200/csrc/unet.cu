@@ -116,6 +116,7 @@ struct Plan {
     size_t bytes = 0;
     int64_t temb_buf = NONE, gn_scratch = NONE;
     size_t stats_base = 0, stats_bytes = 0;   // per-channel fp64 statistics slots, zeroed at the start of every forward
+    size_t counters_off = 0;                  // offset (inside that region) of the fp32 GroupNorm's per-sample counters
     std::map<std::string, Tap> taps;
     int launches = 0;
 };
@@ -655,6 +656,11 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     }
     P.release(x);
     p->stats_base = align_up(P.arena.top(), 256);
+    // "last CTA of the sample" counters of the fp32-mode GroupNorm statistics kernel: per plan (i.e. per workspace), inside
+    // the region zeroed at the start of every forward - two UNets running concurrently (the two branches of JointIndi) must
+    // not share them
+    p->counters_off = P.stats_top;
+    P.stats_top += align_up((size_t)B * sizeof(unsigned), 256);
     p->stats_bytes = P.stats_top;
     p->bytes = p->stats_base + p->stats_bytes;
     int launches = d.with_time_emb ? 1 : 0;
@@ -672,7 +678,7 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
         run = 0;
         launches += o.kind == OP_GN ? 2 : 1;                                      // GroupNorm = statistics (or their fold) + apply
     }
-    if (P.tc && p->stats_bytes) ++launches;                                      // the statistics-arena memset
+    if (p->stats_bytes) ++launches;                                              // the statistics-arena memset
     p->launches = launches;
     *out = p;
     return DS_OK;
@@ -809,11 +815,6 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
                                           (size_t)r.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         }
     }
-    {
-        unsigned* counters = nullptr;
-        int rc2 = gn_counters(&counters);     // first use allocates: must not happen inside a graph capture
-        if (rc2 != DS_OK) return rc2;
-    }
     if (!n->side_stream) {
         DS_CHECK_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking));
         DS_CHECK_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
@@ -942,9 +943,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         }
     }
     void* gn_scratch = ptr(p->gn_scratch);
-    unsigned* counters = nullptr;
-    rc = gn_counters(&counters);
-    if (rc != DS_OK) return rc;
+    unsigned* counters = reinterpret_cast<unsigned*>(base + p->stats_base + p->counters_off);
     const bool tc = precision == DS_PREC_BF16;
     if (tc && p->tc_ws != d_ws) {
         // (re)encode the TMA descriptors for this workspace address
@@ -1019,7 +1018,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         p->chain_time_len = time_len;
     }
     if (tc) p->tc_ws = d_ws;
-    if (tc && p->stats_bytes) DS_CHECK_CUDA(cudaMemsetAsync(base + p->stats_base, 0, p->stats_bytes, st));
+    if (p->stats_bytes) DS_CHECK_CUDA(cudaMemsetAsync(base + p->stats_base, 0, p->stats_bytes, st));
     size_t op_index = 0;
     for (const Op& o : p->ops) {
         bool used_tc = false;

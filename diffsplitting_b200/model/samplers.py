@@ -272,6 +272,10 @@ class _SamplerBase(nn.Module):
 
     def set_loss(self, device):
         reduction = getattr(self, "lr_reduction", None) or "sum"
+        if self.loss_type is None:
+            # the reference's sr_sr3_* / sample_* JSONs carry no model.loss_type (define_G then passes None and the reference's
+            # set_loss raises NotImplementedError): the upstream SR3 default
+            self.loss_type = "l1"
         if self.loss_type == "l1":
             self.loss_func = nn.L1Loss(reduction=reduction).to(device)
         elif self.loss_type == "l2":
@@ -393,7 +397,9 @@ class _GaussianDiffusion(_SamplerBase):
         return out
 
     @torch.no_grad()
-    def p_sample_loop(self, x_in, clip_denoised=True, continous=False):
+    def p_sample_loop(self, x_in, clip_denoised=True, continous=False, all_samples=False):
+        """sr3 diffusion.py:177-203 / ddpm diffusion.py:205-237.  ``all_samples`` (extension): with ``continous=False`` return
+        the final state of EVERY batch element instead of the reference's ``ret_img[-1]`` (last element only)."""
         net = self.denoise_fn
         T = self.num_timesteps
         inter = 1 | (T // 10)
@@ -447,6 +453,8 @@ class _GaussianDiffusion(_SamplerBase):
                 return eng.x.clone()                                   # ddpm diffusion.py:217-225 returns img
             if continous:
                 return ret
+            if all_samples:
+                return eng.x.clone()
             # `ret_img[-1]`: last batch element of the last snapshot (t == 0 is always a snapshot)
             return eng.x[-1].clone()
 
@@ -456,15 +464,15 @@ class _GaussianDiffusion(_SamplerBase):
         return self.p_sample_loop((batch_size, self.channels, s, s), continous=continous)
 
     @torch.no_grad()
-    def super_resolution(self, x_in, clip_denoised=True, continous=False):
-        return self.p_sample_loop(x_in, clip_denoised=clip_denoised, continous=continous)
+    def super_resolution(self, x_in, clip_denoised=True, continous=False, all_samples=False):
+        return self.p_sample_loop(x_in, clip_denoised=clip_denoised, continous=continous, all_samples=all_samples)
 
     predict = super_resolution                                          # ddpm diffusion.py:245-247
 
     @torch.no_grad()
-    def inference(self, x_in, continuous=False, clip_denoised=True, **kw):
+    def inference(self, x_in, continuous=False, clip_denoised=True, all_samples=False, **kw):
         """The entry ``DDPM.test`` calls (model/model.py:63-76); the reference sr3/ddpm classes lack it."""
-        return self.p_sample_loop(x_in, clip_denoised=clip_denoised, continous=continuous)
+        return self.p_sample_loop(x_in, clip_denoised=clip_denoised, continous=continuous, all_samples=all_samples)
 
 
 class GaussianDiffusionSr3(_GaussianDiffusion):

@@ -242,6 +242,20 @@ int ds_crop_tiles(const void* d_frames, int elem_size, int C, const int32_t data
 int ds_stitch_tiles(const float* d_tiles, int C, const int32_t data_shape[3], const int32_t grid_shape[3],
                     const int32_t patch_shape[3], int mode, float* d_out, void* stream);
 
+/* Multi-GPU exchange of predicted tiles: only the destination box of a tile - the part stitch_predictions reads
+ * (data/tile_stitcher.py:28-57: the inner grid cell, widened to the frame edge where the patch touches it) - travels.
+ * ds_tile_regions:      host table, per tile [first, first+n): (frame, y_lo, y_hi, x_lo, x_hi) of its destination box.
+ * ds_pack_tile_regions: tiles (n,C,P,P) whose GLOBAL indices are d_tile_ids[n] -> d_packed + d_offsets[i] as [C][hy][hx].
+ * ds_stitch_packed:     packed boxes of ALL tiles (d_tile_offsets[total]: element offset of every global tile index) ->
+ *                       frames (F,H,W,C); same last-writer-wins rule and bits as ds_stitch_tiles. */
+int ds_tile_regions(const int32_t data_shape[3], const int32_t grid_shape[3], const int32_t patch_shape[3], int mode,
+                    int64_t first, int64_t n, int32_t* h_regions);
+int ds_pack_tile_regions(const float* d_tiles, int C, const int32_t data_shape[3], const int32_t grid_shape[3],
+                         const int32_t patch_shape[3], int mode, const int64_t* d_tile_ids, const int64_t* d_offsets,
+                         int64_t n, float* d_packed, void* stream);
+int ds_stitch_packed(const float* d_packed, const int64_t* d_tile_offsets, int C, const int32_t data_shape[3],
+                     const int32_t grid_shape[3], const int32_t patch_shape[3], int mode, float* d_out, void* stream);
+
 /* Fused tile loader: crop + normalise + mix of tiles [first, first+n) from 2-channel frames (2,F,H,W) fp32|uint16
  * (SplitDataset.__getitem__ without transforms, data/split_dataset.py:237-278; normalize_target / normalize_inp :195-201).
  * d_input (n,1,P,P), d_target (n,2,P,P) or NULL; bit-exact with the reference's numpy arithmetic (float64 constants,

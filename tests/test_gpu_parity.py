@@ -767,6 +767,30 @@ def test_crop_and_stitch_bit_exact_vs_oracle(data, grid, patch):
     assert torch.equal(out_t.cpu(), torch.from_numpy(frames.transpose(1, 2, 3, 0)))
 
 
+@pytest.mark.parametrize("data,grid,patch,mode", [((3, 100, 130), (1, 16, 16), (1, 32, 32), TilingMode.ShiftBoundary),
+                                                  ((2, 96, 96), (1, 16, 16), (1, 32, 32), TilingMode.TrimBoundary),
+                                                  ((2, 1024, 1024), (1, 256, 256), (1, 512, 512), TilingMode.ShiftBoundary)])
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_packed_region_exchange_stitches_to_the_same_bits(data, grid, patch, mode, world):
+    """The multi-GPU exchange format (parallel.py): every emulated rank packs the destination boxes of ITS round-robin share
+    of random tiles, the buffers are laid side by side as the gather would, and `ds_stitch_packed` must give exactly what
+    `stitch_predictions` (pinned to the reference, bit-exact) gives on the whole tiles - for any number of ranks."""
+    from diffsplitting_b200.parallel import PackedLayout, pack_tile_regions, stitch_packed
+    mng = TileIndexManager(data, grid, patch, mode)
+    total = mng.total_grid_count()
+    tiles = torch.randn((total, 2, patch[1], patch[2]), generator=torch.Generator().manual_seed(3)).to(DEV)
+    ref = stitch_predictions(tiles, mng)
+    lay = PackedLayout(mng, 2, 4, world)
+    gathered = torch.zeros((world * lay.slot,), device=DEV)
+    for r in range(world):
+        if len(lay.ids[r]):
+            pack_tile_regions(tiles[torch.from_numpy(lay.ids[r]).to(DEV)], mng, lay.ids[r], lay.local_off[r],
+                              gathered[r * lay.slot:(r + 1) * lay.slot])
+    out = stitch_packed(gathered, mng, lay.global_off, 2)
+    assert torch.equal(out, ref)
+    assert lay.payload_bytes <= tiles.numel() * 4
+
+
 def test_stitch_golden_and_trim_mode(gold_dir):
     gd = np.load(os.path.join(gold_dir, "tiling.npz"))
     tg = TR.TileGrid((3, 100, 130), (1, 16, 16), (1, 32, 32), TR.SHIFT)
