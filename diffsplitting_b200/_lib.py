@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "libdiffsplit_b200.so")
 
 DS_OK = 0
 UNET_SR3, UNET_DDPM = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 TILE_TRIM, TILE_PAD, TILE_SHIFT = 0, 1, 2
 MAX_LEVELS = 8
 
@@ -21,7 +21,8 @@ class UNetDesc(C.Structure):
                 ("inner_channel", C.c_int32), ("norm_groups", C.c_int32),
                 ("n_mults", C.c_int32), ("channel_mults", C.c_int32 * MAX_LEVELS),
                 ("n_attn_res", C.c_int32), ("attn_res", C.c_int32 * MAX_LEVELS),
-                ("res_blocks", C.c_int32), ("image_size", C.c_int32), ("with_time_emb", C.c_int32)]
+                ("res_blocks", C.c_int32), ("image_size", C.c_int32), ("with_time_emb", C.c_int32),
+                ("tf32_weights", C.c_int32)]
 
 
 class TensorView(C.Structure):
@@ -96,6 +97,14 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "ds_gnconv_bf16_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ds_conv2d_tf32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                 C.c_void_p]),
+    "ds_conv2d_tf32_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ds_gnconv_tf32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "ds_gnconv_tf32_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ds_debug_chain_phases": (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]),
     "ds_debug_halo_phases": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "ds_debug_trace_reset": (C.c_int, [C.c_int]),

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libdiffsplit_b200.so")
-SOURCES = ["api.cu", "conv_f32.cu", "conv_entry.cu", "norm.cu", "attention.cu", "attention_tc.cu", "temb.cu", "sampler.cu", "tiling.cu", "time_head.cu", "tc.cu", "tc_halo.cu", "tc_chain.cu", "unet.cu"]
+SOURCES = ["api.cu", "conv_f32.cu", "conv_entry.cu", "norm.cu", "attention.cu", "attention_tc.cu", "temb.cu", "sampler.cu", "tiling.cu", "time_head.cu", "tc.cu", "tc_halo.cu", "tc_stream.cu", "tc_chain.cu", "unet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

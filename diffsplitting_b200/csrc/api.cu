@@ -244,7 +244,7 @@ extern "C" int ds_conv2d_bf16(const void* d_xa, int ca, const void* d_xb, int cb
                "conv2d_bf16: unsupported shape (channels must be multiples of 16; stride 2 needs even H, W)");
     cudaStream_t st = (cudaStream_t)stream;
     const int kc = tc_pick_kc(ca, cb);
-    int rc = tc_pack_conv_weight(d_w_oihw, (uint8_t*)d_scratch, cout, ca + cb, ksize, upsample2x, kc, st);
+    int rc = tc_pack_conv_weight(d_w_oihw, (uint8_t*)d_scratch, cout, ca + cb, ksize, upsample2x, kc, 0, st);
     if (rc != DS_OK) return rc;
     TcConvPlan plan;
     rc = tc_build_conv(&plan, d_xa, ca, d_xb, cb, H, W, B, cout, ksize, stride, upsample2x);
@@ -273,7 +273,7 @@ extern "C" int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int 
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* wp = (uint8_t*)d_scratch;
     void* gscratch = wp + align_up(halo_packed_weight_bytes(cout, ca + cb, ksize), 1024);
-    int rc = halo_pack_conv_weight(d_w_oihw, wp, cout, ca + cb, ksize, st);
+    int rc = halo_pack_conv_weight(d_w_oihw, wp, cout, ca + cb, ksize, 0, st);
     if (rc != DS_OK) return rc;
     const float2* stats = nullptr;
     if (groups > 0) {
@@ -290,5 +290,69 @@ extern "C" int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int 
     HaloNorm nm;
     nm.stats = stats; nm.sums_a = nullptr; nm.sums_b = nullptr; nm.gamma = d_gamma; nm.beta = d_beta; nm.G = groups;
     nm.swish = apply_swish;
-    return halo_launch_conv(d_xa, ca, d_xb, cb, nm, wp, cout, ksize, B, H, W, e, d_out_f32, d_out_b16, nullptr, nullptr, st);
+    return halo_launch_conv(d_xa, ca, d_xb, cb, nm, wp, cout, ksize, B, H, W, e, d_out_f32, d_out_b16, nullptr, nullptr, 0, st);
+}
+
+// ---- the same two operators with fp32 sources read as TF32 operands (precision mode DS_PREC_TF32)
+extern "C" size_t ds_conv2d_tf32_scratch_bytes(int cin, int cout, int ksize) {
+    return align_up(tc_packed_weight_bytes(cout, cin, ksize, 1), 1024);
+}
+
+extern "C" int ds_conv2d_tf32(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_w_oihw, const float* d_bias,
+                              const float* d_residual, float* d_out_f32, int out_nchw, int B, int H, int W, int cout, int ksize,
+                              int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream) {
+    DS_REQUIRE(d_xa && d_w_oihw && d_out_f32 && d_scratch, "conv2d_tf32: null argument");
+    DS_REQUIRE(ca > 0 && cb >= 0 && (cb == 0 || d_xb), "conv2d_tf32: bad channel split %d+%d", ca, cb);
+    DS_REQUIRE(scratch_bytes >= ds_conv2d_tf32_scratch_bytes(ca + cb, cout, ksize), "conv2d_tf32: scratch too small");
+    DS_REQUIRE(tc_conv_shape_supported(ca, cb, ksize, stride, upsample2x, H, W, 1),
+               "conv2d_tf32: unsupported shape (channels must be multiples of 8; stride 2 needs even H, W)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kc = tc_pick_kc(ca, cb, 1);
+    int rc = tc_pack_conv_weight(d_w_oihw, (uint8_t*)d_scratch, cout, ca + cb, ksize, upsample2x, kc, 1, st);
+    if (rc != DS_OK) return rc;
+    TcConvPlan plan;
+    rc = tc_build_conv(&plan, d_xa, ca, d_xb, cb, H, W, B, cout, ksize, stride, upsample2x, 1);
+    if (rc != DS_OK) return rc;
+    ConvEpi e;
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0;
+    e.residual = d_residual;
+    e.out_nchw = out_nchw; e.out2_bf16 = nullptr;
+    return tc_launch_conv(&plan, (const uint8_t*)d_scratch, e, out_nchw ? nullptr : d_out_f32, nullptr, out_nchw ? d_out_f32 : nullptr,
+                          nullptr, st);
+}
+
+extern "C" size_t ds_gnconv_tf32_scratch_bytes(int B, int groups, int cin, int cout, int ksize) {
+    return align_up(halo_packed_weight_bytes(cout, cin, ksize, 1), 1024) + align_up(gn_scratch_bytes(B, groups), 256);
+}
+
+extern "C" int ds_gnconv_tf32(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma, const float* d_beta,
+                              int groups, int apply_swish, const float* d_w_oihw, const float* d_bias, const float* d_residual,
+                              float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch, size_t scratch_bytes,
+                              void* stream) {
+    DS_REQUIRE(d_xa && d_w_oihw && d_scratch && d_out_f32, "gnconv_tf32: null argument");
+    DS_REQUIRE(scratch_bytes >= ds_gnconv_tf32_scratch_bytes(B, groups > 0 ? groups : 1, ca + cb, cout, ksize),
+               "gnconv_tf32: scratch too small");
+    DS_REQUIRE(halo_conv_supported(ca, cb, cout, ksize, B, H, W, 1),
+               "gnconv_tf32: unsupported shape (channel counts multiples of 8, total a multiple of 16 and <= 224)");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* wp = (uint8_t*)d_scratch;
+    void* gscratch = wp + align_up(halo_packed_weight_bytes(cout, ca + cb, ksize, 1), 1024);
+    int rc = halo_pack_conv_weight(d_w_oihw, wp, cout, ca + cb, ksize, 1, st);
+    if (rc != DS_OK) return rc;
+    const float2* stats = nullptr;
+    if (groups > 0) {
+        unsigned* counters = nullptr;
+        rc = gn_counters(&counters);
+        if (rc != DS_OK) return rc;
+        rc = launch_gn_stats(d_xa, ca, d_xb, cb, B, H * W, groups, gscratch, counters, st);
+        if (rc != DS_OK) return rc;
+        stats = gn_stats_ptr(gscratch, B, groups);
+    }
+    ConvEpi e;
+    e.bias = d_bias; e.temb = nullptr; e.temb_off = 0; e.temb_stride = 0; e.temb_bcast = 0; e.residual = d_residual;
+    e.out_nchw = 0; e.out2_bf16 = nullptr;
+    HaloNorm nm;
+    nm.stats = stats; nm.sums_a = nullptr; nm.sums_b = nullptr; nm.gamma = d_gamma; nm.beta = d_beta; nm.G = groups;
+    nm.swish = apply_swish;
+    return halo_launch_conv(d_xa, ca, d_xb, cb, nm, wp, cout, ksize, B, H, W, e, d_out_f32, nullptr, nullptr, nullptr, 1, st);
 }

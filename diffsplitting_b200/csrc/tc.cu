@@ -42,6 +42,7 @@ struct TcParams {
     int stages;
     int8_t tap_dx[4][TC_MAX_TAPS], tap_dy[4][TC_MAX_TAPS], tap_view[4][TC_MAX_TAPS];   // per class
     int up;                           // output pixel = (2y + class/2, 2x + class%2)
+    int tf32;                         // operands are fp32 read as TF32 (KC <= 32 channels = 128-byte rows), else bf16
     TraceSlot trace;
 };
 
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = 128u * p.KC * 2u, b_bytes = (uint32_t)p.BN * p.KC * 2u;
+    const uint32_t row_bytes = (uint32_t)p.KC * (p.tf32 ? 4u : 2u);
+    const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
     const uint32_t bar_base = base + p.stages * stage_bytes;           // full[stages], empty[stages], tmem_full, tmem slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
     if (warp == 0) {
         if (elect_one()) {
-            const size_t blk16 = (size_t)16 * p.KC * 2;
+            const size_t blk16 = (size_t)16 * row_bytes;
             const uint8_t* wsrc = p.w + ((size_t)cls * U * p.nb16 + (size_t)nt * (p.BN / 16)) * blk16;
             for (int u = 0; u < U; ++u) {
                 const int s = u % p.stages;
@@ -105,9 +107,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t row_bytes = p.KC * 2u;
+            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
+            const int ksteps = (int)(row_bytes >> 5);                 // 32 bytes of every row per MMA (K = 16 bf16 / 8 tf32)
             for (int u = 0; u < U; ++u) {
                 const int s = u % p.stages;
                 const uint32_t ph = (u / p.stages) & 1;
@@ -115,8 +116,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 tc_fence_after();
                 const uint32_t sa = base + s * stage_bytes;
                 const uint64_t adesc = make_smem_desc(sa, row_bytes), bdesc = make_smem_desc(sa + a_bytes, row_bytes);
-                for (int k = 0; k < p.KC / 16; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
+                if (p.tf32) {
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
+                } else {
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
+                }
                 umma_commit(empty_bar(s));        // frees the smem slot once these MMAs have read it
             }
             umma_commit(tfull_bar);               // accumulator complete
@@ -181,6 +187,7 @@ struct TcpParams {
     TcEpi epi;
     int nb16, B, H, W, BN, n_tiles, KC, chunks_a, chunks_b, MT, tiles_x, tiles_y, wstages;
     uint32_t patch_bytes;
+    int tf32;
     TraceSlot trace;
 };
 
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+    const uint32_t row_bytes = (uint32_t)p.KC * (p.tf32 ? 4u : 2u);
     const uint32_t w_bytes = (uint32_t)p.BN * row_bytes;                    // one (tap, chunk) weight tile
     const uint32_t wstage_bytes = (w_bytes + 1023u) & ~1023u;
     const uint32_t wring = base + 2u * p.patch_bytes;
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
 
     if (warp == 0) {
         if (elect_one()) {
-            const size_t blk16 = (size_t)16 * p.KC * 2;
+            const size_t blk16 = (size_t)16 * row_bytes;
             const uint8_t* wsrc = p.w + (size_t)nt * (p.BN / 16) * blk16;
             const uint32_t box_bytes = (uint32_t)(TP_PW * (TP_TH * p.MT + 2)) * row_bytes;
             int u = 0;
@@ -251,7 +258,8 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
+            const int ksteps = (int)(row_bytes >> 5);
             int u = 0;
             for (int cc = 0; cc < nchunks; ++cc) {
                 const int pb = cc & 1;
@@ -266,9 +274,15 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
                     const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
                     for (int t = 0; t < p.MT; ++t) {
                         const uint64_t adesc = make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
-                        for (int k = 0; k < p.KC / 16; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                      (cc | tap | k) ? 1u : 0u);
+                        if (p.tf32) {
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_tf32(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                          (cc | tap | k) ? 1u : 0u);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_bf16(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                          (cc | tap | k) ? 1u : 0u);
+                        }
                     }
                     umma_commit(wempty(s));
                 }
@@ -351,7 +365,7 @@ __host__ __device__ inline uint32_t swizzle_offset(uint32_t row, uint32_t byte_i
 }
 
 struct PackGeom {
-    int cout, cin, ks, up, nb16, KC, chunks, ntaps, nclasses;
+    int cout, cin, ks, up, nb16, KC, chunks, ntaps, nclasses, tf32;
 };
 
 // largest N tile (16..128) that divides the 16-padded channel count
@@ -362,8 +376,9 @@ static int tc_bn(int cout) {
     return 16;
 }
 
-static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc) {
+static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc, int tf32) {
     PackGeom g;
+    g.tf32 = tf32;
     g.cout = cout; g.cin = cin; g.ks = ks; g.up = up;
     g.nb16 = (cout + 15) / 16;
     g.KC = kc;
@@ -373,24 +388,27 @@ static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc) {
     return g;
 }
 
-int tc_pick_kc(int ca, int cb) {
-    for (int kc = 64; kc >= 16; kc >>= 1)
+// channels per K chunk: rows of 128 / 64 / 32 bytes (bf16: 64 / 32 / 16 channels, tf32: 32 / 16 / 8)
+int tc_pick_kc(int ca, int cb, int tf32) {
+    for (int kc = tf32 ? 32 : 64; kc >= (tf32 ? 8 : 16); kc >>= 1)
         if (ca % kc == 0 && cb % kc == 0) return kc;
     return 0;
 }
 
-size_t tc_packed_weight_bytes(int cout, int cin, int ks) {
+size_t tc_packed_weight_bytes(int cout, int cin, int ks, int tf32) {
     // worst case over the variants a layer can be packed for (plain taps vs. 4 upsample classes x 4 taps)
     const size_t npad = (size_t)(cout + 15) / 16 * 16;
-    const size_t plain = npad * ks * ks * cin * 2;
-    const size_t upv = ks == 3 ? (size_t)4 * npad * 4 * cin * 2 : 0;
+    const size_t es = tf32 ? 4 : 2;
+    const size_t plain = npad * ks * ks * cin * es;
+    const size_t upv = ks == 3 ? (size_t)4 * npad * 4 * cin * es : 0;
     return plain > upv ? plain : upv;
 }
 
 __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, PackGeom g) {
     const int U = g.ntaps * g.chunks;
     const size_t total = (size_t)g.nclasses * U * g.nb16 * 16 * g.KC;
-    const uint32_t row_bytes = g.KC * 2;
+    const uint32_t es = g.tf32 ? 4u : 2u;
+    const uint32_t row_bytes = g.KC * es;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int k = (int)(r % g.KC); r /= g.KC;
@@ -419,14 +437,15 @@ __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __re
         }
         // a BN-row operand tile is BN/16 consecutive blocks: the swizzle has an 8-row period, so blocks are independent
         const size_t blk = (((size_t)cls * U + u) * g.nb16 + nb) * ((size_t)16 * row_bytes);
-        *reinterpret_cast<__nv_bfloat16*>(out + blk + swizzle_offset(row, k * 2, row_bytes)) = __float2bfloat16_rn(v);
+        if (g.tf32) *reinterpret_cast<float*>(out + blk + swizzle_offset(row, k * 4, row_bytes)) = to_tf32(v);
+        else *reinterpret_cast<__nv_bfloat16*>(out + blk + swizzle_offset(row, k * 2, row_bytes)) = __float2bfloat16_rn(v);
     }
 }
 
-int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, cudaStream_t st) {
-    DS_REQUIRE(kc == 16 || kc == 32 || kc == 64, "tc_pack: KC %d", kc);
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st) {
+    DS_REQUIRE(tf32 ? (kc == 8 || kc == 16 || kc == 32) : (kc == 16 || kc == 32 || kc == 64), "tc_pack: KC %d", kc);
     DS_REQUIRE(cin % kc == 0, "tc_pack: cin %d not a multiple of KC %d", cin, kc);
-    PackGeom g = pack_geom(cout, cin, ks, up, kc);
+    PackGeom g = pack_geom(cout, cin, ks, up, kc, tf32);
     const size_t total = (size_t)g.nclasses * g.ntaps * g.chunks * g.nb16 * 16 * g.KC;
     int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
     pack_tc_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, packed, g);
@@ -448,13 +467,14 @@ static int get_encoder() {
 }
 
 static int encode_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, size_t sx, size_t sy, size_t sb, int kc,
-                      int tw, int th, int tb) {
+                      int tw, int th, int tb, int tf32) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sb};
     cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+    const int rowb = kc * (tf32 ? 4 : 2);
+    const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = g_encode(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -464,8 +484,8 @@ static int encode_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int 
     return DS_OK;
 }
 
-bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws) {
-    if (tc_pick_kc(ca, cb) == 0 || ca <= 0) return false;
+bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws, int tf32) {
+    if (tc_pick_kc(ca, cb, tf32) == 0 || ca <= 0) return false;
     if (!(ks == 1 || ks == 3)) return false;
     if (stride == 2 && (ks != 3 || up || (Hs & 1) || (Ws & 1))) return false;
     if (up && (ks != 3 || stride != 1)) return false;
@@ -479,12 +499,13 @@ static int pow2_floor(int v) {
 }
 
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
-                  int stride, int up) {
+                  int stride, int up, int tf32) {
     int rc = get_encoder();
     if (rc != DS_OK) return rc;
-    DS_REQUIRE(tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws), "tc conv: unsupported shape");
+    DS_REQUIRE(tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws, tf32), "tc conv: unsupported shape");
     plan->patch = 0;
-    const int kc = tc_pick_kc(ca, cb);
+    const int kc = tc_pick_kc(ca, cb, tf32);
+    const size_t e = tf32 ? 4 : 2;                                  // bytes per source element
     {
         // tall-patch variant: 3x3 stride-1 layers in the throughput regime (DIFFSPLIT_B200_TC_PATCH: 0 never, 2 whenever possible)
         static int patch_env = -1;
@@ -497,7 +518,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
         const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
         const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
-        if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 148 && ca + cb >= 64))) {
+        if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 148 && (size_t)(ca + cb) * e >= 128))) {
             static_assert(sizeof(TcpParams) <= sizeof(plan->params), "TcConvPlan::params too small");
             TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
             memset(&q, 0, sizeof(q));
@@ -506,9 +527,10 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             q.nb16 = (cout + 15) / 16;
             q.BN = bn; q.n_tiles = (q.nb16 * 16) / bn;
             q.KC = kc; q.chunks_a = ca / kc; q.chunks_b = cb / kc;
+            q.tf32 = tf32;
             const int prows = TP_PW * (TP_TH * mt + 2) + 8;             // + the rows the last tile's window runs past the patch
-            q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * 2, 1024);
-            const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * 2, 1024);
+            q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
+            const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
             int wst = (int)((196 * 1024 - 2 * (size_t)q.patch_bytes - 2048 - TP_GROUPS * TC_RED_BYTES) / wstage);
             if (wst > 9) wst = 9;
             if (wst >= 2) {
@@ -517,8 +539,8 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                     const void* ptr = s_ == 0 ? src_a : src_b;
                     const int C = s_ == 0 ? ca : cb;
                     if (!ptr || C == 0) continue;
-                    rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * 2, (size_t)Ws * C * 2, (size_t)Hs * Ws * C * 2, kc, TP_PW,
-                                    TP_TH * mt + 2, 1);
+                    rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, TP_PW,
+                                    TP_TH * mt + 2, 1, tf32);
                     if (rc != DS_OK) return rc;
                 }
                 plan->patch = 1;
@@ -539,6 +561,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     p.B = B; p.H = H; p.W = W;
     p.epi.Ho = up ? 2 * H : H; p.epi.Wo = up ? 2 * W : W;
     p.up = up;
+    p.tf32 = tf32;
     // 128-pixel tile: pick the power-of-two width with the least padded columns, prefer wide
     int best_tw = 1, best_waste = 1 << 30;
     for (int tw = 128; tw >= 1; tw >>= 1) {
@@ -594,24 +617,23 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const void* ptr = s == 0 ? src_a : src_b;
         const int C = s == 0 ? ca : cb;
         if (!ptr || C == 0) continue;
-        const size_t e = 2;
         if (stride == 2) {
             for (int v = 0; v < 4; ++v) {
                 const int py = v >> 1, px = v & 1;
                 const uint8_t* bp = (const uint8_t*)ptr + ((size_t)py * Ws + px) * C * e;
                 rc = encode_map(&p.maps[s * 4 + v], bp, C, Ws / 2, Hs / 2, B, 2 * (size_t)C * e, 2 * (size_t)Ws * C * e,
-                                (size_t)Hs * Ws * C * e, kc, p.tw, p.th, p.tb);
+                                (size_t)Hs * Ws * C * e, kc, p.tw, p.th, p.tb, tf32);
                 if (rc != DS_OK) return rc;
             }
         } else {
             rc = encode_map(&p.maps[s * 4], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, p.tw,
-                            p.th, p.tb);
+                            p.th, p.tb, tf32);
             if (rc != DS_OK) return rc;
         }
     }
     // pipeline depth: every (tap, chunk) unit is one TMA round trip (~1 us), so small units need many slots in flight:
     // up to 16 stages within 72 KB (3 CTAs / SM) for small tiles, up to 160 KB (1 CTA / SM) for the large ones
-    const uint32_t stage_bytes = (uint32_t)align_up(128u * kc * 2u + (uint32_t)p.BN * kc * 2u, 1024);
+    const uint32_t stage_bytes = (uint32_t)align_up((128u + (uint32_t)p.BN) * kc * (uint32_t)e, 1024);
     const int U = p.ntaps * (p.chunks_a + p.chunks_b);
     const uint32_t budget = stage_bytes <= 8192 ? 73728u : 163840u;
     int stages = (int)(budget / stage_bytes);

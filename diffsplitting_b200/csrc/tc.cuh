@@ -10,23 +10,24 @@ struct TcConvPlan {
     int patch;                            // 1: params hold a TcpParams (tall-patch kernel)
 };
 
-int tc_pick_kc(int ca, int cb);                                    // 64 / 32 / 16, or 0 if unsupported
-bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws);
-size_t tc_packed_weight_bytes(int cout, int cin, int ks);          // upper bound over packing variants
-int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, cudaStream_t st);
-// geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 NHWC [B,Hs,Ws,c]
+// tf32 = 1: operands are fp32 tensors / fp32 weight images read by the tensor core as TF32 (kind::tf32), else bf16
+int tc_pick_kc(int ca, int cb, int tf32 = 0);                      // channels per K chunk (rows of 128 / 64 / 32 bytes), 0 if unsupported
+bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws, int tf32 = 0);
+size_t tc_packed_weight_bytes(int cout, int cin, int ks, int tf32 = 0);   // upper bound over packing variants
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st);
+// geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 (tf32: fp32) NHWC [B,Hs,Ws,c]
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
-                  int stride, int up);
+                  int stride, int up, int tf32 = 0);
 // epi.bias / temb / residual (fp32 NHWC) as in the fp32 kernel; any subset of the three outputs may be given
 // sums_out (optional): [B][cout][2] fp64 accumulators (zeroed by the caller) receiving per-channel sum / sum of squares
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
                    float* out_nchw, double* sums_out, cudaStream_t st);
 
 // ---- fused GroupNorm-apply + Swish -> conv, operands staged through registers (tc_halo.cu); sources fp32 NHWC
-bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W);
-bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W);   // supported AND faster than GN-apply + TMA conv
-size_t halo_packed_weight_bytes(int cout, int cin, int ks);
-int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st);
+bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32 = 0);
+bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32 = 0);   // supported AND faster than GN-apply + TMA conv
+size_t halo_packed_weight_bytes(int cout, int cin, int ks, int tf32 = 0);
+int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int tf32, cudaStream_t st);
 // GroupNorm statistics of the concat input: either `stats` = (mean, rstd) [B][G], or per-channel fp64 (sum, sumsq)
 // accumulators of the two sources `sums_a` [B][ca][2] / `sums_b` [B][cb][2] (as emitted by the producers' epilogues);
 // all null: no normalisation.
@@ -38,7 +39,14 @@ struct HaloNorm {
 };
 int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
                      int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
-                     double* sums_out, cudaStream_t st);
+                     double* sums_out, int tf32, cudaStream_t st);
+
+// ---- persistent, software-pipelined variant of the fused kernel for many-tile 3x3 layers whose weights fit in shared memory
+// (tc_stream.cu); same weight pack and arguments as halo_launch_conv, which dispatches to it
+bool stream_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32);
+int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
+                       int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
+                       double* sums_out, int tf32, cudaStream_t st);
 
 // ---- bf16 tensor-core self-attention (attention_tc.cu): qkv bf16 [B,N,3C] -> out bf16 [B,N,C]
 struct AttnTcPlan {

@@ -46,6 +46,9 @@ struct HaloParams {
     TcEpi epi;
     int B, H, W, Wp, HpWp, total_q;
     int C, ksteps, ntaps, BN, n_tiles, Npad;
+    int tf32;                                   // operands staged / packed as fp32 (TF32 MMA): a 16-byte plane row holds 4 channels
+                                                // and a K step is 8 channels (two planes), instead of 8 and 16 for bf16
+    int wloads;                                 // the weights arrive in `wloads` TMA boxes of (taps / wloads) taps each
     // operand buffer geometry, flat tiles: the 128 outputs and their three filter rows are ONE contiguous run of the flat
     // padded index space (130 + 2 (W + 2) positions, W + 2 <= 139; wider images use the 2-D tiles below)
     int plane_px, seg_stride_px;
@@ -71,14 +74,15 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo,
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-template <int MAXT, bool TILE2D>
+template <int MAXT, bool TILE2D, bool TF32>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-    const int P = p.C >> 3;
+    constexpr int CPP = TF32 ? 4 : 8;               // channels per 16-byte plane row
+    const int P = p.C / CPP;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const uint32_t a_bytes_total = P * plane_bytes;
     const uint32_t a_off = 0, b_off = a_bytes_total;
@@ -118,11 +122,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
         fence_barrier_init();
         // ---- weights: ONE bulk copy (constant data: may run before the predecessor kernel has finished)
         mbar_expect_tx(bfull, b_bytes);
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                base + b_off),
-            "l"(reinterpret_cast<uint64_t>(&p.wmap)), "r"(bfull), "r"(0), "r"(nt * (p.BN >> 4)), "r"(0)
-            : "memory");
+        const int per = p.ntaps * p.ksteps * 2 / p.wloads;           // (tap, kstep, plane) images per box
+        for (int l = 0; l < p.wloads; ++l)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                    base + b_off + (uint32_t)l * (uint32_t)per * (uint32_t)p.BN * 16u),
+                "l"(reinterpret_cast<uint64_t>(&p.wmap)), "r"(bfull), "r"(0), "r"(nt * (p.BN >> 4)), "r"(l * per)
+                : "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
@@ -172,40 +178,52 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             }
         }
     };
+    // bf16: a plane = 8 channels = two 16-byte loads (v0, v1);  tf32: a plane = 4 channels = one load (v0)
     auto load_plane = [&](const Pix& px_, int kp, float4& v0, float4& v1) {
         if (!px_.a) return;
-        const int c0 = kp * 8;
+        const int c0 = kp * CPP;
         const float* src = c0 < p.ca ? px_.a + c0 : px_.b + (c0 - p.ca);
         v0 = __ldg(reinterpret_cast<const float4*>(src));
-        v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        if (!TF32) v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
     };
     auto store_plane = [&](const Pix& px_, int kp, const float4& v0, const float4& v1) {
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
         if (px_.a) {
-            const float4* tb = reinterpret_cast<const float4*>(tab + px_.tabi + kp * 8);     // (a, sh) pairs of 2 channels
+            const float4* tb = reinterpret_cast<const float4*>(tab + px_.tabi + kp * CPP);   // (a, sh) pairs of 2 channels
             float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CPP / 2; ++j) {
                 const float4 sc = tb[j];
                 x[2 * j] = fmaf(x[2 * j], sc.x, sc.y);
                 x[2 * j + 1] = fmaf(x[2 * j + 1], sc.z, sc.w);
             }
             if (p.swish) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {           // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
-                    const float h = 0.5f * x[j];
-                    float th;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                    x[j] = fmaf(h, th, h);
+                for (int j = 0; j < CPP; ++j) {
+                    if (TF32) {
+                        // y * sigmoid(y) with the exponential and the division at full fp32 accuracy of the fast intrinsics
+                        // (relative error ~1e-6 << the 2^-11 of the TF32 rounding that follows; tanh.approx is only ~2^-11)
+                        x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));
+                    } else {                            // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                        const float h = 0.5f * x[j];
+                        float th;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                        x[j] = fmaf(h, th, h);
+                    }
                 }
             }
-            uint32_t w[4];
+            if (TF32) {
+                val = make_uint4(__float_as_uint(to_tf32(x[0])), __float_as_uint(to_tf32(x[1])), __float_as_uint(to_tf32(x[2])),
+                                 __float_as_uint(to_tf32(x[3])));
+            } else {
+                uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                val = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            val = make_uint4(w[0], w[1], w[2], w[3]);
         }
         const uint32_t dst = px_.dst + kp * plane_bytes;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             tc_fence_after();
             // Descriptors differ only in the 14-bit start-address field: 32-bit adds.  B image of (tap, kstep): two planes of
             // BN rows x 16 B (LBO = BN * 16), 8-row groups 128 B apart.
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = umma_idesc(p.BN, TF32);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
             const uint32_t a_lo0 = (((base + a_off) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
             const uint32_t b_lo0 = (((base + b_off) & 0x3FFFFu) >> 4) | ((uint32_t)p.BN << 16);      // LBO = BN * 16 B
@@ -311,7 +329,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
                 const int sx = p.ntaps == 9 ? tap - 3 * r : 1;
                 uint32_t a_lo = a_lo0 + (uint32_t)(r * p.seg_stride_px + sx);
                 for (int kk = 0; kk < p.ksteps; ++kk) {
-                    umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
+                    if (TF32) umma_tf32(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
+                    else umma_bf16(tmem_base, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
                     a_lo += a_kstep;
                     b_lo += b_kstep;
                 }
@@ -399,10 +418,11 @@ static int halo_plane_px(int ntaps, int W, bool two_d) {
     return (130 + 2 * (W + 2) + 7) / 8 * 8;
 }
 
-static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d) { return (size_t)(C / 8) * halo_plane_px(ntaps, W, two_d) * 16; }
+// es = bytes per staged operand element: 2 (bf16) or 4 (tf32)
+static size_t halo_a_bytes(int C, int ntaps, int W, bool two_d, int es) { return (size_t)(C * es / 16) * halo_plane_px(ntaps, W, two_d) * 16; }
 
-static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp, bool two_d) {
-    return halo_a_bytes(C, ntaps, W, two_d) + 1024 + (size_t)ntaps * (C / 16) * 2 * BN * 16 + (size_t)nsamp * C * 8 +
+static size_t halo_smem_bytes(int C, int ntaps, int W, int BN, int nsamp, bool two_d, int es) {
+    return halo_a_bytes(C, ntaps, W, two_d, es) + 1024 + (size_t)ntaps * C * BN * es + (size_t)nsamp * C * 8 +
            (size_t)nsamp * HALO_MAX_GROUPS * 8 + (size_t)nsamp * C * 16 + 96 + TC_RED_BYTES + 128;
 }
 
@@ -412,7 +432,7 @@ static int halo_samples_per_tile(int H, int W, bool two_d) {
     return (128 + 2 * Wp + 2) / HpWp + 2;
 }
 
-static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_tiles, bool two_d) {
+static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_tiles, bool two_d, int es) {
     const int npad = (cout + 15) / 16 * 16;
     int bn = 16;
     for (int c = 128; c >= 16; c >>= 1)
@@ -421,19 +441,27 @@ static int halo_pick_bn(int cout, int C, int ntaps, int W, int nsamp, int64_t m_
     // grid would leave most SMs idle
     static int min_ctas = -1;
     if (min_ctas < 0) { const char* e = getenv("DIFFSPLIT_B200_HALO_MIN_CTAS"); min_ctas = e ? atoi(e) : 48; }
-    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp, two_d) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < min_ctas)) bn >>= 1;
+    while (bn > 16 && (halo_smem_bytes(C, ntaps, W, bn, nsamp, two_d, es) > HALO_SMEM_LIMIT || m_tiles * (npad / bn) < min_ctas)) bn >>= 1;
     return bn;
 }
 
-bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) {
-    const int C = ca + cb;
-    if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 224 || ks * ks * (C / 16) * 2 > 256) return false;
+// images of one (tap, kstep, plane) the weight TMA box may hold (box dimension limit 256): the taps are spread over 1, 3 or 9 boxes
+static int halo_weight_loads(int C, int ntaps, int es) {
+    const int per_tap = C * es / 16;                      // (kstep, plane) images per tap
+    for (int l = 1; l <= ntaps; ++l)
+        if (ntaps % l == 0 && (ntaps / l) * per_tap <= 256) return l;
+    return 0;
+}
+
+bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32) {
+    const int C = ca + cb, es = tf32 ? 4 : 2;
+    if (ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 224 || halo_weight_loads(C, ks * ks, es) == 0) return false;
     if (!(ks == 1 || ks == 3)) return false;
     if ((int64_t)B * (H + 2) * (W + 2) >= (1ll << 31) - 4096) return false;
     const bool two_d = halo_use_2d(B, H, W);
     const int nsamp = halo_samples_per_tile(H, W, two_d);
     if (nsamp > HALO_MAX_SAMPLES) return false;
-    return halo_smem_bytes(C, ks * ks, W, 16, nsamp, two_d) <= HALO_SMEM_LIMIT;
+    return halo_smem_bytes(C, ks * ks, W, 16, nsamp, two_d, es) <= HALO_SMEM_LIMIT;
 }
 
 // Is the fused kernel also the FASTER choice (vs GroupNorm-apply into a bf16 tensor + the TMA-fed conv)?  Each CTA stages
@@ -442,13 +470,14 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W) 
 // for many waves, measured on B200 (8 x C x S x S, us, fused vs unfused): C=16 S=512 190 vs 249, C=32 S=512 458 vs 550,
 // C=64 S=256 257 vs 344, C=64 S=512 ~1850 vs 1360 (the re-reads spill from L2 to HBM), C=128 S=128 570 vs 166,
 // C=128 S=256 2260 vs 645.
-bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W) {
-    if (!halo_conv_supported(ca, cb, cout, ks, B, H, W)) return false;
-    const int C = ca + cb, ntaps = ks * ks;
+bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32) {
+    if (ca + cb <= 224 && stream_conv_preferred(ca, cb, cout, ks, B, H, W, tf32)) return true;      // pipelined variant (tc_stream.cu)
+    if (!halo_conv_supported(ca, cb, cout, ks, B, H, W, tf32)) return false;
+    const int C = ca + cb, ntaps = ks * ks, es = tf32 ? 4 : 2;
     const int64_t m_tiles = halo_m_tiles(B, H, W);
     const bool two_d = halo_use_2d(B, H, W);
     const int nsamp = halo_samples_per_tile(H, W, two_d);
-    const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles, two_d);
+    const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles, two_d, es);
     const int n_tiles = (cout + 15) / 16 * 16 / bn;
     if (m_tiles * n_tiles <= 4 * 148) return true;                           // latency regime
     const double redo = (double)halo_plane_px(ntaps, W, two_d) / (two_d ? (double)(HALO_TH * HALO_TW) : 128.0);   // staged per output pixel
@@ -458,44 +487,52 @@ bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W) 
     return true;
 }
 
-size_t halo_packed_weight_bytes(int cout, int cin, int ks) {
-    return (size_t)ks * ks * cin * ((cout + 15) / 16 * 16) * 2;
+size_t halo_packed_weight_bytes(int cout, int cin, int ks, int tf32) {
+    return (size_t)ks * ks * cin * ((cout + 15) / 16 * 16) * (tf32 ? 4 : 2);
 }
 
-__global__ void pack_halo_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int ks,
-                                        int npad) {
+// [16-channel block][tap][kstep][plane(2)][16 rows][CPP channels]; CPP = 8 (bf16) or 4 (tf32, values rounded to TF32)
+template <bool TF32>
+__global__ void pack_halo_weight_kernel(const float* __restrict__ w, void* __restrict__ out, int cout, int cin, int ks, int npad) {
+    constexpr int CPP = TF32 ? 4 : 8;
     const int ntaps = ks * ks;
     const size_t total = (size_t)ntaps * cin * npad;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
-        const int j = (int)(r % 8); r /= 8;
+        const int j = (int)(r % CPP); r /= CPP;
         const int row = (int)(r % 16); r /= 16;
         const int plane = (int)(r % 2); r /= 2;
-        const int kk = (int)(r % (cin / 16)); r /= (cin / 16);
+        const int kk = (int)(r % (cin / (2 * CPP))); r /= (cin / (2 * CPP));
         const int tap = (int)(r % ntaps); r /= ntaps;
         const int n = (int)r * 16 + row;
-        const int c = kk * 16 + plane * 8 + j;
+        const int c = kk * 2 * CPP + plane * CPP + j;
         const float v = n < cout ? w[((size_t)n * cin + c) * ntaps + tap] : 0.f;
-        out[i] = __float2bfloat16_rn(v);
+        if (TF32) reinterpret_cast<float*>(out)[i] = to_tf32(v);
+        else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
     }
 }
 
-int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, cudaStream_t st) {
+int halo_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int tf32, cudaStream_t st) {
     DS_REQUIRE(cin % 16 == 0, "halo_pack: cin %d not a multiple of 16", cin);
     const int npad = (cout + 15) / 16 * 16;
     const size_t total = (size_t)ks * ks * cin * npad;
     int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
-    pack_halo_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, ks, npad);
+    if (tf32) pack_halo_weight_kernel<true><<<blocks, 256, 0, st>>>(w_oihw, packed, cout, cin, ks, npad);
+    else pack_halo_weight_kernel<false><<<blocks, 256, 0, st>>>(w_oihw, packed, cout, cin, ks, npad);
     DS_CHECK_LAUNCH("pack_halo_weight");
     return DS_OK;
 }
 
 int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
                      int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
-                     double* sums_out, cudaStream_t st) {
-    DS_REQUIRE(halo_conv_supported(ca, cb, cout, ks, B, H, W), "halo conv: unsupported shape");
+                     double* sums_out, int tf32, cudaStream_t st) {
+    if (ca + cb <= 224 && stream_conv_preferred(ca, cb, cout, ks, B, H, W, tf32))
+        return stream_launch_conv(src_a, ca, src_b, cb, norm, w_packed, cout, ks, B, H, W, epi, out_f32, out_b16, out_nchw, sums_out, tf32, st);
+    DS_REQUIRE(halo_conv_supported(ca, cb, cout, ks, B, H, W, tf32), "halo conv: unsupported shape");
     HaloParams p;
     memset(&p, 0, sizeof(p));
+    const int es = tf32 ? 4 : 2;
+    p.tf32 = tf32;
     p.src_a = src_a; p.src_b = src_b; p.ca = ca; p.cb = cb;
     p.stats = norm.stats; p.sums_a = norm.sums_a; p.sums_b = norm.sums_b;
     p.gamma = norm.gamma; p.beta = norm.beta; p.G = norm.G > 0 ? norm.G : 1; p.swish = norm.swish;
@@ -509,7 +546,8 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.epi.Cout = cout; p.epi.Ho = H; p.epi.Wo = W;
     p.B = B; p.H = H; p.W = W; p.Wp = W + 2; p.HpWp = (H + 2) * (W + 2);
     p.total_q = B * p.HpWp;
-    p.C = ca + cb; p.ksteps = p.C / 16; p.ntaps = ks * ks;
+    p.C = ca + cb; p.ksteps = p.C * es / 32; p.ntaps = ks * ks;
+    p.wloads = halo_weight_loads(p.C, p.ntaps, es);
     p.Npad = (cout + 15) / 16 * 16;
     const bool two_d = halo_use_2d(B, H, W);
     const int nsamp = halo_samples_per_tile(H, W, two_d);
@@ -519,7 +557,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     p.tiles_y = (H + HALO_TH - 1) / HALO_TH;
     p.div_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
     p.div_tiles_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
-    p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles, two_d);
+    p.BN = halo_pick_bn(cout, p.C, p.ntaps, W, nsamp, m_tiles, two_d, es);
     p.n_tiles = p.Npad / p.BN;
     p.plane_px = halo_plane_px(p.ntaps, W, two_d);
     p.seg_stride_px = p.tile2d ? HALO_PW : (p.ntaps == 1 ? 0 : p.Wp);
@@ -536,13 +574,14 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
             DS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
             enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
         }
+        // (128 bf16 = 256 bytes = one 16-row x 16-byte plane image; the element type only sizes the box, nothing is converted)
         const cuuint64_t tkp = (cuuint64_t)p.ntaps * p.ksteps * 2;
         cuuint64_t dims[3] = {128, (cuuint64_t)(p.Npad / 16), tkp};
         cuuint64_t strides[2] = {tkp * 256, 256};                     // bytes: next 16-channel block, next plane image
-        cuuint32_t box[3] = {128, (cuuint32_t)(p.BN / 16), (cuuint32_t)tkp};
-        cuuint32_t es[3] = {1, 1, 1};
-        DS_REQUIRE(tkp <= 256, "halo conv: %d taps x %d k-steps exceed one TMA box", p.ntaps, p.ksteps);
-        CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint8_t*>(w_packed), dims, strides, box, es,
+        cuuint32_t box[3] = {128, (cuuint32_t)(p.BN / 16), (cuuint32_t)(tkp / p.wloads)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        DS_REQUIRE(p.wloads > 0 && tkp / p.wloads <= 256, "halo conv: %d taps x %d k-steps exceed the TMA boxes", p.ntaps, p.ksteps);
+        CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint8_t*>(w_packed), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -550,7 +589,7 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
             return DS_ERR_CUDA;
         }
     }
-    const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp, two_d);
+    const size_t smem = halo_smem_bytes(p.C, p.ntaps, W, p.BN, nsamp, two_d, es);
     p.trace = trace_next(6);
     static const bool halo_dbg = getenv("DIFFSPLIT_B200_HALO_DBG") != nullptr;
     if (halo_dbg) {
@@ -562,14 +601,6 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
         }
         p.dbg = g_halo_dbg;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<HALO_MAX_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        attr_set = true;
-    }
     // Staging is latency bound (global loads of the raw activations): single-wave grids whose shared-memory footprint leaves
     // one or two CTAs per SM anyway get extra warps that only stage.
     static int thr_env = -1;
@@ -578,13 +609,20 @@ int halo_launch_conv(const float* src_a, int ca, const float* src_b, int cb, con
     int threads = (n_ctas <= 2 * 148 && smem >= 48 * 1024) ? HALO_MAX_THREADS : HALO_THREADS;
     if (thr_env >= HALO_THREADS && thr_env <= HALO_MAX_THREADS && thr_env % 32 == 0) threads = thr_env;
     const dim3 grid((unsigned)m_tiles, p.n_tiles, 1);
-    cudaError_t err;
-    if (threads == HALO_THREADS)
-        err = two_d ? launch_pdl(conv_halo_kernel<HALO_THREADS, true>, grid, dim3(threads), smem, st, p)
-                    : launch_pdl(conv_halo_kernel<HALO_THREADS, false>, grid, dim3(threads), smem, st, p);
-    else
-        err = two_d ? launch_pdl(conv_halo_kernel<HALO_MAX_THREADS, true>, grid, dim3(threads), smem, st, p)
-                    : launch_pdl(conv_halo_kernel<HALO_MAX_THREADS, false>, grid, dim3(threads), smem, st, p);
+    typedef void (*KernelT)(const HaloParams);
+    static const KernelT kernels[8] = {
+        conv_halo_kernel<HALO_THREADS, false, false>, conv_halo_kernel<HALO_THREADS, true, false>,
+        conv_halo_kernel<HALO_MAX_THREADS, false, false>, conv_halo_kernel<HALO_MAX_THREADS, true, false>,
+        conv_halo_kernel<HALO_THREADS, false, true>, conv_halo_kernel<HALO_THREADS, true, true>,
+        conv_halo_kernel<HALO_MAX_THREADS, false, true>, conv_halo_kernel<HALO_MAX_THREADS, true, true>};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 8; ++i)
+            DS_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        attr_set = true;
+    }
+    const KernelT kern = kernels[(tf32 ? 4 : 0) + (threads == HALO_THREADS ? 0 : 2) + (two_d ? 1 : 0)];
+    const cudaError_t err = launch_pdl(kern, grid, dim3(threads), smem, st, p);
     DS_CHECK_CUDA(err);
     return DS_OK;
 }

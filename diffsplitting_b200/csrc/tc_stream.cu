@@ -1,0 +1,514 @@
+// Persistent, warp-specialised  GroupNorm-apply + Swish -> 3x3 convolution  for the THROUGHPUT regime (many waves of tiles):
+// the software-pipelined successor of conv_halo_kernel (tc_halo.cu) for layers whose whole weight image fits in shared
+// memory next to the pipeline buffers (9 C BN es <= ~100 KB: the 16..64-channel layers of the 256^2 / 512^2 levels).
+//
+// conv_halo_kernel runs  load -> normalise -> MMA -> epilogue  strictly in sequence inside a CTA and re-fetches the weights
+// for every 112-output tile (74 KB of weights for 43 KB of activations at 64 -> 64); the 64-channel 512^2 layers of
+// sr_sr3_64_512 ran at 135-156 TFLOP/s = 1.1-1.4 TB/s, a third of what HBM allows.  Here ONE CTA per SM keeps the weights
+// resident and walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  through four concurrently running stages:
+//
+//   warp 0      TMA producer   raw fp32 patch (7+2) x (16+2) x C of tile i+2 -> RAW ring (out-of-image = zero fill)
+//   warps 8-15  transform      RAW[i+1]: scale/shift (GroupNorm) + Swish -> bf16 | tf32 -> OP[(i+1)&1], the no-swizzle K-major
+//                              operand image [channel plane][patch pixel][16 B] (padding pixels written as zeros)
+//   warp 1      MMA issuer     OP[i&1]: 9 taps x C/16 tcgen05.mma, a tap = a descriptor start shifted by (18 r + s) pixels;
+//                              accumulators ACC[i&1] in TMEM (two buffers)
+//   warps 4-7   epilogue       ACC[(i-1)&1]: tcgen05.ld, + bias + conditioning vector + fp32 residual (prefetched four
+//                              16-channel chunks ahead), fp32 / bf16 NHWC or fp32 NCHW stores, GroupNorm statistics of the
+//                              output for the consumer
+//
+// linked by mbarriers (TMA complete_tx, tcgen05.commit, warp arrivals).  Geometry, operand layout, weight pack and epilogue
+// are those of conv_halo_kernel's 2-D tiles, so the two kernels are interchangeable per layer (halo_launch_conv picks).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace ds {
+
+constexpr int SK_THREADS = 512;
+constexpr int SK_XF_WARP0 = 8, SK_XF_WARPS = 8, SK_XF_THREADS = SK_XF_WARPS * 32;
+constexpr int SK_TW = 16, SK_TH = 7, SK_PW = SK_TW + 2, SK_PH = SK_TH + 2;
+constexpr int SK_PATCH_PX = SK_PW * SK_PH;               // 162 staged pixels
+constexpr int SK_PLANE_PX = 169;                         // + the rows the last window runs past the patch; 169 * 16 B = 16 mod 128:
+                                                         // the 8 planes a quarter-warp stores to hit 8 different bank groups
+constexpr int SK_NRAW = 2;
+constexpr int SK_SLOTS = 4;                              // residual / bias chunks in flight per epilogue thread
+constexpr size_t SK_SMEM_LIMIT = 225 * 1024;
+
+struct StreamParams {
+    CUtensorMap wmap;                 // packed weights (halo_pack_conv_weight image), as in conv_halo_kernel
+    CUtensorMap rmap[2];              // raw fp32 sources as (C, W, H, B) tensors, box {c, 18, 9, 1}
+    int ca, cb, C;
+    const double* sums_a; const double* sums_b;       // per-channel fp64 (sum, sumsq) [copies][B][c][2], or
+    const float2* stats;                               // (mean, rstd) [B][G]; all null: no normalisation
+    const float* gamma; const float* beta;
+    int G, swish;
+    TcEpi epi;
+    int B, H, W;
+    int ksteps, BN, wloads;
+    int tiles_x, tiles_y, n_tiles_m;
+    FastDiv div_tiles_x, div_tiles_xy;
+    uint32_t raw_bytes, raw_a_bytes, op_bytes, b_bytes;
+    TraceSlot trace;
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid_constant__ StreamParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int CPP = TF32 ? 4 : 8;                    // channels per 16-byte plane row
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t base = (raw0 + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = p.C / CPP;
+    constexpr uint32_t plane_bytes = SK_PLANE_PX * 16u;
+    // shared-memory map
+    const uint32_t w_off = 0;
+    const uint32_t op_off = (w_off + p.b_bytes + 127u) & ~127u;
+    const uint32_t raw_off = (op_off + 2u * p.op_bytes + 127u) & ~127u;
+    const uint32_t tab_off = (raw_off + SK_NRAW * p.raw_bytes + 15u) & ~15u;
+    const uint32_t bar_off = (tab_off + (uint32_t)p.B * p.C * 8u + 15u) & ~15u;
+    const uint32_t bars = base + bar_off;
+    auto full_raw = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_raw = [&](int s) { return bars + 8u * (uint32_t)(SK_NRAW + s); };
+    auto full_op = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + s); };
+    auto empty_op = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 2 + s); };
+    auto full_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 4 + s); };
+    auto empty_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 6 + s); };
+    const uint32_t wfull = bars + 8u * (uint32_t)(2 * SK_NRAW + 8), tmem_slot = wfull + 8u;
+    uint8_t* red = gbase + bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10);
+    const int nt = blockIdx.y;
+    const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : (2u * (uint32_t)p.BN <= 256u ? 256u : 512u)));
+    const int my_tiles = ((int)blockIdx.x < p.n_tiles_m) ? (p.n_tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    trace_begin(p.trace);
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < SK_NRAW; ++s) { mbar_init(full_raw(s), 1); mbar_init(empty_raw(s), SK_XF_WARPS); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full_op(s), SK_XF_WARPS); mbar_init(empty_op(s), 1);
+            mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4);
+        }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+        // weights: constant data, fetched before the predecessor kernel has finished
+        mbar_expect_tx(wfull, p.b_bytes);
+        const int per = 9 * p.ksteps * 2 / p.wloads;
+        for (int l = 0; l < p.wloads; ++l)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                    base + w_off + (uint32_t)l * (uint32_t)per * (uint32_t)p.BN * 16u),
+                "l"(reinterpret_cast<uint64_t>(&p.wmap)), "r"(wfull), "r"(0), "r"(nt * (p.BN >> 4)), "r"(l * per)
+                : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    // the operand rows behind the patch (read by the last windows of rows 126, 127: discarded outputs) must hold finite values
+    for (uint32_t i = tid; i < 2u * (uint32_t)P * (SK_PLANE_PX - SK_PATCH_PX); i += SK_THREADS) {
+        const uint32_t s = i / ((uint32_t)P * (SK_PLANE_PX - SK_PATCH_PX)), r = i - s * (uint32_t)P * (SK_PLANE_PX - SK_PATCH_PX);
+        const uint32_t pl = r / (SK_PLANE_PX - SK_PATCH_PX), px = SK_PATCH_PX + (r - pl * (SK_PLANE_PX - SK_PATCH_PX));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + op_off + s * p.op_bytes + pl * plane_bytes + px * 16u), "r"(0u) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    pdl_wait();
+    pdl_trigger();
+
+    auto tile_coords = [&](int i, int& b, int& y0, int& x0) {
+        const int t = (int)blockIdx.x + i * (int)gridDim.x;
+        b = fdiv(t, p.div_tiles_xy);
+        const int rem = t - b * p.tiles_x * p.tiles_y;
+        const int ty = fdiv(rem, p.div_tiles_x);
+        y0 = ty * SK_TH;
+        x0 = (rem - ty * p.tiles_x) * SK_TW;
+    };
+    auto issue_raw = [&](int i) {              // one elected thread of warp 0
+        const int s = i % SK_NRAW;
+        int b, y0, x0;
+        tile_coords(i, b, y0, x0);
+        mbar_expect_tx(full_raw(s), p.raw_bytes);
+        const uint32_t dst = base + raw_off + (uint32_t)s * p.raw_bytes;
+        tma_load_4d(dst, &p.rmap[0], full_raw(s), 0, x0 - 1, y0 - 1, b);
+        if (p.cb) tma_load_4d(dst + p.raw_a_bytes, &p.rmap[1], full_raw(s), 0, x0 - 1, y0 - 1, b);
+    };
+    if (warp == 0 && elect_one()) {            // the first patches travel while the scale / shift table is built
+        for (int i = 0; i < SK_NRAW && i < my_tiles; ++i) issue_raw(i);
+    }
+
+    // ---- per (sample, channel) scale / shift of the fused GroupNorm: a = rstd * gamma, sh = beta - mean * a  (all threads)
+    float2* tab = reinterpret_cast<float2*>(gbase + tab_off);
+    {
+        const bool norm = p.stats || p.sums_a;
+        const int cpg = norm ? p.C / p.G : 1;
+        double2* chs = reinterpret_cast<double2*>(gbase + op_off + p.op_bytes);      // OP[1] is idle until the second tile
+        if (p.sums_a) {
+            for (int i = tid; i < p.B * p.C; i += SK_THREADS) {
+                const int b = i / p.C, cc = i - b * p.C;
+                const bool first = cc < p.ca;
+                const double2* src = reinterpret_cast<const double2*>(
+                    first ? p.sums_a + ((size_t)b * p.ca + cc) * 2 : p.sums_b + ((size_t)b * p.cb + (cc - p.ca)) * 2);
+                const size_t cstride = (size_t)p.B * (first ? p.ca : p.cb);
+                double2 v[TC_SUM_COPIES];
+#pragma unroll
+                for (int k = 0; k < TC_SUM_COPIES; ++k) v[k] = src[k * cstride];
+                double sm = 0.0, sq = 0.0;
+#pragma unroll
+                for (int k = 0; k < TC_SUM_COPIES; ++k) { sm += v[k].x; sq += v[k].y; }
+                chs[i] = make_double2(sm, sq);
+            }
+            __syncthreads();
+        }
+        const double inv_cnt = norm ? 1.0 / ((double)p.H * p.W * cpg) : 0.0;
+        for (int i = tid; i < p.B * p.C; i += SK_THREADS) {
+            const int b = i / p.C, c = i - b * p.C;
+            float a = 1.f, sh = 0.f;
+            if (p.sums_a) {
+                const double2* cs = chs + b * p.C + c / cpg * cpg;
+                double sm = 0.0, sq = 0.0;
+                for (int k = 0; k < cpg; ++k) { sm += cs[k].x; sq += cs[k].y; }
+                const double mu = sm * inv_cnt;
+                double var = sq * inv_cnt - mu * mu;
+                if (var < 0.0) var = 0.0;
+                a = rsqrtf((float)var + 1e-5f) * p.gamma[c];
+                sh = p.beta[c] - (float)mu * a;
+            } else if (norm) {
+                const float2 st = p.stats[(size_t)b * p.G + c / cpg];
+                a = st.y * p.gamma[c];
+                sh = p.beta[c] - st.x * a;
+            }
+            tab[i] = make_float2(a, sh);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== TMA producer: patch of tile i once the transform warps have released its ring slot
+        if (elect_one()) {
+            for (int i = SK_NRAW; i < my_tiles; ++i) {
+                mbar_wait(empty_raw(i % SK_NRAW), (uint32_t)((i / SK_NRAW) & 1) ^ 1u);
+                issue_raw(i);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        if (elect_one()) {
+            mbar_wait(wfull, 0);
+            const uint32_t idesc = umma_idesc(p.BN, TF32);
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+            const uint32_t b_lo0 = (((base + w_off) & 0x3FFFFu) >> 4) | ((uint32_t)p.BN << 16);      // LBO = BN * 16 B
+            const uint32_t a_kstep = (2u * plane_bytes) >> 4, b_kstep = (uint32_t)p.BN * 2u;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(full_op(s), ph);
+                mbar_wait(empty_acc(s), ph ^ 1u);
+                tc_fence_after();
+                const uint32_t a_lo0 = (((base + op_off + (uint32_t)s * p.op_bytes) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
+                const uint32_t acc = tmem_base + (uint32_t)(s * p.BN);
+                uint32_t b_lo = b_lo0;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int r = tap / 3, sx = tap - 3 * r;
+                    uint32_t a_lo = a_lo0 + (uint32_t)(r * SK_PW + sx);
+                    for (int kk = 0; kk < p.ksteps; ++kk) {
+                        if (TF32) umma_tf32(acc, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
+                        else umma_bf16(acc, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
+                        a_lo += a_kstep;
+                        b_lo += b_kstep;
+                    }
+                }
+                umma_commit(empty_op(s));         // the operand image may be overwritten once these MMAs have read it
+                umma_commit(full_acc(s));         // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue: warp q owns TMEM lanes [32q, 32q + 32) = patch positions = output pixels (pr, pc)
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int te = tid - 128;
+        const int pr = m / SK_PW, pc = m - pr * SK_PW;
+        const int nchunks = p.BN >> 4;
+        const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
+        float add[SK_SLOTS][16];
+        // chunk stream over (tile, 16-channel chunk): addends are requested SK_SLOTS chunks ahead of their use
+        auto where = [&](int g, int& b, int& y, int& x, int& c0, bool& valid) {
+            const int i = g / nchunks;
+            int y0, x0;
+            tile_coords(i, b, y0, x0);
+            c0 = (g - i * nchunks) * 16;
+            y = y0 + pr;
+            x = x0 + pc;
+            valid = pr < SK_TH && pc < SK_TW && y < p.H && x < p.W;
+        };
+        const int total = my_tiles * nchunks;
+        auto request = [&](int g, float (&a)[16]) {
+            if (g >= total) return;
+            int b, y, x, c0; bool valid;
+            where(g, b, y, x, c0, valid);
+            if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, a);
+        };
+#pragma unroll
+        for (int k = 0; k < SK_SLOTS; ++k) request(k, add[k]);
+        for (int g0 = 0; g0 < total; g0 += SK_SLOTS) {
+#pragma unroll
+            for (int k = 0; k < SK_SLOTS; ++k) {
+                const int g = g0 + k;
+                if (g < total) {
+                    const int i = g / nchunks, s = i & 1;
+                    int b, y, x, c0; bool valid;
+                    where(g, b, y, x, c0, valid);
+                    if (c0 == 0) {
+                        mbar_wait(full_acc(s), (uint32_t)(i >> 1) & 1u);
+                        tc_fence_after();
+                    }
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
+                    if (c0 + 16 == p.BN) {        // last read of this accumulator buffer: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_acc(s)) : "memory");
+                    }
+                    float f[16];
+                    if (valid) tc_epilogue_write(p.epi, v, add[k], b, y, x, nt * p.BN + c0, f);
+                    request(g + SK_SLOTS, add[k]);
+                    if (p.epi.sums_out) tc_epilogue_stats_shfl<1>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, red);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp >= SK_XF_WARP0) {
+        // ===== transform: raw fp32 patch -> normalise -> Swish -> operand image
+        const int xt = tid - SK_XF_WARP0 * 32;
+        const uint32_t ca4 = (uint32_t)p.ca * 4u, cb4 = (uint32_t)p.cb * 4u;
+        const bool fixed = (SK_XF_THREADS % P) == 0;        // the thread's channel plane is the same for all its items
+        for (int i = 0; i < my_tiles; ++i) {
+            const int r = i % SK_NRAW, s = i & 1;
+            int b, y0, x0;
+            tile_coords(i, b, y0, x0);
+            const float2* tb_s = tab + b * p.C;
+            float4 sc[CPP / 2];
+            if (fixed) {
+                const int kp = xt % P;
+#pragma unroll
+                for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + kp * CPP)[j];
+            }
+            mbar_wait(full_raw(r), (uint32_t)((i / SK_NRAW) & 1));
+            mbar_wait(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            const uint32_t rawb = base + raw_off + (uint32_t)r * p.raw_bytes;
+            const uint32_t opb = base + op_off + (uint32_t)s * p.op_bytes;
+            const int items = P * SK_PATCH_PX;
+            for (int it = xt; it < items; it += SK_XF_THREADS) {
+                const int px = it / P, kp = it - px * P;
+                const int pr = px / SK_PW, pc = px - pr * SK_PW;
+                const int yy = y0 + pr - 1, xx = x0 + pc - 1;
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                    const int c0 = kp * CPP;
+                    const uint32_t src = c0 < p.ca ? rawb + (uint32_t)px * ca4 + (uint32_t)c0 * 4u
+                                                    : rawb + p.raw_a_bytes + (uint32_t)px * cb4 + (uint32_t)(c0 - p.ca) * 4u;
+                    float x[CPP];
+                    {
+                        float4 v0;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src));
+                        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                        if (!TF32) {
+                            float4 v1;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + 16u));
+                            x[CPP - 4] = v1.x; x[CPP - 3] = v1.y; x[CPP - 2] = v1.z; x[CPP - 1] = v1.w;
+                        }
+                    }
+                    if (!fixed) {
+#pragma unroll
+                        for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + c0)[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < CPP / 2; ++j) {
+                        x[2 * j] = fmaf(x[2 * j], sc[j].x, sc[j].y);
+                        x[2 * j + 1] = fmaf(x[2 * j + 1], sc[j].z, sc[j].w);
+                    }
+                    if (p.swish) {
+#pragma unroll
+                        for (int j = 0; j < CPP; ++j) {
+                            if (TF32) {
+                                x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));
+                            } else {                    // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                                const float h = 0.5f * x[j];
+                                float th;
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                                x[j] = fmaf(h, th, h);
+                            }
+                        }
+                    }
+                    if (TF32) {
+                        val = make_uint4(__float_as_uint(to_tf32(x[0])), __float_as_uint(to_tf32(x[1])), __float_as_uint(to_tf32(x[2])),
+                                         __float_as_uint(to_tf32(x[3])));
+                    } else {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(x[(2 * j) % CPP], x[(2 * j + 1) % CPP]);
+                            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        val = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(opb + (uint32_t)kp * plane_bytes + (uint32_t)px * 16u), "r"(val.x),
+                             "r"(val.y), "r"(val.z), "r"(val.w)
+                             : "memory");
+            }
+            fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_op(s)) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_raw(r)) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+    trace_end(p.trace);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static size_t stream_smem_bytes(int C, int BN, int B, int es) {
+    const size_t b_bytes = (size_t)9 * C * BN * es;
+    const size_t op_bytes = (size_t)(C * es / 16) * SK_PLANE_PX * 16;
+    const size_t raw_bytes = (size_t)SK_PATCH_PX * C * 4;
+    return 1024 + align_up(b_bytes, 128) + align_up(2 * op_bytes, 128) + SK_NRAW * raw_bytes + 128 + (size_t)B * C * 8 + 16 +
+           8 * (2 * SK_NRAW + 10) + TC_RED_BYTES + 256;
+}
+
+static int stream_weight_loads(int C, int es) {
+    const int per_tap = C * es / 16;
+    for (int l = 1; l <= 9; ++l)
+        if (9 % l == 0 && (9 / l) * per_tap <= 256) return l;
+    return 0;
+}
+
+static int stream_pick_bn(int cout, int C, int B, int es) {
+    const int npad = (cout + 15) / 16 * 16;
+    for (int bn = npad; bn >= 16; bn -= 16) {
+        if (npad % bn || bn > 256) continue;
+        if (stream_smem_bytes(C, bn, B, es) <= SK_SMEM_LIMIT) return bn;
+    }
+    return 0;
+}
+
+// The pipelined kernel pays off when every CTA walks several tiles (weights / table / TMEM once per CTA, stages overlapped)
+// and the input need not be staged more than twice (N split only when the weights force it).
+bool stream_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("DIFFSPLIT_B200_STREAM"); mode = e ? atoi(e) : 1; }
+    if (mode == 0) return false;
+    const int C = ca + cb, es = tf32 ? 4 : 2;
+    if (ks != 3 || ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 256 || W < 8) return false;
+    if (ca * 4 > 1024 || cb * 4 > 1024) return false;                 // TMA box: <= 256 elements per dimension
+    if (stream_weight_loads(C, es) == 0) return false;
+    const int bn = stream_pick_bn(cout, C, B, es);
+    if (bn == 0) return false;
+    const int n_tiles = (cout + 15) / 16 * 16 / bn;
+    if (n_tiles > 2) return false;
+    if ((size_t)B * C * 16 > (size_t)(C * es / 16) * SK_PLANE_PX * 16) return false;     // statistics fold scratch = OP[1]
+    const int64_t m_tiles = (int64_t)B * ((H + SK_TH - 1) / SK_TH) * ((W + SK_TW - 1) / SK_TW);
+    return mode == 2 || m_tiles * n_tiles >= 4 * 148;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
+static int stream_encoder() {
+    if (g_enc) return DS_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DS_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return DS_OK;
+}
+
+int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, const HaloNorm& norm, const uint8_t* w_packed,
+                       int cout, int ks, int B, int H, int W, const ConvEpi& epi, float* out_f32, void* out_b16, float* out_nchw,
+                       double* sums_out, int tf32, cudaStream_t st) {
+    DS_REQUIRE(ks == 3 && stream_conv_preferred(ca, cb, cout, ks, B, H, W, tf32) , "stream conv: unsupported shape");
+    int rc = stream_encoder();
+    if (rc != DS_OK) return rc;
+    StreamParams p;
+    memset(&p, 0, sizeof(p));
+    const int es = tf32 ? 4 : 2;
+    p.ca = ca; p.cb = cb; p.C = ca + cb;
+    p.stats = norm.stats; p.sums_a = norm.sums_a; p.sums_b = norm.sums_b;
+    p.gamma = norm.gamma; p.beta = norm.beta; p.G = norm.G > 0 ? norm.G : 1; p.swish = norm.swish;
+    p.epi.sums_out = sums_out; p.epi.sums_B = B;
+    p.epi.bias = epi.bias; p.epi.temb = epi.temb; p.epi.temb_off = epi.temb_off; p.epi.temb_stride = epi.temb_stride;
+    p.epi.temb_bcast = epi.temb_bcast; p.epi.residual = epi.residual;
+    p.epi.out_f32 = out_f32; p.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); p.epi.out_nchw = out_nchw;
+    p.epi.Cout = cout; p.epi.Ho = H; p.epi.Wo = W;
+    p.B = B; p.H = H; p.W = W;
+    p.ksteps = p.C * es / 32;
+    p.wloads = stream_weight_loads(p.C, es);
+    p.BN = stream_pick_bn(cout, p.C, B, es);
+    const int npad = (cout + 15) / 16 * 16;
+    const int n_tiles = npad / p.BN;
+    p.tiles_x = (W + SK_TW - 1) / SK_TW;
+    p.tiles_y = (H + SK_TH - 1) / SK_TH;
+    p.n_tiles_m = B * p.tiles_x * p.tiles_y;
+    p.div_tiles_x = make_fastdiv((uint32_t)p.tiles_x);
+    p.div_tiles_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
+    p.b_bytes = (uint32_t)(9 * p.C * p.BN * es);
+    p.op_bytes = (uint32_t)((p.C * es / 16) * SK_PLANE_PX * 16);
+    p.raw_a_bytes = (uint32_t)(SK_PATCH_PX * ca * 4);
+    p.raw_bytes = (uint32_t)(SK_PATCH_PX * p.C * 4);
+    {
+        const cuuint64_t tkp = (cuuint64_t)9 * p.ksteps * 2;
+        cuuint64_t dims[3] = {128, (cuuint64_t)(npad / 16), tkp};
+        cuuint64_t strides[2] = {tkp * 256, 256};
+        cuuint32_t box[3] = {128, (cuuint32_t)(p.BN / 16), (cuuint32_t)(tkp / p.wloads)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = g_enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint8_t*>(w_packed), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("stream conv: cuTensorMapEncodeTiled for the weights failed (%d)", (int)r); return DS_ERR_CUDA; }
+    }
+    for (int s = 0; s < 2; ++s) {
+        const float* ptr = s == 0 ? src_a : src_b;
+        const int c = s == 0 ? ca : cb;
+        if (!ptr || c == 0) continue;
+        cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)W * c * 4, (cuuint64_t)H * W * c * 4};
+        cuuint32_t box[4] = {(cuuint32_t)c, SK_PW, SK_PH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_enc(&p.rmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("stream conv: cuTensorMapEncodeTiled for source %d failed (%d)", s, (int)r); return DS_ERR_CUDA; }
+    }
+    const size_t smem = stream_smem_bytes(p.C, p.BN, B, es);
+    p.trace = trace_next(6);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_LIMIT + 2048));
+        DS_CHECK_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_LIMIT + 2048));
+        attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        DS_CHECK_CUDA(cudaGetDevice(&dev));
+        DS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int gx = sms / n_tiles;
+    if (gx > p.n_tiles_m) gx = p.n_tiles_m;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)n_tiles, 1);
+    const cudaError_t err = tf32 ? launch_pdl(conv_stream_kernel<true>, grid, dim3(SK_THREADS), smem, st, p)
+                                 : launch_pdl(conv_stream_kernel<false>, grid, dim3(SK_THREADS), smem, st, p);
+    DS_CHECK_CUDA(err);
+    return DS_OK;
+}
+
+}  // namespace ds

@@ -31,6 +31,10 @@ struct WeightSpec {
     size_t off_halo;   // byte offset of that pack in the bf16 arena
     bool chain;        // additionally packed for the per-sample persistent chain kernel (tc_chain.cu)
     size_t off_chain;
+    int tc_kc32;       // TF32 images (ds_unet_desc.tf32_weights): K chunk of the TMA-fed pack (0 = none) ...
+    size_t off_tf32;   // ... its byte offset in the tensor-core arena ...
+    bool halo32;       // ... and the fused kernel's TF32 pack
+    size_t off_halo32;
     bool loaded;
 };
 
@@ -81,6 +85,8 @@ struct Op {
     int halo = 0;
     const GNW* fgn = nullptr;
     int fswish = 0;
+    // tensor-core conv whose sources are the fp32 copies, read as TF32 operands (DS_PREC_TF32)
+    int tf32 = 0;
     // conv executed inside a per-sample persistent chain launch (tc_chain.cu): consecutive chain ops form one launch
     int chain = 0, chain_src_b16 = 0;
     // chain conv2 with the block's 1x1 res_conv folded in: raw second operand (fp32 copies) and its weights
@@ -221,6 +227,10 @@ static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initia
     s.off_halo = 0;
     s.chain = false;
     s.off_chain = 0;
+    s.tc_kc32 = 0;
+    s.off_tf32 = 0;
+    s.halo32 = false;
+    s.off_halo32 = 0;
     size_t elems = 1;
     if (kind == WK_CONV) elems = (size_t)s.shape[1] * s.shape[2] * s.shape[3] * npad;
     else if (kind == WK_VEC) elems = (size_t)(npad ? npad : s.shape[0]);
@@ -259,6 +269,18 @@ static ConvW add_conv(ds_unet* n, const std::string& p, int cin, int cout, int k
         n->specs[c.w].halo = true;
         n->specs[c.w].off_halo = n->arena_bf16_bytes;
         n->arena_bf16_bytes += align_up(halo_packed_weight_bytes(cout, cin, ks), 1024);
+    }
+    if (n->d.tf32_weights) {
+        if (tc && tc_pick_kc(ca, cb, 1)) {
+            n->specs[c.w].tc_kc32 = tc_pick_kc(ca, cb, 1);
+            n->specs[c.w].off_tf32 = n->arena_bf16_bytes;
+            n->arena_bf16_bytes += align_up(tc_packed_weight_bytes(cout, cin, ks, 1), 1024);
+        }
+        if (halo && cin % 16 == 0 && cin <= 224) {
+            n->specs[c.w].halo32 = true;
+            n->specs[c.w].off_halo32 = n->arena_bf16_bytes;
+            n->arena_bf16_bytes += align_up(halo_packed_weight_bytes(cout, cin, ks, 1), 1024);
+        }
     }
     if (tc && !up && cin % 16 == 0 && cin <= 256 && (cout + 15) / 16 * 16 <= 256) {
         n->specs[c.w].chain = true;
@@ -408,7 +430,9 @@ struct Planner {
     Plan* p;
     Arena arena;
     int B;
-    bool tc;          // bf16 mode: tensor-core convs (bf16 operands), fp32 residual stream
+    bool tc;          // bf16 / tf32 mode: tensor-core convs, fp32 residual stream
+    bool tf32 = false;   // tf32 mode: the convs read the fp32 tensors themselves as TF32 operands - no bf16 copies except around
+                         // the attention kernel (bf16 q / k / v)
     size_t stats_top = 0;
     Planner(ds_unet* n_, Plan* p_, bool reuse) : n(n_), p(p_), arena(reuse) {}
 
@@ -418,6 +442,7 @@ struct Planner {
         Act a;
         a.C = C; a.H = H; a.W = W;
         if (!tc) fmt = F32;
+        if (tf32 && (fmt & F32)) fmt = F32;
         if (tc && (fmt & F32) && want_sums) {       // a GroupNorm will read this tensor: its producer emits the statistics
             a.sums = (int64_t)stats_top;
             stats_top += align_up((size_t)TC_SUM_COPIES * B * C * 2 * sizeof(double), 256);
@@ -436,7 +461,8 @@ struct Planner {
     void tap(const std::string& name, const Act& a) {
         p->taps[name] = a.f32 != NONE ? Tap{a.f32, a.C, a.H, a.W, 0} : Tap{a.b16, a.C, a.H, a.W, 1};
     }
-    int64_t conv_src(const Act& a) const { return tc ? a.b16 : a.f32; }
+    bool src_tf32(const Act& a) const { return tf32 && a.f32 != NONE; }
+    int64_t conv_src(const Act& a) const { return (tc && !src_tf32(a)) ? a.b16 : a.f32; }
 
     void gn(const Act& a, const Act* b, const GNW& g, int swish, const Act& out) {
         Op o; o.kind = OP_GN;
@@ -452,7 +478,7 @@ struct Planner {
     // 128-row tiles
     int chain_mtiles = 1;
     bool chain_ok(const Act& a, const Act* b, const ConvW& w, int stride, int up) const {
-        if (!tc || chain_mtiles <= 0 || stride != 1 || up || !n->specs[w.w].chain) return false;
+        if (!tc || tf32 || chain_mtiles <= 0 || stride != 1 || up || !n->specs[w.w].chain) return false;
         if ((a.H + 2) * (a.W + 2) > 128 * chain_mtiles) return false;
         return chain_conv_supported(a.C, b ? b->C : 0, w.cout, w.ks, a.H, a.W);
     }
@@ -477,6 +503,7 @@ struct Planner {
             return;
         }
         Op o; o.kind = OP_CONV;
+        o.tf32 = src_tf32(a) ? 1 : 0;
         o.src_a = conv_src(a); o.ca = a.C; o.Hs = a.H; o.Ws = a.W;
         if (b) { o.src_b = conv_src(*b); o.cb = b->C; }
         o.cw = &w; o.stride = stride; o.up = up; o.temb_off = temb_off;
@@ -496,8 +523,9 @@ struct Planner {
             chain_conv(a, b, &g, swish, w, temb_off, residual, out);
             return;
         }
-        if (tc && n->specs[w.w].halo && halo_conv_preferred(a.C, cb, w.cout, w.ks, B, a.H, a.W)) {
+        if (tc && (tf32 ? n->specs[w.w].halo32 : n->specs[w.w].halo) && halo_conv_preferred(a.C, cb, w.cout, w.ks, B, a.H, a.W, tf32)) {
             Op o; o.kind = OP_CONV;
+            o.tf32 = tf32 ? 1 : 0;
             o.sums_a = a.sums;
             if (b) o.sums_b = b->sums;
             o.sums_out = out.sums;
@@ -510,7 +538,7 @@ struct Planner {
             p->ops.push_back(o);
             return;
         }
-        Act act = make(a.C + cb, a.H, a.W, B16);
+        Act act = make(a.C + cb, a.H, a.W, tf32 ? F32 : B16, false);
         gn(a, b, g, swish, act);
         conv(act, nullptr, w, 1, 0, temb_off, residual, out);
         release(act);
@@ -575,12 +603,14 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
     DS_REQUIRE(B > 0 && H > 0 && W > 0, "unet: bad shape B=%d H=%d W=%d", B, H, W);
     DS_REQUIRE(B <= GN_MAX_BATCH, "unet: batch %d > %d", B, GN_MAX_BATCH);
     DS_REQUIRE(H % down == 0 && W % down == 0, "unet: H=%d W=%d must be divisible by %d", H, W, down);
-    DS_REQUIRE(prec == DS_PREC_FP32 || prec == DS_PREC_BF16, "unet: unknown precision %d", prec);
+    DS_REQUIRE(prec == DS_PREC_FP32 || prec == DS_PREC_BF16 || prec == DS_PREC_TF32, "unet: unknown precision %d", prec);
+    DS_REQUIRE(prec != DS_PREC_TF32 || d.tf32_weights, "unet: DS_PREC_TF32 needs a handle created with ds_unet_desc.tf32_weights = 1");
     Plan* p = new Plan();
     p->B = B; p->H = H; p->W = W; p->prec = prec;
     Planner P(n, p, !n->keep_taps);
     P.B = B;
-    P.tc = prec == DS_PREC_BF16;
+    P.tc = prec != DS_PREC_FP32;
+    P.tf32 = prec == DS_PREC_TF32;
     {
         const char* e = getenv("DIFFSPLIT_B200_CHAIN_MTILES");      // 0 disables the per-sample persistent chains
         P.chain_mtiles = e ? atoi(e) : 1;
@@ -770,11 +800,20 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
             if (rc != DS_OK) return rc;
             if (s.tc_kc) {
                 rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_bf16, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
-                                         s.tc_up, s.tc_kc, st);
+                                         s.tc_up, s.tc_kc, 0, st);
                 if (rc != DS_OK) return rc;
             }
             if (s.halo) {
-                rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], st);
+                rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], 0, st);
+                if (rc != DS_OK) return rc;
+            }
+            if (s.tc_kc32) {
+                rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_tf32, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
+                                         s.tc_up, s.tc_kc32, 1, st);
+                if (rc != DS_OK) return rc;
+            }
+            if (s.halo32) {
+                rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo32, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], 1, st);
                 if (rc != DS_OK) return rc;
             }
             if (s.chain) {
@@ -944,7 +983,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
     }
     void* gn_scratch = ptr(p->gn_scratch);
     unsigned* counters = reinterpret_cast<unsigned*>(base + p->stats_base + p->counters_off);
-    const bool tc = precision == DS_PREC_BF16;
+    const bool tc = precision != DS_PREC_FP32;
     if (tc && p->tc_ws != d_ws) {
         // (re)encode the TMA descriptors for this workspace address
         p->tc.assign(p->ops.size(), TcConvPlan());
@@ -956,14 +995,15 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 if (rc != DS_OK) return rc;
             }
             if (o.kind != OP_CONV || o.src_nchw || o.halo || o.chain) continue;
-            if (!n->specs[o.cw->w].tc_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws)) {
-                set_error("unet_forward: bf16 mode needs channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
+            const int want_kc = o.tf32 ? n->specs[o.cw->w].tc_kc32 : n->specs[o.cw->w].tc_kc;
+            if (!want_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws, o.tf32)) {
+                set_error("unet_forward: the tensor-core modes need channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
                           n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
                 return DS_ERR_INVALID;
             }
-            rc = tc_build_conv(&p->tc[i], ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, o.Hs, o.Ws, B, o.cw->cout, o.cw->ks, o.stride, o.up);
+            rc = tc_build_conv(&p->tc[i], ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, o.Hs, o.Ws, B, o.cw->cout, o.cw->ks, o.stride, o.up, o.tf32);
             if (rc != DS_OK) return rc;
-            if (p->tc[i].kc != n->specs[o.cw->w].tc_kc) {
+            if (p->tc[i].kc != want_kc) {
                 set_error("unet_forward: internal error, K-chunk mismatch for %s", n->specs[o.cw->w].name.c_str());
                 return DS_ERR_INVALID;
             }
@@ -1029,9 +1069,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
         if (prof && rep_i == 1) cudaEventRecord(prof->e0, st);
         switch (o.kind) {
             case OP_GN:
-                if (tc)
+                if (tc)      // the normalised conv operand: bf16, or fp32 when the consumer reads it as TF32
                     rc = launch_gn_apply_sums(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, sums(o.sums_a), sums(o.sums_b), n->wp(o.gw->w),
-                                              n->wp(o.gw->b), ptr(o.dst_b16), B, o.HW, n->d.norm_groups, o.swish, 1, gn_scratch, st);
+                                              n->wp(o.gw->b), o.dst_b16 != NONE ? (void*)ptr(o.dst_b16) : (void*)ptr(o.dst), B, o.HW,
+                                              n->d.norm_groups, o.swish, o.dst_b16 != NONE ? 1 : 0, gn_scratch, st);
                 else
                     rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
                                           n->d.norm_groups, o.swish, gn_scratch, counters, 0, st);
@@ -1080,12 +1121,14 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     HaloNorm nm;
                     nm.stats = nullptr; nm.sums_a = sums(o.sums_a); nm.sums_b = sums(o.sums_b);
                     nm.gamma = n->wp(o.fgn->w); nm.beta = n->wp(o.fgn->b); nm.G = n->d.norm_groups; nm.swish = o.fswish;
-                    rc = halo_launch_conv(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, nm, n->d_arena_bf16 + n->specs[o.cw->w].off_halo,
+                    rc = halo_launch_conv(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, nm,
+                                          n->d_arena_bf16 + (o.tf32 ? n->specs[o.cw->w].off_halo32 : n->specs[o.cw->w].off_halo),
                                           o.cw->cout, o.cw->ks, B, o.Hs, o.Ws, e, o.out_nchw ? nullptr : ptr(o.dst), ptr(o.dst_b16),
-                                          o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st);
+                                          o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), o.tf32, st);
                 } else if (tc && !o.src_nchw) {
                     used_tc = true;
-                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + n->specs[o.cw->w].off_bf16, e, o.out_nchw ? nullptr : ptr(o.dst),
+                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + (o.tf32 ? n->specs[o.cw->w].off_tf32 : n->specs[o.cw->w].off_bf16), e,
+                                        o.out_nchw ? nullptr : ptr(o.dst),
                                         ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st);
                 } else {
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,

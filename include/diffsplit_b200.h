@@ -37,7 +37,10 @@ typedef enum ds_status {
 } ds_status;
 
 enum { DS_UNET_SR3 = 0, DS_UNET_DDPM = 1 };       /* sr3_modules/unet.py vs ddpm_modules/unet.py */
-enum { DS_PREC_FP32 = 0, DS_PREC_BF16 = 1 };      /* fp32: CUDA-core path (<=1e-5 gate); bf16: tcgen05 path */
+enum { DS_PREC_FP32 = 0, DS_PREC_BF16 = 1, DS_PREC_TF32 = 2 };
+/* fp32: CUDA-core path (<= 1e-5 gate).  bf16: tcgen05 path, bf16 MMA operands.  tf32: tcgen05 path with fp32 tensors read as
+ * TF32 operands (kind::tf32, 10-bit mantissa: what the reference's own cuDNN convolutions use on a GPU by default) - for the
+ * narrow latency-bound splitting nets, where the halved MMA rate is free; needs ds_unet_desc.tf32_weights. */
 enum { DS_TILE_TRIM = 0, DS_TILE_PAD = 1, DS_TILE_SHIFT = 2 };   /* data/tiling_manager.py:6-12 */
 
 const char* ds_last_error(void);
@@ -56,6 +59,7 @@ typedef struct ds_unet_desc {
     int32_t res_blocks;
     int32_t image_size;                     /* seeds the attn_res matching, as in the reference ctor */
     int32_t with_time_emb;                  /* 0: time=None (TimePredictor style) */
+    int32_t tf32_weights;                   /* 1: also keep TF32 weight images (required for DS_PREC_TF32 forwards) */
 } ds_unet_desc;
 
 typedef struct ds_tensor_view {
@@ -139,6 +143,17 @@ int ds_gnconv_bf16(const float* d_xa, int ca, const float* d_xb, int cb, const f
                    void* d_out_b16, float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch,
                    size_t scratch_bytes, void* stream);
 size_t ds_gnconv_bf16_scratch_bytes(int B, int groups, int cin, int cout, int ksize);
+/* The same two operators with fp32 NHWC sources read by the tensor core as TF32 operands (precision mode DS_PREC_TF32:
+ * kind::tf32, weights rounded to TF32 at pack time, fp32 accumulation); channel counts multiples of 8 (conv) / 16 (fused). */
+int ds_conv2d_tf32(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_w_oihw, const float* d_bias,
+                   const float* d_residual, float* d_out_f32, int out_nchw, int B, int H, int W, int cout, int ksize,
+                   int stride, int upsample2x, void* d_scratch, size_t scratch_bytes, void* stream);
+size_t ds_conv2d_tf32_scratch_bytes(int cin, int cout, int ksize);
+int ds_gnconv_tf32(const float* d_xa, int ca, const float* d_xb, int cb, const float* d_gamma, const float* d_beta,
+                   int groups, int apply_swish, const float* d_w_oihw, const float* d_bias, const float* d_residual,
+                   float* d_out_f32, int B, int H, int W, int cout, int ksize, void* d_scratch, size_t scratch_bytes,
+                   void* stream);
+size_t ds_gnconv_tf32_scratch_bytes(int B, int groups, int cin, int cout, int ksize);
 /* debugging aid (DIFFSPLIT_B200_HALO_DBG=1): mean clock64 cycles of the 7 phases of the last fused-conv launch:
  * setup | wait for predecessor | loads + scale table | transform + stage | MMA | epilogue | teardown */
 int ds_debug_halo_phases(double* h_out7, int* n_ctas);

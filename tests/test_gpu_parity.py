@@ -1,12 +1,12 @@
 """GPU suite: the CUDA path (through the C ABI / the reference-shaped Python boundary) against the oracle, the
 golden vectors recorded from the real reference, and size-independent properties at BASELINE sizes.
 
-Tolerances: per-step UNet output, rel-err = max|y - ref| / max|ref|: <= 1e-5 in fp32 mode (north_star's gate);
-bf16 mode (bf16 MMA operands, fp32 accumulation / residual stream / normalisation): max-rel-err <= 2e-2 and rel-RMS
-<= 1.5e-2 over the whole ~50-conv network.  north_star's "e.g. 1e-2" holds per operator (test_conv_tc_operator: 3e-3);
-for the whole random-weight network the bound is set by operand rounding itself: rounding ONLY the conv operands to
-bf16 inside the fp32 CPU oracle gives max-rel 1.3e-2 / rel-RMS 9.6e-3 on the hagen net, the kernels measure 1.25e-2 /
-9.6e-3.  Final PSNR within 0.1 dB (measured 0.02 dB);
+Tolerances: per-step UNet output, rel-err = max|y - ref| / max|ref|: <= 1e-5 in fp32 mode and <= 1e-2 in the tensor-core
+mode a network runs in by default (north_star's two gates): "auto" = TF32 operands for the narrow splitting nets (inner
+channel <= 32; measured ~3e-3), bf16 operands for the wide SR3 nets (measured 0.5-0.8e-2).  bf16 operands on a NARROW
+random-weight net (not the default; kept as a selectable mode) sit at the rounding floor of bf16 itself - rounding ONLY the
+conv operands to bf16 inside the fp32 CPU oracle gives max-rel 1.3e-2 on the hagen net - and are held to 2e-2.
+Final PSNR within 0.1 dB at a 34 dB operating point;
 sampler updates with injected noise: <= 2e-5 abs on O(1) images; tile indexing / stitching: bit-exact; Philox replay vs
 torch.randn on the same device: bit-exact.
 """
@@ -34,8 +34,18 @@ from oracle.make_golden import TIMEPRED_CASES, UNET_CASES, Replay
 from tests.configs import make_opt
 
 DEV = "cuda"
-TOL = {"fp32": 1e-5, "bf16": 2e-2}
-TOL_RMS = {"fp32": 5e-6, "bf16": 1.5e-2}
+PRECISIONS = ["fp32", "auto", "bf16"]
+
+
+def tol(net, requested):
+    """(max-rel, rel-RMS) gate for `net` built with precision `requested`."""
+    if net.precision == "fp32":
+        return 1e-5, 5e-6
+    if requested == "bf16" and net.inner_channel <= 32:
+        return 2e-2, 1.5e-2            # non-default mode: bf16 operands on a narrow net (see the module docstring)
+    return 1e-2, 7.5e-3                # north_star: <= 1e-2 in the tensor-core mode
+
+
 
 
 def relerr(y, ref):
@@ -161,7 +171,10 @@ def test_conv_tc_operator(ca, cb, cout, ks, stride, up, B, H, W, residual, out_n
     (16, 0, 16, 3, 0, 0, 1, 24, 20, 0), (64, 64, 128, 3, 32, 1, 5, 4, 4, 0), (48, 0, 16, 3, 16, 1, 1, 128, 96, 0),
     (128, 64, 64, 3, 16, 1, 3, 16, 16, 1), (128, 96, 48, 3, 16, 1, 2, 12, 12, 0),
     # wide images: 2-D tiles of 7 x 16 outputs (ragged in both directions), 3x3 and 1x1, concat
-    (16, 0, 16, 3, 16, 1, 2, 40, 150, 1), (32, 16, 16, 3, 16, 1, 1, 33, 141, 0), (32, 0, 48, 1, 8, 0, 1, 20, 160, 0)])
+    (16, 0, 16, 3, 16, 1, 2, 40, 150, 1), (32, 16, 16, 3, 16, 1, 1, 33, 141, 0), (32, 0, 48, 1, 8, 0, 1, 20, 160, 0),
+    # >= 4 waves of tiles: the persistent pipelined variant (conv_stream_kernel), ragged tiles, concat, N split, 3 outputs
+    (64, 0, 64, 3, 16, 1, 8, 128, 128, 1), (32, 32, 64, 3, 16, 1, 5, 100, 150, 0), (64, 0, 3, 3, 16, 1, 6, 133, 121, 0),
+    (64, 0, 128, 3, 16, 1, 4, 96, 160, 1), (16, 0, 16, 3, 16, 1, 8, 200, 168, 1)])
 def test_fused_gn_swish_conv_operator(ca, cb, cout, ks, G, swish, B, H, W, residual):
     """conv_halo_kernel: GroupNorm statistics pass + ONE tensor-core kernel (normalise + Swish in the operand staging)
     vs fp64 conv of the bf16-rounded normalised activations and weights."""
@@ -199,6 +212,94 @@ def test_fused_gn_swish_conv_operator(ca, cb, cout, ks, G, swish, B, H, W, resid
     # the fp32 output differs from the reference only by bf16 re-rounding of activations whose fp32 value differs in the
     # last bits (fast exp, fp32 statistics): a handful of 1-ulp bf16 flips
     assert e32 <= 2e-3 and e16 <= 6e-3
+
+
+TF32_CONV_CASES = [
+    # ca, cb, cout, ks, stride, up, B, H, W, residual, out_nchw
+    (16, 0, 16, 3, 1, 0, 2, 16, 16, 0, 0), (32, 0, 32, 3, 1, 0, 1, 32, 32, 1, 0), (32, 16, 16, 3, 1, 0, 2, 16, 16, 0, 0),
+    (128, 64, 128, 1, 1, 0, 1, 16, 16, 0, 0), (16, 0, 16, 3, 2, 0, 2, 16, 16, 0, 0), (64, 0, 64, 3, 2, 0, 1, 32, 32, 0, 0),
+    (32, 0, 32, 3, 1, 1, 2, 8, 8, 0, 0), (128, 0, 128, 3, 1, 1, 1, 16, 16, 0, 0), (16, 0, 1, 3, 1, 0, 2, 16, 16, 0, 1),
+    (8, 0, 24, 1, 1, 0, 1, 12, 20, 0, 0), (192, 0, 64, 3, 1, 0, 2, 16, 16, 1, 0), (256, 0, 128, 3, 1, 0, 1, 8, 8, 0, 0),
+    # tall-patch variant (many tiles, >= 32 channels)
+    (32, 0, 32, 3, 1, 0, 8, 128, 128, 1, 0), (64, 32, 32, 3, 1, 0, 10, 100, 90, 0, 0), (32, 0, 16, 3, 1, 0, 8, 128, 128, 0, 0),
+    (32, 0, 128, 3, 1, 0, 8, 32, 32, 0, 0)]
+
+
+@pytest.mark.parametrize("ca,cb,cout,ks,stride,up,B,H,W,residual,out_nchw", TF32_CONV_CASES)
+def test_conv_tf32_operator(ca, cb, cout, ks, stride, up, B, H, W, residual, out_nchw):
+    """The TMA-fed tcgen05 conv with fp32 tensors read as TF32 operands (kind::tf32) vs an fp64 conv of the fp32 operands:
+    the difference is the TF32 operand rounding (2^-11 per operand), far below bf16's."""
+    g = torch.Generator().manual_seed(ca * 3 + cout + ks + H)
+    cin = ca + cb
+    x = torch.randn((B, cin, H, W), generator=g)
+    w = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5)
+    b = torch.randn((cout,), generator=g)
+    xr = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    ref = F.conv2d(xr.double(), w.double(), b.double(), stride=stride, padding=ks // 2)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    res = None
+    if residual:
+        res = torch.randn((B, cout, Ho, Wo), generator=g)
+        ref = ref + res.double()
+    xa = x[:, :ca].permute(0, 2, 3, 1).contiguous().to(DEV)
+    xb = x[:, ca:].permute(0, 2, 3, 1).contiguous().to(DEV) if cb else None
+    rd = res.permute(0, 2, 3, 1).contiguous().to(DEV) if residual else None
+    out = torch.full((B, cout, Ho, Wo) if out_nchw else (B, Ho, Wo, cout), float("nan"), device=DEV)
+    nb = _lib.lib().ds_conv2d_tf32_scratch_bytes(cin, cout, ks)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+    wd, bd = w.to(DEV), b.to(DEV)
+    _lib.check(_lib.lib().ds_conv2d_tf32(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, wd.data_ptr(), bd.data_ptr(),
+                                         None if rd is None else rd.data_ptr(), out.data_ptr(), out_nchw, B, H, W, cout, ks, stride,
+                                         up, scratch.data_ptr(), nb, sptr()))
+    torch.cuda.synchronize()
+    y = out if out_nchw else out.permute(0, 3, 1, 2)
+    e = relerr(y, ref.float())
+    print(f"[conv_tf32 {ca}+{cb}->{cout} k{ks} s{stride} up{up} {B}x{H}x{W}] rel err {e:.3e}")
+    assert e <= 1.5e-3
+
+
+@pytest.mark.parametrize("ca,cb,cout,ks,G,swish,B,H,W,residual", [
+    (16, 0, 16, 3, 16, 1, 2, 16, 16, 0), (16, 0, 16, 3, 16, 1, 16, 64, 64, 1), (32, 16, 16, 3, 16, 1, 2, 64, 64, 0),
+    (32, 0, 32, 3, 8, 1, 3, 32, 32, 1), (64, 32, 32, 3, 16, 1, 1, 32, 32, 0), (64, 0, 64, 3, 16, 1, 2, 16, 16, 1),
+    (128, 0, 128, 3, 16, 1, 4, 8, 8, 1), (128, 0, 384, 1, 16, 0, 2, 8, 8, 0), (16, 0, 1, 3, 16, 1, 2, 32, 32, 0),
+    (16, 0, 16, 3, 0, 0, 1, 24, 20, 0), (48, 0, 16, 3, 16, 1, 1, 128, 96, 0), (64, 64, 64, 3, 16, 1, 3, 16, 16, 1),
+    (16, 0, 16, 3, 16, 1, 2, 40, 150, 1), (32, 16, 16, 3, 16, 1, 1, 33, 141, 0), (32, 0, 48, 1, 8, 0, 1, 20, 160, 0),
+    # the persistent pipelined variant (>= 4 waves of tiles)
+    (16, 0, 16, 3, 16, 1, 8, 200, 168, 1), (32, 16, 16, 3, 16, 1, 5, 150, 140, 0), (32, 0, 32, 3, 8, 1, 8, 128, 128, 1),
+    (48, 0, 16, 3, 16, 1, 6, 133, 121, 0), (64, 0, 64, 3, 16, 1, 8, 128, 128, 1)])
+def test_fused_gn_swish_conv_tf32_operator(ca, cb, cout, ks, G, swish, B, H, W, residual):
+    """conv_halo_kernel with TF32 operands: GroupNorm + Swish in the operand staging, fp32 -> tf32 (round to nearest),
+    vs the fp64 reference of the fp32 operands."""
+    g = torch.Generator().manual_seed(ca + cb + cout + H)
+    cin = ca + cb
+    x = torch.randn((B, cin, H, W), generator=g) * 1.5 + 0.3
+    gamma, beta = 1 + 0.3 * torch.randn(cin, generator=g), 0.3 * torch.randn(cin, generator=g)
+    w = torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5
+    b = torch.randn((cout,), generator=g)
+    a = x.double()
+    if G:
+        a = F.group_norm(a, G, gamma.double(), beta.double(), eps=1e-5)
+    if swish:
+        a = a * torch.sigmoid(a)
+    ref = F.conv2d(a, w.double(), b.double(), padding=ks // 2)
+    res = None
+    if residual:
+        res = torch.randn((B, cout, H, W), generator=g)
+        ref = ref + res.double()
+    xa = x[:, :ca].permute(0, 2, 3, 1).contiguous().to(DEV)
+    xb = x[:, ca:].permute(0, 2, 3, 1).contiguous().to(DEV) if cb else None
+    rd = res.permute(0, 2, 3, 1).contiguous().to(DEV) if residual else None
+    out32 = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    nb = _lib.lib().ds_gnconv_tf32_scratch_bytes(B, max(G, 1), cin, cout, ks)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+    gd, bd, wd, biasd = gamma.to(DEV), beta.to(DEV), w.to(DEV), b.to(DEV)
+    _lib.check(_lib.lib().ds_gnconv_tf32(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, gd.data_ptr(), bd.data_ptr(),
+                                         G, swish, wd.data_ptr(), biasd.data_ptr(), None if rd is None else rd.data_ptr(),
+                                         out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sptr()))
+    torch.cuda.synchronize()
+    e32 = relerr(out32.permute(0, 3, 1, 2), ref.float())
+    print(f"[gnconv tf32 {ca}+{cb}->{cout} k{ks} G{G} {B}x{H}x{W}] rel err {e32:.3e}")
+    assert e32 <= 1.5e-3
 
 
 @pytest.mark.parametrize("ca,cb,cmid,cout,ks,G,B,H,W,residual", [
@@ -305,7 +406,7 @@ def test_attention_tensor_core_operator(B, N, Cc, scale):
 
 
 # ------------------------------------------------------------------------------------------------ UNet
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case", list(UNET_CASES))
 def test_unet_matches_reference_golden(gold_dir, case, precision):
     cfg, B, H, W = UNET_CASES[case]
@@ -314,11 +415,11 @@ def test_unet_matches_reference_golden(gold_dir, case, precision):
     net = build(cfg, sd, precision)
     y = net(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]).to(DEV))
     e, r = relerr(y, torch.from_numpy(gd["y"])), relrms(y, torch.from_numpy(gd["y"]))
-    print(f"[unet {case} {precision}] vs reference golden: max-rel {e:.3e} rel-rms {r:.3e}")
-    assert e <= TOL[precision] and r <= TOL_RMS[precision]
+    print(f"[unet {case} {precision}->{net.precision}] vs reference golden: max-rel {e:.3e} rel-rms {r:.3e}")
+    assert e <= tol(net, precision)[0] and r <= tol(net, precision)[1]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name,cfg,B,H,W,cond", [
     ("hagen64_b16", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 16, 64, 64, 0),
     ("cifar_sr3_cond", U.make_cfg("sr3", 9, 6, 16, 16, (1, 2, 4, 8), (), 1, 32), 1, 32, 32, 3),
@@ -340,11 +441,11 @@ def test_unet_matches_oracle(name, cfg, B, H, W, cond, precision):
     else:
         y = net(x.to(DEV), t.to(DEV))
     e, r = relerr(y, ref), relrms(y, ref)
-    print(f"[unet {name} {precision}] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
-    assert e <= TOL[precision] and r <= TOL_RMS[precision]
+    print(f"[unet {name} {precision}->{net.precision}] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
+    assert e <= tol(net, precision)[0] and r <= tol(net, precision)[1]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
 @pytest.mark.parametrize("name,cfg,H,W,cond", [
     ("hagen_512", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 512, 512, 0),
     ("splitting_512", U.make_cfg("sr3", 3, 2, 16, 16, (1, 2, 4, 8), (), 1, 512), 512, 512, 1),
@@ -362,11 +463,11 @@ def test_unet_baseline_configs_at_full_resolution(name, cfg, H, W, cond, precisi
     ref = U.unet_forward(sd, cfg, x, t)
     y = net(x[:, cond:].to(DEV), t.to(DEV), cond=x[:, :cond].to(DEV)) if cond else net(x.to(DEV), t.to(DEV))
     e, r = relerr(y, ref), relrms(y, ref)
-    print(f"[unet {name} {precision} full resolution] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
-    assert e <= TOL[precision] and r <= TOL_RMS[precision]
+    print(f"[unet {name} {precision}->{net.precision} full resolution] vs oracle: max-rel {e:.3e} rel-rms {r:.3e}")
+    assert e <= tol(net, precision)[0] and r <= tol(net, precision)[1]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case", list(TIMEPRED_CASES))
 def test_time_predictor_matches_reference_golden(gold_dir, case, precision):
     """TimePredictor (UNet without time embedding + fused mask / masked-mean tail) vs outputs recorded from the reference's
@@ -724,26 +825,60 @@ def test_step_rate_against_torch_eager_on_the_same_gpu():
 
 
 def test_final_psnr_within_point1_db_of_oracle():
-    """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds (T = 16 InDI chain;
-    T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation)."""
+    """north_star: final split channels within 0.1 dB PSNR of the reference for the same seeds.  T = 16 JointIndi chain
+    (T = 20 would trip the reference's own `delta_t <= t_cur` assertion through float accumulation), both precision modes.
+    The gate is taken at the published operating point: the target is the ORACLE's prediction plus noise sized so that the
+    oracle scores 34 dB against it (notebooks/EvaluateJointIndi.ipynb:1868: 33.8 / 36.0 dB) - against an unrelated random
+    target both scores would be noise-vs-noise and insensitive to the kernels.  Also asserted directly: PSNR(ours, oracle)."""
     cfgi = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32)
     sd1, sd2 = U.random_state_dict(cfgi, seed=7), U.random_state_dict(cfgi, seed=8)
     g = torch.Generator().manual_seed(4)
     x_in = torch.rand((2, 1, 64, 64), generator=g) * 2 - 1
-    target = torch.rand((2, 2, 64, 64), generator=g) * 2 - 1
-    for precision in ("fp32", "bf16"):
+    draws = _cuda_draws(5, [(2, 1, 64, 64)] * 34)
+    ref = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), lambda x, t: U.unet_forward(sd2, cfgi, x, t),
+                                 x_in, 16, Replay(draws), continuous=True)[-2:]
+    rng = (ref.reshape(2, 2, -1).max(dim=2).values - ref.reshape(2, 2, -1).min(dim=2).values).reshape(2, 2, 1, 1)
+    target = ref + torch.randn(ref.shape, generator=g) * rng / 10 ** (34.0 / 20.0)
+    for precision in ("fp32", "auto"):
         joint = JointIndi(None, 32, channels=1, out_channel=1, conditional=False, denoise_fn_ch1=build(cfgi, sd1, precision),
                           denoise_fn_ch2=build(cfgi, sd2, precision), val_schedule_opt={"n_timestep": 16}).to(DEV)
         joint.set_new_noise_schedule({"n_timestep": 16}, DEV)
-        draws = _cuda_draws(5, [(2, 1, 64, 64)] * 34)
         torch.manual_seed(5)
         y = joint.inference(x_in.to(DEV), continuous=True)[-2:].cpu()
-        ref = S.joint_indi_inference(lambda x, t: U.unet_forward(sd1, cfgi, x, t), lambda x, t: U.unet_forward(sd2, cfgi, x, t),
-                                     x_in, 16, Replay(draws), continuous=True)[-2:]
         for c in range(2):
-            d = (S.psnr(target[:, c], y[:, c]) - S.psnr(target[:, c], ref[:, c])).abs().max()
-            print(f"[psnr {precision}] ch{c} delta {float(d):.4f} dB")
+            p_ref, p_our = S.psnr(target[:, c], ref[:, c]), S.psnr(target[:, c], y[:, c])
+            direct = S.psnr(ref[:, c], y[:, c])
+            d = (p_our - p_ref).abs().max()
+            print(f"[psnr {precision}->{joint.indi1.denoise_fn.precision}] ch{c}: oracle {p_ref.tolist()} dB, ours {p_our.tolist()} dB, "
+                  f"delta {float(d):.4f} dB; PSNR(ours, oracle) {direct.tolist()} dB")
+            assert 33.5 < float(p_ref.min()) and float(p_ref.max()) < 34.5
             assert float(d) < 0.1
+            assert float(direct.min()) > (80.0 if precision == "fp32" else 44.0)
+
+
+def test_sr3_step_at_the_noisiest_timestep():
+    """sr3_modules/diffusion.py:141-168 at t = T-1 of the shipped schedule (linear 1e-6..1e-2, T = 2000): x0_hat = c1 x - c2 eps
+    with c1 ~ c2 ~ 151, i.e. the UNet's error is amplified 151x before the clamp.  The state and the update stay fp32, so the
+    step must still match the oracle: tightly with clip_denoised (the reference's default), and within the amplified
+    network tolerance without it."""
+    cfg = U.make_cfg("sr3", 3, 2, 16, 8, (1, 2), (), 1, 16)
+    sd = U.random_state_dict(cfg, seed=3)
+    sched = dict(schedule="linear", n_timestep=2000, linear_start=1e-6, linear_end=1e-2)
+    tab = S.schedule_tables(sched)
+    assert 140 < float(np.sqrt(1.0 / np.cumprod(1 - np.linspace(1e-6, 1e-2, 2000))[-1])) < 160
+    g = torch.Generator().manual_seed(2)
+    cond = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    x = torch.randn((2, 2, 16, 16), generator=g)
+    z = torch.randn((2, 2, 16, 16), generator=g)
+    for precision in ("fp32", "auto"):
+        netG = GaussianDiffusionSr3(build(cfg, sd, precision), 16, channels=2, conditional=True).to(DEV)
+        netG.set_new_noise_schedule(sched, DEV)
+        for clip in (True, False):
+            ref = S.sr3_p_sample(tab, lambda a, t: U.unet_forward(sd, cfg, a, t), x, 1999, cond, clip, z)
+            y = netG.p_sample(x.to(DEV), 1999, clip_denoised=clip, condition_x=cond.to(DEV), noise=z).cpu()
+            e = float((y - ref).abs().max() / ref.abs().max())
+            print(f"[sr3 step t=T-1 {precision} clip={clip}] max err / max|ref| {e:.3e}")
+            assert e <= (2e-5 if precision == "fp32" else 1e-2)
 
 
 # ------------------------------------------------------------------------------------------------ tiling
