@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 4 : 1)) conv_halo_kernel(
             if (p.epi.sums_out) {
                 const int bt0 = TILE2D ? b_first : fdiv(q0, p.div_hpwp);
                 const int nsr = TILE2D ? 1 : fdiv(min(q0 + 127, p.total_q - 1), p.div_hpwp) - bt0 + 1;
-                if (nsr <= 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, tid - 64, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                if (nsr == 1) tc_epilogue_stats_smem(p.epi, f, valid, bt0, nt * p.BN + c0, tid - 64, (int)(blockIdx.x % TC_SUM_COPIES), red);
+                else if (nsr == 2) tc_epilogue_stats_shfl(p.epi, f, valid, b, nt * p.BN + c0, tid - 64, bt0, nsr, (int)(blockIdx.x % TC_SUM_COPIES), red);
                 else tc_epilogue_stats(p.epi, f, valid, b, nt * p.BN + c0, m, tid - 64, bt0, (int)(blockIdx.x % TC_SUM_COPIES), red);
             }
         }

@@ -36,6 +36,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// the same for waits that are expected to be long (a whole pipeline stage): the hardware may park the thread for up to
+// ~20 us per try (it still wakes when the phase completes), so a waiting warp does not spend issue slots on the poll loop
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 // One lane of a fully converged warp.  Selecting the issuing thread with elect.sync (instead of `lane == 0`) lets ptxas prove
 // that a single thread is active: without it every UTCHMMA / UTMALDG is wrapped in an ELECT / R2UR / BRA.U.ANY loop over
 // the "possibly several" active lanes, which alone costs more than a small-N MMA (tools/mma_probe.cu: 52 vs 39 cycles).
@@ -203,7 +222,9 @@ __device__ __forceinline__ float tc_colsum16(const float (&v)[16], int lane) {
 }
 
 constexpr int TC_RED_LD = 17;                                   // padded row of the epilogue reduction buffer
-constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD * 4 + 128 * 4;   // [128 rows][17] fp32 + [128] sample ids
+constexpr int TC_RED_LD4 = 20;                                  // row pitch of the 16-byte-store variant (conflict-free STS.128)
+// [128 rows][20] fp32 (or [128][17] + [128] sample ids) followed by [8 row groups][2 kinds][16 columns] partial sums
+constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD4 * 4 + 8 * 2 * 16 * 4;
 
 // one thread = one output pixel (b, oy, ox), 16 consecutive output channels starting at n0, accumulators in v[16]
 // Everything the epilogue ADDS to the accumulators of one (pixel, 16-channel chunk): bias + conditioning vector + fp32
@@ -214,18 +235,39 @@ template <bool COHERENT = false>
 __device__ __forceinline__ void tc_epilogue_addend(const TcEpi& p, int b, int oy, int ox, int n0, float (&add)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) add[j] = 0.f;
+    const bool full = n0 + 16 <= p.Cout;
     if (p.bias) {
+        // 16-byte loads where the 16 channels exist and the vector is aligned (the library's own arenas always are; an epilogue
+        // warp issues ~40 instructions per chunk less than with scalar loads, and it is instruction-issue bound)
+        if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+            const float4* v = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] = __ldg(p.bias + n0 + j);
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = __ldg(v + j);
+                add[4 * j] = t.x; add[4 * j + 1] = t.y; add[4 * j + 2] = t.z; add[4 * j + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] = __ldg(p.bias + n0 + j);
+        }
     }
     if (p.temb) {
         const float* te = p.temb + (size_t)(p.temb_bcast ? 0 : b) * p.temb_stride + p.temb_off + n0;
+        if (full && (reinterpret_cast<uintptr_t>(te) & 15) == 0) {
+            const float4* v = reinterpret_cast<const float4*>(te);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += __ldg(te + j);
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = COHERENT ? __ldcg(v + j) : __ldg(v + j);
+                add[4 * j] += t.x; add[4 * j + 1] += t.y; add[4 * j + 2] += t.z; add[4 * j + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + j < p.Cout) add[j] += COHERENT ? __ldcg(te + j) : __ldg(te + j);
+        }
     }
     if (p.residual) {
         const size_t off = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + n0;
-        if (n0 + 16 <= p.Cout) {
+        if (full) {
             const float4* r = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -379,6 +421,46 @@ __device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const flo
             atomicAdd(p.sums_out + (((size_t)copy * p.sums_B + bb) * p.Cout + n0 + col) * 2 + kind, (double)tot);
     }
     asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");            // `red` may be reused
+}
+
+
+// The same statistics for tiles whose 128 rows belong to ONE sample, through shared memory instead of shuffles: every thread
+// stores its 16 values with four 16-byte stores (row pitch 20 floats: conflict free), 128 threads then add 16 rows x 1 column each
+// (8 interleaved row groups), 32 threads fold the 8 groups -> ONE fp64 atomic per (kind, channel).  ~60 instructions and two
+// 128-thread barriers per chunk instead of ~190 and two: the epilogue warps are instruction-issue bound.
+template <int BAR = 1>
+__device__ __forceinline__ void tc_epilogue_stats_smem(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int te, int copy,
+                                                       uint8_t* red_raw) {
+    float* red = reinterpret_cast<float*>(red_raw);
+    float* part = red + 128 * TC_RED_LD4;                       // [8 groups][2 kinds][16 columns]
+    float4* row = reinterpret_cast<float4*>(red + te * TC_RED_LD4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        row[j] = valid ? make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+    {
+        const int c = te & 15, g = te >> 4;
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float v = red[(r * 8 + g) * TC_RED_LD4 + c];
+            s += v;
+            q = fmaf(v, v, q);
+        }
+        part[(g * 2 + 0) * 16 + c] = s;
+        part[(g * 2 + 1) * 16 + c] = q;
+    }
+    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+    if (te < 32) {
+        const int kind = te >> 4, c = te & 15;
+        float tot = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) tot += part[(g * 2 + kind) * 16 + c];
+        if (n0 + c < p.Cout && tot != 0.f)
+            atomicAdd(p.sums_out + (((size_t)copy * p.sums_B + b) * p.Cout + n0 + c) * 2 + kind, (double)tot);
+    }
+    // no third barrier: the next call's first barrier orders these reads of `part` before its writes to it, and its writes to
+    // `red` only follow reads that completed before the second barrier above
 }
 
 }  // namespace ds

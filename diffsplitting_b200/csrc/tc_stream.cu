@@ -7,14 +7,17 @@
 // sr_sr3_64_512 ran at 135-156 TFLOP/s = 1.1-1.4 TB/s, a third of what HBM allows.  Here ONE CTA per SM keeps the weights
 // resident and walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  through four concurrently running stages:
 //
-//   warp 0      TMA producer   raw fp32 patch (7+2) x (16+2) x C of tile i+2 -> RAW ring (out-of-image = zero fill)
-//   warps 8-15  transform      RAW[i+1]: scale/shift (GroupNorm) + Swish -> bf16 | tf32 -> OP[(i+1)&1], the no-swizzle K-major
-//                              operand image [channel plane][patch pixel][16 B] (padding pixels written as zeros)
-//   warp 1      MMA issuer     OP[i&1]: 9 taps x C/16 tcgen05.mma, a tap = a descriptor start shifted by (18 r + s) pixels;
-//                              accumulators ACC[i&1] in TMEM (two buffers)
-//   warps 4-7   epilogue       ACC[(i-1)&1]: tcgen05.ld, + bias + conditioning vector + fp32 residual (prefetched four
-//                              16-channel chunks ahead), fp32 / bf16 NHWC or fp32 NCHW stores, GroupNorm statistics of the
-//                              output for the consumer
+//   warp 0            TMA producer   raw fp32 patch (7+2) x (16+2) x C of tile i+2 -> RAW ring (out-of-image = zero fill)
+//   warps 2-3, 12-15  transform      RAW[i+1]: scale/shift (GroupNorm) + Swish -> bf16 | tf32 -> OP[(i+1)&1], the no-swizzle
+//                                    K-major operand image [channel plane][patch pixel][16 B] (padding pixels = zeros)
+//   warp 1            MMA issuer     OP[i&1]: 9 taps x C/16 tcgen05.mma, a tap = a descriptor start shifted by (18 r + s)
+//                                    pixels; accumulators ACC[i&1] in TMEM (two buffers)
+//   warps 4-7, 8-11   epilogue       ACC[(i-1)&1]: two groups of four warps (one warp per TMEM lane quadrant each) take the even
+//                                    / odd 16-channel chunks: tcgen05.ld, + bias + conditioning vector + fp32 residual
+//                                    (requested four chunks ahead), fp32 / bf16 NHWC or fp32 NCHW stores, GroupNorm statistics
+//                                    of the output for the consumer.  The epilogue is instruction-issue bound (~150
+//                                    instructions per warp and chunk): eight warps, not four (first version: 1.10 ms for the
+//                                    64 -> 64 layer at 8 x 512^2, no faster than conv_halo_kernel, 7 % tensor-pipe activity)
 //
 // linked by mbarriers (TMA complete_tx, tcgen05.commit, warp arrivals).  Geometry, operand layout, weight pack and epilogue
 // are those of conv_halo_kernel's 2-D tiles, so the two kernels are interchangeable per layer (halo_launch_conv picks).
@@ -27,7 +30,8 @@
 namespace ds {
 
 constexpr int SK_THREADS = 512;
-constexpr int SK_XF_WARP0 = 8, SK_XF_WARPS = 8, SK_XF_THREADS = SK_XF_WARPS * 32;
+constexpr int SK_XF_WARPS = 6, SK_XF_THREADS = SK_XF_WARPS * 32;      // warps 2, 3, 12 .. 15
+constexpr int SK_EPI_GROUPS = 2;                                       // warps 4-7 and 8-11
 constexpr int SK_TW = 16, SK_TH = 7, SK_PW = SK_TW + 2, SK_PH = SK_TH + 2;
 constexpr int SK_PATCH_PX = SK_PW * SK_PH;               // 162 staged pixels
 constexpr int SK_PLANE_PX = 169;                         // + the rows the last window runs past the patch; 169 * 16 B = 16 mod 128:
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
     auto full_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 4 + s); };
     auto empty_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 6 + s); };
     const uint32_t wfull = bars + 8u * (uint32_t)(2 * SK_NRAW + 8), tmem_slot = wfull + 8u;
-    uint8_t* red = gbase + bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10);
+    uint8_t* red = gbase + ((bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10) + 15u) & ~15u);      // SK_EPI_GROUPS x TC_RED_BYTES
     const int nt = blockIdx.y;
     const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : (2u * (uint32_t)p.BN <= 256u ? 256u : 512u)));
     const int my_tiles = ((int)blockIdx.x < p.n_tiles_m) ? (p.n_tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         for (int s = 0; s < SK_NRAW; ++s) { mbar_init(full_raw(s), 1); mbar_init(empty_raw(s), SK_XF_WARPS); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(full_op(s), SK_XF_WARPS); mbar_init(empty_op(s), 1);
-            mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4);
+            mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4 * ((p.BN >> 4) >= SK_EPI_GROUPS ? SK_EPI_GROUPS : 1));
         }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         // ===== TMA producer: patch of tile i once the transform warps have released its ring slot
         if (elect_one()) {
             for (int i = SK_NRAW; i < my_tiles; ++i) {
-                mbar_wait(empty_raw(i % SK_NRAW), (uint32_t)((i / SK_NRAW) & 1) ^ 1u);
+                mbar_wait_relaxed(empty_raw(i % SK_NRAW), (uint32_t)((i / SK_NRAW) & 1) ^ 1u);
                 issue_raw(i);
             }
         }
@@ -225,64 +229,75 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 8) {
-        // ===== epilogue: warp q owns TMEM lanes [32q, 32q + 32) = patch positions = output pixels (pr, pc)
+    } else if (warp >= 4 && warp < 12) {
+        // ===== epilogue: group gi = chunks gi, gi + 2, ... of every tile; warp q of a group owns TMEM lanes [32q, 32q + 32) =
+        // patch positions = output pixels (pr, pc)
+        const int gi = (warp - 4) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int te = tid - 128;
+        const int te = tid - 128 - gi * 128;
+        uint8_t* redg = red + (size_t)gi * TC_RED_BYTES;
         const int pr = m / SK_PW, pc = m - pr * SK_PW;
         const int nchunks = p.BN >> 4;
+        const int ncg = (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
         float add[SK_SLOTS][16];
-        // chunk stream over (tile, 16-channel chunk): addends are requested SK_SLOTS chunks ahead of their use
-        auto where = [&](int g, int& b, int& y, int& x, int& c0, bool& valid) {
-            const int i = g / nchunks;
+        const int total = my_tiles * ncg;
+        const bool in_tile = pr < SK_TH && pc < SK_TW;
+        // chunk stream g -> (tile g / ncg, chunk gi + 2 (g % ncg)); addends are requested SK_SLOTS chunks ahead of their use
+        auto where = [&](int g, int& i, int& b, int& y, int& x, int& c0, bool& valid) {
+            i = g / ncg;
             int y0, x0;
             tile_coords(i, b, y0, x0);
-            c0 = (g - i * nchunks) * 16;
+            c0 = (gi + SK_EPI_GROUPS * (g - i * ncg)) * 16;
             y = y0 + pr;
             x = x0 + pc;
-            valid = pr < SK_TH && pc < SK_TW && y < p.H && x < p.W;
+            valid = in_tile && y < p.H && x < p.W;
         };
-        const int total = my_tiles * nchunks;
         auto request = [&](int g, float (&a)[16]) {
             if (g >= total) return;
-            int b, y, x, c0; bool valid;
-            where(g, b, y, x, c0, valid);
+            int i, b, y, x, c0; bool valid;
+            where(g, i, b, y, x, c0, valid);
             if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, a);
         };
+        if (ncg > 0) {
 #pragma unroll
-        for (int k = 0; k < SK_SLOTS; ++k) request(k, add[k]);
-        for (int g0 = 0; g0 < total; g0 += SK_SLOTS) {
+            for (int k = 0; k < SK_SLOTS; ++k) request(k, add[k]);
+            for (int g0 = 0; g0 < total; g0 += SK_SLOTS) {
 #pragma unroll
-            for (int k = 0; k < SK_SLOTS; ++k) {
-                const int g = g0 + k;
-                if (g < total) {
-                    const int i = g / nchunks, s = i & 1;
-                    int b, y, x, c0; bool valid;
-                    where(g, b, y, x, c0, valid);
-                    if (c0 == 0) {
-                        mbar_wait(full_acc(s), (uint32_t)(i >> 1) & 1u);
-                        tc_fence_after();
+                for (int k = 0; k < SK_SLOTS; ++k) {
+                    const int g = g0 + k;
+                    if (g < total) {
+                        int i, b, y, x, c0; bool valid;
+                        where(g, i, b, y, x, c0, valid);
+                        const int s = i & 1;
+                        const int kk = g - i * ncg;
+                        if (kk == 0) {
+                            mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
+                            tc_fence_after();
+                        }
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
+                        if (kk == ncg - 1) {          // this warp's last read of the accumulator buffer: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_acc(s)) : "memory");
+                        }
+                        float f[16];
+                        if (valid) tc_epilogue_write(p.epi, v, add[k], b, y, x, nt * p.BN + c0, f);
+                        request(g + SK_SLOTS, add[k]);
+                        if (p.epi.sums_out) {
+                            if (gi == 0) tc_epilogue_stats_smem<1>(p.epi, f, valid, b, nt * p.BN + c0, te, copy, redg);
+                            else tc_epilogue_stats_smem<2>(p.epi, f, valid, b, nt * p.BN + c0, te, copy, redg);
+                        }
                     }
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
-                    if (c0 + 16 == p.BN) {        // last read of this accumulator buffer: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_acc(s)) : "memory");
-                    }
-                    float f[16];
-                    if (valid) tc_epilogue_write(p.epi, v, add[k], b, y, x, nt * p.BN + c0, f);
-                    request(g + SK_SLOTS, add[k]);
-                    if (p.epi.sums_out) tc_epilogue_stats_shfl<1>(p.epi, f, valid, b, nt * p.BN + c0, te, b, 1, copy, red);
                 }
             }
         }
         tc_fence_before();
-    } else if (warp >= SK_XF_WARP0) {
-        // ===== transform: raw fp32 patch -> normalise -> Swish -> operand image
-        const int xt = tid - SK_XF_WARP0 * 32;
+    } else {
+        // ===== transform (warps 2, 3, 12 .. 15): raw fp32 patch -> normalise -> Swish -> operand image
+        const int xt = warp < 4 ? tid - 64 : tid - 384 + 64;
         const uint32_t ca4 = (uint32_t)p.ca * 4u, cb4 = (uint32_t)p.cb * 4u;
         const bool fixed = (SK_XF_THREADS % P) == 0;        // the thread's channel plane is the same for all its items
         for (int i = 0; i < my_tiles; ++i) {
@@ -296,8 +311,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + kp * CPP)[j];
             }
-            mbar_wait(full_raw(r), (uint32_t)((i / SK_NRAW) & 1));
-            mbar_wait(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            mbar_wait_relaxed(full_raw(r), (uint32_t)((i / SK_NRAW) & 1));
+            mbar_wait_relaxed(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u);
             const uint32_t rawb = base + raw_off + (uint32_t)r * p.raw_bytes;
             const uint32_t opb = base + op_off + (uint32_t)s * p.op_bytes;
             const int items = P * SK_PATCH_PX;
@@ -382,7 +397,7 @@ static size_t stream_smem_bytes(int C, int BN, int B, int es) {
     const size_t op_bytes = (size_t)(C * es / 16) * SK_PLANE_PX * 16;
     const size_t raw_bytes = (size_t)SK_PATCH_PX * C * 4;
     return 1024 + align_up(b_bytes, 128) + align_up(2 * op_bytes, 128) + SK_NRAW * raw_bytes + 128 + (size_t)B * C * 8 + 16 +
-           8 * (2 * SK_NRAW + 10) + TC_RED_BYTES + 256;
+           8 * (2 * SK_NRAW + 10) + 16 + SK_EPI_GROUPS * TC_RED_BYTES + 256;
 }
 
 static int stream_weight_loads(int C, int es) {
