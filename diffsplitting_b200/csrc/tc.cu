@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
     const uint32_t tfull_bar = bar_base + 16u * p.stages;
     const uint32_t tmem_slot = tfull_bar + 8u;
-    uint8_t* red = smem_raw + (tmem_slot + 16u - smem_u32(smem_raw));      // epilogue reduction buffer (TC_RED_BYTES)
+    uint8_t* red = smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw));      // epilogue reduction buffer (TC_RED_BYTES, 16-byte aligned)
 
     // tile coordinates
     int bid = blockIdx.x;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
     auto pfull = [&](int i) { return pfull0 + 8u * (uint32_t)i; };
     auto pempty = [&](int i) { return pfull0 + 16u + 8u * (uint32_t)i; };
     const uint32_t tfull = pfull0 + 32u, tmem_slot = pfull0 + 40u;
-    uint8_t* red = smem_raw + (tmem_slot + 16u - smem_u32(smem_raw));
+    uint8_t* red = smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw));       // 16-byte aligned
 
     int bid = blockIdx.x;
     const int tx_i = bid % p.tiles_x; bid /= p.tiles_x;
@@ -547,7 +547,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                     if (rc != DS_OK) return rc;
                 }
                 plan->patch = 1;
-                plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 16 * wst + 64 + 1024 + TP_GROUPS * TC_RED_BYTES);
+                plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 16 * wst + 80 + 1024 + TP_GROUPS * TC_RED_BYTES);
                 plan->grid_x = tiles_x * tiles_y * B;
                 plan->grid_y = q.n_tiles;
                 plan->grid_z = 1;
@@ -644,7 +644,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
     if (stages > U) stages = U;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    plan->smem_bytes = stages * stage_bytes + 16 * stages + 32 + 1024 + TC_RED_BYTES;
+    plan->smem_bytes = stages * stage_bytes + 16 * stages + 48 + 1024 + TC_RED_BYTES;
     plan->grid_x = p.tiles_x * p.tiles_y * tiles_b;
     plan->grid_y = p.n_tiles;
     plan->grid_z = p.nclasses;

@@ -222,9 +222,9 @@ __device__ __forceinline__ float tc_colsum16(const float (&v)[16], int lane) {
 }
 
 constexpr int TC_RED_LD = 17;                                   // padded row of the epilogue reduction buffer
-constexpr int TC_RED_LD4 = 20;                                  // row pitch of the 16-byte-store variant (conflict-free STS.128)
-// [128 rows][20] fp32 (or [128][17] + [128] sample ids) followed by [8 row groups][2 kinds][16 columns] partial sums
-constexpr uint32_t TC_RED_BYTES = 128 * TC_RED_LD4 * 4 + 8 * 2 * 16 * 4;
+constexpr int TC_RED_LDT = 132;                                 // column pitch of the transposed variant: [16 columns][128 rows + 4]
+// [16][132] fp32 (or [128][17] fp32 + [128] sample ids) followed by [8 row groups][2 kinds][16 columns] partial sums
+constexpr uint32_t TC_RED_BYTES = 16 * TC_RED_LDT * 4 + 8 * 2 * 16 * 4;
 
 // one thread = one output pixel (b, oy, ox), 16 consecutive output channels starting at n0, accumulators in v[16]
 // Everything the epilogue ADDS to the accumulators of one (pixel, 16-channel chunk): bias + conditioning vector + fp32
@@ -425,27 +425,27 @@ __device__ __forceinline__ void tc_epilogue_stats_shfl(const TcEpi& p, const flo
 
 
 // The same statistics for tiles whose 128 rows belong to ONE sample, through shared memory instead of shuffles: every thread
-// stores its 16 values with four 16-byte stores (row pitch 20 floats: conflict free), 128 threads then add 16 rows x 1 column each
-// (8 interleaved row groups), 32 threads fold the 8 groups -> ONE fp64 atomic per (kind, channel).  ~60 instructions and two
+// stores its 16 values transposed ([column][row], pitch 132: conflict free), 128 threads then add 16 rows x 1 column each with
+// four 16-byte loads, 32 threads fold the 8 row groups -> ONE fp64 atomic per (kind, channel).  ~75 instructions and two
 // 128-thread barriers per chunk instead of ~190 and two: the epilogue warps are instruction-issue bound.
+// `red_raw` must be 16-byte aligned.
 template <int BAR = 1>
 __device__ __forceinline__ void tc_epilogue_stats_smem(const TcEpi& p, const float (&f)[16], bool valid, int b, int n0, int te, int copy,
                                                        uint8_t* red_raw) {
     float* red = reinterpret_cast<float*>(red_raw);
-    float* part = red + 128 * TC_RED_LD4;                       // [8 groups][2 kinds][16 columns]
-    float4* row = reinterpret_cast<float4*>(red + te * TC_RED_LD4);
+    float* part = red + 16 * TC_RED_LDT;                        // [8 groups][2 kinds][16 columns]
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        row[j] = valid ? make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 16; ++j) red[j * TC_RED_LDT + te] = valid ? f[j] : 0.f;
     asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
     {
         const int c = te & 15, g = te >> 4;
+        const float4* src = reinterpret_cast<const float4*>(red + c * TC_RED_LDT + g * 16);
         float s = 0.f, q = 0.f;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const float v = red[(r * 8 + g) * TC_RED_LD4 + c];
-            s += v;
-            q = fmaf(v, v, q);
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = src[k];
+            s += (v.x + v.y) + (v.z + v.w);
+            q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
         }
         part[(g * 2 + 0) * 16 + c] = s;
         part[(g * 2 + 1) * 16 + c] = q;
