@@ -37,7 +37,9 @@ constexpr int SK_PATCH_PX = SK_PW * SK_PH;               // 162 staged pixels
 constexpr int SK_PLANE_PX = 169;                         // + the rows the last window runs past the patch; 169 * 16 B = 16 mod 128:
                                                          // the 8 planes a quarter-warp stores to hit 8 different bank groups
 constexpr int SK_NRAW = 2;
-constexpr int SK_SLOTS = 4;                              // residual / bias chunks in flight per epilogue thread
+constexpr int SK_SLOTS = 4;                              // residual chunks in flight per epilogue thread
+constexpr int SK_STG_LD = 20;                            // row pitch (floats) of the epilogue staging buffer: conflict-free STS.128
+constexpr uint32_t SK_RED_BYTES = 128 * SK_STG_LD * 4 + 4 * 2 * 16 * 4;     // per epilogue group
 constexpr size_t SK_SMEM_LIMIT = 225 * 1024;
 
 struct StreamParams {
@@ -72,7 +74,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
     const uint32_t op_off = (w_off + p.b_bytes + 127u) & ~127u;
     const uint32_t raw_off = (op_off + 2u * p.op_bytes + 127u) & ~127u;
     const uint32_t tab_off = (raw_off + SK_NRAW * p.raw_bytes + 15u) & ~15u;
-    const uint32_t bar_off = (tab_off + (uint32_t)p.B * p.C * 8u + 15u) & ~15u;
+    const uint32_t bt_off = (tab_off + (uint32_t)p.B * p.C * 8u + 15u) & ~15u;       // [B][BN] bias + conditioning vector
+    const uint32_t bar_off = (bt_off + (uint32_t)p.B * p.BN * 4u + 15u) & ~15u;
     const uint32_t bars = base + bar_off;
     auto full_raw = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_raw = [&](int s) { return bars + 8u * (uint32_t)(SK_NRAW + s); };
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
     auto full_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 4 + s); };
     auto empty_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 6 + s); };
     const uint32_t wfull = bars + 8u * (uint32_t)(2 * SK_NRAW + 8), tmem_slot = wfull + 8u;
-    uint8_t* red = gbase + ((bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10) + 15u) & ~15u);      // SK_EPI_GROUPS x TC_RED_BYTES
+    uint8_t* red = gbase + ((bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10) + 15u) & ~15u);      // SK_EPI_GROUPS x SK_RED_BYTES
     const int nt = blockIdx.y;
     const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : (2u * (uint32_t)p.BN <= 256u ? 256u : 512u)));
     const int my_tiles = ((int)blockIdx.x < p.n_tiles_m) ? (p.n_tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -185,6 +188,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
             }
             tab[i] = make_float2(a, sh);
         }
+        // what the epilogue adds per (sample, output channel): bias + conditioning vector (zero beyond Cout)
+        float* btw = reinterpret_cast<float*>(gbase + bt_off);
+        for (int i = tid; i < p.B * p.BN; i += SK_THREADS) {
+            const int b = i / p.BN, n = nt * p.BN + (i - b * p.BN);
+            float v = 0.f;
+            if (n < p.epi.Cout) {
+                if (p.epi.bias) v = __ldg(p.epi.bias + n);
+                if (p.epi.temb) v += __ldg(p.epi.temb + (size_t)(p.epi.temb_bcast ? 0 : b) * p.epi.temb_stride + p.epi.temb_off + n);
+            }
+            btw[i] = v;
+        }
     }
     __syncthreads();
 
@@ -230,48 +244,71 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 12) {
-        // ===== epilogue: group gi = chunks gi, gi + 2, ... of every tile; warp q of a group owns TMEM lanes [32q, 32q + 32) =
-        // patch positions = output pixels (pr, pc)
+        // ===== epilogue: group gi = chunks gi, gi + 2, ... of every tile, two phases per 16-channel chunk:
+        //  1. ROW view - warp q owns TMEM lanes [32q, 32q + 32) = patch positions: tcgen05.ld, + (bias + conditioning vector) from
+        //     the shared-memory table, four 16-byte stores into the group's staging buffer [128 rows][20];
+        //  2. QUAD view - thread (row te / 4 + 32 j, quad te % 4), j = 0..3: reads its 4 channels back, adds the fp32 residual and
+        //     stores fp32 / bf16 NHWC (or fp32 NCHW): four neighbouring lanes cover the 64 contiguous bytes of one pixel, so
+        //     one instruction touches 8 lines instead of 32 (the per-row view made the epilogue LSU bound: ~5 k wavefront
+        //     cycles per tile).  The residual is requested SK_SLOTS chunks ahead as pure loads in this view (no arithmetic
+        //     on the loaded registers until they are used), the GroupNorm statistics of the output are summed in this view
+        //     (4 rows x 4 channels per thread, three shuffle levels, one fold through shared memory).
         const int gi = (warp - 4) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int te = tid - 128 - gi * 128;
-        uint8_t* redg = red + (size_t)gi * TC_RED_BYTES;
-        const int pr = m / SK_PW, pc = m - pr * SK_PW;
+        float* stg = reinterpret_cast<float*>(red + (size_t)gi * SK_RED_BYTES);      // [128][20] staging + [4 warps][2][16] partials
+        float* part = stg + 128 * SK_STG_LD;
         const int nchunks = p.BN >> 4;
         const int ncg = (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
-        float add[SK_SLOTS][16];
         const int total = my_tiles * ncg;
-        const bool in_tile = pr < SK_TH && pc < SK_TW;
-        // chunk stream g -> (tile g / ncg, chunk gi + 2 (g % ncg)); addends are requested SK_SLOTS chunks ahead of their use
-        auto where = [&](int g, int& i, int& b, int& y, int& x, int& c0, bool& valid) {
-            i = g / ncg;
+        const int quad = te & 3, r0 = te >> 2;
+        const int Cout = p.epi.Cout;
+        const float* bt = reinterpret_cast<const float*>(gbase + bt_off);
+        float4 res[SK_SLOTS][4];
+        // QUAD-view geometry of the tile a chunk belongs to: pixel index (or -1) of rows r0 + 32 j
+        auto pixels = [&](int i, int& b, int (&pix)[4]) {
             int y0, x0;
             tile_coords(i, b, y0, x0);
-            c0 = (gi + SK_EPI_GROUPS * (g - i * ncg)) * 16;
-            y = y0 + pr;
-            x = x0 + pc;
-            valid = in_tile && y < p.H && x < p.W;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int r = r0 + 32 * jj;
+                const int pr = r / SK_PW, pc = r - pr * SK_PW;
+                const int y = y0 + pr, x = x0 + pc;
+                pix[jj] = (pr < SK_TH && pc < SK_TW && y < p.H && x < p.W) ? (b * p.H + y) * p.W + x : -1;
+            }
         };
-        auto request = [&](int g, float (&a)[16]) {
-            if (g >= total) return;
-            int i, b, y, x, c0; bool valid;
-            where(g, i, b, y, x, c0, valid);
-            if (valid) tc_epilogue_addend(p.epi, b, y, x, nt * p.BN + c0, a);
+        auto request = [&](int g, float4 (&rr)[4]) {
+            if (!p.epi.residual || g >= total) return;
+            const int i = g / ncg;
+            int b, pix[4];
+            pixels(i, b, pix);
+            const int n0 = nt * p.BN + (gi + SK_EPI_GROUPS * (g - i * ncg)) * 16 + quad * 4;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (pix[jj] >= 0 && n0 + 4 <= Cout) rr[jj] = __ldg(reinterpret_cast<const float4*>(p.epi.residual + (size_t)pix[jj] * Cout + n0));
+                else if (pix[jj] >= 0) {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (n0 + e < Cout) t[e] = __ldg(p.epi.residual + (size_t)pix[jj] * Cout + n0 + e);
+                    rr[jj] = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
         };
         if (ncg > 0) {
 #pragma unroll
-            for (int k = 0; k < SK_SLOTS; ++k) request(k, add[k]);
+            for (int k = 0; k < SK_SLOTS; ++k) request(k, res[k]);
             for (int g0 = 0; g0 < total; g0 += SK_SLOTS) {
 #pragma unroll
                 for (int k = 0; k < SK_SLOTS; ++k) {
                     const int g = g0 + k;
                     if (g < total) {
-                        int i, b, y, x, c0; bool valid;
-                        where(g, i, b, y, x, c0, valid);
-                        const int s = i & 1;
-                        const int kk = g - i * ncg;
+                        const int i = g / ncg, s = i & 1, kk = g - i * ncg;
+                        const int c0 = (gi + SK_EPI_GROUPS * kk) * 16;
+                        int b, pix[4];
+                        pixels(i, b, pix);
+                        // ---- phase 1 (ROW view)
                         if (kk == 0) {
                             mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
                             tc_fence_after();
@@ -283,12 +320,81 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                             __syncwarp();
                             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_acc(s)) : "memory");
                         }
-                        float f[16];
-                        if (valid) tc_epilogue_write(p.epi, v, add[k], b, y, x, nt * p.BN + c0, f);
-                        request(g + SK_SLOTS, add[k]);
+                        {
+                            const float4* btv = reinterpret_cast<const float4*>(bt + b * p.BN + c0);
+                            float4* row = reinterpret_cast<float4*>(stg + m * SK_STG_LD);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 a = btv[e];
+                                row[e] = make_float4(__uint_as_float(v[4 * e]) + a.x, __uint_as_float(v[4 * e + 1]) + a.y,
+                                                     __uint_as_float(v[4 * e + 2]) + a.z, __uint_as_float(v[4 * e + 3]) + a.w);
+                            }
+                        }
+                        if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                        // ---- phase 2 (QUAD view)
+                        const int n0 = nt * p.BN + c0 + quad * 4;
+                        float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float4 x = *reinterpret_cast<const float4*>(stg + (r0 + 32 * jj) * SK_STG_LD + quad * 4);
+                            if (pix[jj] < 0) continue;
+                            if (p.epi.residual) { x.x += res[k][jj].x; x.y += res[k][jj].y; x.z += res[k][jj].z; x.w += res[k][jj].w; }
+                            const float xs[4] = {x.x, x.y, x.z, x.w};
+                            if (p.epi.out_nchw) {
+                                const int pb = pix[jj] / (p.H * p.W), pp = pix[jj] - pb * p.H * p.W;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (n0 + e < Cout) p.epi.out_nchw[((size_t)pb * Cout + n0 + e) * p.H * p.W + pp] = xs[e];
+                            } else if (n0 + 4 <= Cout) {
+                                const size_t off = (size_t)pix[jj] * Cout + n0;
+                                if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + off) = x;
+                                if (p.epi.out_b16) {
+                                    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                                    uint2 pk;
+                                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                                    *reinterpret_cast<uint2*>(p.epi.out_b16 + off) = pk;
+                                }
+                            } else {
+                                const size_t off = (size_t)pix[jj] * Cout + n0;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (n0 + e < Cout) {
+                                        if (p.epi.out_f32) p.epi.out_f32[off + e] = xs[e];
+                                        if (p.epi.out_b16) p.epi.out_b16[off + e] = __float2bfloat16_rn(xs[e]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { sm[e] += xs[e]; sq[e] = fmaf(xs[e], xs[e], sq[e]); }
+                        }
+                        request(g + SK_SLOTS, res[k]);
                         if (p.epi.sums_out) {
-                            if (gi == 0) tc_epilogue_stats_smem<1>(p.epi, f, valid, b, nt * p.BN + c0, te, copy, redg);
-                            else tc_epilogue_stats_smem<2>(p.epi, f, valid, b, nt * p.BN + c0, te, copy, redg);
+                            // lanes with the same quad (lane % 4) hold partial sums of the same 4 channels: fold the 8 of a warp
+#pragma unroll
+                            for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], o);
+                                    sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], o);
+                                }
+                            }
+                            if (lane < 4) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    part[(q * 2 + 0) * 16 + lane * 4 + e] = sm[e];
+                                    part[(q * 2 + 1) * 16 + lane * 4 + e] = sq[e];
+                                }
+                            }
+                        }
+                        // orders this chunk's reads of the staging buffer before the next chunk's writes, and publishes `part`
+                        if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (p.epi.sums_out && te < 32) {
+                            const int kind = te >> 4, c = te & 15;
+                            const float tot = (part[(0 * 2 + kind) * 16 + c] + part[(1 * 2 + kind) * 16 + c]) +
+                                              (part[(2 * 2 + kind) * 16 + c] + part[(3 * 2 + kind) * 16 + c]);
+                            if (nt * p.BN + c0 + c < Cout && tot != 0.f)
+                                atomicAdd(p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + nt * p.BN + c0 + c) * 2 + kind, (double)tot);
                         }
                     }
                 }
@@ -397,7 +503,7 @@ static size_t stream_smem_bytes(int C, int BN, int B, int es) {
     const size_t op_bytes = (size_t)(C * es / 16) * SK_PLANE_PX * 16;
     const size_t raw_bytes = (size_t)SK_PATCH_PX * C * 4;
     return 1024 + align_up(b_bytes, 128) + align_up(2 * op_bytes, 128) + SK_NRAW * raw_bytes + 128 + (size_t)B * C * 8 + 16 +
-           8 * (2 * SK_NRAW + 10) + 16 + SK_EPI_GROUPS * TC_RED_BYTES + 256;
+           (size_t)B * BN * 4 + 16 + 8 * (2 * SK_NRAW + 10) + 16 + SK_EPI_GROUPS * SK_RED_BYTES + 256;
 }
 
 static int stream_weight_loads(int C, int es) {
