@@ -107,6 +107,7 @@ _SIGS = {
     "ds_gnconv_tf32_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ds_debug_chain_phases": (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]),
     "ds_debug_halo_phases": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "ds_debug_stream_phases": (C.c_int, [C.POINTER(C.c_longlong)]),
     "ds_debug_trace_reset": (C.c_int, [C.c_int]),
     "ds_debug_trace_read": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_int]),
     "ds_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

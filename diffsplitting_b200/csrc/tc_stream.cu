@@ -56,8 +56,11 @@ struct StreamParams {
     int tiles_x, tiles_y, n_tiles_m;
     FastDiv div_tiles_x, div_tiles_xy;
     uint32_t raw_bytes, raw_a_bytes, op_bytes, b_bytes;
+    long long* dbg;                   // DIFFSPLIT_B200_STREAM_DBG: per-role wait / work cycle sums of CTA 0 (16 slots)
     TraceSlot trace;
 };
+#define SK_T0() const long long _t0 = p.dbg ? clock64() : 0
+#define SK_ACC(slot) do { if (p.dbg) acc_dbg[slot] += clock64() - _t0; } while (0)
 
 template <bool TF32>
 __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid_constant__ StreamParams p) {
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
     const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : (2u * (uint32_t)p.BN <= 256u ? 256u : 512u)));
     const int my_tiles = ((int)blockIdx.x < p.n_tiles_m) ? (p.n_tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+    long long acc_dbg[4] = {0, 0, 0, 0};
+    const long long t_start = p.dbg ? clock64() : 0;
     trace_begin(p.trace);
     if (warp == 0 && elect_one()) {
         for (int s = 0; s < SK_NRAW; ++s) { mbar_init(full_raw(s), 1); mbar_init(empty_raw(s), SK_XF_WARPS); }
@@ -206,9 +211,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         // ===== TMA producer: patch of tile i once the transform warps have released its ring slot
         if (elect_one()) {
             for (int i = SK_NRAW; i < my_tiles; ++i) {
-                mbar_wait_relaxed(empty_raw(i % SK_NRAW), (uint32_t)((i / SK_NRAW) & 1) ^ 1u);
+                { SK_T0(); mbar_wait_relaxed(empty_raw(i % SK_NRAW), (uint32_t)((i / SK_NRAW) & 1) ^ 1u); SK_ACC(0); }
                 issue_raw(i);
             }
+            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) { p.dbg[0] = acc_dbg[0]; p.dbg[15] = clock64() - t_start; p.dbg[14] = my_tiles; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -222,9 +228,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i & 1;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait(full_op(s), ph);
-                mbar_wait(empty_acc(s), ph ^ 1u);
+                { SK_T0(); mbar_wait(full_op(s), ph); SK_ACC(0); }
+                { SK_T0(); mbar_wait(empty_acc(s), ph ^ 1u); SK_ACC(1); }
                 tc_fence_after();
+                SK_T0();
                 const uint32_t a_lo0 = (((base + op_off + (uint32_t)s * p.op_bytes) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
                 const uint32_t acc = tmem_base + (uint32_t)(s * p.BN);
                 uint32_t b_lo = b_lo0;
@@ -240,7 +247,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 }
                 umma_commit(empty_op(s));         // the operand image may be overwritten once these MMAs have read it
                 umma_commit(full_acc(s));         // accumulator complete
+                SK_ACC(2);
             }
+            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) { p.dbg[1] = acc_dbg[0]; p.dbg[2] = acc_dbg[1]; p.dbg[3] = acc_dbg[2]; }
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 12) {
@@ -310,9 +319,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                         pixels(i, b, pix);
                         // ---- phase 1 (ROW view)
                         if (kk == 0) {
+                            SK_T0();
                             mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
+                            SK_ACC(0);
                             tc_fence_after();
                         }
+                        SK_T0();
                         uint32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
                         if (kk == ncg - 1) {          // this warp's last read of the accumulator buffer: hand it back to the MMA warp
@@ -396,10 +408,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                             if (nt * p.BN + c0 + c < Cout && tot != 0.f)
                                 atomicAdd(p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + nt * p.BN + c0 + c) * 2 + kind, (double)tot);
                         }
+                        SK_ACC(1);
                     }
                 }
             }
         }
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && q == 0) { p.dbg[4 + 2 * gi] = acc_dbg[0]; p.dbg[5 + 2 * gi] = acc_dbg[1]; }
         tc_fence_before();
     } else {
         // ===== transform (warps 2, 3, 12 .. 15): raw fp32 patch -> normalise -> Swish -> operand image
@@ -417,8 +431,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + kp * CPP)[j];
             }
-            mbar_wait_relaxed(full_raw(r), (uint32_t)((i / SK_NRAW) & 1));
-            mbar_wait_relaxed(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            { SK_T0(); mbar_wait_relaxed(full_raw(r), (uint32_t)((i / SK_NRAW) & 1)); SK_ACC(0); }
+            { SK_T0(); mbar_wait_relaxed(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u); SK_ACC(1); }
+            SK_T0();
             const uint32_t rawb = base + raw_off + (uint32_t)r * p.raw_bytes;
             const uint32_t opb = base + op_off + (uint32_t)s * p.op_bytes;
             const int items = P * SK_PATCH_PX;
@@ -487,7 +502,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_op(s)) : "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_raw(r)) : "memory");
             }
+            SK_ACC(2);
         }
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && xt == 0) { p.dbg[8] = acc_dbg[0]; p.dbg[9] = acc_dbg[1]; p.dbg[10] = acc_dbg[2]; }
     }
     __syncthreads();
     if (warp == 1) {
@@ -542,6 +559,7 @@ bool stream_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
+static long long* g_stream_dbg = nullptr;
 static int stream_encoder() {
     if (g_enc) return DS_OK;
     void* fn = nullptr;
@@ -610,6 +628,12 @@ int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, c
     }
     const size_t smem = stream_smem_bytes(p.C, p.BN, B, es);
     p.trace = trace_next(6);
+    static const bool dbg_on = getenv("DIFFSPLIT_B200_STREAM_DBG") != nullptr;
+    if (dbg_on) {
+        if (!g_stream_dbg) DS_CHECK_CUDA(cudaMalloc(&g_stream_dbg, 16 * sizeof(long long)));
+        DS_CHECK_CUDA(cudaMemsetAsync(g_stream_dbg, 0, 16 * sizeof(long long), st));
+        p.dbg = g_stream_dbg;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_LIMIT + 2048));
@@ -633,3 +657,14 @@ int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, c
 }
 
 }  // namespace ds
+
+// debugging aid (DIFFSPLIT_B200_STREAM_DBG=1): cycle sums of CTA 0 of the last conv_stream launch:
+// [0] producer wait empty_raw | [1..3] MMA wait full_op, wait empty_acc, issue+commit | [4,5] / [6,7] epilogue group 0 / 1 wait
+// full_acc, work | [8..10] transform wait full_raw, wait empty_op, work | [14] tiles of the CTA | [15] producer lifetime
+extern "C" int ds_debug_stream_phases(long long* out16) {
+    using namespace ds;
+    DS_REQUIRE(g_stream_dbg && out16, "stream debug buffer not active (DIFFSPLIT_B200_STREAM_DBG=1)");
+    DS_CHECK_CUDA(cudaDeviceSynchronize());
+    DS_CHECK_CUDA(cudaMemcpy(out16, g_stream_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return DS_OK;
+}

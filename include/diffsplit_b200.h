@@ -156,6 +156,7 @@ int ds_gnconv_tf32(const float* d_xa, int ca, const float* d_xb, int cb, const f
 size_t ds_gnconv_tf32_scratch_bytes(int B, int groups, int cin, int cout, int ksize);
 /* debugging aid (DIFFSPLIT_B200_HALO_DBG=1): mean clock64 cycles of the 7 phases of the last fused-conv launch:
  * setup | wait for predecessor | loads + scale table | transform + stage | MMA | epilogue | teardown */
+int ds_debug_stream_phases(long long* out16);   /* per-role wait / work cycles of the pipelined fused conv (tc_stream.cu) */
 int ds_debug_halo_phases(double* h_out7, int* n_ctas);
 /* debugging aid (DIFFSPLIT_B200_TRACE=1): GPU-timer (ns) start / end of every tensor-core conv launch, also inside
  * CUDA-graph replays.  reset(1) forgets the launch ids, reset(0) re-arms the recorded ones; read returns the count. */

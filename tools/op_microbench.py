@@ -81,16 +81,32 @@ def main():
     out16 = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=DEV)
     out32 = torch.empty((B, H, W, cout), device=DEV)
     res = torch.randn((B, H, W, cout), generator=g).to(DEV)
-    if kind == "gnconv":
-        nb = L.ds_gnconv_bf16_scratch_bytes(B, 16, cin, cout, ks)
+    if kind in ("gnconv", "gnconv_tf32"):
+        tf32 = kind == "gnconv_tf32"
+        nb = (L.ds_gnconv_tf32_scratch_bytes if tf32 else L.ds_gnconv_bf16_scratch_bytes)(B, 16, cin, cout, ks)
         scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
+        use_res = os.environ.get("MB_NO_RESIDUAL") is None
 
         def fn():
-            _lib.check(L.ds_gnconv_bf16(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
-                                        beta.data_ptr(), 16, 1, w.data_ptr(), bias.data_ptr(), res.data_ptr(), out16.data_ptr(),
-                                        out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sp()))
+            if tf32:
+                _lib.check(L.ds_gnconv_tf32(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
+                                            beta.data_ptr(), 16, 1, w.data_ptr(), bias.data_ptr(), res.data_ptr() if use_res else None,
+                                            out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sp()))
+            else:
+                _lib.check(L.ds_gnconv_bf16(xa32.data_ptr(), ca, None if xb32 is None else xb32.data_ptr(), cb, gamma.data_ptr(),
+                                            beta.data_ptr(), 16, 1, w.data_ptr(), bias.data_ptr(), res.data_ptr() if use_res else None,
+                                            out16.data_ptr(), out32.data_ptr(), B, H, W, cout, ks, scratch.data_ptr(), nb, sp()))
         us = timed_graph(fn)
-        print(f"gnconv (pack + gn_stats + conv_halo) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (3 kernels)")
+        print(f"{kind} (pack + gn_stats + fused conv) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W} residual={use_res}: {us:.2f} us per call (3 kernels)")
+        if os.environ.get("DIFFSPLIT_B200_STREAM_DBG"):
+            fn()
+            ph = (C.c_longlong * 16)()
+            _lib.check(L.ds_debug_stream_phases(ph))
+            nt_ = max(1, ph[14])
+            names = {0: "producer wait empty_raw", 1: "mma wait full_op", 2: "mma wait empty_acc", 3: "mma issue", 4: "epi0 wait full_acc",
+                     5: "epi0 work", 6: "epi1 wait full_acc", 7: "epi1 work", 8: "xf wait full_raw", 9: "xf wait empty_op", 10: "xf work"}
+            print(f"  stream phases, CTA 0, {ph[14]} tiles, lifetime {ph[15]} cycles = {ph[15] / nt_:.0f} per tile; per tile:",
+                  {v: round(ph[k] / nt_) for k, v in names.items()})
         if os.environ.get("DIFFSPLIT_B200_HALO_DBG"):
             fn()
             ph = (C.c_double * 7)()
