@@ -37,9 +37,8 @@ constexpr int SK_PATCH_PX = SK_PW * SK_PH;               // 162 staged pixels
 constexpr int SK_PLANE_PX = 169;                         // + the rows the last window runs past the patch; 169 * 16 B = 16 mod 128:
                                                          // the 8 planes a quarter-warp stores to hit 8 different bank groups
 constexpr int SK_NRAW = 2;
-constexpr int SK_SLOTS = 4;                              // residual chunks in flight per epilogue thread
 constexpr int SK_STG_LD = 20;                            // row pitch (floats) of the epilogue staging buffer: conflict-free STS.128
-constexpr uint32_t SK_RED_BYTES = 128 * SK_STG_LD * 4 + 4 * 2 * 16 * 4;     // per epilogue group
+constexpr uint32_t SK_RED_BYTES = 128 * SK_STG_LD * 4;                     // per epilogue group
 constexpr size_t SK_SMEM_LIMIT = 225 * 1024;
 
 struct StreamParams {
@@ -61,6 +60,28 @@ struct StreamParams {
 };
 #define SK_T0() const long long _t0 = p.dbg ? clock64() : 0
 #define SK_ACC(slot) do { if (p.dbg) acc_dbg[slot] += clock64() - _t0; } while (0)
+
+// rare epilogue paths kept out of line: fp32 NCHW output (the network's last conv) and channel counts that are not multiples of 4
+__device__ __noinline__ void stream_store_tail(const TcEpi& e, float4 x, int pix, int n0, int HW) {
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    if (e.out_nchw) {
+        const int pb = pix / HW, pp = pix - pb * HW;
+        for (int k = 0; k < 4; ++k)
+            if (n0 + k < e.Cout) e.out_nchw[((size_t)pb * e.Cout + n0 + k) * HW + pp] = xs[k];
+        return;
+    }
+    const size_t off = (size_t)pix * e.Cout + n0;
+    for (int k = 0; k < 4; ++k) {
+        if (n0 + k < e.Cout) {
+            if (e.out_f32) e.out_f32[off + k] = xs[k];
+            if (e.out_b16) e.out_b16[off + k] = __float2bfloat16_rn(xs[k]);
+        }
+    }
+}
+
+__device__ __noinline__ float4 stream_load_tail(const float* src, int n) {
+    return make_float4(__ldg(src), n > 1 ? __ldg(src + 1) : 0.f, n > 2 ? __ldg(src + 2) : 0.f, n > 3 ? __ldg(src + 3) : 0.f);
+}
 
 template <bool TF32>
 __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid_constant__ StreamParams p) {
@@ -253,31 +274,38 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 12) {
-        // ===== epilogue: group gi = chunks gi, gi + 2, ... of every tile, two phases per 16-channel chunk:
+        // ===== epilogue: group gi = chunks gi, gi + 2 (BN <= 64: at most two chunks per group and tile), two phases per chunk:
         //  1. ROW view - warp q owns TMEM lanes [32q, 32q + 32) = patch positions: tcgen05.ld, + (bias + conditioning vector) from
         //     the shared-memory table, four 16-byte stores into the group's staging buffer [128 rows][20];
         //  2. QUAD view - thread (row te / 4 + 32 j, quad te % 4), j = 0..3: reads its 4 channels back, adds the fp32 residual and
         //     stores fp32 / bf16 NHWC (or fp32 NCHW): four neighbouring lanes cover the 64 contiguous bytes of one pixel, so
-        //     one instruction touches 8 lines instead of 32 (the per-row view made the epilogue LSU bound: ~5 k wavefront
-        //     cycles per tile).  The residual is requested SK_SLOTS chunks ahead as pure loads in this view (no arithmetic
-        //     on the loaded registers until they are used), the GroupNorm statistics of the output are summed in this view
-        //     (4 rows x 4 channels per thread, three shuffle levels, one fold through shared memory).
+        //     one instruction touches 8 lines instead of 32.
+        // The kernel is instruction-issue bound (first pipelined version: 17.5 k warp instructions per tile, 8.2 k cycles), so:
+        // the residual of the NEXT tile is loaded into the registers the current chunk has just consumed (pure loads, one tile
+        // of latency hidden, no rotation); pixel offsets are computed once per tile; the GroupNorm statistics of the output
+        // stay in registers (4 channels x 4 rows per thread and chunk) and are folded - shuffles + fp64 atomics - only when
+        // the CTA moves on to another sample.
         const int gi = (warp - 4) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int te = tid - 128 - gi * 128;
-        float* stg = reinterpret_cast<float*>(red + (size_t)gi * SK_RED_BYTES);      // [128][20] staging + [4 warps][2][16] partials
-        float* part = stg + 128 * SK_STG_LD;
+        float* stg = reinterpret_cast<float*>(red + (size_t)gi * SK_RED_BYTES);      // [128][20] staging
         const int nchunks = p.BN >> 4;
-        const int ncg = (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile
+        const int ncg = (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile: 0, 1 or 2
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
-        const int total = my_tiles * ncg;
         const int quad = te & 3, r0 = te >> 2;
         const int Cout = p.epi.Cout;
         const float* bt = reinterpret_cast<const float*>(gbase + bt_off);
-        float4 res[SK_SLOTS][4];
-        // QUAD-view geometry of the tile a chunk belongs to: pixel index (or -1) of rows r0 + 32 j
-        auto pixels = [&](int i, int& b, int (&pix)[4]) {
+        const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
+        const int nq = nt * p.BN + gi * 16 + quad * 4;            // first channel of this thread's quad in chunk kk = 0 (+ 32 kk)
+        float4 res[2][4];
+        float acc[2][8];                                           // (sum x4, sum of squares x4) per chunk of the current sample
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+        // element offsets (pixel * Cout + nq, or -1) of rows r0 + 32 j of a tile
+        auto offsets = [&](int i, int& b, int (&off)[4]) {
             int y0, x0;
             tile_coords(i, b, y0, x0);
 #pragma unroll
@@ -285,46 +313,70 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 const int r = r0 + 32 * jj;
                 const int pr = r / SK_PW, pc = r - pr * SK_PW;
                 const int y = y0 + pr, x = x0 + pc;
-                pix[jj] = (pr < SK_TH && pc < SK_TW && y < p.H && x < p.W) ? (b * p.H + y) * p.W + x : -1;
+                off[jj] = (pr < SK_TH && pc < SK_TW && y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout + nq : -1;
             }
         };
-        auto request = [&](int g, float4 (&rr)[4]) {
-            if (!p.epi.residual || g >= total) return;
-            const int i = g / ncg;
-            int b, pix[4];
-            pixels(i, b, pix);
-            const int n0 = nt * p.BN + (gi + SK_EPI_GROUPS * (g - i * ncg)) * 16 + quad * 4;
+        auto load_res = [&](const int (&off)[4], int kk, float4 (&rr)[4]) {
+            if (!p.epi.residual) return;
+            const int n0 = nq + 32 * kk;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                if (pix[jj] >= 0 && n0 + 4 <= Cout) rr[jj] = __ldg(reinterpret_cast<const float4*>(p.epi.residual + (size_t)pix[jj] * Cout + n0));
-                else if (pix[jj] >= 0) {
-                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                if (off[jj] < 0 || n0 >= Cout) continue;
+                const float* src = p.epi.residual + off[jj] + 32 * kk;
+                if (vec_ok) rr[jj] = __ldg(reinterpret_cast<const float4*>(src));
+                else rr[jj] = stream_load_tail(src, Cout - n0);
+            }
+        };
+        auto flush = [&](int b) {                                  // fold the register statistics of sample b
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) if (n0 + e < Cout) t[e] = __ldg(p.epi.residual + (size_t)pix[jj] * Cout + n0 + e);
-                    rr[jj] = make_float4(t[0], t[1], t[2], t[3]);
+            for (int k = 0; k < 2; ++k) {
+                if (k < ncg) {
+#pragma unroll
+                    for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[k][e] += __shfl_xor_sync(0xffffffffu, acc[k][e], o);
+                    if (lane < 4) {
+                        const int n0 = nq + 32 * k;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (n0 + e < Cout) {
+                                double* dst = p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + n0 + e) * 2;
+                                atomicAdd(dst, (double)acc[k][e]);
+                                atomicAdd(dst + 1, (double)acc[k][4 + e]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
                 }
             }
         };
-        if (ncg > 0) {
+        if (ncg > 0 && my_tiles > 0) {
+            int b = 0, off[4], b_acc = -1;
+            offsets(0, b, off);
+            b_acc = b;
 #pragma unroll
-            for (int k = 0; k < SK_SLOTS; ++k) request(k, res[k]);
-            for (int g0 = 0; g0 < total; g0 += SK_SLOTS) {
+            for (int k = 0; k < 2; ++k)
+                if (k < ncg) load_res(off, k, res[k]);
+#pragma unroll 1
+            for (int i = 0;; ++i) {
+                if (p.epi.sums_out && (i == my_tiles || b != b_acc)) { flush(b_acc); b_acc = b; }      // the one call site of flush
+                if (i == my_tiles) break;
+                const int s = i & 1;
+                int b_next = b, off_next[4] = {-1, -1, -1, -1};
+                if (i + 1 < my_tiles) offsets(i + 1, b_next, off_next);
+                {
+                    SK_T0();
+                    mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
+                    SK_ACC(0);
+                }
+                tc_fence_after();
+                SK_T0();
 #pragma unroll
-                for (int k = 0; k < SK_SLOTS; ++k) {
-                    const int g = g0 + k;
-                    if (g < total) {
-                        const int i = g / ncg, s = i & 1, kk = g - i * ncg;
+                for (int kk = 0; kk < 2; ++kk) {
+                    if (kk < ncg) {
                         const int c0 = (gi + SK_EPI_GROUPS * kk) * 16;
-                        int b, pix[4];
-                        pixels(i, b, pix);
                         // ---- phase 1 (ROW view)
-                        if (kk == 0) {
-                            SK_T0();
-                            mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
-                            SK_ACC(0);
-                            tc_fence_after();
-                        }
-                        SK_T0();
                         uint32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
                         if (kk == ncg - 1) {          // this warp's last read of the accumulator buffer: hand it back to the MMA warp
@@ -344,108 +396,72 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                         }
                         if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                         // ---- phase 2 (QUAD view)
-                        const int n0 = nt * p.BN + c0 + quad * 4;
-                        float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+                        const int n0 = nq + 32 * kk;
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             float4 x = *reinterpret_cast<const float4*>(stg + (r0 + 32 * jj) * SK_STG_LD + quad * 4);
-                            if (pix[jj] < 0) continue;
-                            if (p.epi.residual) { x.x += res[k][jj].x; x.y += res[k][jj].y; x.z += res[k][jj].z; x.w += res[k][jj].w; }
-                            const float xs[4] = {x.x, x.y, x.z, x.w};
-                            if (p.epi.out_nchw) {
-                                const int pb = pix[jj] / (p.H * p.W), pp = pix[jj] - pb * p.H * p.W;
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (n0 + e < Cout) p.epi.out_nchw[((size_t)pb * Cout + n0 + e) * p.H * p.W + pp] = xs[e];
-                            } else if (n0 + 4 <= Cout) {
-                                const size_t off = (size_t)pix[jj] * Cout + n0;
-                                if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + off) = x;
+                            if (off[jj] < 0 || n0 >= Cout) continue;
+                            if (p.epi.residual) { x.x += res[kk][jj].x; x.y += res[kk][jj].y; x.z += res[kk][jj].z; x.w += res[kk][jj].w; }
+                            if (vec_ok) {
+                                const int o = off[jj] + 32 * kk;
+                                if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + o) = x;
                                 if (p.epi.out_b16) {
                                     const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
                                     uint2 pk;
                                     pk.x = *reinterpret_cast<const uint32_t*>(&lo);
                                     pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                                    *reinterpret_cast<uint2*>(p.epi.out_b16 + off) = pk;
+                                    *reinterpret_cast<uint2*>(p.epi.out_b16 + o) = pk;
                                 }
                             } else {
-                                const size_t off = (size_t)pix[jj] * Cout + n0;
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (n0 + e < Cout) {
-                                        if (p.epi.out_f32) p.epi.out_f32[off + e] = xs[e];
-                                        if (p.epi.out_b16) p.epi.out_b16[off + e] = __float2bfloat16_rn(xs[e]);
-                                    }
-                                }
+                                stream_store_tail(p.epi, x, (off[jj] - nq) / Cout, n0, p.H * p.W);
+                                if (n0 + 1 >= Cout) x.y = 0.f;
+                                if (n0 + 2 >= Cout) x.z = 0.f;
+                                if (n0 + 3 >= Cout) x.w = 0.f;
                             }
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { sm[e] += xs[e]; sq[e] = fmaf(xs[e], xs[e], sq[e]); }
+                            acc[kk][0] += x.x; acc[kk][1] += x.y; acc[kk][2] += x.z; acc[kk][3] += x.w;
+                            acc[kk][4] = fmaf(x.x, x.x, acc[kk][4]); acc[kk][5] = fmaf(x.y, x.y, acc[kk][5]);
+                            acc[kk][6] = fmaf(x.z, x.z, acc[kk][6]); acc[kk][7] = fmaf(x.w, x.w, acc[kk][7]);
                         }
-                        request(g + SK_SLOTS, res[k]);
-                        if (p.epi.sums_out) {
-                            // lanes with the same quad (lane % 4) hold partial sums of the same 4 channels: fold the 8 of a warp
-#pragma unroll
-                            for (int o = 4; o <= 16; o <<= 1) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], o);
-                                    sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], o);
-                                }
-                            }
-                            if (lane < 4) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    part[(q * 2 + 0) * 16 + lane * 4 + e] = sm[e];
-                                    part[(q * 2 + 1) * 16 + lane * 4 + e] = sq[e];
-                                }
-                            }
-                        }
-                        // orders this chunk's reads of the staging buffer before the next chunk's writes, and publishes `part`
+                        load_res(off_next, kk, res[kk]);      // next tile's residual into the registers just consumed
+                        // orders this chunk's reads of the staging buffer before the next chunk's writes
                         if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-                        if (p.epi.sums_out && te < 32) {
-                            const int kind = te >> 4, c = te & 15;
-                            const float tot = (part[(0 * 2 + kind) * 16 + c] + part[(1 * 2 + kind) * 16 + c]) +
-                                              (part[(2 * 2 + kind) * 16 + c] + part[(3 * 2 + kind) * 16 + c]);
-                            if (nt * p.BN + c0 + c < Cout && tot != 0.f)
-                                atomicAdd(p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + nt * p.BN + c0 + c) * 2 + kind, (double)tot);
-                        }
-                        SK_ACC(1);
                     }
                 }
+                b = b_next;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) off[jj] = off_next[jj];
+                SK_ACC(1);
             }
         }
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && q == 0) { p.dbg[4 + 2 * gi] = acc_dbg[0]; p.dbg[5 + 2 * gi] = acc_dbg[1]; }
         tc_fence_before();
     } else {
-        // ===== transform (warps 2, 3, 12 .. 15): raw fp32 patch -> normalise -> Swish -> operand image
+        // ===== transform (warps 2, 3, 12 .. 15): raw fp32 patch -> normalise -> Swish -> operand image.  Thread xt owns channel plane
+        // kp = xt % P (its scale / shift pairs stay in registers for the tile) and the patch pixels xt / P, + 192 / P, ...
         const int xt = warp < 4 ? tid - 64 : tid - 384 + 64;
-        const uint32_t ca4 = (uint32_t)p.ca * 4u, cb4 = (uint32_t)p.cb * 4u;
-        const bool fixed = (SK_XF_THREADS % P) == 0;        // the thread's channel plane is the same for all its items
+        const int kp = xt % P, px_first = xt / P, px_step = SK_XF_THREADS / P;
+        const int c0 = kp * CPP;
+        const bool from_a = c0 < p.ca;
+        const uint32_t src_pitch = (uint32_t)(from_a ? p.ca : p.cb) * 4u;
+        const uint32_t src_first = (from_a ? (uint32_t)c0 * 4u : p.raw_a_bytes + (uint32_t)(c0 - p.ca) * 4u) + (uint32_t)px_first * src_pitch;
+        const uint32_t dst_first = (uint32_t)kp * plane_bytes + (uint32_t)px_first * 16u;
         for (int i = 0; i < my_tiles; ++i) {
             const int r = i % SK_NRAW, s = i & 1;
             int b, y0, x0;
             tile_coords(i, b, y0, x0);
-            const float2* tb_s = tab + b * p.C;
             float4 sc[CPP / 2];
-            if (fixed) {
-                const int kp = xt % P;
 #pragma unroll
-                for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + kp * CPP)[j];
-            }
+            for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tab + b * p.C + c0)[j];
             { SK_T0(); mbar_wait_relaxed(full_raw(r), (uint32_t)((i / SK_NRAW) & 1)); SK_ACC(0); }
             { SK_T0(); mbar_wait_relaxed(empty_op(s), ((uint32_t)(i >> 1) & 1u) ^ 1u); SK_ACC(1); }
             SK_T0();
-            const uint32_t rawb = base + raw_off + (uint32_t)r * p.raw_bytes;
-            const uint32_t opb = base + op_off + (uint32_t)s * p.op_bytes;
-            const int items = P * SK_PATCH_PX;
-            for (int it = xt; it < items; it += SK_XF_THREADS) {
-                const int px = it / P, kp = it - px * P;
+            uint32_t src = base + raw_off + (uint32_t)r * p.raw_bytes + src_first;
+            uint32_t dst = base + op_off + (uint32_t)s * p.op_bytes + dst_first;
+#pragma unroll 1
+            for (int px = px_first; px < SK_PATCH_PX; px += px_step, src += (uint32_t)px_step * src_pitch, dst += (uint32_t)px_step * 16u) {
                 const int pr = px / SK_PW, pc = px - pr * SK_PW;
-                const int yy = y0 + pr - 1, xx = x0 + pc - 1;
                 uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-                    const int c0 = kp * CPP;
-                    const uint32_t src = c0 < p.ca ? rawb + (uint32_t)px * ca4 + (uint32_t)c0 * 4u
-                                                    : rawb + p.raw_a_bytes + (uint32_t)px * cb4 + (uint32_t)(c0 - p.ca) * 4u;
+                if ((unsigned)(y0 + pr - 1) < (unsigned)p.H && (unsigned)(x0 + pc - 1) < (unsigned)p.W) {
                     float x[CPP];
                     {
                         float4 v0;
@@ -456,10 +472,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + 16u));
                             x[CPP - 4] = v1.x; x[CPP - 3] = v1.y; x[CPP - 2] = v1.z; x[CPP - 1] = v1.w;
                         }
-                    }
-                    if (!fixed) {
-#pragma unroll
-                        for (int j = 0; j < CPP / 2; ++j) sc[j] = reinterpret_cast<const float4*>(tb_s + c0)[j];
                     }
 #pragma unroll
                     for (int j = 0; j < CPP / 2; ++j) {
@@ -492,9 +504,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                         val = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(opb + (uint32_t)kp * plane_bytes + (uint32_t)px * 16u), "r"(val.x),
-                             "r"(val.y), "r"(val.z), "r"(val.w)
-                             : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
             }
             fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -533,7 +543,7 @@ static int stream_weight_loads(int C, int es) {
 static int stream_pick_bn(int cout, int C, int B, int es) {
     const int npad = (cout + 15) / 16 * 16;
     for (int bn = npad; bn >= 16; bn -= 16) {
-        if (npad % bn || bn > 256) continue;
+        if (npad % bn || bn > 64) continue;          // two epilogue groups x at most two 16-channel chunks per tile
         if (stream_smem_bytes(C, bn, B, es) <= SK_SMEM_LIMIT) return bn;
     }
     return 0;
@@ -549,6 +559,8 @@ bool stream_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W
     if (ks != 3 || ca <= 0 || ca % 8 || cb % 8 || C % 16 || C > 256 || W < 8) return false;
     if (ca * 4 > 1024 || cb * 4 > 1024) return false;                 // TMA box: <= 256 elements per dimension
     if (stream_weight_loads(C, es) == 0) return false;
+    if (SK_XF_THREADS % (C * es / 16)) return false;                  // a transform thread owns one channel plane
+    if ((int64_t)B * H * W * ((cout + 3) / 4 * 4) >= (1ll << 31)) return false;     // 32-bit element offsets in the epilogue
     const int bn = stream_pick_bn(cout, C, B, es);
     if (bn == 0) return false;
     const int n_tiles = (cout + 15) / 16 * 16 / bn;
