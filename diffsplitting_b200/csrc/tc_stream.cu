@@ -44,6 +44,7 @@ constexpr size_t SK_SMEM_LIMIT = 225 * 1024;
 struct StreamParams {
     CUtensorMap wmap;                 // packed weights (halo_pack_conv_weight image), as in conv_halo_kernel
     CUtensorMap rmap[2];              // raw fp32 sources as (C, W, H, B) tensors, box {c, 18, 9, 1}
+    CUtensorMap resmap;               // the fp32 residual as a (Cout, W, H, B) tensor, box {BN, 16, 7, 1}: L2 prefetch only
     int ca, cb, C;
     const double* sums_a; const double* sums_b;       // per-channel fp64 (sum, sumsq) [copies][B][c][2], or
     const float2* stats;                               // (mean, rstd) [B][G]; all null: no normalisation
@@ -55,6 +56,7 @@ struct StreamParams {
     int tiles_x, tiles_y, n_tiles_m;
     FastDiv div_tiles_x, div_tiles_xy;
     uint32_t raw_bytes, raw_a_bytes, op_bytes, b_bytes;
+    int res_prefetch;                 // resmap is valid
     long long* dbg;                   // DIFFSPLIT_B200_STREAM_DBG: per-role wait / work cycle sums of CTA 0 (16 slots)
     TraceSlot trace;
 };
@@ -166,6 +168,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         const uint32_t dst = base + raw_off + (uint32_t)s * p.raw_bytes;
         tma_load_4d(dst, &p.rmap[0], full_raw(s), 0, x0 - 1, y0 - 1, b);
         if (p.cb) tma_load_4d(dst + p.raw_a_bytes, &p.rmap[1], full_raw(s), 0, x0 - 1, y0 - 1, b);
+        // The epilogue reads the residual with ordinary loads three pipeline stages later: from HBM those are bound by the
+        // outstanding misses an SM's L1 can track (measured: ~6 B/clk per SM, the epilogue stalled on its load addresses);
+        // the copy engine pulls the tile into L2 now, so they become L2 hits.
+        if (p.res_prefetch)
+            asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(&p.resmap)),
+                         "r"(nt * p.BN), "r"(x0), "r"(y0), "r"(b)
+                         : "memory");
     };
     if (warp == 0 && elect_one()) {            // the first patches travel while the scale / shift table is built
         for (int i = 0; i < SK_NRAW && i < my_tiles; ++i) issue_raw(i);
@@ -637,6 +646,19 @@ int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, c
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("stream conv: cuTensorMapEncodeTiled for source %d failed (%d)", s, (int)r); return DS_ERR_CUDA; }
+    }
+    if (epi.residual) {
+        cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)W * cout * 4, (cuuint64_t)H * W * cout * 4};
+        cuuint32_t box[4] = {(cuuint32_t)(p.BN < cout ? p.BN : cout), SK_TW, SK_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if ((cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
+            CUresult r = g_enc(&p.resmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(epi.residual), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("stream conv: cuTensorMapEncodeTiled for the residual failed (%d)", (int)r); return DS_ERR_CUDA; }
+            p.res_prefetch = 1;
+        }
     }
     const size_t smem = stream_smem_bytes(p.C, p.BN, B, es);
     p.trace = trace_next(6);
