@@ -189,6 +189,10 @@ struct TcpParams {
     int nb16, B, H, W, BN, n_tiles, KC, chunks_a, chunks_b, MT, tiles_x, tiles_y, wstages;
     uint32_t patch_bytes;
     int tf32;
+    // persistent variant (conv_tcs_kernel)
+    CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {BN, 16, 7 MT, 1}: L2 prefetch only
+    int res_prefetch, n_items;        // work items = (M supertile, N tile), N fastest
+    FastDiv div_ntiles, div_tiles_x, div_tiles_xy;
     TraceSlot trace;
 };
 
@@ -346,6 +350,337 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
         for (int i = 0; i < nwork; i += 2) {
             work(i, addA);
             if (i + 1 < nwork) work(i + 1, addB);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+    trace_end(p.trace);
+}
+
+// ------------------------------------------------------------------------------------------ persistent tall-patch variant
+// conv_tcp_kernel spends most of a CTA's life outside the MMAs (ncu, 128 -> 128 at 8 x 256^2: tensor pipe 20 % active): TMEM
+// allocation, barrier set-up and pipeline fill per CTA, then an epilogue (residual loads, fp32 + bf16 stores, statistics) that
+// only starts when the last MMA has retired - 12 waves of that on 148 SMs.  Here ONE CTA per SM walks the work items
+// (M supertile of MT = 2 tiles x N tile) w = blockIdx.x, + gridDim.x, ... with TWO accumulator sets in TMEM (2 x MT x BN <= 512
+// columns), so the epilogue of item i runs under the MMAs of item i + 1:
+//   warp 0       TMA producer: per 64-channel chunk one (7 MT + 2) x 18 patch (ring of 2) + 9 weight tiles (ring of wstages);
+//                L2 prefetch of the item's residual tile
+//   warp 1       MMA issuer: 9 taps x MT tiles x 4 k-steps per chunk into ACC[i & 1]
+//   warps 4-11   epilogue, two groups of four warps (one per TMEM lane quadrant) taking alternate 16-column chunks, each chunk
+//                in two views (as conv_stream_kernel): ROW view  tcgen05.ld + (bias + conditioning vector) -> staging buffer;
+//                QUAD view  + residual (requested one chunk ahead), fp32 / bf16 stores with 64 contiguous bytes per four lanes,
+//                statistics in registers, folded once per item
+constexpr int TS_MT = 2;
+constexpr int TS_THREADS = 384;            // warps 0, 1 as above, 2-3 idle, 4-11 epilogue
+constexpr int TS_STG_LD = 20;
+constexpr uint32_t TS_STG_BYTES = 128 * TS_STG_LD * 4 + 128 * 4;     // staging [128][20] + (bias + temb) of the item's BN channels
+
+__device__ __noinline__ void tcs_store_tail(const TcEpi& e, float4 x, int pix, int n0) {
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const int HW = e.Ho * e.Wo;
+    if (e.out_nchw) {
+        const int pb = pix / HW, pp = pix - pb * HW;
+        for (int k = 0; k < 4; ++k)
+            if (n0 + k < e.Cout) e.out_nchw[((size_t)pb * e.Cout + n0 + k) * HW + pp] = xs[k];
+        return;
+    }
+    const size_t off = (size_t)pix * e.Cout + n0;
+    for (int k = 0; k < 4; ++k) {
+        if (n0 + k < e.Cout) {
+            if (e.out_f32) e.out_f32[off + k] = xs[k];
+            if (e.out_b16) e.out_b16[off + k] = __float2bfloat16_rn(xs[k]);
+        }
+    }
+}
+__device__ __noinline__ float4 tcs_load_tail(const float* src, int n) {
+    return make_float4(__ldg(src), n > 1 ? __ldg(src + 1) : 0.f, n > 2 ? __ldg(src + 2) : 0.f, n > 3 ? __ldg(src + 3) : 0.f);
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_constant__ TcpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t row_bytes = (uint32_t)p.KC * (p.tf32 ? 4u : 2u);
+    const uint32_t w_bytes = (uint32_t)p.BN * row_bytes;
+    const uint32_t wstage_bytes = (w_bytes + 1023u) & ~1023u;
+    const uint32_t wring = base + 2u * p.patch_bytes;
+    const uint32_t stg_off = 2u * p.patch_bytes + (uint32_t)p.wstages * wstage_bytes;      // 2 x TS_STG_BYTES
+    const uint32_t bar_base = base + stg_off + 2u * TS_STG_BYTES;
+    auto wfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto wempty = [&](int s) { return bar_base + 8u * (uint32_t)(p.wstages + s); };
+    const uint32_t b2 = bar_base + 16u * (uint32_t)p.wstages;
+    auto pfull = [&](int i) { return b2 + 8u * (uint32_t)i; };
+    auto pempty = [&](int i) { return b2 + 16u + 8u * (uint32_t)i; };
+    auto afull = [&](int i) { return b2 + 32u + 8u * (uint32_t)i; };
+    auto aempty = [&](int i) { return b2 + 48u + 8u * (uint32_t)i; };
+    const uint32_t tmem_slot = b2 + 64u;
+    const int nchunks = p.chunks_a + p.chunks_b;
+    const int cpt = p.BN >> 4;                                    // 16-column chunks per tile
+    const uint32_t acc_cols = (uint32_t)(TS_MT * p.BN);
+    const uint32_t tmem_cols = 2u * acc_cols <= 32u ? 32u : (2u * acc_cols <= 64u ? 64u : (2u * acc_cols <= 128u ? 128u : (2u * acc_cols <= 256u ? 256u : 512u)));
+    const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int egroups = cpt * TS_MT >= 2 ? 2 : 1;                // epilogue groups with work
+
+    trace_begin(p.trace);
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.wstages; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(pfull(i), 1); mbar_init(pempty(i), 1);
+            mbar_init(afull(i), 1); mbar_init(aempty(i), 4 * egroups);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_trigger();
+
+    auto item_coords = [&](int i, int& nt, int& b, int& y0, int& x0) {
+        const int w = (int)blockIdx.x + i * (int)gridDim.x;
+        const int mi = fdiv(w, p.div_ntiles);
+        nt = w - mi * p.n_tiles;
+        b = fdiv(mi, p.div_tiles_xy);
+        const int rem = mi - b * p.tiles_x * p.tiles_y;
+        const int ty = fdiv(rem, p.div_tiles_x);
+        y0 = ty * TP_TH * TS_MT;
+        x0 = (rem - ty * p.tiles_x) * TP_TW;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const size_t blk16 = (size_t)16 * row_bytes;
+            const uint32_t box_bytes = (uint32_t)(TP_PW * (TP_TH * TS_MT + 2)) * row_bytes;
+            uint32_t cg = 0, ug = 0;                             // chunk / weight-unit counters over all items (ring phases)
+            for (int i = 0; i < my_items; ++i) {
+                int nt, b, y0, x0;
+                item_coords(i, nt, b, y0, x0);
+                if (p.res_prefetch)
+                    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(&p.resmap)),
+                                 "r"(nt * p.BN), "r"(x0), "r"(y0), "r"(b)
+                                 : "memory");
+                const uint8_t* wsrc = p.w + (size_t)nt * (p.BN / 16) * blk16;
+                for (int cc = 0; cc < nchunks; ++cc, ++cg) {
+                    const int pb = (int)(cg & 1u);
+                    mbar_wait_relaxed(pempty(pb), ((cg >> 1) & 1u) ^ 1u);
+                    const int src = cc < p.chunks_a ? 0 : 1;
+                    const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
+                    mbar_expect_tx(pfull(pb), box_bytes);
+                    tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.pmap[src], pfull(pb), c0, x0 - 1, y0 - 1, b);
+                    for (int tap = 0; tap < 9; ++tap, ++ug) {
+                        const int s = (int)(ug % (uint32_t)p.wstages);
+                        mbar_wait_relaxed(wempty(s), ((ug / (uint32_t)p.wstages) & 1u) ^ 1u);
+                        mbar_expect_tx(wfull(s), w_bytes);
+                        bulk_load(wring + (uint32_t)s * wstage_bytes, wsrc + (size_t)(tap * nchunks + cc) * p.nb16 * blk16, w_bytes, wfull(s));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
+            const int ksteps = (int)(row_bytes >> 5);
+            uint32_t cg = 0, ug = 0;
+            for (int i = 0; i < my_items; ++i) {
+                const int a = i & 1;
+                mbar_wait(aempty(a), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)a * acc_cols;
+                for (int cc = 0; cc < nchunks; ++cc, ++cg) {
+                    const int pb = (int)(cg & 1u);
+                    mbar_wait(pfull(pb), (cg >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t patch = base + (uint32_t)pb * p.patch_bytes;
+                    for (int tap = 0; tap < 9; ++tap, ++ug) {
+                        const int s = (int)(ug % (uint32_t)p.wstages);
+                        mbar_wait(wfull(s), (ug / (uint32_t)p.wstages) & 1u);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_smem_desc(wring + (uint32_t)s * wstage_bytes, row_bytes);
+                        const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
+#pragma unroll
+                        for (int t = 0; t < TS_MT; ++t) {
+                            const uint64_t adesc = make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
+                            if (p.tf32) {
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_tf32(acc + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
+                            } else {
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16(acc + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(wempty(s));
+                    }
+                    umma_commit(pempty(pb));
+                }
+                umma_commit(afull(a));
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int gi = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int te = tid - 128 - gi * 128;
+        float* stg = reinterpret_cast<float*>(gbase + stg_off + (uint32_t)gi * TS_STG_BYTES);
+        float* btv = stg + 128 * TS_STG_LD;                      // [BN <= 128] bias + conditioning vector of the item
+        const int quad = te & 3, r0 = te >> 2;
+        const int Cout = p.epi.Cout;
+        const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
+        const int G = TS_MT * cpt;                                // chunks per item, chunk g = (tile g / cpt, columns 16 (g % cpt))
+        const int ncg = (G - gi + 1) / 2;                         // this group's chunks: g = gi, gi + 2, ...
+        const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
+        if (gi < egroups) {
+#pragma unroll 1
+            for (int i = 0; i < my_items; ++i) {
+                const int a = i & 1;
+                int nt, b, y0, x0;
+                item_coords(i, nt, b, y0, x0);
+                // (bias + conditioning vector) of the item's channels -> btv (ordered before its use by the first chunk barrier of
+                // the previous item's last chunk / the barrier below)
+                if (te < p.BN) {
+                    const int n = nt * p.BN + te;
+                    float v = 0.f;
+                    if (n < Cout) {
+                        if (p.epi.bias) v = __ldg(p.epi.bias + n);
+                        if (p.epi.temb) v += __ldg(p.epi.temb + (size_t)(p.epi.temb_bcast ? 0 : b) * p.epi.temb_stride + p.epi.temb_off + n);
+                    }
+                    btv[te] = v;
+                }
+                // QUAD-view pixel offsets of rows r0 + 32 j, per tile t: pixel index * Cout (or -1)
+                int off[TS_MT][4];
+#pragma unroll
+                for (int t = 0; t < TS_MT; ++t) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int r = r0 + 32 * jj;
+                        const int pr = r / TP_PW, pc = r - pr * TP_PW;
+                        const int y = y0 + t * TP_TH + pr, x = x0 + pc;
+                        off[t][jj] = (pr < TP_TH && pc < TP_TW && y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
+                    }
+                }
+                float acc[4][8];                                  // statistics per chunk column of this group (cpt <= 8 -> <= 4 per group)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+                auto load_res = [&](int g, float4 (&rr)[4]) {
+                    if (!p.epi.residual || g >= G) return;
+                    const int t = g / cpt, n0 = nt * p.BN + (g - t * cpt) * 16 + quad * 4;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
+                        if (o < 0 || n0 >= Cout) continue;
+                        const float* src = p.epi.residual + o + n0;
+                        rr[jj] = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
+                    }
+                };
+                float4 rcur[4], rnext[4];
+                load_res(gi, rcur);
+                if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");     // btv visible
+                mbar_wait_relaxed(afull(a), (uint32_t)(i >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int kk = 0; kk < ncg; ++kk) {
+                    const int g = gi + 2 * kk;
+                    const int t = g / cpt, c0 = (g - t * cpt) * 16;
+                    load_res(g + 2, rnext);
+                    // ---- ROW view
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)(t * p.BN + c0), v);
+                    if (kk == ncg - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(aempty(a)) : "memory");
+                    }
+                    {
+                        const float4* bv = reinterpret_cast<const float4*>(btv + c0);
+                        float4* row = reinterpret_cast<float4*>(stg + m * TS_STG_LD);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 ad = bv[e];
+                            row[e] = make_float4(__uint_as_float(v[4 * e]) + ad.x, __uint_as_float(v[4 * e + 1]) + ad.y,
+                                                 __uint_as_float(v[4 * e + 2]) + ad.z, __uint_as_float(v[4 * e + 3]) + ad.w);
+                        }
+                    }
+                    if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    // ---- QUAD view
+                    const int n0 = nt * p.BN + c0 + quad * 4;
+                    float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float4 x = *reinterpret_cast<const float4*>(stg + (r0 + 32 * jj) * TS_STG_LD + quad * 4);
+                        const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
+                        if (o < 0 || n0 >= Cout) continue;
+                        if (p.epi.residual) { x.x += rcur[jj].x; x.y += rcur[jj].y; x.z += rcur[jj].z; x.w += rcur[jj].w; }
+                        if (vec_ok) {
+                            if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + o + n0) = x;
+                            if (p.epi.out_b16) {
+                                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                                *reinterpret_cast<uint2*>(p.epi.out_b16 + o + n0) = pk;
+                            }
+                        } else {
+                            tcs_store_tail(p.epi, x, o / Cout, n0);
+                            if (n0 + 1 >= Cout) x.y = 0.f;
+                            if (n0 + 2 >= Cout) x.z = 0.f;
+                            if (n0 + 3 >= Cout) x.w = 0.f;
+                        }
+                        sm[0] += x.x; sm[1] += x.y; sm[2] += x.z; sm[3] += x.w;
+                        sq[0] = fmaf(x.x, x.x, sq[0]); sq[1] = fmaf(x.y, x.y, sq[1]); sq[2] = fmaf(x.z, x.z, sq[2]); sq[3] = fmaf(x.w, x.w, sq[3]);
+                    }
+                    // this chunk's column index within the group: (c0 / 16 - gi) / 2 when cpt is even, else by position; fold by column
+                    if (p.epi.sums_out) {
+                        const int col = (cpt & 1) ? (c0 >> 4) : ((c0 >> 4) >> 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k == (col & 3)) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { acc[k][e] += sm[e]; acc[k][4 + e] += sq[e]; }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) rcur[jj] = rnext[jj];
+                    if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                }
+                // ---- fold the item's statistics: per accumulated column, lanes of equal quad, then one fp64 atomic pair per channel
+                if (p.epi.sums_out) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // column held by slot k (see above); slots beyond the group's columns stay zero and are skipped
+                        int cidx;
+                        if (cpt & 1) cidx = k;                    // odd cpt (1, 3, ...): slot = column index, both groups may touch any column
+                        else cidx = 2 * k + gi;                   // even cpt: group gi owns columns gi, gi + 2, ...
+                        if (cidx >= cpt) continue;
+#pragma unroll
+                        for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[k][e] += __shfl_xor_sync(0xffffffffu, acc[k][e], o);
+                        if (lane < 4) {
+                            const int n0 = nt * p.BN + cidx * 16 + lane * 4;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (n0 + e < Cout && (acc[k][e] != 0.f || acc[k][4 + e] != 0.f)) {
+                                    double* dst = p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + n0 + e) * 2;
+                                    atomicAdd(dst, (double)acc[k][e]);
+                                    atomicAdd(dst + 1, (double)acc[k][4 + e]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
         }
         tc_fence_before();
     }
@@ -521,6 +856,58 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
         const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
         const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
+        // persistent variant: enough work items (M supertile of 2 tiles x N tile) to keep every SM busy for several of them
+        static int persist_env = -1;
+        if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
+        {
+            const int ty2 = (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
+            const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn);
+            const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) < (1ll << 31);
+            if (can && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
+                (persist_env == 2 || items >= 2 * 148)) {
+                TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
+                memset(&q, 0, sizeof(q));
+                q.B = B; q.H = Hs; q.W = Ws; q.MT = TS_MT; q.tiles_x = tiles_x; q.tiles_y = ty2;
+                q.epi.Ho = Hs; q.epi.Wo = Ws; q.epi.Cout = cout;
+                q.nb16 = (cout + 15) / 16;
+                q.BN = bn; q.n_tiles = (q.nb16 * 16) / bn;
+                q.KC = kc; q.chunks_a = ca / kc; q.chunks_b = cb / kc;
+                q.tf32 = tf32;
+                q.n_items = (int)items;
+                q.div_ntiles = make_fastdiv((uint32_t)q.n_tiles);
+                q.div_tiles_x = make_fastdiv((uint32_t)tiles_x);
+                q.div_tiles_xy = make_fastdiv((uint32_t)(tiles_x * ty2));
+                const int prows = TP_PW * (TP_TH * TS_MT + 2) + 8;
+                q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
+                const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
+                int wst = (int)((200 * 1024 - 2 * (size_t)q.patch_bytes - 2 * TS_STG_BYTES - 2048) / wstage);
+                if (wst > 12) wst = 12;
+                if (wst >= 3) {
+                    q.wstages = wst;
+                    for (int s_ = 0; s_ < 2; ++s_) {
+                        const void* ptr = s_ == 0 ? src_a : src_b;
+                        const int C = s_ == 0 ? ca : cb;
+                        if (!ptr || C == 0) continue;
+                        rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, TP_PW,
+                                        TP_TH * TS_MT + 2, 1, tf32);
+                        if (rc != DS_OK) return rc;
+                    }
+                    plan->patch = 2;
+                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 2 * TS_STG_BYTES + 16 * wst + 128 + 1024);
+                    static int sms = 0;
+                    if (!sms) {
+                        int dev = 0;
+                        DS_CHECK_CUDA(cudaGetDevice(&dev));
+                        DS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                    }
+                    plan->grid_x = items < sms ? (int)items : sms;
+                    plan->grid_y = 1;
+                    plan->grid_z = 1;
+                    plan->kc = kc;
+                    return DS_OK;
+                }
+            }
+        }
         if (can && (patch_env == 2 || (patch_env == 1 && ctas >= 148 && (size_t)(ca + cb) * e >= 128 && (size_t)kc * e >= 64))) {
             static_assert(sizeof(TcpParams) <= sizeof(plan->params), "TcConvPlan::params too small");
             TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
@@ -654,6 +1041,34 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
 
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
                    float* out_nchw, double* sums_out, cudaStream_t st) {
+    if (plan->patch == 2) {
+        TcpParams q = *reinterpret_cast<const TcpParams*>(plan->params);
+        q.w = w_packed;
+        q.epi.bias = epi.bias; q.epi.temb = epi.temb; q.epi.temb_off = epi.temb_off; q.epi.temb_stride = epi.temb_stride;
+        q.epi.temb_bcast = epi.temb_bcast; q.epi.residual = epi.residual;
+        q.epi.out_f32 = out_f32; q.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); q.epi.out_nchw = out_nchw;
+        q.epi.sums_out = sums_out; q.epi.sums_B = q.B;
+        q.trace = trace_next(4);
+        q.res_prefetch = 0;
+        const int cout = q.epi.Cout;
+        if (epi.residual && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
+            cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.B};
+            cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)q.W * cout * 4, (cuuint64_t)q.H * q.W * cout * 4};
+            cuuint32_t box[4] = {(cuuint32_t)(q.BN < cout ? q.BN : cout), TP_TW, (cuuint32_t)(TP_TH * TS_MT), 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (g_encode(&q.resmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(epi.residual), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                q.res_prefetch = 1;
+        }
+        static bool sattr = false;
+        if (!sattr) {
+            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+            sattr = true;
+        }
+        DS_CHECK_CUDA(launch_pdl(conv_tcs_kernel, dim3(plan->grid_x, 1, 1), dim3(TS_THREADS), (size_t)plan->smem_bytes, st, q));
+        return DS_OK;
+    }
     if (plan->patch) {
         TcpParams q = *reinterpret_cast<const TcpParams*>(plan->params);
         q.w = w_packed;
