@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         for (int s = 0; s < SK_NRAW; ++s) { mbar_init(full_raw(s), 1); mbar_init(empty_raw(s), SK_XF_WARPS); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(full_op(s), SK_XF_WARPS); mbar_init(empty_op(s), 1);
-            mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4 * ((p.BN >> 4) >= SK_EPI_GROUPS ? SK_EPI_GROUPS : 1));
+            mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4 * ((p.BN >> 4) >= SK_EPI_GROUPS ? SK_EPI_GROUPS : 1));   // BN = 16: one group per buffer
         }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -300,13 +300,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         const int te = tid - 128 - gi * 128;
         float* stg = reinterpret_cast<float*>(red + (size_t)gi * SK_RED_BYTES);      // [128][20] staging
         const int nchunks = p.BN >> 4;
-        const int ncg = (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile: 0, 1 or 2
+        // BN >= 32: group gi takes chunks gi, gi + 2 of EVERY tile;  BN = 16 (one chunk): the groups take alternate TILES (group gi =
+        // accumulator buffer gi), so both halves of the epilogue warps work and a tile may take two tile periods to drain
+        const bool alt = nchunks == 1;
+        const int ncg = alt ? 1 : (nchunks - gi + SK_EPI_GROUPS - 1) / SK_EPI_GROUPS;       // this group's chunks per tile: 1 or 2
+        const int i_first = alt ? gi : 0, i_step = alt ? 2 : 1;
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
         const int quad = te & 3, r0 = te >> 2;
         const int Cout = p.epi.Cout;
         const float* bt = reinterpret_cast<const float*>(gbase + bt_off);
         const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
-        const int nq = nt * p.BN + gi * 16 + quad * 4;            // first channel of this thread's quad in chunk kk = 0 (+ 32 kk)
+        const int nq = nt * p.BN + (alt ? 0 : gi * 16) + quad * 4;     // first channel of this thread's quad in chunk kk = 0 (+ 32 kk)
         float4 res[2][4];
         float acc[2][8];                                           // (sum x4, sum of squares x4) per chunk of the current sample
 #pragma unroll
@@ -360,20 +364,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 }
             }
         };
-        if (ncg > 0 && my_tiles > 0) {
+        if (i_first < my_tiles) {
             int b = 0, off[4], b_acc = -1;
-            offsets(0, b, off);
+            offsets(i_first, b, off);
             b_acc = b;
 #pragma unroll
             for (int k = 0; k < 2; ++k)
                 if (k < ncg) load_res(off, k, res[k]);
 #pragma unroll 1
-            for (int i = 0;; ++i) {
-                if (p.epi.sums_out && (i == my_tiles || b != b_acc)) { flush(b_acc); b_acc = b; }      // the one call site of flush
-                if (i == my_tiles) break;
+            for (int i = i_first;; i += i_step) {
+                if (p.epi.sums_out && (i >= my_tiles || b != b_acc)) { flush(b_acc); b_acc = b; }      // the one call site of flush
+                if (i >= my_tiles) break;
                 const int s = i & 1;
                 int b_next = b, off_next[4] = {-1, -1, -1, -1};
-                if (i + 1 < my_tiles) offsets(i + 1, b_next, off_next);
+                if (i + i_step < my_tiles) offsets(i + i_step, b_next, off_next);
                 {
                     SK_T0();
                     mbar_wait_relaxed(full_acc(s), (uint32_t)(i >> 1) & 1u);
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     if (kk < ncg) {
-                        const int c0 = (gi + SK_EPI_GROUPS * kk) * 16;
+                        const int c0 = alt ? 0 : (gi + SK_EPI_GROUPS * kk) * 16;
                         // ---- phase 1 (ROW view)
                         uint32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
