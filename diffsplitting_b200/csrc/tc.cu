@@ -192,6 +192,10 @@ struct TcpParams {
     // persistent variant (conv_tcs_kernel)
     CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {BN, 16, 7 MT, 1}: L2 prefetch only
     int res_prefetch, n_items;        // work items = (M supertile, N tile), N fastest
+    int geo;                          // 0: supertile = 2 stacked tiles of 7 x 16 outputs (128 MMA rows = patch positions of pitch 18, 112
+                                      //    valid);  1: supertile = 16 x 16 outputs as two 8-wide tiles side by side: MMA row 8 g + i =
+                                      //    output (row g, column i) -> an 8-row core-matrix group is 8 consecutive patch pixels and the
+                                      //    groups are one patch row (18 pixels) apart: SBO = 18 rows instead of 8, all 128 rows valid
     FastDiv div_ntiles, div_tiles_x, div_tiles_xy;
     TraceSlot trace;
 };
@@ -451,14 +455,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         b = fdiv(mi, p.div_tiles_xy);
         const int rem = mi - b * p.tiles_x * p.tiles_y;
         const int ty = fdiv(rem, p.div_tiles_x);
-        y0 = ty * TP_TH * TS_MT;
+        y0 = ty * (p.geo ? 16 : TP_TH * TS_MT);
         x0 = (rem - ty * p.tiles_x) * TP_TW;
     };
 
     if (warp == 0) {
         if (elect_one()) {
             const size_t blk16 = (size_t)16 * row_bytes;
-            const uint32_t box_bytes = (uint32_t)(TP_PW * (TP_TH * TS_MT + 2)) * row_bytes;
+            const uint32_t box_bytes = (uint32_t)(TP_PW * (p.geo ? 18 : TP_TH * TS_MT + 2)) * row_bytes;
             uint32_t cg = 0, ug = 0;                             // chunk / weight-unit counters over all items (ring phases)
             for (int i = 0; i < my_items; ++i) {
                 int nt, b, y0, x0;
@@ -508,7 +512,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
 #pragma unroll
                         for (int t = 0; t < TS_MT; ++t) {
-                            const uint64_t adesc = make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
+                            const uint64_t adesc = p.geo ? make_smem_desc_sbo(patch + ((uint32_t)(t * 8) + shift) * row_bytes, row_bytes, TP_PW * row_bytes)
+                                                         : make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
                             if (p.tf32) {
                                 for (int k = 0; k < ksteps; ++k)
                                     umma_tf32(acc + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
@@ -562,9 +567,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int r = r0 + 32 * jj;
-                        const int pr = r / TP_PW, pc = r - pr * TP_PW;
-                        const int y = y0 + t * TP_TH + pr, x = x0 + pc;
-                        off[t][jj] = (pr < TP_TH && pc < TP_TW && y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
+                        if (p.geo) {
+                            const int y = y0 + (r >> 3), x = x0 + 8 * t + (r & 7);
+                            off[t][jj] = (y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
+                        } else {
+                            const int pr = r / TP_PW, pc = r - pr * TP_PW;
+                            const int y = y0 + t * TP_TH + pr, x = x0 + pc;
+                            off[t][jj] = (pr < TP_TH && pc < TP_TW && y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
+                        }
                     }
                 }
                 float acc[4][8];                                  // statistics per chunk column of this group (cpt <= 8 -> <= 4 per group)
@@ -860,7 +870,10 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         static int persist_env = -1;
         if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
         {
-            const int ty2 = (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
+            static int geo_env = -1;
+            if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
+            const int geo = geo_env ? 1 : 0;
+            const int ty2 = geo ? (Hs + 15) / 16 : (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
             const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn);
             const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) < (1ll << 31);
             if (can && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
@@ -874,10 +887,11 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                 q.KC = kc; q.chunks_a = ca / kc; q.chunks_b = cb / kc;
                 q.tf32 = tf32;
                 q.n_items = (int)items;
+                q.geo = geo;
                 q.div_ntiles = make_fastdiv((uint32_t)q.n_tiles);
                 q.div_tiles_x = make_fastdiv((uint32_t)tiles_x);
                 q.div_tiles_xy = make_fastdiv((uint32_t)(tiles_x * ty2));
-                const int prows = TP_PW * (TP_TH * TS_MT + 2) + 8;
+                const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
                 q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
                 const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
                 int wst = (int)((200 * 1024 - 2 * (size_t)q.patch_bytes - 2 * TS_STG_BYTES - 2048) / wstage);
@@ -889,7 +903,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                         const int C = s_ == 0 ? ca : cb;
                         if (!ptr || C == 0) continue;
                         rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, TP_PW,
-                                        TP_TH * TS_MT + 2, 1, tf32);
+                                        geo ? 18 : TP_TH * TS_MT + 2, 1, tf32);
                         if (rc != DS_OK) return rc;
                     }
                     plan->patch = 2;
@@ -1054,7 +1068,7 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
         if (epi.residual && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
             cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.B};
             cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)q.W * cout * 4, (cuuint64_t)q.H * q.W * cout * 4};
-            cuuint32_t box[4] = {(cuuint32_t)(q.BN < cout ? q.BN : cout), TP_TW, (cuuint32_t)(TP_TH * TS_MT), 1};
+            cuuint32_t box[4] = {(cuuint32_t)(q.BN < cout ? q.BN : cout), TP_TW, (cuuint32_t)(q.geo ? 16 : TP_TH * TS_MT), 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             if (g_encode(&q.resmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(epi.residual), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -481,6 +481,9 @@ bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, 
     const int bn = halo_pick_bn(cout, C, ntaps, W, nsamp, m_tiles, two_d, es);
     const int n_tiles = (cout + 15) / 16 * 16 / bn;
     if (m_tiles * n_tiles <= 4 * 148) return true;                           // latency regime
+    // throughput regime, wide inputs the pipelined variant cannot take: GroupNorm-apply + the persistent TMA-fed conv
+    // (conv_tcs_kernel) beats this kernel's serial load -> normalise -> MMA -> epilogue (128 -> 64 at 8 x 512^2: 2.0 ms fused)
+    if (C >= 128 && m_tiles * n_tiles >= 8 * 148) return false;
     const double redo = (double)halo_plane_px(ntaps, W, two_d) / (two_d ? (double)(HALO_TH * HALO_TW) : 128.0);   // staged per output pixel
     if (redo * n_tiles * C > 320.0) return false;
     const double in_bytes = (double)B * H * W * C * 4.0;

@@ -150,6 +150,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
 }
 
 
+// the same with an explicit stride between the 8-row groups (any multiple of the row size: the swizzle is a function of the
+// shared-memory address, so the groups need not be contiguous)
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
 // n / d for 0 <= n < 2^31 with a precomputed multiplier (CUTLASS FastDivmod scheme): no integer division on device
 struct FastDiv {
     uint32_t d, mul, shr;
