@@ -191,7 +191,10 @@ struct TcpParams {
     int tf32;
     // persistent variant (conv_tcs_kernel)
     CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {BN, 16, 7 MT, 1}: L2 prefetch only
-    int res_prefetch, n_items;        // work items = (M supertile, N tile), N fastest
+    int res_prefetch, n_items;        // work items = (M supertile, N tile[, output parity class]), N (class) fastest
+    int up;                           // nearest x2 upsample + 3x3 as four 2x2 convs on the low-res patch (geo 1 only): H, W = low-res
+                                      //    size, item class (a, b) writes the output pixels (2y + a, 2x + b); w = [class][tap][chunk]
+    uint32_t class_bytes;             // packed weight bytes per class
     int geo;                          // 0: supertile = 2 stacked tiles of 7 x 16 outputs (128 MMA rows = patch positions of pitch 18, 112
                                       //    valid);  1: supertile = 16 x 16 outputs as two 8-wide tiles side by side: MMA row 8 g + i =
                                       //    output (row g, column i) -> an 8-row core-matrix group is 8 consecutive patch pixels and the
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     auto item_coords = [&](int i, int& nt, int& b, int& y0, int& x0) {
         const int w = (int)blockIdx.x + i * (int)gridDim.x;
         const int mi = fdiv(w, p.div_ntiles);
-        nt = w - mi * p.n_tiles;
+        nt = w - mi * (p.up ? 4 * p.n_tiles : p.n_tiles);                      // up: N tile * 4 + class
         b = fdiv(mi, p.div_tiles_xy);
         const int rem = mi - b * p.tiles_x * p.tiles_y;
         const int ty = fdiv(rem, p.div_tiles_x);
@@ -471,7 +474,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(&p.resmap)),
                                  "r"(nt * p.BN), "r"(x0), "r"(y0), "r"(b)
                                  : "memory");
-                const uint8_t* wsrc = p.w + (size_t)nt * (p.BN / 16) * blk16;
+                const int ntaps = p.up ? 4 : 9;
+                const uint8_t* wsrc = p.w + (size_t)(p.up ? nt >> 2 : nt) * (p.BN / 16) * blk16 + (p.up ? (size_t)(nt & 3) * p.class_bytes : 0);
                 for (int cc = 0; cc < nchunks; ++cc, ++cg) {
                     const int pb = (int)(cg & 1u);
                     mbar_wait_relaxed(pempty(pb), ((cg >> 1) & 1u) ^ 1u);
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
                     mbar_expect_tx(pfull(pb), box_bytes);
                     tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.pmap[src], pfull(pb), c0, x0 - 1, y0 - 1, b);
-                    for (int tap = 0; tap < 9; ++tap, ++ug) {
+                    for (int tap = 0; tap < ntaps; ++tap, ++ug) {
                         const int s = (int)(ug % (uint32_t)p.wstages);
                         mbar_wait_relaxed(wempty(s), ((ug / (uint32_t)p.wstages) & 1u) ^ 1u);
                         mbar_expect_tx(wfull(s), w_bytes);
@@ -496,6 +500,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
             uint32_t cg = 0, ug = 0;
             for (int i = 0; i < my_items; ++i) {
                 const int a = i & 1;
+                int cls = 0, ntaps = 9;
+                if (p.up) {
+                    int nt, b, y0, x0;
+                    item_coords(i, nt, b, y0, x0);
+                    cls = nt & 3;
+                    ntaps = 4;
+                }
                 mbar_wait(aempty(a), ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)a * acc_cols;
@@ -504,12 +515,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     mbar_wait(pfull(pb), (cg >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t patch = base + (uint32_t)pb * p.patch_bytes;
-                    for (int tap = 0; tap < 9; ++tap, ++ug) {
+                    for (int tap = 0; tap < ntaps; ++tap, ++ug) {
                         const int s = (int)(ug % (uint32_t)p.wstages);
                         mbar_wait(wfull(s), (ug / (uint32_t)p.wstages) & 1u);
                         tc_fence_after();
                         const uint64_t bdesc = make_smem_desc(wring + (uint32_t)s * wstage_bytes, row_bytes);
-                        const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
+                        // upsample class (a, b), tap (ty, tx): low-res offset (a ? ty : ty - 1, b ? tx : tx - 1) -> patch (+1, +1)
+                        const uint32_t shift = p.up ? (uint32_t)(((tap >> 1) + (cls >> 1)) * TP_PW + (tap & 1) + (cls & 1))
+                                                    : (uint32_t)((tap / 3) * TP_PW + tap % 3);
 #pragma unroll
                         for (int t = 0; t < TS_MT; ++t) {
                             const uint64_t adesc = p.geo ? make_smem_desc_sbo(patch + ((uint32_t)(t * 8) + shift) * row_bytes, row_bytes, TP_PW * row_bytes)
@@ -551,6 +564,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                 item_coords(i, nt, b, y0, x0);
                 // (bias + conditioning vector) of the item's channels -> btv (ordered before its use by the first chunk barrier of
                 // the previous item's last chunk / the barrier below)
+                int oa = 0, ob = 0;                               // upsample: output parity of the item
+                if (p.up) { oa = (nt >> 1) & 1; ob = nt & 1; nt >>= 2; }
                 if (te < p.BN) {
                     const int n = nt * p.BN + te;
                     float v = 0.f;
@@ -569,7 +584,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         const int r = r0 + 32 * jj;
                         if (p.geo) {
                             const int y = y0 + (r >> 3), x = x0 + 8 * t + (r & 7);
-                            off[t][jj] = (y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
+                            if (p.up) off[t][jj] = (y < p.H && x < p.W) ? ((b * p.epi.Ho + 2 * y + oa) * p.epi.Wo + 2 * x + ob) * Cout : -1;
+                            else off[t][jj] = (y < p.H && x < p.W) ? ((b * p.H + y) * p.W + x) * Cout : -1;
                         } else {
                             const int pr = r / TP_PW, pc = r - pr * TP_PW;
                             const int y = y0 + t * TP_TH + pr, x = x0 + pc;
@@ -866,6 +882,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
         const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
         const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
+        const bool can_up = ks == 3 && stride == 1 && up && Ws >= 8;
         // persistent variant: enough work items (M supertile of 2 tiles x N tile) to keep every SM busy for several of them
         static int persist_env = -1;
         if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
@@ -874,21 +891,23 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
             const int geo = geo_env ? 1 : 0;
             const int ty2 = geo ? (Hs + 15) / 16 : (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
-            const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn);
-            const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) < (1ll << 31);
-            if (can && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
+            const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn) * (up ? 4 : 1);
+            const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) * (up ? 4 : 1) < (1ll << 31);
+            if ((can || (can_up && geo)) && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
                 (persist_env == 2 || items >= 2 * 148)) {
                 TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
                 memset(&q, 0, sizeof(q));
                 q.B = B; q.H = Hs; q.W = Ws; q.MT = TS_MT; q.tiles_x = tiles_x; q.tiles_y = ty2;
-                q.epi.Ho = Hs; q.epi.Wo = Ws; q.epi.Cout = cout;
+                q.epi.Ho = up ? 2 * Hs : Hs; q.epi.Wo = up ? 2 * Ws : Ws; q.epi.Cout = cout;
                 q.nb16 = (cout + 15) / 16;
                 q.BN = bn; q.n_tiles = (q.nb16 * 16) / bn;
                 q.KC = kc; q.chunks_a = ca / kc; q.chunks_b = cb / kc;
                 q.tf32 = tf32;
                 q.n_items = (int)items;
                 q.geo = geo;
-                q.div_ntiles = make_fastdiv((uint32_t)q.n_tiles);
+                q.up = up ? 1 : 0;
+                q.class_bytes = (uint32_t)((size_t)4 * (ca + cb) / kc * q.nb16 * 16 * kc * e);
+                q.div_ntiles = make_fastdiv((uint32_t)(q.n_tiles * (up ? 4 : 1)));
                 q.div_tiles_x = make_fastdiv((uint32_t)tiles_x);
                 q.div_tiles_xy = make_fastdiv((uint32_t)(tiles_x * ty2));
                 const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
@@ -1065,7 +1084,7 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
         q.trace = trace_next(4);
         q.res_prefetch = 0;
         const int cout = q.epi.Cout;
-        if (epi.residual && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
+        if (epi.residual && !q.up && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
             cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.B};
             cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)q.W * cout * 4, (cuuint64_t)q.H * q.W * cout * 4};
             cuuint32_t box[4] = {(cuuint32_t)(q.BN < cout ? q.BN : cout), TP_TW, (cuuint32_t)(q.geo ? 16 : TP_TH * TS_MT), 1};

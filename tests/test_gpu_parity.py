@@ -124,7 +124,9 @@ TC_CASES = [
     (16, 0, 16, 3, 1, 0, 16, 64, 64, 1, 0), (48, 0, 16, 3, 1, 0, 1, 128, 128, 0, 0), (192, 0, 64, 3, 1, 0, 2, 16, 16, 0, 0),
     (512, 0, 512, 3, 1, 0, 1, 16, 16, 1, 0),
     # enough tiles for the tall-patch variant (>= 296 CTAs, >= 64 channels): one TMA patch per chunk, taps = row shifts
-    (64, 0, 64, 3, 1, 0, 8, 128, 128, 1, 0), (64, 64, 32, 3, 1, 0, 10, 100, 90, 0, 0)]
+    (64, 0, 64, 3, 1, 0, 8, 128, 128, 1, 0), (64, 64, 32, 3, 1, 0, 10, 100, 90, 0, 0),
+    # upsample x2 + 3x3 in the persistent kernel (parity class = part of the work item), aligned and ragged
+    (128, 0, 128, 3, 1, 1, 8, 64, 64, 0, 0), (64, 0, 96, 3, 1, 1, 6, 40, 36, 0, 0), (256, 0, 256, 3, 1, 1, 3, 32, 32, 0, 0)]
 
 
 @pytest.mark.parametrize("ca,cb,cout,ks,stride,up,B,H,W,residual,out_nchw", TC_CASES)
