@@ -407,6 +407,67 @@ __device__ __noinline__ float4 tcs_load_tail(const float* src, int n) {
     return make_float4(__ldg(src), n > 1 ? __ldg(src + 1) : 0.f, n > 2 ? __ldg(src + 2) : 0.f, n > 3 ? __ldg(src + 3) : 0.f);
 }
 
+// The MMA issuer is ONE thread: every instruction between two tcgen05.mma is serial latency in front of the tensor pipe (a
+// 128 x 128 x 16 MMA is 64 cycles of tensor work, a 128 x 64 x 16 one 32), so the loop carries running ring indices and
+// descriptor words instead of recomputing them: no division, no descriptor assembly, no clock reads on the fast path.
+struct TcsIssue {
+    uint32_t base, wring, wstage_bytes, bar_base, b2, tmem_base, acc_cols, row_bytes;
+    int my_items, nchunks;
+};
+template <bool TF32, int KS>
+__device__ __forceinline__ void tcs_issue(const TcpParams& p, const TcsIssue& ii) {
+    const uint32_t idesc = umma_idesc(p.BN, TF32);
+    const uint32_t rb16 = ii.row_bytes >> 4;                      // descriptor address units (16 B) per row
+    const uint64_t a_hi = p.geo ? make_smem_desc_sbo(0, ii.row_bytes, TP_PW * ii.row_bytes) : make_smem_desc(0, ii.row_bytes);
+    const uint64_t b_hi = make_smem_desc(0, ii.row_bytes) + (uint64_t)(ii.wring >> 4);
+    const uint32_t t_step = (p.geo ? 8u : (uint32_t)(TP_TH * TP_PW)) * rb16;
+    const uint32_t wst16 = ii.wstage_bytes >> 4;
+    const uint32_t nw = (uint32_t)p.wstages;
+    const uint32_t wfull0 = ii.bar_base, wempty0 = ii.bar_base + 8u * nw;
+    const int nt1 = p.up ? 2 : 3;                                 // taps per axis
+    const uint32_t BN = (uint32_t)p.BN;
+    uint32_t s = 0, wph = 0, cg = 0;
+    for (int i = 0; i < ii.my_items; ++i) {
+        const uint32_t a = (uint32_t)i & 1u;
+        // upsample: class (oa, ob) = low two bits of the item index; tap (ty, tx) reads the low-res pixel (ty + oa - 1, tx + ob - 1)
+        uint32_t o0 = 0;
+        if (p.up) {
+            const uint32_t w = blockIdx.x + (uint32_t)i * gridDim.x;
+            o0 = ((w >> 1) & 1u) * TP_PW + (w & 1u);
+        }
+        mbar_wait(ii.b2 + 48u + 8u * a, (((uint32_t)i >> 1) & 1u) ^ 1u);       // aempty
+        tc_fence_after();
+        const uint32_t acc = ii.tmem_base + a * ii.acc_cols;
+        uint32_t first = 0;                                       // accumulate flag of the k = 0 MMAs: 0 on the item's first tap
+        for (int cc = 0; cc < ii.nchunks; ++cc, ++cg) {
+            const uint32_t pb = cg & 1u;
+            mbar_wait_fast(ii.b2 + 8u * pb, (cg >> 1) & 1u);                    // pfull
+            tc_fence_after();
+            const uint64_t abase = a_hi + (uint64_t)(((ii.base + pb * p.patch_bytes) >> 4) + o0 * rb16);
+            for (int ty = 0; ty < nt1; ++ty) {
+                for (int tx = 0; tx < nt1; ++tx) {
+                    mbar_wait_fast(wfull0 + 8u * s, wph);
+                    tc_fence_after();
+                    const uint64_t bdesc = b_hi + (uint64_t)(s * wst16);
+                    const uint64_t adesc = abase + (uint64_t)((uint32_t)(ty * TP_PW + tx) * rb16);
+#pragma unroll
+                    for (int t = 0; t < TS_MT; ++t) {
+#pragma unroll
+                        for (int k = 0; k < KS; ++k)
+                            umma<TF32>(acc + (uint32_t)t * BN, adesc + (uint64_t)((uint32_t)t * t_step + 2u * k), bdesc + (uint64_t)(2 * k), idesc,
+                                       k == 0 ? first : 1u);
+                    }
+                    first = 1u;
+                    umma_commit(wempty0 + 8u * s);
+                    if (++s == nw) { s = 0; wph ^= 1u; }
+                }
+            }
+            umma_commit(ii.b2 + 16u + 8u * pb);                                 // pempty
+        }
+        umma_commit(ii.b2 + 32u + 8u * a);                                      // afull
+    }
+}
+
 __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_constant__ TcpParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -466,7 +527,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         if (elect_one()) {
             const size_t blk16 = (size_t)16 * row_bytes;
             const uint32_t box_bytes = (uint32_t)(TP_PW * (p.geo ? 18 : TP_TH * TS_MT + 2)) * row_bytes;
-            uint32_t cg = 0, ug = 0;                             // chunk / weight-unit counters over all items (ring phases)
+            uint32_t cg = 0, s = 0, wph = 1;                     // chunk counter, weight ring stage and (empty-barrier) phase
             for (int i = 0; i < my_items; ++i) {
                 int nt, b, y0, x0;
                 item_coords(i, nt, b, y0, x0);
@@ -483,11 +544,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
                     mbar_expect_tx(pfull(pb), box_bytes);
                     tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.pmap[src], pfull(pb), c0, x0 - 1, y0 - 1, b);
-                    for (int tap = 0; tap < ntaps; ++tap, ++ug) {
-                        const int s = (int)(ug % (uint32_t)p.wstages);
-                        mbar_wait_relaxed(wempty(s), ((ug / (uint32_t)p.wstages) & 1u) ^ 1u);
-                        mbar_expect_tx(wfull(s), w_bytes);
-                        bulk_load(wring + (uint32_t)s * wstage_bytes, wsrc + (size_t)(tap * nchunks + cc) * p.nb16 * blk16, w_bytes, wfull(s));
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        mbar_wait_relaxed(wempty((int)s), wph);
+                        mbar_expect_tx(wfull((int)s), w_bytes);
+                        bulk_load(wring + s * wstage_bytes, wsrc + (size_t)(tap * nchunks + cc) * p.nb16 * blk16, w_bytes, wfull((int)s));
+                        if (++s == (uint32_t)p.wstages) { s = 0; wph ^= 1u; }
                     }
                 }
             }
@@ -495,51 +556,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
-            const int ksteps = (int)(row_bytes >> 5);
-            uint32_t cg = 0, ug = 0;
-            for (int i = 0; i < my_items; ++i) {
-                const int a = i & 1;
-                int cls = 0, ntaps = 9;
-                if (p.up) {
-                    int nt, b, y0, x0;
-                    item_coords(i, nt, b, y0, x0);
-                    cls = nt & 3;
-                    ntaps = 4;
-                }
-                mbar_wait(aempty(a), ((uint32_t)(i >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)a * acc_cols;
-                for (int cc = 0; cc < nchunks; ++cc, ++cg) {
-                    const int pb = (int)(cg & 1u);
-                    mbar_wait(pfull(pb), (cg >> 1) & 1u);
-                    tc_fence_after();
-                    const uint32_t patch = base + (uint32_t)pb * p.patch_bytes;
-                    for (int tap = 0; tap < ntaps; ++tap, ++ug) {
-                        const int s = (int)(ug % (uint32_t)p.wstages);
-                        mbar_wait(wfull(s), (ug / (uint32_t)p.wstages) & 1u);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(wring + (uint32_t)s * wstage_bytes, row_bytes);
-                        // upsample class (a, b), tap (ty, tx): low-res offset (a ? ty : ty - 1, b ? tx : tx - 1) -> patch (+1, +1)
-                        const uint32_t shift = p.up ? (uint32_t)(((tap >> 1) + (cls >> 1)) * TP_PW + (tap & 1) + (cls & 1))
-                                                    : (uint32_t)((tap / 3) * TP_PW + tap % 3);
-#pragma unroll
-                        for (int t = 0; t < TS_MT; ++t) {
-                            const uint64_t adesc = p.geo ? make_smem_desc_sbo(patch + ((uint32_t)(t * 8) + shift) * row_bytes, row_bytes, TP_PW * row_bytes)
-                                                         : make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
-                            if (p.tf32) {
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_tf32(acc + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
-                            } else {
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_bf16(acc + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
-                            }
-                        }
-                        umma_commit(wempty(s));
-                    }
-                    umma_commit(pempty(pb));
-                }
-                umma_commit(afull(a));
+            TcsIssue ii;
+            ii.base = base; ii.wring = wring; ii.wstage_bytes = wstage_bytes; ii.bar_base = bar_base; ii.b2 = b2;
+            ii.tmem_base = tmem_base; ii.acc_cols = acc_cols; ii.my_items = my_items; ii.row_bytes = row_bytes; ii.nchunks = nchunks;
+            if (p.tf32) {
+                if (row_bytes == 128) tcs_issue<true, 4>(p, ii); else tcs_issue<true, 2>(p, ii);
+            } else {
+                if (row_bytes == 128) tcs_issue<false, 4>(p, ii); else tcs_issue<false, 2>(p, ii);
             }
         }
         __syncwarp();

@@ -36,6 +36,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// hot-loop wait: one poll without the clock reads; the bounded loop only when the phase is not there yet
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait(bar, parity);
+}
 // the same for waits that are expected to be long (a whole pipeline stage): the hardware may park the thread for up to
 // ~20 us per try (it still wakes when the phase completes), so a waiting warp does not spend issue slots on the poll loop
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
@@ -118,6 +123,11 @@ __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -120,12 +120,22 @@ def main():
         nb = L.ds_conv2d_bf16_scratch_bytes(cin, cout, ks)
         scratch = torch.zeros(nb, dtype=torch.uint8, device=DEV)
 
+        use_res = os.environ.get("MB_NO_RESIDUAL") is None
+        use_f32 = os.environ.get("MB_NO_F32") is None
+        up = int(os.environ.get("MB_UP", "0"))
+        if up:
+            out16u = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=DEV)
+            out32u = torch.empty((B, 2 * H, 2 * W, cout), device=DEV)
+
         def fn():
             _lib.check(L.ds_conv2d_bf16(xa.data_ptr(), ca, None if xb is None else xb.data_ptr(), cb, w.data_ptr(), bias.data_ptr(),
-                                        res.data_ptr(), out16.data_ptr(), out32.data_ptr(), 0, B, H, W, cout, ks, 1, 0,
+                                        res.data_ptr() if use_res and not up else None, (out16u if up else out16).data_ptr(),
+                                        (out32u if up else out32).data_ptr() if use_f32 else None, 0, B, H, W, cout, ks, 1, up,
                                         scratch.data_ptr(), nb, sp()))
         us = timed_graph(fn)
-        print(f"conv_tc (pack + conv_tc) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W}: {us:.2f} us per call (2 kernels)")
+        fl = 2.0 * B * H * W * cout * cin * (16 if up else ks * ks)
+        print(f"conv_tc (pack + conv_tc) {ca}+{cb}->{cout} k{ks} {B}x{H}x{W} up={up} residual={use_res} f32out={use_f32}: {us:.2f} us per call "
+              f"(2 kernels), {fl / us / 1e6:.0f} TFLOP/s")
     elif kind == "sampler":
         # fused posterior update + in-register Philox noise: 12 B per element (read x_t, read eps, write x_{t-1})
         from diffsplitting_b200.model import samplers as SM
