@@ -377,12 +377,13 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
 //   warp 0       TMA producer: per 64-channel chunk one (7 MT + 2) x 18 patch (ring of 2) + 9 weight tiles (ring of wstages);
 //                L2 prefetch of the item's residual tile
 //   warp 1       MMA issuer: 9 taps x MT tiles x 4 k-steps per chunk into ACC[i & 1]
-//   warps 4-11   epilogue, two groups of four warps (one per TMEM lane quadrant) taking alternate 16-column chunks, each chunk
+//   warps 4-15   epilogue, three groups of four warps (one per TMEM lane quadrant) sharing the item's 16-column chunks, each chunk
 //                in two views (as conv_stream_kernel): ROW view  tcgen05.ld + (bias + conditioning vector) -> staging buffer;
 //                QUAD view  + residual (requested one chunk ahead), fp32 / bf16 stores with 64 contiguous bytes per four lanes,
 //                statistics in registers, folded once per item
 constexpr int TS_MT = 2;
-constexpr int TS_THREADS = 384;            // warps 0, 1 as above, 2-3 idle, 4-11 epilogue
+constexpr int TS_THREADS = 512;            // warps 0, 1 as above, 2-3 idle, 4-15 epilogue (three groups)
+constexpr int TS_EGROUPS = 3;
 constexpr int TS_STG_LD = 20;
 constexpr uint32_t TS_STG_BYTES = 128 * TS_STG_LD * 4 + 128 * 4;     // staging [128][20] + (bias + temb) of the item's BN channels
 
@@ -477,8 +478,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     const uint32_t w_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t wstage_bytes = (w_bytes + 1023u) & ~1023u;
     const uint32_t wring = base + 2u * p.patch_bytes;
-    const uint32_t stg_off = 2u * p.patch_bytes + (uint32_t)p.wstages * wstage_bytes;      // 2 x TS_STG_BYTES
-    const uint32_t bar_base = base + stg_off + 2u * TS_STG_BYTES;
+    const uint32_t stg_off = 2u * p.patch_bytes + (uint32_t)p.wstages * wstage_bytes;      // TS_EGROUPS x TS_STG_BYTES
+    const uint32_t bar_base = base + stg_off + (uint32_t)TS_EGROUPS * TS_STG_BYTES;
     auto wfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto wempty = [&](int s) { return bar_base + 8u * (uint32_t)(p.wstages + s); };
     const uint32_t b2 = bar_base + 16u * (uint32_t)p.wstages;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     const uint32_t acc_cols = (uint32_t)(TS_MT * p.BN);
     const uint32_t tmem_cols = 2u * acc_cols <= 32u ? 32u : (2u * acc_cols <= 64u ? 64u : (2u * acc_cols <= 128u ? 128u : (2u * acc_cols <= 256u ? 256u : 512u)));
     const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int egroups = cpt * TS_MT >= 2 ? 2 : 1;                // epilogue groups with work
+    const int egroups = cpt * TS_MT >= TS_EGROUPS ? TS_EGROUPS : cpt * TS_MT;          // epilogue groups with work
 
     trace_begin(p.trace);
     if (warp == 0 && elect_one()) {
@@ -567,28 +568,37 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         }
         __syncwarp();
     } else if (warp >= 4) {
-        const int gi = (warp - 4) >> 2;
+        const int gi = (warp - 4) >> 2;                          // epilogue group 0..2
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int te = tid - 128 - gi * 128;
+        const int te = (tid - 128) & 127;
         float* stg = reinterpret_cast<float*>(gbase + stg_off + (uint32_t)gi * TS_STG_BYTES);
         float* btv = stg + 128 * TS_STG_LD;                      // [BN <= 128] bias + conditioning vector of the item
         const int quad = te & 3, r0 = te >> 2;
         const int Cout = p.epi.Cout;
         const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
-        const int G = TS_MT * cpt;                                // chunks per item, chunk g = (tile g / cpt, columns 16 (g % cpt))
-        const int ncg = (G - gi + 1) / 2;                         // this group's chunks: g = gi, gi + 2, ...
+        const int lcpt = 31 - __clz(cpt);                        // BN is a power of two
+        // the item's chunks (tile t, 16-column block c) are dealt to the three groups by column when a tile has 8 of them (a group
+        // then touches at most 3 columns: its statistics stay in 3 register slots), else by chunk index g = t cpt + c (<= 4 columns)
+        const bool bycol = cpt == 8;
+        const int n_mine = bycol ? TS_MT * ((cpt - gi + 2) / 3) : (TS_MT * cpt > gi ? (TS_MT * cpt - gi + 2) / 3 : 0);
+        const float* const resp = p.epi.residual;
+        float* const o32 = p.epi.out_f32;
+        __nv_bfloat16* const o16 = p.epi.out_b16;
+        double* const sums = p.epi.sums_out;
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
-        if (gi < egroups) {
+        const uint32_t bar_id = (uint32_t)gi + 1u;
+        const float* const srow = stg + r0 * TS_STG_LD + quad * 4;
+        if (n_mine > 0) {
 #pragma unroll 1
             for (int i = 0; i < my_items; ++i) {
                 const int a = i & 1;
                 int nt, b, y0, x0;
                 item_coords(i, nt, b, y0, x0);
-                // (bias + conditioning vector) of the item's channels -> btv (ordered before its use by the first chunk barrier of
-                // the previous item's last chunk / the barrier below)
                 int oa = 0, ob = 0;                               // upsample: output parity of the item
                 if (p.up) { oa = (nt >> 1) & 1; ob = nt & 1; nt >>= 2; }
+                // (bias + conditioning vector) of the item's channels -> btv (the previous item's last chunk barrier orders this
+                // write after its last read; the barrier below makes it visible)
                 if (te < p.BN) {
                     const int n = nt * p.BN + te;
                     float v = 0.f;
@@ -616,36 +626,36 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         }
                     }
                 }
-                float acc[4][8];                                  // statistics per chunk column of this group (cpt <= 8 -> <= 4 per group)
+                const int nbase = nt * p.BN + quad * 4;
+                float acc[4][8];                                  // statistics per column slot of this group
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-                auto load_res = [&](int g, float4 (&rr)[4]) {
-                    if (!p.epi.residual || g >= G) return;
-                    const int t = g / cpt, n0 = nt * p.BN + (g - t * cpt) * 16 + quad * 4;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
-                        if (o < 0 || n0 >= Cout) continue;
-                        const float* src = p.epi.residual + o + n0;
-                        rr[jj] = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
-                    }
+                // residual of chunk (t, c) -> rr: issued one chunk ahead, into the registers the current chunk has just consumed
+                float4 rr[4];
+                auto load_res = [&](int t, int c, int jj) {
+                    const int n0 = nbase + c * 16;
+                    const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
+                    if (o < 0 || n0 >= Cout) return;
+                    const float* src = resp + o + n0;
+                    rr[jj] = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
                 };
-                float4 rcur[4], rnext[4];
-                load_res(gi, rcur);
-                if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");     // btv visible
+                int t = bycol ? 0 : gi >> lcpt, c = bycol ? gi : gi & (cpt - 1), slot = bycol ? 0 : c;
+                if (resp) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) load_res(t, c, jj);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");           // btv visible
                 mbar_wait_relaxed(afull(a), (uint32_t)(i >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll 1
-                for (int kk = 0; kk < ncg; ++kk) {
-                    const int g = gi + 2 * kk;
-                    const int t = g / cpt, c0 = (g - t * cpt) * 16;
-                    load_res(g + 2, rnext);
+                for (int kk = 0; kk < n_mine; ++kk) {
+                    const int c0 = c * 16;
                     // ---- ROW view
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)(t * p.BN + c0), v);
-                    if (kk == ncg - 1) {
+                    if (kk == n_mine - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(aempty(a)) : "memory");
@@ -660,57 +670,63 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                                                  __uint_as_float(v[4 * e + 2]) + ad.z, __uint_as_float(v[4 * e + 3]) + ad.w);
                         }
                     }
-                    if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    // the group's next chunk
+                    int tn = t, cn = c, slotn = slot;
+                    if (bycol) {
+                        cn += 3; ++slotn;
+                        if (cn >= 8) { cn = gi; slotn = 0; ++tn; }
+                    } else {
+                        const int g = (t << lcpt) + c + 3;
+                        tn = g >> lcpt; cn = g & (cpt - 1); slotn = cn;
+                    }
+                    const bool more = kk + 1 < n_mine;
                     // ---- QUAD view
-                    const int n0 = nt * p.BN + c0 + quad * 4;
+                    const int n0 = nbase + c0;
                     float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        float4 x = *reinterpret_cast<const float4*>(stg + (r0 + 32 * jj) * TS_STG_LD + quad * 4);
+                        float4 x = *reinterpret_cast<const float4*>(srow + 32 * jj * TS_STG_LD);
                         const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
-                        if (o < 0 || n0 >= Cout) continue;
-                        if (p.epi.residual) { x.x += rcur[jj].x; x.y += rcur[jj].y; x.z += rcur[jj].z; x.w += rcur[jj].w; }
-                        if (vec_ok) {
-                            if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + o + n0) = x;
-                            if (p.epi.out_b16) {
-                                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-                                uint2 pk;
-                                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                                *reinterpret_cast<uint2*>(p.epi.out_b16 + o + n0) = pk;
+                        if (o >= 0 && n0 < Cout) {
+                            if (resp) { x.x += rr[jj].x; x.y += rr[jj].y; x.z += rr[jj].z; x.w += rr[jj].w; }
+                            if (vec_ok) {
+                                if (o32) *reinterpret_cast<float4*>(o32 + o + n0) = x;
+                                if (o16) {
+                                    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                                    uint2 pk;
+                                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                                    *reinterpret_cast<uint2*>(o16 + o + n0) = pk;
+                                }
+                            } else {
+                                tcs_store_tail(p.epi, x, o / Cout, n0);
+                                if (n0 + 1 >= Cout) x.y = 0.f;
+                                if (n0 + 2 >= Cout) x.z = 0.f;
+                                if (n0 + 3 >= Cout) x.w = 0.f;
                             }
-                        } else {
-                            tcs_store_tail(p.epi, x, o / Cout, n0);
-                            if (n0 + 1 >= Cout) x.y = 0.f;
-                            if (n0 + 2 >= Cout) x.z = 0.f;
-                            if (n0 + 3 >= Cout) x.w = 0.f;
+                            sm[0] += x.x; sm[1] += x.y; sm[2] += x.z; sm[3] += x.w;
+                            sq[0] = fmaf(x.x, x.x, sq[0]); sq[1] = fmaf(x.y, x.y, sq[1]); sq[2] = fmaf(x.z, x.z, sq[2]); sq[3] = fmaf(x.w, x.w, sq[3]);
                         }
-                        sm[0] += x.x; sm[1] += x.y; sm[2] += x.z; sm[3] += x.w;
-                        sq[0] = fmaf(x.x, x.x, sq[0]); sq[1] = fmaf(x.y, x.y, sq[1]); sq[2] = fmaf(x.z, x.z, sq[2]); sq[3] = fmaf(x.w, x.w, sq[3]);
+                        if (resp && more) load_res(tn, cn, jj);
                     }
-                    // this chunk's column index within the group: (c0 / 16 - gi) / 2 when cpt is even, else by position; fold by column
-                    if (p.epi.sums_out) {
-                        const int col = (cpt & 1) ? (c0 >> 4) : ((c0 >> 4) >> 1);
+                    if (sums) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (k == (col & 3)) {
+                            if (k == slot) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) { acc[k][e] += sm[e]; acc[k][4 + e] += sq[e]; }
                             }
                         }
                     }
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) rcur[jj] = rnext[jj];
-                    if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    t = tn; c = cn; slot = slotn;
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // staging buffer free again
                 }
-                // ---- fold the item's statistics: per accumulated column, lanes of equal quad, then one fp64 atomic pair per channel
-                if (p.epi.sums_out) {
+                // ---- fold the item's statistics: per column slot, lanes of equal quad, then one fp64 atomic pair per channel
+                if (sums) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        // column held by slot k (see above); slots beyond the group's columns stay zero and are skipped
-                        int cidx;
-                        if (cpt & 1) cidx = k;                    // odd cpt (1, 3, ...): slot = column index, both groups may touch any column
-                        else cidx = 2 * k + gi;                   // even cpt: group gi owns columns gi, gi + 2, ...
+                        const int cidx = bycol ? gi + 3 * k : k;  // column held by slot k
                         if (cidx >= cpt) continue;
 #pragma unroll
                         for (int o = 4; o <= 16; o <<= 1)
@@ -721,7 +737,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 if (n0 + e < Cout && (acc[k][e] != 0.f || acc[k][4 + e] != 0.f)) {
-                                    double* dst = p.epi.sums_out + (((size_t)copy * p.epi.sums_B + b) * Cout + n0 + e) * 2;
+                                    double* dst = sums + (((size_t)copy * p.epi.sums_B + b) * Cout + n0 + e) * 2;
                                     atomicAdd(dst, (double)acc[k][e]);
                                     atomicAdd(dst + 1, (double)acc[k][4 + e]);
                                 }
@@ -909,6 +925,9 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         // persistent variant: enough work items (M supertile of 2 tiles x N tile) to keep every SM busy for several of them
         static int persist_env = -1;
         if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
+        // fewest work items for the persistent kernel: below one per SM the one-tile-per-CTA kernels spread the work better
+        static int persist_min = -1;
+        if (persist_min < 0) { const char* e4 = getenv("DIFFSPLIT_B200_TC_PERSIST_MIN"); persist_min = e4 ? atoi(e4) : 148; }
         {
             static int geo_env = -1;
             if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
@@ -917,7 +936,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn) * (up ? 4 : 1);
             const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) * (up ? 4 : 1) < (1ll << 31);
             if ((can || (can_up && geo)) && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
-                (persist_env == 2 || items >= 2 * 148)) {
+                (persist_env == 2 || items >= persist_min)) {
                 TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
                 memset(&q, 0, sizeof(q));
                 q.B = B; q.H = Hs; q.W = Ws; q.MT = TS_MT; q.tiles_x = tiles_x; q.tiles_y = ty2;
@@ -936,7 +955,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                 const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
                 q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
                 const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
-                int wst = (int)((200 * 1024 - 2 * (size_t)q.patch_bytes - 2 * TS_STG_BYTES - 2048) / wstage);
+                int wst = (int)((212 * 1024 - 2 * (size_t)q.patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage);
                 if (wst > 12) wst = 12;
                 if (wst >= 3) {
                     q.wstages = wst;
@@ -949,7 +968,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                         if (rc != DS_OK) return rc;
                     }
                     plan->patch = 2;
-                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + 2 * TS_STG_BYTES + 16 * wst + 128 + 1024);
+                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + TS_EGROUPS * TS_STG_BYTES + 16 * wst + 128 + 1024);
                     static int sms = 0;
                     if (!sms) {
                         int dev = 0;
@@ -1119,7 +1138,7 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
         }
         static bool sattr = false;
         if (!sattr) {
-            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             sattr = true;
         }
         DS_CHECK_CUDA(launch_pdl(conv_tcs_kernel, dim3(plan->grid_x, 1, 1), dim3(TS_THREADS), (size_t)plan->smem_bytes, st, q));
