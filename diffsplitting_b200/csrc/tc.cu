@@ -190,8 +190,9 @@ struct TcpParams {
     uint32_t patch_bytes;
     int tf32;
     // persistent variant (conv_tcs_kernel)
-    CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {BN, 16, 7 MT, 1}: L2 prefetch only
-    int res_prefetch, n_items;        // work items = (M supertile, N tile[, output parity class]), N (class) fastest
+    CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {20, 8, 16, 1} = one chunk in the staging layout
+    int res_tma, n_items;             // res_tma: the fp32 residual arrives through resmap (box {20, 8, 16, 1}) in the staging buffers
+           // work items = (M supertile, N tile[, output parity class]), N (class) fastest
     int up;                           // nearest x2 upsample + 3x3 as four 2x2 convs on the low-res patch (geo 1 only): H, W = low-res
                                       //    size, item class (a, b) writes the output pixels (2y + a, 2x + b); w = [class][tap][chunk]
     uint32_t class_bytes;             // packed weight bytes per class
@@ -385,7 +386,8 @@ constexpr int TS_MT = 2;
 constexpr int TS_THREADS = 512;            // warps 0, 1 as above, 2-3 idle, 4-15 epilogue (three groups)
 constexpr int TS_EGROUPS = 3;
 constexpr int TS_STG_LD = 20;
-constexpr uint32_t TS_STG_BYTES = 128 * TS_STG_LD * 4 + 128 * 4;     // staging [128][20] + (bias + temb) of the item's BN channels
+constexpr uint32_t TS_STG_BUF = 128 * TS_STG_LD * 4;                 // one staging buffer [128][20] fp32
+constexpr uint32_t TS_STG_BYTES = 2 * TS_STG_BUF + 128 * 4;          // per group: two staging buffers + (bias + temb) of the item's BN channels
 
 __device__ __noinline__ void tcs_store_tail(const TcEpi& e, float4 x, int pix, int n0) {
     const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     auto afull = [&](int i) { return b2 + 32u + 8u * (uint32_t)i; };
     auto aempty = [&](int i) { return b2 + 48u + 8u * (uint32_t)i; };
     const uint32_t tmem_slot = b2 + 64u;
+    auto rfull = [&](int g, uint32_t buf) { return b2 + 80u + 16u * (uint32_t)g + 8u * buf; };
     const int nchunks = p.chunks_a + p.chunks_b;
     const int cpt = p.BN >> 4;                                    // 16-column chunks per tile
     const uint32_t acc_cols = (uint32_t)(TS_MT * p.BN);
@@ -501,6 +504,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         for (int i = 0; i < 2; ++i) {
             mbar_init(pfull(i), 1); mbar_init(pempty(i), 1);
             mbar_init(afull(i), 1); mbar_init(aempty(i), 4 * egroups);
+            for (int g = 0; g < TS_EGROUPS; ++g) mbar_init(rfull(g, (uint32_t)i), 1);
         }
         fence_barrier_init();
     }
@@ -532,10 +536,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
             for (int i = 0; i < my_items; ++i) {
                 int nt, b, y0, x0;
                 item_coords(i, nt, b, y0, x0);
-                if (p.res_prefetch)
-                    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(&p.resmap)),
-                                 "r"(nt * p.BN), "r"(x0), "r"(y0), "r"(b)
-                                 : "memory");
                 const int ntaps = p.up ? 4 : 9;
                 const uint8_t* wsrc = p.w + (size_t)(p.up ? nt >> 2 : nt) * (p.BN / 16) * blk16 + (p.up ? (size_t)(nt & 3) * p.class_bytes : 0);
                 for (int cc = 0; cc < nchunks; ++cc, ++cg) {
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         const int m = q * 32 + lane;
         const int te = (tid - 128) & 127;
         float* stg = reinterpret_cast<float*>(gbase + stg_off + (uint32_t)gi * TS_STG_BYTES);
-        float* btv = stg + 128 * TS_STG_LD;                      // [BN <= 128] bias + conditioning vector of the item
+        float* btv = stg + 2 * 128 * TS_STG_LD;                  // [BN <= 128] bias + conditioning vector of the item
         const int quad = te & 3, r0 = te >> 2;
         const int Cout = p.epi.Cout;
         const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
@@ -589,7 +589,32 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
         const int copy = (int)(blockIdx.x % TC_SUM_COPIES);
         const uint32_t bar_id = (uint32_t)gi + 1u;
         const float* const srow = stg + r0 * TS_STG_LD + quad * 4;
+        const bool rtma = p.res_tma != 0;
+        const int t_first = bycol ? 0 : gi >> lcpt, c_first = bycol ? gi : gi & (cpt - 1);
         if (n_mine > 0) {
+            // residual through TMA: thread 0 of the group runs a cursor two chunks ahead of the group over its (item, chunk)
+            // sequence; chunk n lands in staging buffer n & 1 (in the staging layout: 80-byte rows = 16 + 4 channels), the ROW view
+            // adds the accumulator to it
+            int qi = 0, qt = t_first, qc = c_first;
+            uint32_t qn = 0, cn = 0;
+            auto issue_next = [&]() {
+                if (qi >= my_items) return;
+                int nt, b, y0, x0;
+                item_coords(qi, nt, b, y0, x0);
+                const uint32_t buf = qn & 1u;
+                mbar_expect_tx(rfull(gi, buf), TS_STG_BUF);
+                tma_load_4d(smem_u32(stg) + buf * TS_STG_BUF, &p.resmap, rfull(gi, buf), nt * p.BN + qc * 16, x0 + 8 * qt, y0, b);
+                ++qn;
+                if (bycol) {
+                    qc += 3;
+                    if (qc >= 8) { qc = gi; ++qt; }
+                } else {
+                    const int g = (qt << lcpt) + qc + 3;
+                    qt = g >> lcpt; qc = g & (cpt - 1);
+                }
+                if (qt >= TS_MT) { ++qi; qt = t_first; qc = c_first; }
+            };
+            if (rtma && te == 0) { issue_next(); issue_next(); }
 #pragma unroll 1
             for (int i = 0; i < my_items; ++i) {
                 const int a = i & 1;
@@ -641,8 +666,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     const float* src = resp + o + n0;
                     rr[jj] = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
                 };
-                int t = bycol ? 0 : gi >> lcpt, c = bycol ? gi : gi & (cpt - 1), slot = bycol ? 0 : c;
-                if (resp) {
+                int t = t_first, c = c_first, slot = bycol ? 0 : c;
+                const bool rldg = resp != nullptr && !rtma;       // residual through the LSU, one chunk ahead
+                if (rldg) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) load_res(t, c, jj);
                 }
@@ -650,8 +676,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                 mbar_wait_relaxed(afull(a), (uint32_t)(i >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll 1
-                for (int kk = 0; kk < n_mine; ++kk) {
+                for (int kk = 0; kk < n_mine; ++kk, ++cn) {
                     const int c0 = c * 16;
+                    const uint32_t buf = cn & 1u;
+                    float* const sb = stg + buf * (128 * TS_STG_LD);
                     // ---- ROW view
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)(t * p.BN + c0), v);
@@ -662,23 +690,33 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     }
                     {
                         const float4* bv = reinterpret_cast<const float4*>(btv + c0);
-                        float4* row = reinterpret_cast<float4*>(stg + m * TS_STG_LD);
+                        float4* row = reinterpret_cast<float4*>(sb + m * TS_STG_LD);
+                        if (rtma) {
+                            mbar_wait_relaxed(rfull(gi, buf), (cn >> 1) & 1u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float4 ad = bv[e];
-                            row[e] = make_float4(__uint_as_float(v[4 * e]) + ad.x, __uint_as_float(v[4 * e + 1]) + ad.y,
-                                                 __uint_as_float(v[4 * e + 2]) + ad.z, __uint_as_float(v[4 * e + 3]) + ad.w);
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 ad = bv[e], rs = row[e];
+                                row[e] = make_float4(__uint_as_float(v[4 * e]) + ad.x + rs.x, __uint_as_float(v[4 * e + 1]) + ad.y + rs.y,
+                                                     __uint_as_float(v[4 * e + 2]) + ad.z + rs.z, __uint_as_float(v[4 * e + 3]) + ad.w + rs.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 ad = bv[e];
+                                row[e] = make_float4(__uint_as_float(v[4 * e]) + ad.x, __uint_as_float(v[4 * e + 1]) + ad.y,
+                                                     __uint_as_float(v[4 * e + 2]) + ad.z, __uint_as_float(v[4 * e + 3]) + ad.w);
+                            }
                         }
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     // the group's next chunk
-                    int tn = t, cn = c, slotn = slot;
+                    int tn = t, cn_ = c, slotn = slot;
                     if (bycol) {
-                        cn += 3; ++slotn;
-                        if (cn >= 8) { cn = gi; slotn = 0; ++tn; }
+                        cn_ += 3; ++slotn;
+                        if (cn_ >= 8) { cn_ = gi; slotn = 0; ++tn; }
                     } else {
                         const int g = (t << lcpt) + c + 3;
-                        tn = g >> lcpt; cn = g & (cpt - 1); slotn = cn;
+                        tn = g >> lcpt; cn_ = g & (cpt - 1); slotn = cn_;
                     }
                     const bool more = kk + 1 < n_mine;
                     // ---- QUAD view
@@ -686,10 +724,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        float4 x = *reinterpret_cast<const float4*>(srow + 32 * jj * TS_STG_LD);
+                        float4 x = *reinterpret_cast<const float4*>(srow + buf * (128 * TS_STG_LD) + 32 * jj * TS_STG_LD);
                         const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
                         if (o >= 0 && n0 < Cout) {
-                            if (resp) { x.x += rr[jj].x; x.y += rr[jj].y; x.z += rr[jj].z; x.w += rr[jj].w; }
+                            if (rldg) { x.x += rr[jj].x; x.y += rr[jj].y; x.z += rr[jj].z; x.w += rr[jj].w; }
                             if (vec_ok) {
                                 if (o32) *reinterpret_cast<float4*>(o32 + o + n0) = x;
                                 if (o16) {
@@ -708,7 +746,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                             sm[0] += x.x; sm[1] += x.y; sm[2] += x.z; sm[3] += x.w;
                             sq[0] = fmaf(x.x, x.x, sq[0]); sq[1] = fmaf(x.y, x.y, sq[1]); sq[2] = fmaf(x.z, x.z, sq[2]); sq[3] = fmaf(x.w, x.w, sq[3]);
                         }
-                        if (resp && more) load_res(tn, cn, jj);
+                        if (rldg && more) load_res(tn, cn_, jj);
                     }
                     if (sums) {
 #pragma unroll
@@ -719,8 +757,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                             }
                         }
                     }
-                    t = tn; c = cn; slot = slotn;
-                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // staging buffer free again
+                    t = tn; c = cn_; slot = slotn;
+                    // two staging buffers: the next chunk writes the other one, and its mid-chunk barrier orders this chunk's reads
+                    // before the chunk after next; only the TMA refill of THIS buffer needs everyone to be done with it now
+                    if (rtma) {
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        if (te == 0) { fence_proxy_async(); issue_next(); }
+                    }
                 }
                 // ---- fold the item's statistics: per column slot, lanes of equal quad, then one fp64 atomic pair per channel
                 if (sums) {
@@ -955,7 +998,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                 const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
                 q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
                 const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
-                int wst = (int)((212 * 1024 - 2 * (size_t)q.patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage);
+                int wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage);
                 if (wst > 12) wst = 12;
                 if (wst >= 3) {
                     q.wstages = wst;
@@ -968,7 +1011,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                         if (rc != DS_OK) return rc;
                     }
                     plan->patch = 2;
-                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + TS_EGROUPS * TS_STG_BYTES + 16 * wst + 128 + 1024);
+                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + TS_EGROUPS * TS_STG_BYTES + 16 * wst + 192 + 1024);
                     static int sms = 0;
                     if (!sms) {
                         int dev = 0;
@@ -1124,21 +1167,23 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
         q.epi.out_f32 = out_f32; q.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); q.epi.out_nchw = out_nchw;
         q.epi.sums_out = sums_out; q.epi.sums_B = q.B;
         q.trace = trace_next(4);
-        q.res_prefetch = 0;
+        q.res_tma = 0;
         const int cout = q.epi.Cout;
-        if (epi.residual && !q.up && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
+        static int respf_env = -1;
+        if (respf_env < 0) { const char* e5 = getenv("DIFFSPLIT_B200_TC_RESPF"); respf_env = e5 ? atoi(e5) : 1; }
+        if (respf_env && epi.residual && !q.up && q.geo && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
             cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.B};
             cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)q.W * cout * 4, (cuuint64_t)q.H * q.W * cout * 4};
-            cuuint32_t box[4] = {(cuuint32_t)(q.BN < cout ? q.BN : cout), TP_TW, (cuuint32_t)(q.geo ? 16 : TP_TH * TS_MT), 1};
+            cuuint32_t box[4] = {TS_STG_LD, 8, 16, 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             if (g_encode(&q.resmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(epi.residual), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-                q.res_prefetch = 1;
+                q.res_tma = 1;
         }
         static bool sattr = false;
         if (!sattr) {
-            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            DS_CHECK_CUDA(cudaFuncSetAttribute(conv_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             sattr = true;
         }
         DS_CHECK_CUDA(launch_pdl(conv_tcs_kernel, dim3(plan->grid_x, 1, 1), dim3(TS_THREADS), (size_t)plan->smem_bytes, st, q));

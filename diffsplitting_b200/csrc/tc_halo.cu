@@ -472,6 +472,11 @@ bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W, 
 // C=64 S=256 257 vs 344, C=64 S=512 ~1850 vs 1360 (the re-reads spill from L2 to HBM), C=128 S=128 570 vs 166,
 // C=128 S=256 2260 vs 645.
 bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32) {
+    // throughput regime: GroupNorm-apply + the persistent TMA-fed conv (conv_tcs_kernel) instead of a fused kernel for inputs of at
+    // least DIFFSPLIT_B200_UNFUSE_MINC channels (bf16 operands only: the TF32 nets are the narrow latency-bound ones)
+    static int unfuse_minc = -1;
+    if (unfuse_minc < 0) { const char* e = getenv("DIFFSPLIT_B200_UNFUSE_MINC"); unfuse_minc = e ? atoi(e) : 64; }
+    if (!tf32 && ks == 3 && ca + cb >= unfuse_minc && cout >= 32 && (int64_t)B * H * W >= (int64_t)8 * 148 * 128) return false;
     if (ca + cb <= 224 && stream_conv_preferred(ca, cb, cout, ks, B, H, W, tf32)) return true;      // pipelined variant (tc_stream.cu)
     if (!halo_conv_supported(ca, cb, cout, ks, B, H, W, tf32)) return false;
     const int C = ca + cb, ntaps = ks * ks, es = tf32 ? 4 : 2;
