@@ -476,7 +476,10 @@ bool halo_conv_preferred(int ca, int cb, int cout, int ks, int B, int H, int W, 
     // least DIFFSPLIT_B200_UNFUSE_MINC channels (bf16 operands only: the TF32 nets are the narrow latency-bound ones)
     static int unfuse_minc = -1;
     if (unfuse_minc < 0) { const char* e = getenv("DIFFSPLIT_B200_UNFUSE_MINC"); unfuse_minc = e ? atoi(e) : 64; }
-    if (!tf32 && ks == 3 && ca + cb >= unfuse_minc && cout >= 32 && (int64_t)B * H * W >= (int64_t)8 * 148 * 128) return false;
+    static int unfuse_minc32 = -1;
+    if (unfuse_minc32 < 0) { const char* e = getenv("DIFFSPLIT_B200_UNFUSE_MINC_TF32"); unfuse_minc32 = e ? atoi(e) : 64; }
+    if (ks == 3 && ca + cb >= (tf32 ? unfuse_minc32 : unfuse_minc) && cout >= 32 && (int64_t)B * H * W >= (int64_t)(tf32 ? 2 : 8) * 148 * 128)
+        return false;
     if (ca + cb <= 224 && stream_conv_preferred(ca, cb, cout, ks, B, H, W, tf32)) return true;      // pipelined variant (tc_stream.cu)
     if (!halo_conv_supported(ca, cb, cout, ks, B, H, W, tf32)) return false;
     const int C = ca + cb, ntaps = ks * ks, es = tf32 ? 4 : 2;
