@@ -46,6 +46,27 @@ struct TcParams {
     TraceSlot trace;
 };
 
+// MMA issue loop of conv_tc_kernel: U (tap, chunk) units through a ring of `stages` slots [A 128 x KC | B BN x KC]; barriers
+// full[s] at bar_base + 8 s, empty[s] behind them.
+template <bool TF32, int KS>
+__device__ __forceinline__ void tc_issue_units(int BN, int U, int stages, uint32_t base, uint32_t st16, uint32_t a16, uint32_t row_bytes,
+                                               uint32_t bar_base, uint32_t tmem_base) {
+    const uint32_t idesc = umma_idesc(BN, TF32);
+    const uint64_t hi = make_smem_desc(0, row_bytes) + (uint64_t)(base >> 4);
+    const uint32_t empty0 = bar_base + 8u * (uint32_t)stages;
+    uint32_t s = 0, ph = 0, first = 0;
+    for (int u = 0; u < U; ++u) {
+        mbar_wait_fast(bar_base + 8u * s, ph);
+        tc_fence_after();
+        const uint64_t adesc = hi + (uint64_t)(s * st16), bdesc = adesc + (uint64_t)a16;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) umma<TF32>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? first : 1u);
+        first = 1u;
+        umma_commit(empty0 + 8u * s);             // frees the smem slot once these MMAs have read it
+        if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -90,40 +111,39 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (elect_one()) {
             const size_t blk16 = (size_t)16 * row_bytes;
             const uint8_t* wsrc = p.w + ((size_t)cls * U * p.nb16 + (size_t)nt * (p.BN / 16)) * blk16;
-            for (int u = 0; u < U; ++u) {
-                const int s = u % p.stages;
-                const uint32_t ph = (u / p.stages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const int tap = u / units_per_tap, cc = u - tap * units_per_tap;
-                const int src = cc < p.chunks_a ? 0 : 1;
-                const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
-                const CUtensorMap* map = &p.maps[src * 4 + p.tap_view[cls][tap]];
-                const uint32_t dstA = base + s * stage_bytes;
-                mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
-                tma_load_4d(dstA, map, full_bar(s), c0, x0 + p.tap_dx[cls][tap], y0 + p.tap_dy[cls][tap], b0);
-                bulk_load(dstA + a_bytes, wsrc + (size_t)u * p.nb16 * blk16, b_bytes, full_bar(s));
+            const size_t ustride = (size_t)p.nb16 * blk16;
+            int s = 0;
+            uint32_t eph = 1u;                                        // parity to wait for on empty[s]
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int xs = x0 + p.tap_dx[cls][tap], ys = y0 + p.tap_dy[cls][tap], view = p.tap_view[cls][tap];
+                for (int cc = 0; cc < units_per_tap; ++cc) {
+                    mbar_wait_fast(empty_bar(s), eph);
+                    const int src = cc < p.chunks_a ? 0 : 1;
+                    const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
+                    const uint32_t dstA = base + s * stage_bytes;
+                    mbar_expect_tx(full_bar(s), a_bytes + b_bytes);
+                    tma_load_4d(dstA, &p.maps[src * 4 + view], full_bar(s), c0, xs, ys, b0);
+                    bulk_load(dstA + a_bytes, wsrc, b_bytes, full_bar(s));
+                    wsrc += ustride;
+                    if (++s == p.stages) { s = 0; eph ^= 1u; }
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
-            const int ksteps = (int)(row_bytes >> 5);                 // 32 bytes of every row per MMA (K = 16 bf16 / 8 tf32)
-            for (int u = 0; u < U; ++u) {
-                const int s = u % p.stages;
-                const uint32_t ph = (u / p.stages) & 1;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t sa = base + s * stage_bytes;
-                const uint64_t adesc = make_smem_desc(sa, row_bytes), bdesc = make_smem_desc(sa + a_bytes, row_bytes);
-                if (p.tf32) {
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
-                } else {
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (u | k) ? 1u : 0u);
-                }
-                umma_commit(empty_bar(s));        // frees the smem slot once these MMAs have read it
+            // 32 bytes of every row per MMA (K = 16 bf16 / 8 tf32); one thread issues everything, so the loop is kept lean
+            // (tc_issue_units: running stage index and descriptor words)
+            const int ksteps = (int)(row_bytes >> 5);
+            const uint32_t st16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+            if (p.tf32) {
+                if (ksteps == 4) tc_issue_units<true, 4>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
+                else if (ksteps == 2) tc_issue_units<true, 2>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
+                else tc_issue_units<true, 1>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
+            } else {
+                if (ksteps == 4) tc_issue_units<false, 4>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
+                else if (ksteps == 2) tc_issue_units<false, 2>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
+                else tc_issue_units<false, 1>(p.BN, U, p.stages, base, st16, a16, row_bytes, bar_base, tmem_base);
             }
             umma_commit(tfull_bar);               // accumulator complete
         }
@@ -204,6 +224,48 @@ struct TcpParams {
     TraceSlot trace;
 };
 
+// MMA issue loop of conv_tcp_kernel (one thread; see tcs_issue for why it is written this way)
+struct TcpIssue {
+    uint32_t base, wring, wstage_bytes, bar_base, pfull0, tmem_base, row_bytes;
+    int nchunks;
+};
+template <bool TF32, int KS>
+__device__ __forceinline__ void tcp_issue(const TcpParams& p, const TcpIssue& ii) {
+    const uint32_t idesc = umma_idesc(p.BN, TF32);
+    const uint32_t rb16 = ii.row_bytes >> 4;
+    const uint64_t a_hi = make_smem_desc(0, ii.row_bytes);
+    const uint64_t b_hi = a_hi + (uint64_t)(ii.wring >> 4);
+    const uint32_t t_step = (uint32_t)(TP_TH * TP_PW) * rb16, wst16 = ii.wstage_bytes >> 4;
+    const uint32_t nw = (uint32_t)p.wstages, wempty0 = ii.bar_base + 8u * nw;
+    const uint32_t BN = (uint32_t)p.BN;
+    const int MT = p.MT;
+    uint32_t s = 0, wph = 0, first = 0;
+    for (int cc = 0; cc < ii.nchunks; ++cc) {
+        const uint32_t pb = (uint32_t)cc & 1u;
+        mbar_wait_fast(ii.pfull0 + 8u * pb, ((uint32_t)cc >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t abase = a_hi + (uint64_t)((ii.base + pb * p.patch_bytes) >> 4);
+        for (int ty = 0; ty < 3; ++ty) {
+            for (int tx = 0; tx < 3; ++tx) {
+                mbar_wait_fast(ii.bar_base + 8u * s, wph);
+                tc_fence_after();
+                const uint64_t bdesc = b_hi + (uint64_t)(s * wst16);
+                const uint64_t adesc = abase + (uint64_t)((uint32_t)(ty * TP_PW + tx) * rb16);
+                for (int t = 0; t < MT; ++t) {
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+                        umma<TF32>(ii.tmem_base + (uint32_t)t * BN, adesc + (uint64_t)((uint32_t)t * t_step + 2u * k), bdesc + (uint64_t)(2 * k), idesc,
+                                   k == 0 ? first : 1u);
+                }
+                first = 1u;
+                umma_commit(wempty0 + 8u * s);
+                if (++s == nw) { s = 0; wph ^= 1u; }
+            }
+        }
+        umma_commit(ii.pfull0 + 16u + 8u * pb);                                 // pempty
+    }
+}
+
 __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_constant__ TcpParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -252,54 +314,34 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
             const size_t blk16 = (size_t)16 * row_bytes;
             const uint8_t* wsrc = p.w + (size_t)nt * (p.BN / 16) * blk16;
             const uint32_t box_bytes = (uint32_t)(TP_PW * (TP_TH * p.MT + 2)) * row_bytes;
-            int u = 0;
+            int s = 0;
+            uint32_t eph = 1u;
             for (int cc = 0; cc < nchunks; ++cc) {
                 const int pb = cc & 1;
-                mbar_wait(pempty(pb), (((uint32_t)(cc >> 1)) & 1u) ^ 1u);
+                mbar_wait_fast(pempty(pb), (((uint32_t)(cc >> 1)) & 1u) ^ 1u);
                 const int src = cc < p.chunks_a ? 0 : 1;
                 const int c0 = (src == 0 ? cc : cc - p.chunks_a) * p.KC;
                 mbar_expect_tx(pfull(pb), box_bytes);
                 tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.pmap[src], pfull(pb), c0, x0 - 1, y0 - 1, b);
-                for (int tap = 0; tap < 9; ++tap, ++u) {
-                    const int s = u % p.wstages;
-                    mbar_wait(wempty(s), (((uint32_t)(u / p.wstages)) & 1u) ^ 1u);
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_fast(wempty(s), eph);
                     mbar_expect_tx(wfull(s), w_bytes);
                     bulk_load(wring + (uint32_t)s * wstage_bytes, wsrc + (size_t)(tap * nchunks + cc) * p.nb16 * blk16, w_bytes, wfull(s));
+                    if (++s == p.wstages) { s = 0; eph ^= 1u; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(p.BN, p.tf32 != 0);
+            TcpIssue ii;
+            ii.base = base; ii.wring = wring; ii.wstage_bytes = wstage_bytes; ii.bar_base = bar_base; ii.pfull0 = pfull0;
+            ii.tmem_base = tmem_base; ii.row_bytes = row_bytes; ii.nchunks = nchunks;
             const int ksteps = (int)(row_bytes >> 5);
-            int u = 0;
-            for (int cc = 0; cc < nchunks; ++cc) {
-                const int pb = cc & 1;
-                mbar_wait(pfull(pb), ((uint32_t)(cc >> 1)) & 1u);
-                tc_fence_after();
-                const uint32_t patch = base + (uint32_t)pb * p.patch_bytes;
-                for (int tap = 0; tap < 9; ++tap, ++u) {
-                    const int s = u % p.wstages;
-                    mbar_wait(wfull(s), ((uint32_t)(u / p.wstages)) & 1u);
-                    tc_fence_after();
-                    const uint64_t bdesc = make_smem_desc(wring + (uint32_t)s * wstage_bytes, row_bytes);
-                    const uint32_t shift = (uint32_t)((tap / 3) * TP_PW + tap % 3);
-                    for (int t = 0; t < p.MT; ++t) {
-                        const uint64_t adesc = make_smem_desc(patch + ((uint32_t)(t * TP_TH * TP_PW) + shift) * row_bytes, row_bytes);
-                        if (p.tf32) {
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_tf32(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                          (cc | tap | k) ? 1u : 0u);
-                        } else {
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_bf16(tmem_base + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                          (cc | tap | k) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(wempty(s));
-                }
-                umma_commit(pempty(pb));
+            if (p.tf32) {
+                if (ksteps == 4) tcp_issue<true, 4>(p, ii); else if (ksteps == 2) tcp_issue<true, 2>(p, ii); else tcp_issue<true, 1>(p, ii);
+            } else {
+                if (ksteps == 4) tcp_issue<false, 4>(p, ii); else if (ksteps == 2) tcp_issue<false, 2>(p, ii); else tcp_issue<false, 1>(p, ii);
             }
             umma_commit(tfull);
         }
@@ -968,9 +1010,10 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         // persistent variant: enough work items (M supertile of 2 tiles x N tile) to keep every SM busy for several of them
         static int persist_env = -1;
         if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
-        // fewest work items for the persistent kernel: below one per SM the one-tile-per-CTA kernels spread the work better
+        // fewest work items for the persistent kernel (one per CTA below 148): fewer still and the one-tile-per-CTA kernels,
+        // which cut smaller tiles, spread the work over more SMs
         static int persist_min = -1;
-        if (persist_min < 0) { const char* e4 = getenv("DIFFSPLIT_B200_TC_PERSIST_MIN"); persist_min = e4 ? atoi(e4) : 148; }
+        if (persist_min < 0) { const char* e4 = getenv("DIFFSPLIT_B200_TC_PERSIST_MIN"); persist_min = e4 ? atoi(e4) : 64; }
         {
             static int geo_env = -1;
             if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
