@@ -216,6 +216,11 @@ struct TcpParams {
     int up;                           // nearest x2 upsample + 3x3 as four 2x2 convs on the low-res patch (geo 1 only): H, W = low-res
                                       //    size, item class (a, b) writes the output pixels (2y + a, 2x + b); w = [class][tap][chunk]
     uint32_t class_bytes;             // packed weight bytes per class
+    // folded 1x1 conv of a second input (the res_conv of a ResNet block, out = conv3x3(h) + conv1x1(cat[xa, xb])): extra K chunks
+    // after the 3x3 ones, one tap each, A = the 16 x 16 centre box of the supertile (8-row groups 16 rows apart)
+    CUtensorMap xmap[2];              // sources xa / xb as (C, W, H, B), box {KC, 16, 16, 1}
+    const uint8_t* xw;                // their packed 1x1 weights [chunk][16-row block] (same KC)
+    int xchunks_a, xchunks_b;
     int geo;                          // 0: supertile = 2 stacked tiles of 7 x 16 outputs (128 MMA rows = patch positions of pitch 18, 112
                                       //    valid);  1: supertile = 16 x 16 outputs as two 8-wide tiles side by side: MMA row 8 g + i =
                                       //    output (row g, column i) -> an 8-row core-matrix group is 8 consecutive patch pixels and the
@@ -471,6 +476,8 @@ __device__ __forceinline__ void tcs_issue(const TcpParams& p, const TcsIssue& ii
     const uint32_t wfull0 = ii.bar_base, wempty0 = ii.bar_base + 8u * nw;
     const int nt1 = p.up ? 2 : 3;                                 // taps per axis
     const uint32_t BN = (uint32_t)p.BN;
+    const uint64_t ax_hi = make_smem_desc_sbo(0, ii.row_bytes, 16u * ii.row_bytes);
+    const int xchunks = p.xchunks_a + p.xchunks_b;
     uint32_t s = 0, wph = 0, cg = 0;
     for (int i = 0; i < ii.my_items; ++i) {
         const uint32_t a = (uint32_t)i & 1u;
@@ -508,6 +515,23 @@ __device__ __forceinline__ void tcs_issue(const TcpParams& p, const TcsIssue& ii
                 }
             }
             umma_commit(ii.b2 + 16u + 8u * pb);                                 // pempty
+        }
+        for (int xc = 0; xc < xchunks; ++xc, ++cg) {                            // folded 1x1 conv: one tap per chunk
+            const uint32_t pb = cg & 1u;
+            mbar_wait_fast(ii.b2 + 8u * pb, (cg >> 1) & 1u);
+            mbar_wait_fast(wfull0 + 8u * s, wph);
+            tc_fence_after();
+            const uint64_t bdesc = b_hi + (uint64_t)(s * wst16);
+            const uint64_t adesc = ax_hi + (uint64_t)((ii.base + pb * p.patch_bytes) >> 4);
+#pragma unroll
+            for (int t = 0; t < TS_MT; ++t) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+                    umma<TF32>(acc + (uint32_t)t * BN, adesc + (uint64_t)((uint32_t)t * 8u * rb16 + 2u * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            }
+            umma_commit(wempty0 + 8u * s);
+            if (++s == nw) { s = 0; wph ^= 1u; }
+            umma_commit(ii.b2 + 16u + 8u * pb);
         }
         umma_commit(ii.b2 + 32u + 8u * a);                                      // afull
     }
@@ -594,6 +618,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         if (++s == (uint32_t)p.wstages) { s = 0; wph ^= 1u; }
                     }
                 }
+                const int xchunks = p.xchunks_a + p.xchunks_b;
+                for (int xc = 0; xc < xchunks; ++xc, ++cg) {
+                    const int pb = (int)(cg & 1u);
+                    mbar_wait_relaxed(pempty(pb), ((cg >> 1) & 1u) ^ 1u);
+                    const int src = xc < p.xchunks_a ? 0 : 1;
+                    const int c0 = (src == 0 ? xc : xc - p.xchunks_a) * p.KC;
+                    mbar_expect_tx(pfull(pb), 256u * row_bytes);
+                    tma_load_4d(base + (uint32_t)pb * p.patch_bytes, &p.xmap[src], pfull(pb), c0, x0, y0, b);
+                    mbar_wait_relaxed(wempty((int)s), wph);
+                    mbar_expect_tx(wfull((int)s), w_bytes);
+                    bulk_load(wring + s * wstage_bytes, p.xw + ((size_t)xc * p.nb16 + (size_t)nt * (p.BN / 16)) * blk16, w_bytes, wfull((int)s));
+                    if (++s == (uint32_t)p.wstages) { s = 0; wph ^= 1u; }
+                }
             }
         }
         __syncwarp();
@@ -671,6 +708,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     float v = 0.f;
                     if (n < Cout) {
                         if (p.epi.bias) v = __ldg(p.epi.bias + n);
+                        if (p.epi.bias2) v += __ldg(p.epi.bias2 + n);
                         if (p.epi.temb) v += __ldg(p.epi.temb + (size_t)(p.epi.temb_bcast ? 0 : b) * p.epi.temb_stride + p.epi.temb_off + n);
                     }
                     btv[te] = v;
@@ -986,8 +1024,44 @@ static int pow2_floor(int v) {
     return p;
 }
 
+// does tc_build_conv pick the persistent kernel (conv_tcs_kernel) for this layer?  geo / items: its tile geometry
+static bool tcs_selected(int ca, int cb, int Hs, int Ws, int B, int cout, int ks, int stride, int up, int tf32, int* geo_out, int64_t* items_out) {
+    static int patch_env = -1, persist_env = -1, persist_min = -1, geo_env = -1;
+    if (patch_env < 0) { const char* e = getenv("DIFFSPLIT_B200_TC_PATCH"); patch_env = e ? atoi(e) : 1; }
+    if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
+    // fewest work items for the persistent kernel (one per CTA below 148): fewer still and the one-tile-per-CTA kernels,
+    // which cut smaller tiles, spread the work over more SMs
+    if (persist_min < 0) { const char* e4 = getenv("DIFFSPLIT_B200_TC_PERSIST_MIN"); persist_min = e4 ? atoi(e4) : 64; }
+    if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
+    const int kc = tc_pick_kc(ca, cb, tf32);
+    const size_t e = tf32 ? 4 : 2;
+    const int geo = geo_env ? 1 : 0;
+    const int tiles_x = (Ws + TP_TW - 1) / TP_TW;
+    const int bn = tc_bn(cout);
+    const int ty2 = geo ? (Hs + 15) / 16 : (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
+    const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn) * (up ? 4 : 1);
+    const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) * (up ? 4 : 1) < (1ll << 31);
+    const bool can = ks == 3 && stride == 1 && Ws >= 8 && (!up || geo);
+    if (geo_out) *geo_out = geo;
+    if (items_out) *items_out = items;
+    return kc > 0 && can && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
+           (persist_env == 2 || items >= persist_min);
+}
+
+bool tc_conv_persistent(int ca, int cb, int Hs, int Ws, int B, int cout, int ks, int stride, int up, int tf32) {
+    if (!tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws, tf32)) return false;
+    const int kc = tc_pick_kc(ca, cb, tf32);
+    const size_t e = tf32 ? 4 : 2;
+    int geo = 0;
+    if (!tcs_selected(ca, cb, Hs, Ws, B, cout, ks, stride, up, tf32, &geo, nullptr)) return false;
+    // at least three weight stages must fit beside the patches and the staging buffers
+    const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
+    const size_t patch_bytes = align_up((size_t)prows * kc * e, 1024), wstage = align_up((size_t)tc_bn(cout) * kc * e, 1024);
+    return (225 * 1024 - 2 * patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage >= 3;
+}
+
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
-                  int stride, int up, int tf32) {
+                  int stride, int up, int tf32, const void* xsrc_a, int xca, const void* xsrc_b, int xcb) {
     int rc = get_encoder();
     if (rc != DS_OK) return rc;
     DS_REQUIRE(tc_conv_shape_supported(ca, cb, ks, stride, up, Hs, Ws, tf32), "tc conv: unsupported shape");
@@ -1006,23 +1080,11 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
         const int tiles_y = (Hs + TP_TH * mt - 1) / (TP_TH * mt);
         const int64_t ctas = (int64_t)B * tiles_x * tiles_y * (((cout + 15) / 16 * 16) / bn);
         const bool can = ks == 3 && stride == 1 && !up && Ws >= 8 && mt >= 1;
-        const bool can_up = ks == 3 && stride == 1 && up && Ws >= 8;
-        // persistent variant: enough work items (M supertile of 2 tiles x N tile) to keep every SM busy for several of them
-        static int persist_env = -1;
-        if (persist_env < 0) { const char* e2 = getenv("DIFFSPLIT_B200_TC_PERSIST"); persist_env = e2 ? atoi(e2) : 1; }
-        // fewest work items for the persistent kernel (one per CTA below 148): fewer still and the one-tile-per-CTA kernels,
-        // which cut smaller tiles, spread the work over more SMs
-        static int persist_min = -1;
-        if (persist_min < 0) { const char* e4 = getenv("DIFFSPLIT_B200_TC_PERSIST_MIN"); persist_min = e4 ? atoi(e4) : 64; }
         {
-            static int geo_env = -1;
-            if (geo_env < 0) { const char* e3 = getenv("DIFFSPLIT_B200_TC_GEO"); geo_env = e3 ? atoi(e3) : 1; }
-            const int geo = geo_env ? 1 : 0;
-            const int ty2 = geo ? (Hs + 15) / 16 : (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
-            const int64_t items = (int64_t)B * tiles_x * ty2 * (((cout + 15) / 16 * 16) / bn) * (up ? 4 : 1);
-            const bool small_idx = (int64_t)B * Hs * Ws * ((cout + 3) / 4 * 4) * (up ? 4 : 1) < (1ll << 31);
-            if ((can || (can_up && geo)) && patch_env != 0 && persist_env != 0 && (size_t)kc * e >= 64 && small_idx && 2 * TS_MT * bn <= 512 &&
-                (persist_env == 2 || items >= persist_min)) {
+            int geo = 0;
+            int64_t items = 0;
+            if (tcs_selected(ca, cb, Hs, Ws, B, cout, ks, stride, up, tf32, &geo, &items)) {
+                const int ty2 = geo ? (Hs + 15) / 16 : (Hs + TP_TH * TS_MT - 1) / (TP_TH * TS_MT);
                 TcpParams& q = *reinterpret_cast<TcpParams*>(plan->params);
                 memset(&q, 0, sizeof(q));
                 q.B = B; q.H = Hs; q.W = Ws; q.MT = TS_MT; q.tiles_x = tiles_x; q.tiles_y = ty2;
@@ -1052,6 +1114,19 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                         rc = encode_map(&q.pmap[s_], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, TP_PW,
                                         geo ? 18 : TP_TH * TS_MT + 2, 1, tf32);
                         if (rc != DS_OK) return rc;
+                    }
+                    if (xsrc_a) {
+                        DS_REQUIRE(!up && geo && xca > 0 && tc_pick_kc(xca, xcb, tf32) == kc && (xcb == 0 || xsrc_b),
+                                   "tc conv: folded 1x1 input %d+%d does not match the layer's K chunk %d", xca, xcb, kc);
+                        for (int s_ = 0; s_ < 2; ++s_) {
+                            const void* ptr = s_ == 0 ? xsrc_a : xsrc_b;
+                            const int C = s_ == 0 ? xca : xcb;
+                            if (!ptr || C == 0) continue;
+                            rc = encode_map(&q.xmap[s_], ptr, C, Ws, Hs, B, (size_t)C * e, (size_t)Ws * C * e, (size_t)Hs * Ws * C * e, kc, 16, 16, 1,
+                                            tf32);
+                            if (rc != DS_OK) return rc;
+                        }
+                        q.xchunks_a = xca / kc; q.xchunks_b = xcb / kc;
                     }
                     plan->patch = 2;
                     plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + TS_EGROUPS * TS_STG_BYTES + 16 * wst + 192 + 1024);
@@ -1104,6 +1179,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
             }
         }
     }
+    DS_REQUIRE(!xsrc_a, "tc conv: a folded 1x1 input needs the persistent kernel (check tc_conv_persistent first)");
     TcParams& p = *reinterpret_cast<TcParams*>(plan->params);
     static_assert(sizeof(TcParams) <= sizeof(plan->params), "TcConvPlan::params too small");
     memset(&p, 0, sizeof(p));
@@ -1201,10 +1277,15 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
 }
 
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
-                   float* out_nchw, double* sums_out, cudaStream_t st) {
+                   float* out_nchw, double* sums_out, cudaStream_t st, const uint8_t* xw_packed, const float* bias2) {
+    DS_REQUIRE(plan->patch == 2 || !xw_packed, "tc conv: folded 1x1 weights without the persistent kernel");
     if (plan->patch == 2) {
         TcpParams q = *reinterpret_cast<const TcpParams*>(plan->params);
+        static_assert(sizeof(TcpParams) <= sizeof(plan->params), "TcConvPlan::params too small");
+        DS_REQUIRE((q.xchunks_a + q.xchunks_b > 0) == (xw_packed != nullptr), "tc conv: plan / launch disagree about the folded 1x1 input");
         q.w = w_packed;
+        q.xw = xw_packed;
+        q.epi.bias2 = bias2;
         q.epi.bias = epi.bias; q.epi.temb = epi.temb; q.epi.temb_off = epi.temb_off; q.epi.temb_stride = epi.temb_stride;
         q.epi.temb_bcast = epi.temb_bcast; q.epi.residual = epi.residual;
         q.epi.out_f32 = out_f32; q.epi.out_b16 = reinterpret_cast<__nv_bfloat16*>(out_b16); q.epi.out_nchw = out_nchw;

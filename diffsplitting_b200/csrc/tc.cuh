@@ -16,12 +16,16 @@ bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs,
 size_t tc_packed_weight_bytes(int cout, int cin, int ks, int tf32 = 0);   // upper bound over packing variants
 int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st);
 // geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 (tf32: fp32) NHWC [B,Hs,Ws,c]
+// xsrc_a / xsrc_b (optional): a second input whose 1x1 conv is accumulated into the same output (the res_conv of a ResNet block);
+// only with the persistent kernel: ask tc_conv_persistent first
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
-                  int stride, int up, int tf32 = 0);
+                  int stride, int up, int tf32 = 0, const void* xsrc_a = nullptr, int xca = 0, const void* xsrc_b = nullptr, int xcb = 0);
+bool tc_conv_persistent(int ca, int cb, int Hs, int Ws, int B, int cout, int ks, int stride, int up, int tf32);
 // epi.bias / temb / residual (fp32 NHWC) as in the fp32 kernel; any subset of the three outputs may be given
 // sums_out (optional): [B][cout][2] fp64 accumulators (zeroed by the caller) receiving per-channel sum / sum of squares
+// xw_packed / bias2: the folded 1x1 conv's weights (packed with ks = 1 and the same K chunk) and bias
 int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEpi& epi, float* out_f32, void* out_b16,
-                   float* out_nchw, double* sums_out, cudaStream_t st);
+                   float* out_nchw, double* sums_out, cudaStream_t st, const uint8_t* xw_packed = nullptr, const float* bias2 = nullptr);
 
 // ---- fused GroupNorm-apply + Swish -> conv, operands staged through registers (tc_halo.cu); sources fp32 NHWC
 bool halo_conv_supported(int ca, int cb, int cout, int ks, int B, int H, int W, int tf32 = 0);

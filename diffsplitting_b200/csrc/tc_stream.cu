@@ -656,7 +656,9 @@ int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, c
         cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)W * cout * 4, (cuuint64_t)H * W * cout * 4};
         cuuint32_t box[4] = {(cuuint32_t)(p.BN < cout ? p.BN : cout), SK_TW, SK_TH, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        if ((cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
+        static int respf_env = -1;
+        if (respf_env < 0) { const char* e5 = getenv("DIFFSPLIT_B200_STREAM_RESPF"); respf_env = e5 ? atoi(e5) : 1; }
+        if (respf_env && (cout * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0) {
             CUresult r = g_enc(&p.resmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(epi.residual), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -563,7 +563,21 @@ struct Planner {
         const bool fold_res = r.has_res && getenv("DIFFSPLIT_B200_NO_RES_FOLD") == nullptr && x.f32 != NONE &&
                               (!skip || skip->f32 != NONE) && chain_ok(x, skip, r.res, 1, 0) && chain_ok(hprobe, nullptr, r.conv2, 1, 0) &&
                               chain_ok(x, skip, r.conv1, 1, 0);
-        if (r.has_res && !fold_res) {   // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
+        // throughput regime: conv2 on the persistent TMA-fed kernel takes the 1x1 res_conv as extra K chunks (no res_conv launch, no
+        // fp32 round trip of its output through the residual operand)
+        bool fold_tcs = false;
+        if (r.has_res && !fold_res && tc && getenv("DIFFSPLIT_B200_NO_RES_FOLD") == nullptr) {
+            const int t32 = tf32 ? 1 : 0;                       // conv2 reads the GroupNorm-apply output: fp32 (tf32 mode) or bf16
+            const int kc2 = t32 ? n->specs[r.conv2.w].tc_kc32 : n->specs[r.conv2.w].tc_kc;
+            const int kcr = t32 ? n->specs[r.res.w].tc_kc32 : n->specs[r.res.w].tc_kc;
+            const bool srcs_ok = t32 ? (x.f32 != NONE && (!skip || skip->f32 != NONE)) : (x.b16 != NONE && (!skip || skip->b16 != NONE));
+            const bool unfused = !(n->specs[r.conv2.w].halo32 && t32 && halo_conv_preferred(r.cout, 0, r.cout, 3, B, H, W, 1)) &&
+                                 !(!t32 && n->specs[r.conv2.w].halo && halo_conv_preferred(r.cout, 0, r.cout, 3, B, H, W, 0)) &&
+                                 !(t32 && !tf32_strict && n->specs[r.conv2.w].halo && halo_conv_preferred(r.cout, 0, r.cout, 3, B, H, W, 0));
+            fold_tcs = kc2 > 0 && kc2 == kcr && srcs_ok && unfused && !chain_ok(hprobe, nullptr, r.conv2, 1, 0) &&
+                       tc_conv_persistent(r.cout, 0, H, W, B, r.cout, 3, 1, 0, t32);
+        }
+        if (r.has_res && !fold_res && !fold_tcs) {   // res_conv(x) first: it runs on the side stream while conv1 runs on the main one
             rbuf = make(r.cout, H, W, F32, false);
             conv(x, skip, r.res, 1, 0, -1, nullptr, rbuf);
             p->ops.back().side = (tc && !p->ops.back().chain) ? 1 : 0;
@@ -573,7 +587,14 @@ struct Planner {
         Act h = make(r.cout, H, W, F32);
         gn_conv(x, skip, r.gn1, 1, r.conv1, r.temb_off, nullptr, h);
         Act out = make(r.cout, H, W, F32 | B16);
-        gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, fold_res ? nullptr : &resid, out);
+        gn_conv(h, nullptr, r.gn2, 1, r.conv2, -1, (fold_res || fold_tcs) ? nullptr : &resid, out);
+        if (fold_tcs) {
+            Op& o2 = p->ops.back();
+            if (!(o2.kind == OP_CONV && !o2.chain && !o2.halo && o2.cw == &r.conv2)) { fprintf(stderr, "diffsplit_b200: internal error, res fold on an unexpected op\n"); abort(); }
+            o2.xsrc_a = conv_src(x); o2.xca = x.C;
+            if (skip) { o2.xsrc_b = conv_src(*skip); o2.xcb = skip->C; }
+            o2.xw = &r.res;
+        }
         if (fold_res) {
             Op& o2 = p->ops.back();
             DS_ASSERT_CHAIN(o2);
@@ -586,7 +607,7 @@ struct Planner {
                 if (p->ops[i].kind == OP_CONV && p->ops[i].cw == &r.conv2) { p->ops[i].join = 1; break; }
         }
         release(h);
-        if (r.has_res && !fold_res) release(rbuf);
+        if (r.has_res && !fold_res && !fold_tcs) release(rbuf);
         if (r.attn) {
             Act qkv = make(3 * r.cout, H, W, B16);
             gn_conv(out, nullptr, r.agn, 0, r.qkv, -1, nullptr, qkv);
@@ -1010,7 +1031,8 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                           n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
                 return DS_ERR_INVALID;
             }
-            rc = tc_build_conv(&p->tc[i], ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, o.Hs, o.Ws, B, o.cw->cout, o.cw->ks, o.stride, o.up, o.tf32);
+            rc = tc_build_conv(&p->tc[i], ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, o.Hs, o.Ws, B, o.cw->cout, o.cw->ks, o.stride, o.up, o.tf32,
+                               o.xw ? ptr(o.xsrc_a) : nullptr, o.xw ? o.xca : 0, o.xw ? ptr(o.xsrc_b) : nullptr, o.xw ? o.xcb : 0);
             if (rc != DS_OK) return rc;
             if (p->tc[i].kc != want_kc) {
                 set_error("unet_forward: internal error, K-chunk mismatch for %s", n->specs[o.cw->w].name.c_str());
@@ -1138,7 +1160,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     used_tc = true;
                     rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + (o.tf32 ? n->specs[o.cw->w].off_tf32 : n->specs[o.cw->w].off_bf16), e,
                                         o.out_nchw ? nullptr : ptr(o.dst),
-                                        ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st);
+                                        ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st,
+                                        o.xw ? n->d_arena_bf16 + (o.tf32 ? n->specs[o.xw->w].off_tf32 : n->specs[o.xw->w].off_bf16) : nullptr,
+                                        (o.xw && o.xw->b >= 0) ? n->wp(o.xw->b) : nullptr);
                 } else {
                     rc = launch_conv_f32(s, n->wp(o.cw->w), o.cw->npad, o.cw->cout, o.cw->ks, o.stride, B, o.Ho, o.Wo, e,
                                          ptr(o.dst), st);
@@ -1173,6 +1197,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 r.flops = 2.0 * B * o.Ho * o.Wo * (double)o.cw->ks * o.cw->ks * cin * o.cw->cout;
                 r.bytes = 4.0 * B * ((double)o.Hs * o.Ws * cin + (double)o.Ho * o.Wo * o.cw->cout *
                                      (o.residual != NONE ? 2.0 : 1.0)) + 4.0 * o.cw->ks * o.cw->ks * cin * o.cw->cout;
+                if (o.xw) {   // folded 1x1 res_conv: its flops and its input
+                    r.flops += 2.0 * B * o.Ho * o.Wo * (double)(o.xca + o.xcb) * o.cw->cout;
+                    r.bytes += 4.0 * B * (double)o.Hs * o.Ws * (o.xca + o.xcb) + 4.0 * (o.xca + o.xcb) * o.cw->cout;
+                }
             } else if (o.kind == OP_GN_STATS || o.kind == OP_CH_SUMS) {
                 r.kind = 5;
                 r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;
