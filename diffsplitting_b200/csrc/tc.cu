@@ -890,6 +890,7 @@ __host__ __device__ inline uint32_t swizzle_offset(uint32_t row, uint32_t byte_i
 
 struct PackGeom {
     int cout, cin, ks, up, nb16, KC, chunks, ntaps, nclasses, tf32;
+    int cin_src;                      // input channels of the OIHW tensor (<= cin: the rest are zero weights)
 };
 
 // largest N tile (16..128) that divides the 16-padded channel count
@@ -903,6 +904,7 @@ static int tc_bn(int cout) {
 static PackGeom pack_geom(int cout, int cin, int ks, int up, int kc, int tf32) {
     PackGeom g;
     g.tf32 = tf32;
+    g.cin_src = cin;
     g.cout = cout; g.cin = cin; g.ks = ks; g.up = up;
     g.nb16 = (cout + 15) / 16;
     g.KC = kc;
@@ -945,8 +947,8 @@ __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __re
         const int tap = u / g.chunks, c = (u - tap * g.chunks) * g.KC + k;
         const int n = nb * 16 + row;
         float v = 0.f;
-        if (n < g.cout) {
-            const float* wn = w + ((size_t)n * g.cin + c) * g.ks * g.ks;
+        if (n < g.cout && c < g.cin_src) {
+            const float* wn = w + ((size_t)n * g.cin_src + c) * g.ks * g.ks;
             if (!g.up) {
                 v = wn[tap];
             } else {
@@ -968,10 +970,13 @@ __global__ void pack_tc_weight_kernel(const float* __restrict__ w, uint8_t* __re
     }
 }
 
-int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st) {
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st,
+                        int cin_src) {
     DS_REQUIRE(tf32 ? (kc == 8 || kc == 16 || kc == 32) : (kc == 16 || kc == 32 || kc == 64), "tc_pack: KC %d", kc);
     DS_REQUIRE(cin % kc == 0, "tc_pack: cin %d not a multiple of KC %d", cin, kc);
+    DS_REQUIRE(cin_src >= 0 && cin_src <= cin, "tc_pack: %d source channels > %d", cin_src, cin);
     PackGeom g = pack_geom(cout, cin, ks, up, kc, tf32);
+    if (cin_src) g.cin_src = cin_src;
     const size_t total = (size_t)g.nclasses * g.ntaps * g.chunks * g.nb16 * 16 * g.KC;
     int blocks = (int)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
     pack_tc_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, packed, g);
@@ -1350,6 +1355,44 @@ int tc_launch_conv(const TcConvPlan* plan, const uint8_t* w_packed, const ConvEp
     }
     DS_CHECK_CUDA(launch_pdl(conv_tc_kernel, dim3(plan->grid_x, plan->grid_y, plan->grid_z), dim3(TC_THREADS),
                              (size_t)plan->smem_bytes, st, p));
+    return DS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ network input -> TF32 NHWC, 8 channels
+// The first conv of the net reads the caller's fp32 NCHW tensors (condition and x_t: the torch.cat of p_mean_variance).  With
+// <= 8 channels in total they are repacked once into an NHWC tensor of 8 or 16 channels (zero padded, values rounded to TF32), so the
+// conv runs on the tensor cores as a TF32 implicit GEMM (16 channels = 64-byte rows: the persistent kernel) instead of on the CUDA cores.
+template <int CP>
+__global__ void pack_input_kernel(const float* __restrict__ xa, int ca, const float* __restrict__ xb, int cb, float* __restrict__ out,
+                                  int B, int HW) {
+    pdl_wait();
+    pdl_trigger();
+    const size_t total = (size_t)B * HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / HW, px = i - b * HW;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float x = 0.f;
+            if (c < ca) x = __ldg(xa + (b * ca + c) * HW + px);
+            else if (c < ca + cb) x = __ldg(xb + (b * cb + (c - ca)) * HW + px);
+            v[c] = to_tf32(x);
+        }
+        float4* dst = reinterpret_cast<float4*>(out + i * CP);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int c = 2; c < CP / 4; ++c) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int tc_pack_input(const float* xa, int ca, const float* xb, int cb, float* out, int cpad, int B, int H, int W, cudaStream_t st) {
+    DS_REQUIRE(xa && ca > 0 && cb >= 0 && ca + cb <= 8 && (cb == 0 || xb) && out && (cpad == 8 || cpad == 16), "pack_input: %d+%d -> %d channels",
+               ca, cb, cpad);
+    const size_t total = (size_t)B * H * W;
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (cpad == 8) DS_CHECK_CUDA(launch_pdl(pack_input_kernel<8>, dim3(blocks), dim3(256), 0, st, xa, ca, xb, cb, out, B, H * W));
+    else DS_CHECK_CUDA(launch_pdl(pack_input_kernel<16>, dim3(blocks), dim3(256), 0, st, xa, ca, xb, cb, out, B, H * W));
     return DS_OK;
 }
 

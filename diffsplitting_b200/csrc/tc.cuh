@@ -14,7 +14,12 @@ struct TcConvPlan {
 int tc_pick_kc(int ca, int cb, int tf32 = 0);                      // channels per K chunk (rows of 128 / 64 / 32 bytes), 0 if unsupported
 bool tc_conv_shape_supported(int ca, int cb, int ks, int stride, int up, int Hs, int Ws, int tf32 = 0);
 size_t tc_packed_weight_bytes(int cout, int cin, int ks, int tf32 = 0);   // upper bound over packing variants
-int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st);
+// cin_src (optional): channels present in w_oihw; the packed image has cin >= cin_src channels, the extra ones zero
+int tc_pack_conv_weight(const float* w_oihw, uint8_t* packed, int cout, int cin, int ks, int up, int kc, int tf32, cudaStream_t st,
+                        int cin_src = 0);
+// the network input (one or two fp32 NCHW tensors, <= 8 channels together) -> [B,H,W,cpad] fp32 NHWC (cpad 8 or 16), zero padded,
+// rounded to TF32
+int tc_pack_input(const float* xa, int ca, const float* xb, int cb, float* out, int cpad, int B, int H, int W, cudaStream_t st);
 // geometry + tensor maps for: out = conv(cat[src_a, src_b]) ; sources bf16 (tf32: fp32) NHWC [B,Hs,Ws,c]
 // xsrc_a / xsrc_b (optional): a second input whose 1x1 conv is accumulated into the same output (the res_conv of a ResNet block);
 // only with the persistent kernel: ask tc_conv_persistent first

@@ -31,6 +31,8 @@ struct WeightSpec {
     size_t off_halo;   // byte offset of that pack in the bf16 arena
     bool chain;        // additionally packed for the per-sample persistent chain kernel (tc_chain.cu)
     size_t off_chain;
+    bool entry32;      // the net's first conv: a TF32 TMA-fed image with the input channels padded to 8 (K chunk 8) ...
+    size_t off_entry32;   // ... at this byte offset of the tensor-core arena
     int tc_kc32;       // TF32 images (ds_unet_desc.tf32_weights): K chunk of the TMA-fed pack (0 = none) ...
     size_t off_tf32;   // ... its byte offset in the tensor-core arena ...
     bool halo32;       // ... and the fused kernel's TF32 pack
@@ -63,7 +65,8 @@ struct Layer {
 };
 
 // ------------------------------------------------------------------------------------------ plan
-enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN, OP_GN_STATS, OP_CH_SUMS };
+constexpr int ENTRY_CPAD = 16;   // channels of the TF32 NHWC repack of the network input (64-byte rows: the persistent conv takes it)
+enum OpKind { OP_TEMB, OP_CONV, OP_GN, OP_ATTN, OP_GN_STATS, OP_CH_SUMS, OP_PACK_IN };
 constexpr int64_t EXT_XA = -1, EXT_XB = -2, EXT_OUT = -3, NONE = -100;
 
 struct Op {
@@ -95,6 +98,8 @@ struct Op {
     const ConvW* xw = nullptr;
     // the network's first conv on the dedicated small-Cin kernel (conv_entry.cu), which also emits the statistics
     int entry = 0;
+    // ... or, in the throughput regime, on the TMA-fed TF32 kernel reading the 8-channel NHWC repack of the input (OP_PACK_IN)
+    int entry32 = 0;
     // bf16 mode GroupNorm statistics: per-channel fp64 (sum, sumsq) slots in the plan's statistics arena
     int64_t sums_out = NONE;             // slot the producer's epilogue accumulates into
     int64_t sums_a = NONE, sums_b = NONE;   // slots of the (two) sources a fused / apply-only GroupNorm reads
@@ -229,6 +234,8 @@ static int add_spec(ds_unet* n, const std::string& name, WKind kind, std::initia
     s.off_chain = 0;
     s.tc_kc32 = 0;
     s.off_tf32 = 0;
+    s.entry32 = false;
+    s.off_entry32 = 0;
     s.halo32 = false;
     s.off_halo32 = 0;
     size_t elems = 1;
@@ -353,6 +360,11 @@ static int build_arch(ds_unet* n) {
     {
         Layer L; L.kind = L_CONV; L.name = "downs.0"; L.section = 0;
         L.conv = add_conv(n, "downs.0", d.in_channel, inner, 3, true, -1, 0, 0, false);
+        if (d.in_channel <= 8) {
+            n->specs[L.conv.w].entry32 = true;
+            n->specs[L.conv.w].off_entry32 = n->arena_bf16_bytes;
+            n->arena_bf16_bytes += align_up(tc_packed_weight_bytes(inner, ENTRY_CPAD, 3, 1), 1024);
+        }
         n->layers.push_back(L);
         skip_ch.push_back(inner);
         idx = 1;
@@ -659,6 +671,28 @@ static int build_plan(ds_unet* n, int B, int H, int W, int prec, Plan** out) {
                 Op op; op.kind = OP_CONV;
                 op.src_a = EXT_XA; op.src_b = EXT_XB; op.src_nchw = 1; op.Hs = h; op.Ws = w;
                 op.cw = &L.conv; op.Ho = h; op.Wo = w; op.dst = o.f32; op.dst_b16 = o.b16;
+                // throughput regime (>= 4 tiles of 128 pixels per SM): repack to 8-channel TF32 NHWC + the TMA-fed tensor-core conv
+                // (wide first layers only: at 16 output channels the small-Cin CUDA-core kernel is faster)
+                const bool entry_tc = P.tc && n->specs[L.conv.w].entry32 && (int64_t)B * h * w >= (int64_t)4 * 148 * 128 &&
+                                      L.conv.cout >= 64 && getenv("DIFFSPLIT_B200_NO_ENTRY_TC") == nullptr &&
+                                      tc_conv_shape_supported(ENTRY_CPAD, 0, L.conv.ks, 1, 0, h, w, 1);
+                if (entry_tc) {
+                    Act in8 = P.make(ENTRY_CPAD, h, w, F32, false);
+                    Op pk; pk.kind = OP_PACK_IN;
+                    pk.src_a = EXT_XA; pk.src_b = EXT_XB; pk.dst = in8.f32; pk.Hs = h; pk.Ws = w; pk.HW = h * w;
+                    p->ops.push_back(pk);
+                    Op c8; c8.kind = OP_CONV;
+                    c8.tf32 = 1; c8.entry32 = 1;
+                    c8.src_a = in8.f32; c8.ca = ENTRY_CPAD; c8.Hs = h; c8.Ws = w;
+                    c8.cw = &L.conv; c8.Ho = h; c8.Wo = w; c8.dst = o.f32; c8.dst_b16 = o.b16; c8.sums_out = o.sums;
+                    p->ops.push_back(c8);
+                    P.release(in8);
+                    x = o;
+                    P.retain(x);
+                    Act s0 = x;
+                    skips.push_back(s0);
+                    continue;
+                }
                 const bool entry_kernel = P.tc && entry_conv_supported(d.in_channel, 0, L.conv.cout, L.conv.ks) &&
                                           getenv("DIFFSPLIT_B200_NO_ENTRY_KERNEL") == nullptr;
                 if (entry_kernel) { op.entry = 1; op.sums_out = o.sums; }
@@ -835,6 +869,10 @@ extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cn
             }
             if (s.halo) {
                 rc = halo_pack_conv_weight(src, n->d_arena_bf16 + s.off_halo, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], 0, st);
+                if (rc != DS_OK) return rc;
+            }
+            if (s.entry32) {
+                rc = tc_pack_conv_weight(src, n->d_arena_bf16 + s.off_entry32, (int)s.shape[0], ENTRY_CPAD, (int)s.shape[2], 0, ENTRY_CPAD, 1, st, (int)s.shape[1]);
                 if (rc != DS_OK) return rc;
             }
             if (s.tc_kc32) {
@@ -1025,7 +1063,7 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                 if (rc != DS_OK) return rc;
             }
             if (o.kind != OP_CONV || o.src_nchw || o.halo || o.chain) continue;
-            const int want_kc = o.tf32 ? n->specs[o.cw->w].tc_kc32 : n->specs[o.cw->w].tc_kc;
+            const int want_kc = o.entry32 ? ENTRY_CPAD : (o.tf32 ? n->specs[o.cw->w].tc_kc32 : n->specs[o.cw->w].tc_kc);
             if (!want_kc || !tc_conv_shape_supported(o.ca, o.cb, o.cw->ks, o.stride, o.up, o.Hs, o.Ws, o.tf32)) {
                 set_error("unet_forward: the tensor-core modes need channel counts that are multiples of 16 (layer %s: %d+%d -> %d); use fp32",
                           n->specs[o.cw->w].name.c_str(), o.ca, o.cb, o.cw->cout);
@@ -1108,6 +1146,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     rc = launch_groupnorm(ptr(o.src_a), o.ca, ptr(o.src_b), o.cb, n->wp(o.gw->w), n->wp(o.gw->b), ptr(o.dst), B, o.HW,
                                           n->d.norm_groups, o.swish, gn_scratch, counters, 0, st);
                 break;
+            case OP_PACK_IN:
+                rc = tc_pack_input(d_xa, ca, d_xb, cb, ptr(o.dst), ENTRY_CPAD, B, o.Hs, o.Ws, st);
+                break;
             case OP_CH_SUMS:
                 rc = launch_ch_sums(ptr(o.src_a), o.ca, B, o.HW, sums(o.sums_out), st);
                 break;
@@ -1158,7 +1199,9 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                                           o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), o.tf32, st);
                 } else if (tc && !o.src_nchw) {
                     used_tc = true;
-                    rc = tc_launch_conv(&p->tc[oi], n->d_arena_bf16 + (o.tf32 ? n->specs[o.cw->w].off_tf32 : n->specs[o.cw->w].off_bf16), e,
+                    rc = tc_launch_conv(&p->tc[oi],
+                                        n->d_arena_bf16 + (o.entry32 ? n->specs[o.cw->w].off_entry32
+                                                                     : (o.tf32 ? n->specs[o.cw->w].off_tf32 : n->specs[o.cw->w].off_bf16)), e,
                                         o.out_nchw ? nullptr : ptr(o.dst),
                                         ptr(o.dst_b16), o.out_nchw ? ptr(o.dst) : nullptr, sums(o.sums_out), st,
                                         o.xw ? n->d_arena_bf16 + (o.tf32 ? n->specs[o.xw->w].off_tf32 : n->specs[o.xw->w].off_bf16) : nullptr,
@@ -1201,6 +1244,10 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
                     r.flops += 2.0 * B * o.Ho * o.Wo * (double)(o.xca + o.xcb) * o.cw->cout;
                     r.bytes += 4.0 * B * (double)o.Hs * o.Ws * (o.xca + o.xcb) + 4.0 * (o.xca + o.xcb) * o.cw->cout;
                 }
+            } else if (o.kind == OP_PACK_IN) {
+                r.kind = 1;
+                r.cin = ca + cb; r.cout = ENTRY_CPAD; r.h = o.Hs; r.w = o.Ws;
+                r.bytes = 4.0 * B * (double)o.HW * (ca + cb + ENTRY_CPAD);
             } else if (o.kind == OP_GN_STATS || o.kind == OP_CH_SUMS) {
                 r.kind = 5;
                 r.cin = r.cout = o.ca + o.cb; r.h = o.HW; r.w = 1;

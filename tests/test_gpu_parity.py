@@ -224,7 +224,9 @@ TF32_CONV_CASES = [
     (8, 0, 24, 1, 1, 0, 1, 12, 20, 0, 0), (192, 0, 64, 3, 1, 0, 2, 16, 16, 1, 0), (256, 0, 128, 3, 1, 0, 1, 8, 8, 0, 0),
     # tall-patch variant (many tiles, >= 32 channels)
     (32, 0, 32, 3, 1, 0, 8, 128, 128, 1, 0), (64, 32, 32, 3, 1, 0, 10, 100, 90, 0, 0), (32, 0, 16, 3, 1, 0, 8, 128, 128, 0, 0),
-    (32, 0, 128, 3, 1, 0, 8, 32, 32, 0, 0)]
+    (32, 0, 128, 3, 1, 0, 8, 32, 32, 0, 0),
+    # 8 input channels (K = 8 per tap): the network's first conv on the 8-channel repack of the input
+    (8, 0, 64, 3, 1, 0, 2, 40, 36, 0, 0)]
 
 
 @pytest.mark.parametrize("ca,cb,cout,ks,stride,up,B,H,W,residual,out_nchw", TF32_CONV_CASES)
