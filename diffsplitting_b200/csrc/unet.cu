@@ -203,6 +203,7 @@ struct ds_unet {
     size_t arena_bf16_bytes = 0;
     float* d_arena = nullptr;
     uint8_t* d_arena_bf16 = nullptr;
+    int arena_device = -1;               // device the weight arenas (and streams / events) were created on: the handle is bound to it
     bool weights_ready = false;
     std::vector<Plan*> plans;
     bool keep_taps = false;
@@ -808,8 +809,18 @@ extern "C" int ds_unet_create(const ds_unet_desc* desc, ds_unet** out) {
     return DS_OK;
 }
 
+// the handle's device becomes current for the scope (weights, streams and events live there)
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) {
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" void ds_unet_destroy(ds_unet* n) {
     if (!n) return;
+    DeviceScope scope(n->arena_device);
     if (n->d_arena) cudaFree(n->d_arena);
     if (n->d_arena_bf16) cudaFree(n->d_arena_bf16);
     if (n->side_stream) cudaStreamDestroy(n->side_stream);
@@ -837,7 +848,13 @@ extern "C" int ds_unet_weight_shape(const ds_unet* n, int i, int32_t* ndim, int6
 extern "C" int ds_unet_load_weights(ds_unet* n, const ds_tensor_view* ws, int cnt, void* stream) {
     DS_REQUIRE(n && ws && cnt > 0, "unet_load_weights: null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    int cur_dev = -1;
+    DS_CHECK_CUDA(cudaGetDevice(&cur_dev));
+    DS_REQUIRE(n->arena_device < 0 || n->arena_device == cur_dev,
+               "unet_load_weights: this handle's weights live on device %d, the current device is %d (create a new handle per device)",
+               n->arena_device, cur_dev);
     if (!n->d_arena) {
+        n->arena_device = cur_dev;
         DS_CHECK_CUDA(cudaMalloc(&n->d_arena, n->arena_floats * sizeof(float)));
         DS_CHECK_CUDA(cudaMemsetAsync(n->d_arena, 0, n->arena_floats * sizeof(float), st));
         DS_CHECK_CUDA(cudaMalloc(&n->d_arena_bf16, n->arena_bf16_bytes ? n->arena_bf16_bytes : 256));
@@ -990,6 +1007,12 @@ static int run_forward(ds_unet* n, const float* d_xa, int ca, const float* d_xb,
     DS_REQUIRE(!n->d.with_time_emb || (d_time && (time_len == 1 || time_len == B)),
                "unet_forward: time must have 1 or B=%d entries (got %d)", B, time_len);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int cur_dev = -1;
+        DS_CHECK_CUDA(cudaGetDevice(&cur_dev));
+        DS_REQUIRE(cur_dev == n->arena_device, "unet_forward: the handle's weights live on device %d, the current device is %d", n->arena_device,
+                   cur_dev);
+    }
     Plan* p = nullptr;
     int rc = get_plan(n, B, H, W, precision, &p);
     if (rc != DS_OK) return rc;

@@ -84,9 +84,11 @@ class UNet(nn.Module):
             d.attn_res[i] = int(r)
         d.res_blocks, d.image_size, d.with_time_emb = self.res_blocks, self.image_size, int(self.with_time_emb)
         d.tf32_weights = int(self.precision == "tf32")
+        self._desc = d
         handle = C.c_void_p()
         _lib.check(_lib.lib().ds_unet_create(C.byref(d), C.byref(handle)))
         self._handle = handle
+        self._handle_device = None            # CUDA device the library-side weight arenas live on (set by the first commit)
         self._names = []
         self._build_tree()
         self._sig = None
@@ -167,6 +169,15 @@ class UNet(nn.Module):
             return
         for t in ts:
             _lib.require_cuda(t, "UNet parameter")
+        dev = ts[0].device
+        if self._handle_device is not None and dev != self._handle_device:
+            # .to(another GPU): the handle's arenas, streams and events are bound to the device of the first commit -> new handle
+            _lib.lib().ds_unet_destroy(self._handle)
+            handle = C.c_void_p()
+            _lib.check(_lib.lib().ds_unet_create(C.byref(self._desc), C.byref(handle)))
+            self._handle = handle
+            self._ws = {}
+        self._handle_device = dev
         views = (_lib.TensorView * len(ts))()
         keep = []
         for i, (name, t) in enumerate(zip(self._names, ts)):

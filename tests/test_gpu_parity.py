@@ -449,6 +449,23 @@ def test_unet_matches_oracle(name, cfg, B, H, W, cond, precision):
     assert e <= tol(net, precision)[0] and r <= tol(net, precision)[1]
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_unet_follows_its_parameters_to_another_gpu():
+    """The library-side weight arenas are bound to the device of the first commit: after ``.to('cuda:1')`` the
+    wrapper creates a fresh handle there, and both placements give the same result."""
+    cfg = U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4), (), 1, 32)
+    sd = U.random_state_dict(cfg, seed=5)
+    net = build(cfg, sd, "fp32")
+    g = torch.Generator().manual_seed(2)
+    x, t = torch.randn((2, 1, 32, 32), generator=g), torch.rand((2,), generator=g)
+    y0 = net(x.to("cuda:0"), t.to("cuda:0")).cpu()
+    net = net.to("cuda:1")
+    y1 = net(x.to("cuda:1"), t.to("cuda:1")).cpu()
+    assert torch.equal(y0, y1)
+    net = net.to("cuda:0")
+    assert torch.equal(net(x.to("cuda:0"), t.to("cuda:0")).cpu(), y0)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "auto"])
 @pytest.mark.parametrize("name,cfg,H,W,cond", [
     ("hagen_512", U.make_cfg("ddpm", 1, 1, 16, 16, (1, 2, 4, 8), (), 1, 32), 512, 512, 0),
