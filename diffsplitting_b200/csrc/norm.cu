@@ -388,9 +388,12 @@ template <typename Tout>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_tab_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b,
                                                                    int cb, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, Tout* __restrict__ out, int HW,
-                                                                   int G, int nchunk, int swish, const float2* __restrict__ stats) {
+                                                                   int G, int nchunk, int swish, const float2* __restrict__ stats, int reverse) {
     extern __shared__ float2 gn_tab[];                 // [C] (scale, shift):  y = x * scale + shift
-    const int C = ca + cb, cpg = C / G, bi = blockIdx.y, t = threadIdx.x;
+    // reverse: walk the tensor back to front.  The producer conv wrote it front to back, so its tail is what is still in L2 (126 MB
+    // of a 0.13 - 0.8 GB tensor); and the consumer conv, which reads front to back, finds the head of THIS kernel's output there
+    const int C = ca + cb, cpg = C / G, bi = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, t = threadIdx.x;
+    const int chunk = reverse ? nchunk - 1 - (int)blockIdx.x : (int)blockIdx.x;
     constexpr bool kFast = sizeof(Tout) == 2;
     pdl_wait();
     pdl_trigger();
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_tab_kernel(const float* _
     const size_t base = (size_t)bi * HW;
     const int q = C >> 2;
     const int64_t total = (int64_t)HW * q;
-    const int64_t v0 = total * blockIdx.x / nchunk, v1 = total * (blockIdx.x + 1) / nchunk;
+    const int64_t v0 = total * chunk / nchunk, v1 = total * (chunk + 1) / nchunk;
     auto one = [&](int64_t v) {
         const int p = (int)(v / q), c = (int)(v - (int64_t)p * q) * 4;
         const float4 x = load4(a, ca, b, cb, base + p, c);
@@ -454,8 +457,10 @@ int launch_gn_apply_sums(const float* a, int ca, const float* b, int cb, const d
         if (nchunk > 65535) nchunk = 65535;
         const dim3 grid(nchunk, B);
         const size_t smem = (size_t)C * sizeof(float2);
-        if (out_bf16) launch_pdl(gn_apply_tab_kernel<bf>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, (const float2*)stats);
-        else launch_pdl(gn_apply_tab_kernel<float>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, (const float2*)stats);
+        static int rev = -1;
+        if (rev < 0) { const char* e = getenv("DIFFSPLIT_B200_GN_REVERSE"); rev = e ? atoi(e) : 1; }
+        if (out_bf16) launch_pdl(gn_apply_tab_kernel<bf>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (bf*)out, HW, G, nchunk, swish, (const float2*)stats, rev);
+        else launch_pdl(gn_apply_tab_kernel<float>, grid, dim3(GN_THREADS), smem, st, a, ca, b, cb, gamma, beta, (float*)out, HW, G, nchunk, swish, (const float2*)stats, rev);
         DS_CHECK_LAUNCH("gn_apply_tab");
         return DS_OK;
     }

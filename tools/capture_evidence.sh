@@ -1,3 +1,4 @@
+# Evidence captures of profiles/ (round 2): run on the GPU box as  gpurun -- bash tools/capture_evidence.sh ; outputs in gpurun_out/
 set -x
 B="python bench.py --steps 2 --warmup 1 --no-graph --no-extras --no-cpu-baseline --e2e-calls 0"
 $B > gpurun_out/r2_ev_plain.json 2> gpurun_out/r2_ev_plain.err || exit 1
