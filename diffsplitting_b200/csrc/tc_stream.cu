@@ -264,15 +264,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 SK_T0();
                 const uint32_t a_lo0 = (((base + op_off + (uint32_t)s * p.op_bytes) & 0x3FFFFu) >> 4) | ((plane_bytes >> 4) << 16);
                 const uint32_t acc = tmem_base + (uint32_t)(s * p.BN);
-                uint32_t b_lo = b_lo0;
+                // one thread issues everything: taps unrolled (constant shifts), descriptors = one 64-bit add per operand and MMA
+                const uint64_t a_d0 = ((uint64_t)desc_hi << 32) | a_lo0, b_d0 = ((uint64_t)desc_hi << 32) | b_lo0;
+                const int ks = p.ksteps;
+                uint64_t b_d = b_d0;
+                uint32_t first = 0;
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const int r = tap / 3, sx = tap - 3 * r;
-                    uint32_t a_lo = a_lo0 + (uint32_t)(r * SK_PW + sx);
-                    for (int kk = 0; kk < p.ksteps; ++kk) {
-                        if (TF32) umma_tf32(acc, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
-                        else umma_bf16(acc, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (tap | kk) ? 1u : 0u);
-                        a_lo += a_kstep;
-                        b_lo += b_kstep;
+                    uint64_t a_d = a_d0 + (uint64_t)((tap / 3) * SK_PW + tap % 3);
+#pragma unroll 2
+                    for (int kk = 0; kk < ks; ++kk) {
+                        umma<TF32>(acc, a_d, b_d, idesc, first);
+                        first = 1u;
+                        a_d += a_kstep;
+                        b_d += b_kstep;
                     }
                 }
                 umma_commit(empty_op(s));         // the operand image may be overwritten once these MMAs have read it
@@ -470,54 +475,69 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
             SK_T0();
             uint32_t src = base + raw_off + (uint32_t)r * p.raw_bytes + src_first;
             uint32_t dst = base + op_off + (uint32_t)s * p.op_bytes + dst_first;
-#pragma unroll 1
-            for (int px = px_first; px < SK_PATCH_PX; px += px_step, src += (uint32_t)px_step * src_pitch, dst += (uint32_t)px_step * 16u) {
-                const int pr = px / SK_PW, pc = px - pr * SK_PW;
-                uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                if ((unsigned)(y0 + pr - 1) < (unsigned)p.H && (unsigned)(x0 + pc - 1) < (unsigned)p.W) {
-                    float x[CPP];
-                    {
-                        float4 v0;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src));
-                        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-                        if (!TF32) {
-                            float4 v1;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + 16u));
-                            x[CPP - 4] = v1.x; x[CPP - 3] = v1.y; x[CPP - 2] = v1.z; x[CPP - 1] = v1.w;
-                        }
-                    }
+            // two patch pixels per iteration: the two load -> fma -> ex2 -> rcp -> cvt -> store chains are independent, so their
+            // latencies overlap (one pixel per iteration: ~400 cycles each, the transform bound the 16-channel layers)
+            auto xform = [&](float (&x)[CPP]) -> uint4 {
 #pragma unroll
-                    for (int j = 0; j < CPP / 2; ++j) {
-                        x[2 * j] = fmaf(x[2 * j], sc[j].x, sc[j].y);
-                        x[2 * j + 1] = fmaf(x[2 * j + 1], sc[j].z, sc[j].w);
-                    }
-                    if (p.swish) {
+                for (int j = 0; j < CPP / 2; ++j) {
+                    x[2 * j] = fmaf(x[2 * j], sc[j].x, sc[j].y);
+                    x[2 * j + 1] = fmaf(x[2 * j + 1], sc[j].z, sc[j].w);
+                }
+                if (p.swish) {
 #pragma unroll
-                        for (int j = 0; j < CPP; ++j) {
-                            if (TF32) {
-                                x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));
-                            } else {                    // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
-                                const float h = 0.5f * x[j];
-                                float th;
-                                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                                x[j] = fmaf(h, th, h);
-                            }
+                    for (int j = 0; j < CPP; ++j) {
+                        if (TF32) {
+                            x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));
+                        } else {                    // y * sigmoid(y) = h * tanh(h) + h, h = y / 2: one MUFU op
+                            const float h = 0.5f * x[j];
+                            float th;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                            x[j] = fmaf(h, th, h);
                         }
-                    }
-                    if (TF32) {
-                        val = make_uint4(__float_as_uint(to_tf32(x[0])), __float_as_uint(to_tf32(x[1])), __float_as_uint(to_tf32(x[2])),
-                                         __float_as_uint(to_tf32(x[3])));
-                    } else {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(x[(2 * j) % CPP], x[(2 * j + 1) % CPP]);
-                            w[j] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        val = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+                if (TF32) {
+                    return make_uint4(__float_as_uint(to_tf32(x[0])), __float_as_uint(to_tf32(x[1])), __float_as_uint(to_tf32(x[2])),
+                                      __float_as_uint(to_tf32(x[3])));
+                } else {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(x[(2 * j) % CPP], x[(2 * j + 1) % CPP]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    return make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            };
+            auto load_px = [&](uint32_t a, float (&x)[CPP]) {
+                float4 v0;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(a));
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                if (!TF32) {
+                    float4 v1;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(a + 16u));
+                    x[CPP - 4] = v1.x; x[CPP - 3] = v1.y; x[CPP - 2] = v1.z; x[CPP - 1] = v1.w;
+                }
+            };
+            auto inside = [&](int px) {
+                const int pr = px / SK_PW, pc = px - pr * SK_PW;
+                return (unsigned)(y0 + pr - 1) < (unsigned)p.H && (unsigned)(x0 + pc - 1) < (unsigned)p.W;
+            };
+            const uint32_t sstep = (uint32_t)px_step * src_pitch, dstep = (uint32_t)px_step * 16u;
+#pragma unroll 1
+            for (int px = px_first; px < SK_PATCH_PX; px += 2 * px_step, src += 2u * sstep, dst += 2u * dstep) {
+                const int px2 = px + px_step;
+                const bool have2 = px2 < SK_PATCH_PX;
+                float xa[CPP], xb[CPP];
+                load_px(src, xa);
+                load_px(have2 ? src + sstep : src, xb);            // (a repeated in-range address when there is no second pixel)
+                const bool in1 = inside(px), in2 = have2 && inside(px2);
+                uint4 va = xform(xa), vb = xform(xb);
+                if (!in1) va = make_uint4(0u, 0u, 0u, 0u);         // the conv's zero padding is applied AFTER the normalisation
+                if (!in2) vb = make_uint4(0u, 0u, 0u, 0u);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(va.x), "r"(va.y), "r"(va.z), "r"(va.w) : "memory");
+                if (have2)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + dstep), "r"(vb.x), "r"(vb.y), "r"(vb.z), "r"(vb.w) : "memory");
             }
             fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
