@@ -38,13 +38,14 @@ constexpr int SK_PLANE_PX = 169;                         // + the rows the last 
                                                          // the 8 planes a quarter-warp stores to hit 8 different bank groups
 constexpr int SK_NRAW = 2;
 constexpr int SK_STG_LD = 20;                            // row pitch (floats) of the epilogue staging buffer: conflict-free STS.128
-constexpr uint32_t SK_RED_BYTES = 128 * SK_STG_LD * 4;                     // per epilogue group
+constexpr uint32_t SK_RED_BYTES = 128 * SK_STG_LD * 4;                     // one staging buffer; two per epilogue group
+constexpr uint32_t SK_RES_BOX_BYTES = SK_STG_LD * SK_PW * SK_TH * 4;       // residual box {20 ch, 18, 7}: rows of the staging layout
 constexpr size_t SK_SMEM_LIMIT = 225 * 1024;
 
 struct StreamParams {
     CUtensorMap wmap;                 // packed weights (halo_pack_conv_weight image), as in conv_halo_kernel
     CUtensorMap rmap[2];              // raw fp32 sources as (C, W, H, B) tensors, box {c, 18, 9, 1}
-    CUtensorMap resmap;               // the fp32 residual as a (Cout, W, H, B) tensor, box {BN, 16, 7, 1}: L2 prefetch only
+    CUtensorMap resmap;               // the fp32 residual as a (Cout, W, H, B) tensor, box {20, 18, 7, 1} = one chunk in the staging layout
     int ca, cb, C;
     const double* sums_a; const double* sums_b;       // per-channel fp64 (sum, sumsq) [copies][B][c][2], or
     const float2* stats;                               // (mean, rstd) [B][G]; all null: no normalisation
@@ -56,7 +57,7 @@ struct StreamParams {
     int tiles_x, tiles_y, n_tiles_m;
     FastDiv div_tiles_x, div_tiles_xy;
     uint32_t raw_bytes, raw_a_bytes, op_bytes, b_bytes;
-    int res_prefetch;                 // resmap is valid
+    int res_prefetch;                 // resmap is valid: the residual arrives by TMA in the staging buffers
     long long* dbg;                   // DIFFSPLIT_B200_STREAM_DBG: per-role wait / work cycle sums of CTA 0 (16 slots)
     TraceSlot trace;
 };
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
     auto full_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 4 + s); };
     auto empty_acc = [&](int s) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 6 + s); };
     const uint32_t wfull = bars + 8u * (uint32_t)(2 * SK_NRAW + 8), tmem_slot = wfull + 8u;
-    uint8_t* red = gbase + ((bar_off + 8u * (uint32_t)(2 * SK_NRAW + 10) + 15u) & ~15u);      // SK_EPI_GROUPS x SK_RED_BYTES
+    auto rfull = [&](int g, uint32_t buf) { return bars + 8u * (uint32_t)(2 * SK_NRAW + 10) + 16u * (uint32_t)g + 8u * buf; };
+    uint8_t* red = gbase + ((bar_off + 8u * (uint32_t)(2 * SK_NRAW + 14) + 127u) & ~127u);    // SK_EPI_GROUPS x 2 x SK_RED_BYTES, 128-byte aligned (TMA destination)
     const int nt = blockIdx.y;
     const uint32_t tmem_cols = 2u * (uint32_t)p.BN <= 32u ? 32u : (2u * (uint32_t)p.BN <= 64u ? 64u : (2u * (uint32_t)p.BN <= 128u ? 128u : (2u * (uint32_t)p.BN <= 256u ? 256u : 512u)));
     const int my_tiles = ((int)blockIdx.x < p.n_tiles_m) ? (p.n_tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
             mbar_init(full_acc(s), 1); mbar_init(empty_acc(s), 4 * ((p.BN >> 4) >= SK_EPI_GROUPS ? SK_EPI_GROUPS : 1));   // BN = 16: one group per buffer
         }
         mbar_init(wfull, 1);
+        for (int g = 0; g < SK_EPI_GROUPS; ++g) { mbar_init(rfull(g, 0), 1); mbar_init(rfull(g, 1), 1); }
         fence_barrier_init();
         // weights: constant data, fetched before the predecessor kernel has finished
         mbar_expect_tx(wfull, p.b_bytes);
@@ -168,13 +171,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         const uint32_t dst = base + raw_off + (uint32_t)s * p.raw_bytes;
         tma_load_4d(dst, &p.rmap[0], full_raw(s), 0, x0 - 1, y0 - 1, b);
         if (p.cb) tma_load_4d(dst + p.raw_a_bytes, &p.rmap[1], full_raw(s), 0, x0 - 1, y0 - 1, b);
-        // The epilogue reads the residual with ordinary loads three pipeline stages later: from HBM those are bound by the
-        // outstanding misses an SM's L1 can track (measured: ~6 B/clk per SM, the epilogue stalled on its load addresses);
-        // the copy engine pulls the tile into L2 now, so they become L2 hits.
-        if (p.res_prefetch)
-            asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(&p.resmap)),
-                         "r"(nt * p.BN), "r"(x0), "r"(y0), "r"(b)
-                         : "memory");
     };
     if (warp == 0 && elect_one()) {            // the first patches travel while the scale / shift table is built
         for (int i = 0; i < SK_NRAW && i < my_tiles; ++i) issue_raw(i);
@@ -303,7 +299,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int te = tid - 128 - gi * 128;
-        float* stg = reinterpret_cast<float*>(red + (size_t)gi * SK_RED_BYTES);      // [128][20] staging
+        float* stg = reinterpret_cast<float*>(red + (size_t)gi * 2 * SK_RED_BYTES);      // two [128][20] staging buffers
         const int nchunks = p.BN >> 4;
         // BN >= 32: group gi takes chunks gi, gi + 2 of EVERY tile;  BN = 16 (one chunk): the groups take alternate TILES (group gi =
         // accumulator buffer gi), so both halves of the epilogue warps work and a tile may take two tile periods to drain
@@ -369,13 +365,34 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 }
             }
         };
+        // The fp32 residual: read with ordinary loads from HBM it is bound by the misses an SM's L1 can track (~6 B/clk per SM: the
+        // epilogue took 5 k cycles per chunk); instead thread 0 of the group has TMA bring the chunk (box {20 ch, 18, 7} = the
+        // staging layout, rows m = 18 pr + pc) into the staging buffer two chunks ahead, and the ROW view adds the accumulator to it.
+        const bool rtma = p.res_prefetch != 0;
+        const bool rldg = p.epi.residual != nullptr && !rtma;
+        int qi = i_first, qk = 0;
+        uint32_t qn = 0, cn = 0;
+        auto issue_next = [&]() {
+            if (qi >= my_tiles) return;
+            int qb, qy0, qx0;
+            tile_coords(qi, qb, qy0, qx0);
+            const int c0 = alt ? 0 : (gi + SK_EPI_GROUPS * qk) * 16;
+            const uint32_t buf = qn & 1u;
+            mbar_expect_tx(rfull(gi, buf), SK_RES_BOX_BYTES);
+            tma_load_4d(smem_u32(stg) + buf * SK_RED_BYTES, &p.resmap, rfull(gi, buf), nt * p.BN + c0, qx0, qy0, qb);
+            ++qn;
+            if (++qk == ncg) { qk = 0; qi += i_step; }
+        };
+        if (rtma && te == 0 && ncg > 0) { issue_next(); issue_next(); }
         if (i_first < my_tiles) {
             int b = 0, off[4], b_acc = -1;
             offsets(i_first, b, off);
             b_acc = b;
+            if (rldg) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-                if (k < ncg) load_res(off, k, res[k]);
+                for (int k = 0; k < 2; ++k)
+                    if (k < ncg) load_res(off, k, res[k]);
+            }
 #pragma unroll 1
             for (int i = i_first;; i += i_step) {
                 if (p.epi.sums_out && (i >= my_tiles || b != b_acc)) { flush(b_acc); b_acc = b; }      // the one call site of flush
@@ -394,6 +411,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                 for (int kk = 0; kk < 2; ++kk) {
                     if (kk < ncg) {
                         const int c0 = alt ? 0 : (gi + SK_EPI_GROUPS * kk) * 16;
+                        const uint32_t buf = cn & 1u;
+                        float* const sb = stg + buf * (128 * SK_STG_LD);
                         // ---- phase 1 (ROW view)
                         uint32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.BN + c0), v);
@@ -404,12 +423,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                         }
                         {
                             const float4* btv = reinterpret_cast<const float4*>(bt + b * p.BN + c0);
-                            float4* row = reinterpret_cast<float4*>(stg + m * SK_STG_LD);
+                            float4* row = reinterpret_cast<float4*>(sb + m * SK_STG_LD);
+                            if (rtma) {
+                                mbar_wait_relaxed(rfull(gi, buf), (cn >> 1) & 1u);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float4 a = btv[e];
-                                row[e] = make_float4(__uint_as_float(v[4 * e]) + a.x, __uint_as_float(v[4 * e + 1]) + a.y,
-                                                     __uint_as_float(v[4 * e + 2]) + a.z, __uint_as_float(v[4 * e + 3]) + a.w);
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 a = btv[e], rs = row[e];
+                                    row[e] = make_float4(__uint_as_float(v[4 * e]) + a.x + rs.x, __uint_as_float(v[4 * e + 1]) + a.y + rs.y,
+                                                         __uint_as_float(v[4 * e + 2]) + a.z + rs.z, __uint_as_float(v[4 * e + 3]) + a.w + rs.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 a = btv[e];
+                                    row[e] = make_float4(__uint_as_float(v[4 * e]) + a.x, __uint_as_float(v[4 * e + 1]) + a.y,
+                                                         __uint_as_float(v[4 * e + 2]) + a.z, __uint_as_float(v[4 * e + 3]) + a.w);
+                                }
                             }
                         }
                         if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -417,9 +446,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                         const int n0 = nq + 32 * kk;
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            float4 x = *reinterpret_cast<const float4*>(stg + (r0 + 32 * jj) * SK_STG_LD + quad * 4);
+                            float4 x = *reinterpret_cast<const float4*>(sb + (r0 + 32 * jj) * SK_STG_LD + quad * 4);
                             if (off[jj] < 0 || n0 >= Cout) continue;
-                            if (p.epi.residual) { x.x += res[kk][jj].x; x.y += res[kk][jj].y; x.z += res[kk][jj].z; x.w += res[kk][jj].w; }
+                            if (rldg) { x.x += res[kk][jj].x; x.y += res[kk][jj].y; x.z += res[kk][jj].z; x.w += res[kk][jj].w; }
                             if (vec_ok) {
                                 const int o = off[jj] + 32 * kk;
                                 if (p.epi.out_f32) *reinterpret_cast<float4*>(p.epi.out_f32 + o) = x;
@@ -440,9 +469,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) conv_stream_kernel(const __grid
                             acc[kk][4] = fmaf(x.x, x.x, acc[kk][4]); acc[kk][5] = fmaf(x.y, x.y, acc[kk][5]);
                             acc[kk][6] = fmaf(x.z, x.z, acc[kk][6]); acc[kk][7] = fmaf(x.w, x.w, acc[kk][7]);
                         }
-                        load_res(off_next, kk, res[kk]);      // next tile's residual into the registers just consumed
-                        // orders this chunk's reads of the staging buffer before the next chunk's writes
-                        if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (rldg) load_res(off_next, kk, res[kk]);      // next tile's residual into the registers just consumed
+                        // two staging buffers: the next chunk writes the other one and its mid-chunk barrier orders this chunk's reads
+                        // before the chunk after next; only the TMA refill of THIS buffer needs everyone to be done with it now
+                        if (rtma) {
+                            if (gi == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                            if (te == 0) { fence_proxy_async(); issue_next(); }
+                        }
+                        ++cn;
                     }
                 }
                 b = b_next;
@@ -563,7 +597,7 @@ static size_t stream_smem_bytes(int C, int BN, int B, int es) {
     const size_t op_bytes = (size_t)(C * es / 16) * SK_PLANE_PX * 16;
     const size_t raw_bytes = (size_t)SK_PATCH_PX * C * 4;
     return 1024 + align_up(b_bytes, 128) + align_up(2 * op_bytes, 128) + SK_NRAW * raw_bytes + 128 + (size_t)B * C * 8 + 16 +
-           (size_t)B * BN * 4 + 16 + 8 * (2 * SK_NRAW + 10) + 16 + SK_EPI_GROUPS * SK_RED_BYTES + 256;
+           (size_t)B * BN * 4 + 16 + 8 * (2 * SK_NRAW + 14) + 128 + SK_EPI_GROUPS * 2 * SK_RED_BYTES + 256;
 }
 
 static int stream_weight_loads(int C, int es) {
@@ -674,7 +708,7 @@ int stream_launch_conv(const float* src_a, int ca, const float* src_b, int cb, c
     if (epi.residual) {
         cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)W * cout * 4, (cuuint64_t)H * W * cout * 4};
-        cuuint32_t box[4] = {(cuuint32_t)(p.BN < cout ? p.BN : cout), SK_TW, SK_TH, 1};
+        cuuint32_t box[4] = {SK_STG_LD, SK_PW, SK_TH, 1};         // one 16-channel chunk (+ 4) of a tile in the staging layout
         cuuint32_t estr[4] = {1, 1, 1, 1};
         static int respf_env = -1;
         if (respf_env < 0) { const char* e5 = getenv("DIFFSPLIT_B200_STREAM_RESPF"); respf_env = e5 ? atoi(e5) : 1; }

@@ -575,6 +575,7 @@ def test_seeded_loops_replay_the_reference_rng_stream(graph, monkeypatch):
     (cfg, sd), (cfgd, sdd), (cfgi, sd1, sd2) = _nets()
     g = torch.Generator().manual_seed(1)
     cond = torch.rand((2, 1, 16, 16), generator=g) * 2 - 1
+    torch.cuda.init()                                  # default_generators is empty until CUDA is initialised (test run on its own)
     gen = torch.cuda.default_generators[0]
     tab = S.schedule_tables(SCHED)
     # SR3: initial draw + one per step with t > 0
