@@ -406,14 +406,18 @@ def tiles_leg(device, rank, world, precision, barrier):
 
         run()                            # warm-up: graph capture, NCCL connection
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        e0.record()
         out = run()
+        e1.record()
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        wall = time.perf_counter() - t0
+        dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=device)      # device time, max over ranks
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if rank == 0:
-            res[f"T{T}"] = {"tiles_per_sec": len(tf) / float(dt), "seconds": float(dt), "unet_steps_per_tile": 2 * T,
+            res[f"T{T}"] = {"tiles_per_sec": len(tf) / float(dt), "seconds": float(dt), "seconds_wall_rank0": wall, "unet_steps_per_tile": 2 * T,
                             "unet_steps_per_sec": len(tf) * 2 * T / float(dt),
                             "stitched_shape": list(out.shape), "checksum": float(out.double().sum()),
                             "checksum_abs": float(out.double().abs().sum())}
