@@ -442,6 +442,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if os.environ.get("BENCH_BATCH"):                  # probing only (L2-residency experiments): not a bench configuration
+        w = dict(w, B=int(os.environ["BENCH_BATCH"]))
     if args.no_graph:
         os.environ["DIFFSPLIT_B200_GRAPH"] = "0"
     rank = int(os.environ.get("RANK", "0"))
