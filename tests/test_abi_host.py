@@ -309,3 +309,29 @@ def test_indi_last_step_rounding_is_tolerated():
     S.indi_one_step(lambda x, t: x, torch.zeros(1, 1, 2, 2), d, cur, 0.01, torch.zeros(1, 1, 2, 2), strict=False)
     with pytest.raises(AssertionError):
         indi.inference_one_step(torch.zeros(1, 1, 2, 2), 0.2, 0.1)       # a genuinely too large delta still asserts
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (no GPU needed): one JSON line with the contract's keys, the unmodified reference from
+    baseline/_ref when it is installed, and the same `config` dict our own arm prints for that workload."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cifar10_ddpm_32_b1_T50",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "unet_denoising_steps_per_sec" and d["unit"] == "steps/s" and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    from baseline import refshim
+    assert d["cpu_baseline"]["kind"] == ("reference" if refshim.available() else "port")
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.config_dict("cifar10_ddpm_32_b1_T50", bench.WORKLOADS["cifar10_ddpm_32_b1_T50"])
