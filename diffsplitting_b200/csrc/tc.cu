@@ -213,6 +213,7 @@ struct TcpParams {
     CUtensorMap resmap;               // fp32 residual as (Cout, W, H, B), box {20, 8, 16, 1} = one chunk in the staging layout
     int res_tma, n_items;             // res_tma: the fp32 residual arrives through resmap (box {20, 8, 16, 1}) in the staging buffers
            // work items = (M supertile, N tile[, output parity class]), N (class) fastest
+    int ngroups;                      // epilogue groups in use: 4, or 3 (BN = 128 with 128-byte rows: shared memory goes to the weight ring)
     int up;                           // nearest x2 upsample + 3x3 as four 2x2 convs on the low-res patch (geo 1 only): H, W = low-res
                                       //    size, item class (a, b) writes the output pixels (2y + a, 2x + b); w = [class][tap][chunk]
     uint32_t class_bytes;             // packed weight bytes per class
@@ -425,13 +426,13 @@ __global__ void __launch_bounds__(TP_THREADS) conv_tcp_kernel(const __grid_const
 //   warp 0       TMA producer: per 64-channel chunk one (7 MT + 2) x 18 patch (ring of 2) + 9 weight tiles (ring of wstages);
 //                L2 prefetch of the item's residual tile
 //   warp 1       MMA issuer: 9 taps x MT tiles x 4 k-steps per chunk into ACC[i & 1]
-//   warps 4-15   epilogue, three groups of four warps (one per TMEM lane quadrant) sharing the item's 16-column chunks, each chunk
+//   warps 2-17   epilogue, four (or three) groups of four warps (one per TMEM lane quadrant) sharing the item's 16-column chunks, each chunk
 //                in two views (as conv_stream_kernel): ROW view  tcgen05.ld + (bias + conditioning vector) -> staging buffer;
 //                QUAD view  + residual (requested one chunk ahead), fp32 / bf16 stores with 64 contiguous bytes per four lanes,
 //                statistics in registers, folded once per item
 constexpr int TS_MT = 2;
-constexpr int TS_THREADS = 512;            // warps 0, 1 as above, 2-3 idle, 4-15 epilogue (three groups)
-constexpr int TS_EGROUPS = 3;
+constexpr int TS_THREADS = 576;            // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue: up to four groups of four warps
+constexpr int TS_EGROUPS = 4;              // most epilogue groups (TcpParams::ngroups = 3 when four staging areas do not fit)
 constexpr int TS_STG_LD = 20;
 constexpr uint32_t TS_STG_BUF = 128 * TS_STG_LD * 4;                 // one staging buffer [128][20] fp32
 constexpr uint32_t TS_STG_BYTES = 2 * TS_STG_BUF + 128 * 4;          // per group: two staging buffers + (bias + temb) of the item's BN channels
@@ -546,8 +547,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     const uint32_t w_bytes = (uint32_t)p.BN * row_bytes;
     const uint32_t wstage_bytes = (w_bytes + 1023u) & ~1023u;
     const uint32_t wring = base + 2u * p.patch_bytes;
-    const uint32_t stg_off = 2u * p.patch_bytes + (uint32_t)p.wstages * wstage_bytes;      // TS_EGROUPS x TS_STG_BYTES
-    const uint32_t bar_base = base + stg_off + (uint32_t)TS_EGROUPS * TS_STG_BYTES;
+    const int NG = p.ngroups;
+    const uint32_t stg_off = 2u * p.patch_bytes + (uint32_t)p.wstages * wstage_bytes;      // NG x TS_STG_BYTES
+    const uint32_t bar_base = base + stg_off + (uint32_t)NG * TS_STG_BYTES;
     auto wfull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto wempty = [&](int s) { return bar_base + 8u * (uint32_t)(p.wstages + s); };
     const uint32_t b2 = bar_base + 16u * (uint32_t)p.wstages;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
     const uint32_t acc_cols = (uint32_t)(TS_MT * p.BN);
     const uint32_t tmem_cols = 2u * acc_cols <= 32u ? 32u : (2u * acc_cols <= 64u ? 64u : (2u * acc_cols <= 128u ? 128u : (2u * acc_cols <= 256u ? 256u : 512u)));
     const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int egroups = cpt * TS_MT >= TS_EGROUPS ? TS_EGROUPS : cpt * TS_MT;          // epilogue groups with work
+    const int egroups = cpt * TS_MT >= NG ? NG : cpt * TS_MT;                         // epilogue groups with work
 
     trace_begin(p.trace);
     if (warp == 0 && elect_one()) {
@@ -646,21 +648,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
-        const int gi = (warp - 4) >> 2;                          // epilogue group 0..2
-        const int q = warp & 3;
+    } else if (warp >= 2 && ((warp - 2) >> 2) < NG) {
+        const int gi = (warp - 2) >> 2;                          // epilogue group 0 .. NG - 1 (any four consecutive warps cover the
+        const int q = warp & 3;                                  // four TMEM lane quadrants: a warp reads lanes [32 (warp % 4), + 32))
         const int m = q * 32 + lane;
-        const int te = (tid - 128) & 127;
+        const int te = tid - 64 - gi * 128;
         float* stg = reinterpret_cast<float*>(gbase + stg_off + (uint32_t)gi * TS_STG_BYTES);
         float* btv = stg + 2 * 128 * TS_STG_LD;                  // [BN <= 128] bias + conditioning vector of the item
         const int quad = te & 3, r0 = te >> 2;
         const int Cout = p.epi.Cout;
         const bool vec_ok = (Cout & 3) == 0 && !p.epi.out_nchw;
         const int lcpt = 31 - __clz(cpt);                        // BN is a power of two
-        // the item's chunks (tile t, 16-column block c) are dealt to the three groups by column when a tile has 8 of them (a group
-        // then touches at most 3 columns: its statistics stay in 3 register slots), else by chunk index g = t cpt + c (<= 4 columns)
-        const bool bycol = cpt == 8;
-        const int n_mine = bycol ? TS_MT * ((cpt - gi + 2) / 3) : (TS_MT * cpt > gi ? (TS_MT * cpt - gi + 2) / 3 : 0);
+        // the item's chunks (tile t, 16-column block c) are dealt to the groups so that a group touches at most 3 columns (its
+        // statistics stay in 3 register slots): four groups - by chunk index g = t cpt + c = gi, gi + 4, ... (columns gi mod cpt and
+        // + 4); three groups (only with 8 columns per tile) - by column c = gi, gi + 3, gi + 6, both tiles of a column in turn
+        const bool bycol = NG == 3;
+        const int n_mine = bycol ? TS_MT * ((cpt - gi + 2) / 3) : (TS_MT * cpt > gi ? (TS_MT * cpt - gi + 3) / 4 : 0);
         const float* const resp = p.epi.residual;
         float* const o32 = p.epi.out_f32;
         __nv_bfloat16* const o16 = p.epi.out_b16;
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     qc += 3;
                     if (qc >= 8) { qc = gi; ++qt; }
                 } else {
-                    const int g = (qt << lcpt) + qc + 3;
+                    const int g = (qt << lcpt) + qc + 4;
                     qt = g >> lcpt; qc = g & (cpt - 1);
                 }
                 if (qt >= TS_MT) { ++qi; qt = t_first; qc = c_first; }
@@ -732,26 +735,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                     }
                 }
                 const int nbase = nt * p.BN + quad * 4;
-                float acc[4][8];                                  // statistics per column slot of this group
+                float acc[3][8];                                  // statistics per column slot of this group
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 3; ++k)
 #pragma unroll
                     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-                // residual of chunk (t, c) -> rr: issued one chunk ahead, into the registers the current chunk has just consumed
-                float4 rr[4];
-                auto load_res = [&](int t, int c, int jj) {
-                    const int n0 = nbase + c * 16;
-                    const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
-                    if (o < 0 || n0 >= Cout) return;
-                    const float* src = resp + o + n0;
-                    rr[jj] = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
-                };
-                int t = t_first, c = c_first, slot = bycol ? 0 : c;
-                const bool rldg = resp != nullptr && !rtma;       // residual through the LSU, one chunk ahead
-                if (rldg) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) load_res(t, c, jj);
-                }
+                int t = t_first, c = c_first, slot = bycol ? 0 : c >> 2;
+                // residual that cannot come by TMA (channel count not a multiple of 4, unaligned, upsample): plain loads where it is
+                // added - slow, and not a case the networks produce
+                const bool rldg = resp != nullptr && !rtma;
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");           // btv visible
                 mbar_wait_relaxed(afull(a), (uint32_t)(i >> 1) & 1u);
                 tc_fence_after();
@@ -795,10 +787,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         cn_ += 3; ++slotn;
                         if (cn_ >= 8) { cn_ = gi; slotn = 0; ++tn; }
                     } else {
-                        const int g = (t << lcpt) + c + 3;
-                        tn = g >> lcpt; cn_ = g & (cpt - 1); slotn = cn_;
+                        const int g = (t << lcpt) + c + 4;
+                        tn = g >> lcpt; cn_ = g & (cpt - 1); slotn = cn_ >> 2;
                     }
-                    const bool more = kk + 1 < n_mine;
                     // ---- QUAD view
                     const int n0 = nbase + c0;
                     float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -807,7 +798,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                         float4 x = *reinterpret_cast<const float4*>(srow + buf * (128 * TS_STG_LD) + 32 * jj * TS_STG_LD);
                         const int o = t == 0 ? off[0][jj] : off[TS_MT - 1][jj];
                         if (o >= 0 && n0 < Cout) {
-                            if (rldg) { x.x += rr[jj].x; x.y += rr[jj].y; x.z += rr[jj].z; x.w += rr[jj].w; }
+                            if (rldg) {
+                                const float* src = resp + o + n0;
+                                const float4 r4 = vec_ok ? __ldg(reinterpret_cast<const float4*>(src)) : tcs_load_tail(src, Cout - n0);
+                                x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                            }
                             if (vec_ok) {
                                 if (o32) *reinterpret_cast<float4*>(o32 + o + n0) = x;
                                 if (o16) {
@@ -826,11 +821,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                             sm[0] += x.x; sm[1] += x.y; sm[2] += x.z; sm[3] += x.w;
                             sq[0] = fmaf(x.x, x.x, sq[0]); sq[1] = fmaf(x.y, x.y, sq[1]); sq[2] = fmaf(x.z, x.z, sq[2]); sq[3] = fmaf(x.w, x.w, sq[3]);
                         }
-                        if (rldg && more) load_res(tn, cn_, jj);
                     }
                     if (sums) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 3; ++k) {
                             if (k == slot) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) { acc[k][e] += sm[e]; acc[k][4 + e] += sq[e]; }
@@ -848,9 +842,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_tcs_kernel(const __grid_co
                 // ---- fold the item's statistics: per column slot, lanes of equal quad, then one fp64 atomic pair per channel
                 if (sums) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int cidx = bycol ? gi + 3 * k : k;  // column held by slot k
-                        if (cidx >= cpt) continue;
+                    for (int k = 0; k < 3; ++k) {
+                        const int cidx = bycol ? gi + 3 * k : (gi & (cpt - 1)) + 4 * k;       // column held by slot k
+                        if (cidx >= cpt || (!bycol && k >= 2)) continue;
 #pragma unroll
                         for (int o = 4; o <= 16; o <<= 1)
 #pragma unroll
@@ -1062,7 +1056,7 @@ bool tc_conv_persistent(int ca, int cb, int Hs, int Ws, int B, int cout, int ks,
     // at least three weight stages must fit beside the patches and the staging buffers
     const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
     const size_t patch_bytes = align_up((size_t)prows * kc * e, 1024), wstage = align_up((size_t)tc_bn(cout) * kc * e, 1024);
-    return (225 * 1024 - 2 * patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage >= 3;
+    return (225 * 1024 - 2 * patch_bytes - 3 * TS_STG_BYTES - 2048) / wstage >= 3;
 }
 
 int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b, int cb, int Hs, int Ws, int B, int cout, int ks,
@@ -1108,7 +1102,15 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                 const int prows = geo ? TP_PW * 18 : TP_PW * (TP_TH * TS_MT + 2) + 8;
                 q.patch_bytes = (uint32_t)align_up((size_t)prows * kc * e, 1024);
                 const uint32_t wstage = (uint32_t)align_up((size_t)bn * kc * e, 1024);
-                int wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - TS_EGROUPS * TS_STG_BYTES - 2048) / wstage);
+                // four epilogue groups when their staging areas leave at least five weight stages, else three (with three groups the
+                // chunks are dealt by column, which needs eight columns per tile)
+                int ng = 4;
+                int wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - 4 * TS_STG_BYTES - 2048) / wstage);
+                if (wst < 5 && bn == 128) {
+                    ng = 3;
+                    wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - 3 * TS_STG_BYTES - 2048) / wstage);
+                }
+                q.ngroups = ng;
                 if (wst > 12) wst = 12;
                 if (wst >= 3) {
                     q.wstages = wst;
@@ -1134,7 +1136,7 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                         q.xchunks_a = xca / kc; q.xchunks_b = xcb / kc;
                     }
                     plan->patch = 2;
-                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + TS_EGROUPS * TS_STG_BYTES + 16 * wst + 192 + 1024);
+                    plan->smem_bytes = (int)(2 * (size_t)q.patch_bytes + (size_t)wst * wstage + ng * TS_STG_BYTES + 16 * wst + 192 + 1024);
                     static int sms = 0;
                     if (!sms) {
                         int dev = 0;
