@@ -1106,7 +1106,9 @@ int tc_build_conv(TcConvPlan* plan, const void* src_a, int ca, const void* src_b
                 // chunks are dealt by column, which needs eight columns per tile)
                 int ng = 4;
                 int wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - 4 * TS_STG_BYTES - 2048) / wstage);
-                if (wst < 5 && bn == 128) {
+                static int ng_env = -1;
+                if (ng_env < 0) { const char* e6 = getenv("DIFFSPLIT_B200_TC_NG"); ng_env = e6 ? atoi(e6) : 0; }
+                if ((ng_env == 3 || (ng_env != 4 && wst < 5) || wst < 3) && bn == 128) {
                     ng = 3;
                     wst = (int)((225 * 1024 - 2 * (size_t)q.patch_bytes - 3 * TS_STG_BYTES - 2048) / wstage);
                 }
